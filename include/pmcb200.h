@@ -1,0 +1,178 @@
+/* pmcb200.h — the C-ABI of libpmcb200.so: pmclib's Population Monte Carlo iteration on one B200.
+ *
+ * Plain pointers and sizes only; no torch, no C++ types.  This is what a binding (cgo / ctypes / the drop-in
+ * C layer in pmclib_abi.h) calls.  Every entry point cites the reference interface it replaces; paths are
+ * relative to the reference tree (CosmoStat/pmclib).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative code: the reference's own codes where one applies
+ *     (pmc.h:23-43, mvdens.h:54-68), PMCGPU_ERR_* below for CUDA/NCCL/usage failures.  pmcgpu_last_error()
+ *     gives the text.  Nothing aborts; there is no CPU fallback: without a CUDA device pmcgpu_create fails.
+ *   - a mixture is passed as the reference stores it after mvdens_cholesky_decomp (mvdens.h:83-110):
+ *     wght[K], mean[K*d], L[K*d*d] row-major lower Cholesky factors (upper triangle ignored), detL[K] = prod L_ii,
+ *     df[K] (-1 = Gaussian, else Student-t degrees of freedom).
+ *   - the sample store mirrors pmc_simu (pmc.h:76-108): X[N*d] row-major, weights[N], log_rho[N],
+ *     indices[N] (size_t), flg[N] (short); it lives in HBM and is copied to/from host buffers only by
+ *     pmcgpu_upload / pmcgpu_download.
+ *   - one context = one GPU = one caller thread (the reference is not re-entrant either).
+ */
+#ifndef PMCB200_H
+#define PMCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmcgpu_ctx pmcgpu_ctx;
+
+#define PMCGPU_ERR_CUDA (-6021)    /* pmc_base - 21: CUDA runtime failure */
+#define PMCGPU_ERR_NCCL (-6022)    /* pmc_base - 22: NCCL failure / NCCL not loadable */
+#define PMCGPU_ERR_USAGE (-6023)   /* pmc_base - 23: bad argument / call order */
+#define PMCGPU_ERR_NODEVICE (-6024)
+
+enum { PMCGPU_TGT_NONE = 0, PMCGPU_TGT_BANANA = 1, PMCGPU_TGT_MVDENS = 2, PMCGPU_TGT_MIX = 3, PMCGPU_TGT_HOST = 4 };
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+int pmcgpu_create(int device, pmcgpu_ctx **out);
+void pmcgpu_destroy(pmcgpu_ctx *ctx);
+const char *pmcgpu_last_error(const pmcgpu_ctx *ctx);
+int pmcgpu_version(void);
+/* the CUDA stream all work of this context is enqueued on (a cudaStream_t), for callers that time with events */
+void *pmcgpu_stream(pmcgpu_ctx *ctx);
+
+/* tuning / test knobs: "force_generic" (1 = never use the fused small-d kernel), "spl" (samples per lane of the fused
+ * kernel, 1 or 2), "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass
+ * update), "guard_ratio" (pivot guard threshold of the one-pass update) */
+int pmcgpu_set_option(pmcgpu_ctx *ctx, const char *name, double value);
+
+/* ---- model: proposal, target, box ------------------------------------------------------------- */
+/* replaces the host-side mix_mvdens the reference passes around (mvdens.h:102-110) */
+int pmcgpu_set_proposal(pmcgpu_ctx *ctx, int K, int d, const double *wght, const double *mean, const double *L,
+                        const double *detL, const int *df);
+/* mvdens.band_limit (mvdens.h:96, used at pmc.c:1444): band_limit[K], NULL = full matrices; reset by set_proposal */
+int pmcgpu_set_band_limit(pmcgpu_ctx *ctx, const size_t *band_limit);
+/* device targets; replace the posterior_log_pdf_func callback (allmc.h:21) for the densities the reference ships:
+ * bentGauss_lkl (examples/target/sampleTarget.c:89-110), mvdens_log_pdf (mvdens.c:354-385),
+ * mix_mvdens_log_pdf (mvdens.c:784-825) */
+int pmcgpu_set_target_banana(pmcgpu_ctx *ctx, int d, double b, double sig1);
+int pmcgpu_set_target_mix(pmcgpu_ctx *ctx, int kind, int K, int d, const double *wght, const double *mean,
+                          const double *L, const double *detL, const int *df);
+/* conditional ("default") parameters of distribution_fill_pars (distribution.c:193-209): the target sees a vector of
+ * nfull = d + ndef entries, full[i] = is_def[i] ? value[i] : x[next free].  nfull = 0 clears the map. */
+int pmcgpu_set_target_defaults(pmcgpu_ctx *ctx, int nfull, const int *is_def, const double *value);
+/* opaque host callback: the caller evaluates the target on the host and passes post[N] to pmcgpu_weights_host_post */
+int pmcgpu_set_target_host(pmcgpu_ctx *ctx, int d);
+/* parabox (parabox.h:22-26): faces[nfaces*(d+1)]; nfaces = 0 removes the box */
+int pmcgpu_set_box(pmcgpu_ctx *ctx, int d, int nfaces, const double *faces);
+
+/* ---- sample store ----------------------------------------------------------------------------- */
+/* pmc_simu_init / pmc_simu_realloc (pmc.c:29-74, 222-246): N local samples of dimension d */
+int pmcgpu_resize(pmcgpu_ctx *ctx, long N, int d);
+/* any pointer may be NULL (that array is left untouched) */
+int pmcgpu_upload(pmcgpu_ctx *ctx, const double *X, const size_t *indices, const double *weights,
+                  const double *log_rho, const short *flg);
+int pmcgpu_download(pmcgpu_ctx *ctx, double *X, size_t *indices, double *weights, double *log_rho, short *flg);
+/* device addresses of the store, for zero-copy consumers: out[5] = X, indices, weights, log_rho, flg */
+int pmcgpu_device_arrays(pmcgpu_ctx *ctx, void **out);
+
+/* ---- the phases of one iteration, on the resident store ------------------------------------------ */
+/* simulate_mix_mvdens (pmc.c:266-298): draws N samples from the proposal inside the box; Philox4x32-10 keyed by
+ * (seed, iter) and counted by the global sample index first_index + i, so the stream does not depend on how
+ * samples are sharded.  Sets X, indices, flg=1.  n_reject may be NULL. */
+int pmcgpu_draw(pmcgpu_ctx *ctx, uint64_t seed, uint32_t iter, long first_index, long *n_reject);
+/* generic_get_importance_weight_and_deduced_verb (pmc.c:484-600) with the device target: fills log_rho, weights
+ * (log-weights t*post - log_rho), flg; returns the ok count and the running maxima exactly as the reference
+ * defines them (the i==0 quirk applies to the sample whose global index is 0: pass first_index). */
+int pmcgpu_weights(pmcgpu_ctx *ctx, double t_temper, long first_index, long *nok, double *maxW, double *maxR);
+/* same with the target evaluated by the caller on the host (PMCGPU_TGT_HOST): post[N]; ok[N] (may be NULL) = 0
+ * where the callback raised an error (sample is flagged out, pmc.c:563) */
+int pmcgpu_weights_host_post(pmcgpu_ctx *ctx, const double *post, const short *ok, double t_temper,
+                             long first_index, long *nok, double *maxW, double *maxR);
+/* mix_mvdens_log_pdf (mvdens.c:784-825) of the PROPOSAL / the device TARGET on n host points: out[n] */
+int pmcgpu_proposal_log_pdf(pmcgpu_ctx *ctx, long n, const double *x, double *out);
+int pmcgpu_target_log_pdf(pmcgpu_ctx *ctx, long n, const double *x, double *out);
+/* normalize_importance_weight (pmc.c:641-697): weights <- exp(lw - maxW + 500)/S over flg==1, non-finite
+ * entries flagged out; logSum = log S + maxW - 500.  count = number of samples summed. */
+int pmcgpu_normalize(pmcgpu_ctx *ctx, double maxW, double *logSum, long *count);
+/* perplexity_and_ess (pmc.c:1041-1077, MC_UNORM) and the flagged-out count evidence() needs (pmc.c:1088-1105) */
+int pmcgpu_perplexity_ess(pmcgpu_ctx *ctx, double *perp, double *ess, long *n_flagged_out);
+/* prepare_update's histogram (pmc.c:1559-1564): count[K] of indices over flg==1 */
+int pmcgpu_count_indices(pmcgpu_ctx *ctx, size_t *count);
+/* update_prop_rb (pmc.c:1323-1469) + prepare_update + cleanup_after_update on the resident, normalised sample:
+ * two passes over the samples exactly as the reference (responsibilities against the stored log_rho and maxR, then
+ * covariances centred on the new means).  N_total = psim->nsamples of the whole (all-rank) sample, for the
+ * 1/N weight floor.  The proposal held by the context is replaced; outputs (any may be NULL) receive it in
+ * reference layout: o_wght[K], o_mean[K*d], o_L[K*d*d] (factor with the upper triangle mirrored, zeros for dead
+ * components), o_detL[K], o_alive[K].  *retry is psim->retry, in/out. */
+int pmcgpu_update_rb(pmcgpu_ctx *ctx, double maxR, long N_total, int *retry, double *o_wght, double *o_mean,
+                     double *o_L, double *o_detL, int *o_alive);
+/* update_prop (pmc.c:1194-1310), the hard-assignment variant */
+int pmcgpu_update_hard(pmcgpu_ctx *ctx, long N_total, int *retry, double *o_wght, double *o_mean, double *o_L,
+                       double *o_detL, int *o_alive);
+/* ranindx (mvdens.c:766-782) on injected uniforms z[n] with the proposal's cumulative weights: idx[n] */
+int pmcgpu_ranindx(pmcgpu_ctx *ctx, long n, const double *z, size_t *idx);
+/* isinBox (parabox.c:112-136) on n host points: inside[n] */
+int pmcgpu_isinbox(pmcgpu_ctx *ctx, long n, const double *x, int *inside);
+
+/* ---- the fused iteration ---------------------------------------------------------------------- */
+typedef struct {
+  double perplexity;   /* perplexity(psim, MC_UNORM), what pmc_simu_pmc_step returns (pmc.c:216) */
+  double ess;
+  double logSum;       /* psim->logSum */
+  double ln_evidence;  /* evidence() */
+  double maxW, maxR;
+  long nok;            /* samples with flg==1 after normalisation (all ranks) */
+  long n_reject;       /* box rejections during the draw (all ranks) */
+  int retry;           /* psim->retry after the update */
+  int n_alive;         /* components with weight > 0 after the update */
+  int used_precise_path;  /* 1 if the pivot guard sent the update through the two-pass path */
+} pmcgpu_step_result;
+
+/* pmc_simu_pmc_step (pmc.c:196-219) with t_iter_tempered = 1 (the evident intent; the reference's own call passes
+ * -1 and fails): draw + weights + normalise + Rao-Blackwellised update + perplexity, one pass over
+ * the samples for everything that scales with N.  do_update = 0 gives pmc_simu_importance + perplexity/evidence
+ * (vanilla_importance.c:56-82).  N_total / first_index describe the shard (N_total = local N and first_index = 0
+ * on one GPU); with a communicator attached the sufficient statistics are all-reduced.  The updated proposal
+ * replaces the context's and is returned like pmcgpu_update_rb's. */
+int pmcgpu_pmc_step(pmcgpu_ctx *ctx, uint64_t seed, uint32_t iter, long first_index, long N_total, int do_update,
+                    int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean, double *o_L,
+                    double *o_detL, int *o_alive);
+/* same on samples already in the store (no draw): indices must be valid for the update */
+int pmcgpu_step_given(pmcgpu_ctx *ctx, long first_index, long N_total, double t_temper, int do_update, int *retry,
+                      pmcgpu_step_result *res, double *o_wght, double *o_mean, double *o_L, double *o_detL,
+                      int *o_alive);
+/* read back the proposal currently installed (after a step): reference layout as above */
+int pmcgpu_get_proposal(pmcgpu_ctx *ctx, double *o_wght, double *o_mean, double *o_L, double *o_detL, int *o_alive);
+
+/* ---- multi-GPU: one context per GPU, samples sharded, statistics all-reduced (pmc_mpi.c:44-125) --------- */
+/* shard layout of send_simulation (pmc_mpi.c:344-352) generalised to "every rank works": rank r of P owns
+ * [first, first+len) with len = N/P (+1 for the first N%P ranks) */
+void pmcgpu_shard_range(long N_total, int rank, int nranks, long *first, long *len);
+/* NCCL (dlopen'ed libnccl.so.2): id is PMCGPU_NCCL_ID_BYTES bytes obtained on rank 0 and broadcast by the caller */
+#define PMCGPU_NCCL_ID_BYTES 128
+int pmcgpu_nccl_unique_id(void *id_out);
+int pmcgpu_comm_init(pmcgpu_ctx *ctx, const void *id, int rank, int nranks);
+/* alternative for callers that own the collective (tests on CPU, MPI hosts): called on a HOST buffer of n doubles,
+ * op 0 = sum, 1 = max; must return 0 on success */
+typedef int (*pmcgpu_allreduce_fn)(void *user, double *buf, long n, int op);
+int pmcgpu_comm_set_callback(pmcgpu_ctx *ctx, pmcgpu_allreduce_fn fn, void *user, int rank, int nranks);
+
+/* ---- host-side finalisation, exposed for tests and for hosts that reduce the statistics themselves -------- */
+/* number of doubles in the sufficient-statistics block for (K, d): K*(2 + d + d*d) + 8 */
+long pmcgpu_stats_len(int K, int d);
+/* new proposal from reduced statistics: W[K], G[K], s1[K*d] = sum g (x - pivot), S2[K*d*d] = sum g (x-pivot)(x-pivot)^T,
+ * count[K]; old mixture (for the retry snapshot) in reference layout; writes the new one in place.  Host only: it is
+ * the literal cleanup_after_update logic (pmc.c:1471-1533) around a GSL-1.14-semantics Cholesky. */
+int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const double *s1, const double *S2,
+                           const double *pivot, int pivot_per_component, const size_t *count, long N_total,
+                           const size_t *band_limit, int *retry, double *wght, double *mean, double *L, double *detL,
+                           int *alive);
+/* mvdens_cholesky_decomp (mvdens.c:229-277): in place; returns mv_cholesky (-706) and restores a[] if not PD */
+int pmcgpu_cholesky(int d, double *a, double *detL);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

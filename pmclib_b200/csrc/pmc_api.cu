@@ -1,0 +1,1233 @@
+// pmc_api.cu — the C-ABI of libpmcb200.so (include/pmcb200.h): context, HBM-resident sample store, kernel
+// orchestration for one PMC iteration, the optional NCCL all-reduce of the sufficient statistics.
+// Host code here is orchestration only; everything that scales with the number of samples runs in the kernels of
+// pmc_fused.cu / pmc_generic.cu.  There is no CPU fallback: without a CUDA device pmcgpu_create fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+#include "pmc_kernels.h"
+#include "pmc_hostonly.h"
+
+using namespace pmcb200;
+
+namespace {
+
+constexpr int kErrNegWeight = -6005, kErrUndef = -6008, kErrTooManySteps = -6011, kErrNoSample = -6017,
+              kErrMvNegWeight = -705, kErrMvOutOfBound = -703;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostMix {
+  int K = 0, d = 0;
+  std::vector<double> wght, mean, L, detL, logdet, gam, norm, cw;
+  std::vector<int> df;
+  std::vector<size_t> band;
+  bool student = false;
+  int n_alive() const { int n = 0; for (double w : wght) n += (w > 0.0); return n; }
+};
+
+struct DevMixBuf {
+  DevBuf buf;
+  MixDev view{};
+};
+
+// ---- NCCL through dlopen (no link-time dependency) ---------------------------------------------------------------
+struct IdByValue { char internal[PMCGPU_NCCL_ID_BYTES]; };  // ncclUniqueId is passed by value
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, IdByValue, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool load_nccl(std::string &why) {
+  if (g_nccl.h) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) { why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+  g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void **, int, IdByValue, int))dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    why = "libnccl.so.2 lacks the expected symbols";
+    g_nccl.h = nullptr;
+    return false;
+  }
+  return true;
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+
+}  // namespace
+
+struct pmcgpu_ctx {
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // model
+  HostMix prop;
+  DevMixBuf dprop;
+  DevBuf dprop_pack;
+  int prop_pack_doubles = 0;
+  int tkind = PMCGPU_TGT_NONE, td = 0;
+  double tb = 0, tsig1 = 1;
+  HostMix tmix;
+  DevMixBuf dtmix;
+  DevBuf dt_pack;
+  int t_pack_doubles = 0;
+  int nfull = 0;
+  std::vector<int> is_def;
+  std::vector<double> def_val;
+  DevBuf ddef;
+  int nfaces = 0, box_d = 0;
+  std::vector<double> faces;
+  DevBuf dfaces;
+  bool box_slab = false;
+  double lo_thr[FUSED_MAXD], hi_thr[FUSED_MAXD];
+  // store
+  long N = 0;
+  int d = 0;
+  DevBuf X, W, R, Idx, Flg;
+  // scratch
+  DevBuf ld, blkmax, partials, stats, small, rbg, rbw, rbacc, rbpart, newmean, hostpost, hostok, tmpx, tmpo;
+  double *hstage = nullptr;  // pinned
+  size_t hstage_doubles = 0;
+  // options
+  int force_generic = 0, spl = 1, max_attempts = 10000, force_precise = 0;
+  double guard_ratio = 200.0;
+  // comm
+  int rank = 0, nranks = 1;
+  void *nccl_comm = nullptr;
+  pmcgpu_allreduce_fn cb = nullptr;
+  void *cb_user = nullptr;
+  DevBuf dcoll;
+};
+
+namespace {
+
+int fail(pmcgpu_ctx *c, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(call)                                                                                           \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess) return fail(c, PMCGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define RC(call) do { int r_ = (call); if (r_) return r_; } while (0)
+
+int stage(pmcgpu_ctx *c, size_t doubles) {
+  if (doubles <= c->hstage_doubles) return 0;
+  if (c->hstage) cudaFreeHost(c->hstage);
+  c->hstage = nullptr;
+  c->hstage_doubles = 0;
+  CU(cudaMallocHost((void **)&c->hstage, doubles * sizeof(double)));
+  c->hstage_doubles = doubles;
+  return 0;
+}
+
+// small device block: counters[CNT_NUM] (ull) | count_k[64] (ull) | first_vals[4] (double) = 8+64+4 = 76 x 8 bytes
+constexpr int SM_COUNTERS = 0, SM_COUNTK = CNT_NUM, SM_FIRST = CNT_NUM + 64, SM_LEN = CNT_NUM + 64 + 4;
+
+int upload_mix(pmcgpu_ctx *c, const HostMix &m, DevMixBuf &o) {
+  const size_t K = m.K, d = m.d;
+  const size_t nd = K * 6 + K * d + K * d * d;  // alpha,cw,logdet,gam,norm + pad | mean | L
+  const size_t bytes = nd * sizeof(double) + K * sizeof(int);
+  CU(o.buf.ensure(bytes));
+  RC(stage(c, nd + K));
+  double *h = c->hstage;
+  size_t off = 0;
+  auto put = [&](const std::vector<double> &v) { memcpy(h + off, v.data(), v.size() * sizeof(double)); size_t r = off; off += v.size(); return r; };
+  const size_t oa = put(m.wght), ocw = put(m.cw), old = put(m.logdet), og = put(m.gam), on = put(m.norm);
+  off += K;
+  const size_t om = put(m.mean), oL = put(m.L);
+  memcpy(h + off, m.df.data(), K * sizeof(int));
+  CU(cudaMemcpyAsync(o.buf.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double *b = o.buf.as<double>();
+  o.view = MixDev{(int)K, (int)d, b + oa, b + ocw, b + om, b + oL, b + old, b + og, b + on, reinterpret_cast<const int *>(b + nd)};
+  return 0;
+}
+
+// derived quantities of a mixture: log det, Student-t constants (mvdens.c:376-377), cumulative weights (mvdens.c:748-750)
+void derive_mix(HostMix &m) {
+  const int K = m.K, d = m.d;
+  m.logdet.assign(K, 0.0);
+  m.gam.assign(K, 0.0);
+  m.norm.assign(K, 0.0);
+  m.cw.assign(K, 0.0);
+  m.student = false;
+  for (int k = 0; k < K; ++k) {
+    m.logdet[k] = std::log(m.detL[k]);
+    if (m.df[k] != -1) {
+      m.student = true;
+      const size_t n = (size_t)m.df[k], p = (size_t)d;
+      m.gam[k] = lgamma(0.5 * (n + p));
+      m.norm[k] = lgamma(0.5 * n) + 0.5 * p * std::log(n * kPi);
+    }
+  }
+  double cacc = 0.0;
+  for (int k = 0; k < K; ++k) { cacc = (k == 0) ? m.wght[0] : cacc + m.wght[k]; m.cw[k] = cacc; }
+}
+
+int fill_mix(pmcgpu_ctx *c, HostMix &m, int K, int d, const double *wght, const double *mean, const double *L,
+             const double *detL, const int *df) {
+  if (K < 1 || d < 1 || d > PMCB200_MAXD) return fail(c, PMCGPU_ERR_USAGE, "mixture shape K=%d d=%d not supported (d <= %d)", K, d, PMCB200_MAXD);
+  m.K = K;
+  m.d = d;
+  m.wght.assign(wght, wght + K);
+  m.mean.assign(mean, mean + (size_t)K * d);
+  m.L.assign(L, L + (size_t)K * d * d);
+  m.detL.resize(K);
+  for (int k = 0; k < K; ++k) {
+    if (detL) m.detL[k] = detL[k];
+    else { double det = 1.0; for (int a = 0; a < d; ++a) det *= L[(size_t)k * d * d + (size_t)a * d + a]; m.detL[k] = det; }
+  }
+  m.df.assign(K, -1);
+  if (df) m.df.assign(df, df + K);
+  derive_mix(m);
+  return 0;
+}
+
+int pack_small(pmcgpu_ctx *c, const HostMix &m, DevBuf &out, int &ndoubles) {
+  ndoubles = 0;
+  if (m.d > FUSED_MAXD || m.student) return 0;
+  const int n = m.K * fused_comp_stride(m.d);
+  CU(out.ensure((size_t)n * sizeof(double)));
+  RC(stage(c, n));
+  fused_pack_mixture(m.K, m.d, m.wght.data(), m.mean.data(), m.L.data(), m.logdet.data(), c->hstage);
+  CU(cudaMemcpyAsync(out.p, c->hstage, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  ndoubles = n;
+  return 0;
+}
+
+int install_proposal(pmcgpu_ctx *c) {
+  derive_mix(c->prop);
+  int rc = upload_mix(c, c->prop, c->dprop);
+  if (rc) return rc;
+  return pack_small(c, c->prop, c->dprop_pack, c->prop_pack_doubles);
+}
+
+TargetDev target_view(const pmcgpu_ctx *c) {
+  TargetDev t{};
+  t.kind = c->tkind;
+  t.d = c->td;
+  t.b = c->tb;
+  t.sig1 = c->tsig1;
+  t.mix = c->dtmix.view;
+  t.nfull = c->nfull;
+  t.is_def = c->nfull ? c->ddef.as<int>() : nullptr;
+  t.def_val = c->nfull ? reinterpret_cast<const double *>(c->ddef.as<char>() + ((c->nfull * sizeof(int) + 15) / 16) * 16) : nullptr;
+  return t;
+}
+
+FusedPlan plan_for(const pmcgpu_ctx *c) {
+  FusedPlan none{};
+  if (c->force_generic || c->prop.K == 0 || c->prop.student || c->prop.d > FUSED_MAXD || c->nfull != 0) return none;
+  if (c->prop_pack_doubles == 0) return none;
+  int Kt = 0;
+  if (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX) {
+    if (c->tmix.student || c->t_pack_doubles == 0 || c->tmix.d != c->prop.d) return none;
+    Kt = c->tmix.K;
+  } else if (c->tkind == PMCGPU_TGT_BANANA) {
+    if (c->td != c->prop.d || c->td < 2) return none;
+  } else if (c->tkind != PMCGPU_TGT_HOST) {
+    return none;
+  }
+  if (c->nfaces > 0 && !c->box_slab) return none;
+  return fused_plan(c->prop.d, c->prop.K, Kt, c->sm_count, c->spl);
+}
+
+// ---- collectives on small host buffers ------------------------------------------------------------------------
+int allreduce_host(pmcgpu_ctx *c, double *buf, long n, int op /*0 sum, 1 max*/) {
+  if (c->nranks <= 1) return 0;
+  if (c->cb) {
+    if (c->cb(c->cb_user, buf, n, op) != 0) return fail(c, PMCGPU_ERR_NCCL, "allreduce callback failed");
+    return 0;
+  }
+  if (!c->nccl_comm) return fail(c, PMCGPU_ERR_NCCL, "nranks=%d but no communicator attached", c->nranks);
+  CU(c->dcoll.ensure((size_t)n * sizeof(double)));
+  CU(cudaMemcpyAsync(c->dcoll.p, buf, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const int r = g_nccl.AllReduce(c->dcoll.p, c->dcoll.p, (size_t)n, kNcclFloat64, op == 0 ? kNcclSum : kNcclMax, c->nccl_comm, c->stream);
+  if (r != 0) return fail(c, PMCGPU_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  CU(cudaMemcpyAsync(buf, c->dcoll.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// the reference's running maximum with its unconditional i==0 assignment (pmc.c:535,552,579)
+double fold_max(double m_all, bool has_first, bool reached0, double v0) {
+  if (has_first && reached0) return std::isnan(v0) ? v0 : (m_all > v0 ? m_all : v0);
+  return m_all > kNegInit ? m_all : kNegInit;
+}
+
+int zero_small(pmcgpu_ctx *c) {
+  CU(c->small.ensure(SM_LEN * 8));
+  CU(cudaMemsetAsync(c->small.p, 0, SM_LEN * 8, c->stream));
+  return 0;
+}
+int read_small(pmcgpu_ctx *c, unsigned long long *counters, unsigned long long *count_k, double *first) {
+  RC(stage(c, SM_LEN));
+  CU(cudaMemcpyAsync(c->hstage, c->small.p, SM_LEN * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const unsigned long long *u = reinterpret_cast<const unsigned long long *>(c->hstage);
+  if (counters) memcpy(counters, u + SM_COUNTERS, CNT_NUM * 8);
+  if (count_k) memcpy(count_k, u + SM_COUNTK, 64 * 8);
+  if (first) memcpy(first, c->hstage + SM_FIRST, 4 * 8);
+  return 0;
+}
+
+struct WeightOut {
+  double M_all = -INFINITY, R_all = -INFINITY, S = 0.0;  // NaN-ignoring maxima over local samples; S = sum exp(lw - M_all)
+  double first[4] = {0, 0, 0, 0};
+  bool has_first = false;
+  unsigned long long counters[CNT_NUM] = {0};
+  unsigned long long count_k[64] = {0};
+  std::vector<double> stats;  // canonical K*E statistics relative to M_all (fused path with do_stats)
+};
+
+int ensure_cwght_normalised(pmcgpu_ctx *c) {
+  // mix_mvdens_ran renormalises the weights in place before building cwght (mvdens.c:736-751)
+  HostMix &m = c->prop;
+  double s = 0.0;
+  for (int k = 0; k < m.K; ++k) s += m.wght[k];
+  if (std::fabs(s - 1.0) > 1e-6) {
+    if (s == 0) return fail(c, kErrMvNegWeight, "All weights to zero !! cannot sample");
+    const double inv = 1.0 / s;
+    for (int k = 0; k < m.K; ++k) m.wght[k] *= inv;
+    return install_proposal(c);
+  }
+  return 0;
+}
+
+int check_ready(pmcgpu_ctx *c, bool need_target) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  if (c->prop.K == 0) return fail(c, PMCGPU_ERR_USAGE, "no proposal set");
+  if (c->N <= 0 || c->d != c->prop.d) return fail(c, PMCGPU_ERR_USAGE, "sample store not sized for the proposal (N=%ld d=%d, proposal d=%d)", c->N, c->d, c->prop.d);
+  if (need_target && c->tkind == PMCGPU_TGT_NONE) return fail(c, PMCGPU_ERR_USAGE, "no target set");
+  if (c->prop.n_alive() == 0) return fail(c, kErrMvOutOfBound, "Indice out of bonds: no component with positive weight");
+  return 0;
+}
+
+// Fused kernel over the resident store.  do_draw / do_stats select the phases.
+int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint64_t seed, uint32_t iter,
+              long first_index, double t_temper, const double *post_in, const short *ok_in, WeightOut &o) {
+  FusedArgs a{};
+  a.mixpack = c->dprop_pack.as<double>();
+  a.mix_doubles = c->prop_pack_doubles;
+  a.comp_stride = fused_comp_stride(c->prop.d);
+  a.K = c->prop.K;
+  a.tgt_kind = c->tkind;
+  if (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX) {
+    a.tgtpack = c->dt_pack.as<double>();
+    a.tgt_doubles = c->t_pack_doubles;
+    a.tgt_stride = fused_comp_stride(c->prop.d);
+    a.Kt = c->tmix.K;
+  }
+  a.b = c->tb;
+  a.sig1 = c->tsig1;
+  a.t_temper = t_temper;
+  a.post_in = post_in;
+  a.ok_in = ok_in;
+  a.has_box = c->nfaces > 0;
+  for (int j = 0; j < FUSED_MAXD; ++j) { a.lo_thr[j] = c->lo_thr[j]; a.hi_thr[j] = c->hi_thr[j]; a.pivot[j] = 0.0; }
+  {  // pivot = mixture mean (weights of live components)
+    const HostMix &m = c->prop;
+    double sw = 0.0;
+    for (int k = 0; k < m.K; ++k) if (m.wght[k] > 0) sw += m.wght[k];
+    for (int j = 0; j < m.d; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < m.K; ++k) if (m.wght[k] > 0) s += m.wght[k] * m.mean[(size_t)k * m.d + j];
+      a.pivot[j] = s / sw;
+    }
+  }
+  a.do_draw = do_draw;
+  a.do_stats = do_stats;
+  a.N = c->N;
+  a.first_index = first_index;
+  a.seed = seed;
+  a.iter = iter;
+  a.max_attempts = c->max_attempts;
+  a.X = c->X.as<double>();
+  a.lw = c->W.as<double>();
+  a.log_rho = c->R.as<double>();
+  a.indices = c->Idx.as<unsigned long long>();
+  a.flg = c->Flg.as<short>();
+  CU(c->partials.ensure((size_t)p.grid * p.partial_len * sizeof(double)));
+  CU(c->stats.ensure((size_t)(p.nstat + 4) * sizeof(double)));
+  a.partials = c->partials.as<double>();
+  a.partial_len = p.partial_len;
+  int rc = zero_small(c);
+  if (rc) return rc;
+  unsigned long long *sm = c->small.as<unsigned long long>();
+  a.counters = sm + SM_COUNTERS;
+  a.count_k = sm + SM_COUNTK;
+  a.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
+  if (launch_fused(p, a, c->stream) != 0) return fail(c, PMCGPU_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (launch_fused_combine(p, a.partials, c->prop.K, c->stats.as<double>(), c->stream) != 0)
+    return fail(c, PMCGPU_ERR_CUDA, "combine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  RC(stage(c, (size_t)p.nstat + 4 + SM_LEN));
+  CU(cudaMemcpyAsync(c->hstage, c->stats.p, (size_t)(p.nstat + 4) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->hstage + p.nstat + 4, c->small.p, SM_LEN * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  o.stats.assign(c->hstage, c->hstage + p.nstat);
+  o.M_all = c->hstage[p.nstat];
+  o.S = c->hstage[p.nstat + 1];
+  o.R_all = c->hstage[p.nstat + 2];
+  const unsigned long long *u = reinterpret_cast<const unsigned long long *>(c->hstage + p.nstat + 4);
+  memcpy(o.counters, u + SM_COUNTERS, CNT_NUM * 8);
+  memcpy(o.count_k, u + SM_COUNTK, 64 * 8);
+  memcpy(o.first, c->hstage + p.nstat + 4 + SM_FIRST, 4 * 8);
+  o.has_first = (first_index == 0);
+  return 0;
+}
+
+constexpr long GEN_CHUNK = 1L << 18;
+
+int run_weights_generic(pmcgpu_ctx *c, int mode, const double *post_in, const short *ok_in, double t_temper,
+                        long first_index, WeightOut &o) {
+  const long N = c->N;
+  const int Kmax = c->prop.K > c->tmix.K ? c->prop.K : c->tmix.K;
+  const long chunk = N < GEN_CHUNK ? N : GEN_CHUNK;
+  CU(c->ld.ensure((size_t)chunk * Kmax * sizeof(double)));
+  const int nb = (int)((chunk + GEN_WEIGHT_THREADS - 1) / GEN_WEIGHT_THREADS);
+  CU(c->blkmax.ensure((size_t)2 * nb * sizeof(double)));
+  int rc = zero_small(c);
+  if (rc) return rc;
+  unsigned long long *sm = c->small.as<unsigned long long>();
+  const TargetDev tv = target_view(c);
+  RC(stage(c, (size_t)2 * nb + SM_LEN));
+  for (long base = 0; base < N; base += chunk) {
+    const long n = (N - base) < chunk ? (N - base) : chunk;
+    const int nbc = (int)((n + GEN_WEIGHT_THREADS - 1) / GEN_WEIGHT_THREADS);
+    launch_weights_generic(c->dprop.view, tv, mode, post_in ? post_in + base : nullptr, ok_in ? ok_in + base : nullptr,
+                           t_temper, first_index + base, n, c->X.as<double>() + (size_t)base * c->d,
+                           c->W.as<double>() + base, c->R.as<double>() + base, c->Flg.as<short>() + base,
+                           c->ld.as<double>(), Kmax, c->blkmax.as<double>(), c->blkmax.as<double>() + nb,
+                           sm + SM_COUNTERS, reinterpret_cast<double *>(sm + SM_FIRST), c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->hstage, c->blkmax.p, (size_t)2 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < nbc; ++b) {
+      if (c->hstage[b] > o.M_all) o.M_all = c->hstage[b];
+      if (c->hstage[nb + b] > o.R_all) o.R_all = c->hstage[nb + b];
+    }
+  }
+  rc = read_small(c, o.counters, nullptr, o.first);
+  o.has_first = (first_index == 0);
+  return rc;
+}
+
+int normalize_impl(pmcgpu_ctx *c, double maxW, double *S_out, long *count_out, bool reduce_ranks) {
+  const int nb = c->sm_count * 8;
+  CU(c->blkmax.ensure((size_t)2 * nb * sizeof(double)));
+  int rc = zero_small(c);
+  if (rc) return rc;
+  unsigned long long *sm = c->small.as<unsigned long long>();
+  launch_norm_exp_sum(c->N, maxW, c->W.as<double>(), c->Flg.as<short>(), c->blkmax.as<double>(), nb, sm + SM_COUNTERS, c->stream);
+  CU(cudaGetLastError());
+  RC(stage(c, (size_t)nb + SM_LEN));
+  CU(cudaMemcpyAsync(c->hstage, c->blkmax.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->hstage + nb, c->small.p, SM_LEN * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double red[2] = {0.0, 0.0};
+  for (int b = 0; b < nb; ++b) red[0] += c->hstage[b];
+  red[1] = (double)reinterpret_cast<const unsigned long long *>(c->hstage + nb)[SM_COUNTERS + CNT_NORMCOUNT];
+  if (reduce_ranks) { rc = allreduce_host(c, red, 2, 0); if (rc) return rc; }
+  *S_out = red[0];
+  *count_out = (long)red[1];
+  return 0;
+}
+
+int scale_perp_impl(pmcgpu_ctx *c, double S, bool scale, double *H, double *Q, long *nexit, bool reduce_ranks) {
+  const int nb = c->sm_count * 8;
+  CU(c->blkmax.ensure((size_t)2 * nb * sizeof(double)));
+  int rc = zero_small(c);
+  if (rc) return rc;
+  unsigned long long *sm = c->small.as<unsigned long long>();
+  if (scale) launch_norm_scale_perp(c->N, S, c->W.as<double>(), c->Flg.as<short>(), c->blkmax.as<double>(), nb, sm + SM_COUNTERS, c->stream);
+  else launch_perplexity(c->N, c->W.as<double>(), c->Flg.as<short>(), c->blkmax.as<double>(), nb, sm + SM_COUNTERS, c->stream);
+  CU(cudaGetLastError());
+  RC(stage(c, (size_t)2 * nb + SM_LEN));
+  CU(cudaMemcpyAsync(c->hstage, c->blkmax.p, (size_t)2 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->hstage + 2 * nb, c->small.p, SM_LEN * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double red[3] = {0.0, 0.0, 0.0};
+  for (int b = 0; b < nb; ++b) { red[0] += c->hstage[2 * b]; red[1] += c->hstage[2 * b + 1]; }
+  red[2] = (double)reinterpret_cast<const unsigned long long *>(c->hstage + 2 * nb)[SM_COUNTERS + CNT_FLAGGED];
+  if (reduce_ranks) { rc = allreduce_host(c, red, 3, 0); if (rc) return rc; }
+  *H = red[0];
+  *Q = red[1];
+  *nexit = (long)red[2];
+  return 0;
+}
+
+int count_indices_impl(pmcgpu_ctx *c, std::vector<size_t> &count, bool reduce_ranks) {
+  const int K = c->prop.K;
+  CU(c->tmpo.ensure((size_t)K * 8));
+  CU(cudaMemsetAsync(c->tmpo.p, 0, (size_t)K * 8, c->stream));
+  launch_count_indices(c->N, K, c->Idx.as<unsigned long long>(), c->Flg.as<short>(), c->tmpo.as<unsigned long long>(), c->sm_count * 4, c->stream);
+  CU(cudaGetLastError());
+  RC(stage(c, K));
+  CU(cudaMemcpyAsync(c->hstage, c->tmpo.p, (size_t)K * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::vector<double> tmp(K);
+  for (int k = 0; k < K; ++k) tmp[k] = (double)reinterpret_cast<const unsigned long long *>(c->hstage)[k];
+  if (reduce_ranks) { int rc = allreduce_host(c, tmp.data(), K, 0); if (rc) return rc; }
+  count.resize(K);
+  for (int k = 0; k < K; ++k) count[k] = (size_t)tmp[k];
+  return 0;
+}
+
+void export_proposal(const pmcgpu_ctx *c, double *o_wght, double *o_mean, double *o_L, double *o_detL, int *o_alive) {
+  const HostMix &m = c->prop;
+  if (o_wght) memcpy(o_wght, m.wght.data(), m.K * sizeof(double));
+  if (o_mean) memcpy(o_mean, m.mean.data(), (size_t)m.K * m.d * sizeof(double));
+  if (o_L) memcpy(o_L, m.L.data(), (size_t)m.K * m.d * m.d * sizeof(double));
+  if (o_detL) memcpy(o_detL, m.detL.data(), m.K * sizeof(double));
+  if (o_alive) for (int k = 0; k < m.K; ++k) o_alive[k] = m.wght[k] > 0.0;
+}
+
+// two-pass update exactly as the reference (pmc.c:1323-1469): weights must be normalised, log_rho/maxR as stored
+int update_two_pass(pmcgpu_ctx *c, double maxR, long N_total, int hard, int *retry, const std::vector<size_t> &count) {
+  HostMix &m = c->prop;
+  const int K = m.K, d = m.d;
+  const long N = c->N;
+  const long chunk = N < GEN_CHUNK ? N : GEN_CHUNK;
+  const size_t dd = (size_t)d * d;
+  CU(c->rbg.ensure((size_t)chunk * K * sizeof(double)));
+  CU(c->rbw.ensure((size_t)chunk * K * sizeof(double)));
+  const int nsplit = (int)std::max<long>(1, std::min<long>(64, chunk / 8192));
+  CU(c->rbpart.ensure((size_t)nsplit * K * (dd + d + 2) * sizeof(double)));
+  CU(c->rbacc.ensure((size_t)K * (dd + d + 2) * sizeof(double)));
+  CU(c->tmpo.ensure((size_t)K * 8));
+  CU(cudaMemsetAsync(c->rbacc.p, 0, (size_t)K * (dd + d + 2) * sizeof(double), c->stream));
+  {
+    RC(stage(c, K));
+    unsigned long long *hc = reinterpret_cast<unsigned long long *>(c->hstage);
+    for (int k = 0; k < K; ++k) hc[k] = count[k];
+    CU(cudaMemcpyAsync(c->tmpo.p, hc, (size_t)K * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  double *acc_mean = c->rbacc.as<double>();           // [K*(d+2)]
+  double *acc_cov = acc_mean + (size_t)K * (d + 2);   // [K*d*d]
+  // pass A
+  for (long base = 0; base < N; base += chunk) {
+    const long n = (N - base) < chunk ? (N - base) : chunk;
+    launch_rb_resp(c->dprop.view, n, base, c->X.as<double>(), c->W.as<double>(), c->R.as<double>(), c->Flg.as<short>(),
+                   c->Idx.as<unsigned long long>(), c->tmpo.as<unsigned long long>(), maxR, hard, c->rbg.as<double>(), c->rbw.as<double>(), c->stream);
+    launch_rb_reduce_mean(K, d, n, base, nsplit, c->X.as<double>(), c->rbg.as<double>(), c->rbw.as<double>(), c->rbpart.as<double>(), acc_mean, c->stream);
+    CU(cudaGetLastError());
+  }
+  std::vector<double> am((size_t)K * (d + 2));
+  RC(stage(c, am.size()));
+  CU(cudaMemcpyAsync(c->hstage, acc_mean, am.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(am.data(), c->hstage, am.size() * sizeof(double));
+  int rc = allreduce_host(c, am.data(), (long)am.size(), 0);
+  if (rc) return rc;
+  // new means (pmc.c:1409-1426)
+  std::vector<double> newmean((size_t)K * d, 0.0), W(K, 0.0), G(K, 0.0);
+  for (int k = 0; k < K; ++k) {
+    G[k] = am[(size_t)k * (d + 2) + d];
+    W[k] = am[(size_t)k * (d + 2) + d + 1];
+    if (count[k] > (size_t)kMinCount)
+      for (int j = 0; j < d; ++j) newmean[(size_t)k * d + j] = am[(size_t)k * (d + 2) + j] / G[k];
+  }
+  CU(c->newmean.ensure(newmean.size() * sizeof(double)));
+  RC(stage(c, newmean.size()));
+  memcpy(c->hstage, newmean.data(), newmean.size() * sizeof(double));
+  CU(cudaMemcpyAsync(c->newmean.p, c->hstage, newmean.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  // pass B
+  for (long base = 0; base < N; base += chunk) {
+    const long n = (N - base) < chunk ? (N - base) : chunk;
+    if (N > chunk)  // responsibilities of a single chunk are still in the scratch from pass A
+      launch_rb_resp(c->dprop.view, n, base, c->X.as<double>(), c->W.as<double>(), c->R.as<double>(), c->Flg.as<short>(),
+                     c->Idx.as<unsigned long long>(), c->tmpo.as<unsigned long long>(), maxR, hard, c->rbg.as<double>(), c->rbw.as<double>(), c->stream);
+    launch_rb_reduce_cov(K, d, n, base, nsplit, c->X.as<double>(), c->rbg.as<double>(), c->newmean.as<double>(), c->rbpart.as<double>(), acc_cov, c->stream);
+    CU(cudaGetLastError());
+  }
+  std::vector<double> cov(K * dd);
+  RC(stage(c, cov.size()));
+  CU(cudaMemcpyAsync(c->hstage, acc_cov, cov.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(cov.data(), c->hstage, cov.size() * sizeof(double));
+  rc = allreduce_host(c, cov.data(), (long)cov.size(), 0);
+  if (rc) return rc;
+  // finish (pmc.c:1455-1462) + cleanup
+  std::vector<double> snapshot(m.L);
+  for (int k = 0; k < K; ++k) {
+    double *Ck = m.L.data() + k * dd;
+    m.wght[k] = W[k];
+    if (count[k] > (size_t)kMinCount) {
+      const size_t bl = m.band.empty() ? (size_t)d : m.band[k];
+      const double inv = 1.0 / m.wght[k];
+      for (int a = 0; a < d; ++a)
+        for (int b = a; b < d; ++b) {
+          const double v = ((size_t)(b - a) < bl) ? cov[k * dd + (size_t)a * d + b] * inv : 0.0;
+          Ck[(size_t)a * d + b] = v;
+          Ck[(size_t)b * d + a] = v;
+        }
+      memcpy(m.mean.data() + (size_t)k * d, newmean.data() + (size_t)k * d, d * sizeof(double));
+    } else {
+      memset(Ck, 0, dd * sizeof(double));
+      memset(m.mean.data() + (size_t)k * d, 0, d * sizeof(double));
+    }
+  }
+  rc = host_cleanup_after_update(K, d, count.data(), 1.0 / (double)N_total, retry, snapshot.data(), m.wght.data(), m.mean.data(), m.L.data(), m.detL.data());
+  if (rc) return fail(c, rc, "Sum of weight is <= 0 after the update");
+  return 0;
+}
+
+// dead components keep whatever detL they had; log() of it must stay finite for the device tables
+void sanitize_dead(HostMix &m) {
+  for (int k = 0; k < m.K; ++k)
+    if (!(m.wght[k] > 0.0) || !(m.detL[k] > 0.0)) { if (!(m.detL[k] > 0.0)) m.detL[k] = 1.0; }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pmcgpu_version(void) { return 100; }
+
+int pmcgpu_create(int device, pmcgpu_ctx **out) {
+  if (!out) return PMCGPU_ERR_USAGE;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PMCGPU_ERR_NODEVICE;
+  if (device < 0 || device >= ndev) return PMCGPU_ERR_NODEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return PMCGPU_ERR_CUDA;
+  pmcgpu_ctx *c = new pmcgpu_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return PMCGPU_ERR_CUDA; }
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return PMCGPU_ERR_CUDA; }
+  for (int j = 0; j < FUSED_MAXD; ++j) { c->lo_thr[j] = INFINITY; c->hi_thr[j] = INFINITY; }
+  if (const char *e = getenv("PMCB200_FORCE_GENERIC")) c->force_generic = atoi(e);
+  if (const char *e = getenv("PMCB200_SPL")) c->spl = atoi(e);
+  *out = c;
+  return 0;
+}
+
+void pmcgpu_destroy(pmcgpu_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+  DevBuf *bufs[] = {&c->dprop.buf, &c->dprop_pack, &c->dtmix.buf, &c->dt_pack, &c->ddef, &c->dfaces, &c->X, &c->W, &c->R,
+                    &c->Idx, &c->Flg, &c->ld, &c->blkmax, &c->partials, &c->stats, &c->small, &c->rbg, &c->rbw, &c->rbacc,
+                    &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll};
+  for (DevBuf *b : bufs) b->release();
+  if (c->hstage) cudaFreeHost(c->hstage);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *pmcgpu_last_error(const pmcgpu_ctx *c) { return c ? c->err.c_str() : "null context"; }
+void *pmcgpu_stream(pmcgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
+  if (!c || !name) return PMCGPU_ERR_USAGE;
+  if (!strcmp(name, "force_generic")) c->force_generic = (int)value;
+  else if (!strcmp(name, "spl")) c->spl = (int)value;
+  else if (!strcmp(name, "max_attempts")) c->max_attempts = (int)value;
+  else if (!strcmp(name, "force_precise")) c->force_precise = (int)value;
+  else if (!strcmp(name, "guard_ratio")) c->guard_ratio = value;
+  else return fail(c, PMCGPU_ERR_USAGE, "unknown option %s", name);
+  return 0;
+}
+
+int pmcgpu_set_proposal(pmcgpu_ctx *c, int K, int d, const double *wght, const double *mean, const double *L,
+                        const double *detL, const int *df) {
+  if (!c || !wght || !mean || !L) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  int rc = fill_mix(c, c->prop, K, d, wght, mean, L, detL, df);
+  if (rc) return rc;
+  c->prop.band.clear();
+  sanitize_dead(c->prop);
+  return install_proposal(c);
+}
+
+int pmcgpu_set_band_limit(pmcgpu_ctx *c, const size_t *band_limit) {
+  if (!c || c->prop.K == 0) return PMCGPU_ERR_USAGE;
+  if (band_limit) c->prop.band.assign(band_limit, band_limit + c->prop.K);
+  else c->prop.band.clear();
+  return 0;
+}
+
+int pmcgpu_set_target_banana(pmcgpu_ctx *c, int d, double b, double sig1) {
+  if (!c || d < 2) return fail(c, PMCGPU_ERR_USAGE, "bentGauss needs d >= 2");
+  c->tkind = PMCGPU_TGT_BANANA;
+  c->td = d;
+  c->tb = b;
+  c->tsig1 = sig1;
+  c->tmix = HostMix();
+  return 0;
+}
+
+int pmcgpu_set_target_mix(pmcgpu_ctx *c, int kind, int K, int d, const double *wght, const double *mean,
+                          const double *L, const double *detL, const int *df) {
+  if (!c || (kind != PMCGPU_TGT_MVDENS && kind != PMCGPU_TGT_MIX)) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  std::vector<double> one(1, 1.0);
+  if (kind == PMCGPU_TGT_MVDENS) { K = 1; if (!wght) wght = one.data(); }
+  int rc = fill_mix(c, c->tmix, K, d, wght, mean, L, detL, df);
+  if (rc) return rc;
+  c->tkind = kind;
+  c->td = d;
+  rc = upload_mix(c, c->tmix, c->dtmix);
+  if (rc) return rc;
+  return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles);
+}
+
+int pmcgpu_set_target_host(pmcgpu_ctx *c, int d) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  c->tkind = PMCGPU_TGT_HOST;
+  c->td = d;
+  c->tmix = HostMix();
+  return 0;
+}
+
+int pmcgpu_set_target_defaults(pmcgpu_ctx *c, int nfull, const int *is_def, const double *value) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  if (nfull <= 0) { c->nfull = 0; return 0; }
+  if (nfull > PMCB200_MAXD || !is_def || !value) return fail(c, PMCGPU_ERR_USAGE, "bad defaults map");
+  c->is_def.assign(is_def, is_def + nfull);
+  c->def_val.assign(value, value + nfull);
+  const size_t ioff = ((nfull * sizeof(int) + 15) / 16) * 16;
+  std::vector<char> blob(ioff + nfull * sizeof(double));
+  memcpy(blob.data(), is_def, nfull * sizeof(int));
+  memcpy(blob.data() + ioff, value, nfull * sizeof(double));
+  CU(c->ddef.ensure(blob.size()));
+  CU(cudaMemcpy(c->ddef.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  c->nfull = nfull;
+  return 0;
+}
+
+int pmcgpu_set_box(pmcgpu_ctx *c, int d, int nfaces, const double *faces) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  c->nfaces = 0;
+  c->box_slab = false;
+  for (int j = 0; j < FUSED_MAXD; ++j) { c->lo_thr[j] = INFINITY; c->hi_thr[j] = INFINITY; }
+  if (nfaces <= 0 || !faces) return 0;
+  if (d < 1 || d > PMCB200_MAXD) return fail(c, PMCGPU_ERR_USAGE, "box dimension %d", d);
+  c->faces.assign(faces, faces + (size_t)nfaces * (d + 1));
+  c->box_d = d;
+  CU(c->dfaces.ensure(c->faces.size() * sizeof(double)));
+  CU(cudaMemcpy(c->dfaces.p, c->faces.data(), c->faces.size() * sizeof(double), cudaMemcpyHostToDevice));
+  c->nfaces = nfaces;
+  // canonical slab form: every face is -e_j or +e_j (then thr - c.x reduces to one exact-coefficient operation and the
+  // tightest threshold per axis decides, rounding being monotone) -> the fused kernel can test it bit-exactly
+  bool slab = d <= FUSED_MAXD;
+  for (int f = 0; f < nfaces && slab; ++f) {
+    const double *cf = faces + (size_t)f * (d + 1);
+    int axis = -1;
+    for (int j = 0; j < d; ++j) {
+      if (cf[j] != 0.0) { if (axis >= 0 || (cf[j] != 1.0 && cf[j] != -1.0)) { slab = false; break; } axis = j; }
+    }
+    if (!slab) break;
+    if (axis < 0) { if (cf[d] < 0) slab = false; continue; }
+    if (cf[axis] < 0) { if (cf[d] < c->lo_thr[axis]) c->lo_thr[axis] = cf[d]; }
+    else { if (cf[d] < c->hi_thr[axis]) c->hi_thr[axis] = cf[d]; }
+  }
+  c->box_slab = slab;
+  return 0;
+}
+
+int pmcgpu_resize(pmcgpu_ctx *c, long N, int d) {
+  if (!c || N < 0 || d < 1 || d > PMCB200_MAXD) return fail(c, PMCGPU_ERR_USAGE, "resize(N=%ld, d=%d)", N, d);
+  cudaSetDevice(c->device);
+  CU(c->X.ensure((size_t)N * d * sizeof(double) + 16));
+  CU(c->W.ensure((size_t)N * sizeof(double) + 16));
+  CU(c->R.ensure((size_t)N * sizeof(double) + 16));
+  CU(c->Idx.ensure((size_t)N * sizeof(unsigned long long) + 16));
+  CU(c->Flg.ensure((size_t)N * sizeof(short) + 16));
+  c->N = N;
+  c->d = d;
+  return 0;
+}
+
+int pmcgpu_upload(pmcgpu_ctx *c, const double *X, const size_t *indices, const double *weights, const double *log_rho, const short *flg) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  const size_t N = c->N;
+  if (X) CU(cudaMemcpyAsync(c->X.p, X, N * c->d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (indices) CU(cudaMemcpyAsync(c->Idx.p, indices, N * sizeof(size_t), cudaMemcpyHostToDevice, c->stream));
+  if (weights) CU(cudaMemcpyAsync(c->W.p, weights, N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (log_rho) CU(cudaMemcpyAsync(c->R.p, log_rho, N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (flg) CU(cudaMemcpyAsync(c->Flg.p, flg, N * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int pmcgpu_download(pmcgpu_ctx *c, double *X, size_t *indices, double *weights, double *log_rho, short *flg) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  const size_t N = c->N;
+  if (X) CU(cudaMemcpyAsync(X, c->X.p, N * c->d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (indices) CU(cudaMemcpyAsync(indices, c->Idx.p, N * sizeof(size_t), cudaMemcpyDeviceToHost, c->stream));
+  if (weights) CU(cudaMemcpyAsync(weights, c->W.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (log_rho) CU(cudaMemcpyAsync(log_rho, c->R.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (flg) CU(cudaMemcpyAsync(flg, c->Flg.p, N * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int pmcgpu_device_arrays(pmcgpu_ctx *c, void **out) {
+  if (!c || !out) return PMCGPU_ERR_USAGE;
+  out[0] = c->X.p; out[1] = c->Idx.p; out[2] = c->W.p; out[3] = c->R.p; out[4] = c->Flg.p;
+  return 0;
+}
+
+int pmcgpu_draw(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, long *n_reject) {
+  int rc = check_ready(c, false);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  rc = ensure_cwght_normalised(c);
+  if (rc) return rc;
+  rc = zero_small(c);
+  if (rc) return rc;
+  BoxDev bx{c->nfaces, c->box_d, c->dfaces.as<double>()};
+  if (c->nfaces > 0 && c->box_d != c->d) return fail(c, PMCGPU_ERR_USAGE, "box dimension %d != %d", c->box_d, c->d);
+  launch_draw_generic(c->dprop.view, bx, seed, iter, first_index, c->N, c->max_attempts, c->X.as<double>(),
+                      c->Idx.as<unsigned long long>(), c->Flg.as<short>(), c->small.as<unsigned long long>() + SM_COUNTERS, c->stream);
+  CU(cudaGetLastError());
+  unsigned long long cnt[CNT_NUM];
+  rc = read_small(c, cnt, nullptr, nullptr);
+  if (rc) return rc;
+  if (n_reject) *n_reject = (long)cnt[CNT_REJECT];
+  if (cnt[CNT_DRAWFAIL] || (long)cnt[CNT_REJECT] > 5 * c->N)
+    return fail(c, kErrTooManySteps, "Too many points (%llu) outside of box", cnt[CNT_REJECT]);
+  return 0;
+}
+
+static int weights_common(pmcgpu_ctx *c, int mode, const double *post, const short *ok, double t_temper,
+                          long first_index, long *nok, double *maxW, double *maxR) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  if (t_temper < 0) return fail(c, -6019, "t_iter_tempered=%g should be > 0", t_temper);  // pmc.c:508
+  const double *dpost = nullptr;
+  const short *dok = nullptr;
+  if (mode == 1) {
+    if (!post) return PMCGPU_ERR_USAGE;
+    CU(c->hostpost.ensure((size_t)c->N * sizeof(double)));
+    CU(cudaMemcpyAsync(c->hostpost.p, post, (size_t)c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dpost = c->hostpost.as<double>();
+    if (ok) {
+      CU(c->hostok.ensure((size_t)c->N * sizeof(short)));
+      CU(cudaMemcpyAsync(c->hostok.p, ok, (size_t)c->N * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+      dok = c->hostok.as<short>();
+    }
+  }
+  WeightOut o;
+  const int saved_kind = c->tkind;
+  if (mode == 1) c->tkind = PMCGPU_TGT_HOST;
+  const FusedPlan p = plan_for(c);
+  if (p.valid) rc = run_fused(c, p, 0, 0, 0, 0, first_index, t_temper, dpost, dok, o);
+  else rc = run_weights_generic(c, mode, dpost, dok, t_temper, first_index, o);
+  c->tkind = saved_kind;
+  if (rc) return rc;
+  if (nok) *nok = (long)o.counters[CNT_NOK];
+  double mw = o.M_all;
+  if (o.counters[CNT_POSINF]) mw = INFINITY;
+  if (maxW) *maxW = fold_max(mw, o.has_first, o.first[3] != 0.0, o.first[2]);
+  if (maxR) *maxR = fold_max(o.R_all, o.has_first, o.first[1] != 0.0, o.first[0]);
+  return 0;
+}
+
+int pmcgpu_weights(pmcgpu_ctx *c, double t_temper, long first_index, long *nok, double *maxW, double *maxR) {
+  if (c && c->tkind == PMCGPU_TGT_HOST) return fail(c, PMCGPU_ERR_USAGE, "host target: use pmcgpu_weights_host_post");
+  return weights_common(c, 0, nullptr, nullptr, t_temper, first_index, nok, maxW, maxR);
+}
+int pmcgpu_weights_host_post(pmcgpu_ctx *c, const double *post, const short *ok, double t_temper, long first_index,
+                             long *nok, double *maxW, double *maxR) {
+  if (c && c->tkind == PMCGPU_TGT_NONE) c->tkind = PMCGPU_TGT_HOST;
+  return weights_common(c, 1, post, ok, t_temper, first_index, nok, maxW, maxR);
+}
+
+int pmcgpu_proposal_log_pdf(pmcgpu_ctx *c, long n, const double *x, double *out) {
+  if (!c || c->prop.K == 0 || n < 0) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  if (c->prop.n_alive() == 0) return fail(c, kErrMvOutOfBound, "Indice out of bonds");
+  const int d = c->prop.d, K = c->prop.K;
+  CU(c->tmpx.ensure((size_t)n * d * sizeof(double) + 16));
+  CU(c->tmpo.ensure((size_t)n * sizeof(double) + 16));
+  CU(c->ld.ensure((size_t)n * K * sizeof(double) + 16));
+  CU(cudaMemcpyAsync(c->tmpx.p, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_mix_log_pdf(c->dprop.view, n, c->tmpx.as<double>(), c->tmpo.as<double>(), c->ld.as<double>(), K, c->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, c->tmpo.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int pmcgpu_target_log_pdf(pmcgpu_ctx *c, long n, const double *x, double *out) {
+  if (!c || n < 0 || c->tkind == PMCGPU_TGT_NONE || c->tkind == PMCGPU_TGT_HOST) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  const int dfree = c->nfull ? 0 : c->td;
+  int d = dfree;
+  if (c->nfull) { d = 0; for (int i = 0; i < c->nfull; ++i) d += c->is_def[i] ? 0 : 1; }
+  const int K = c->tmix.K > 0 ? c->tmix.K : 1;
+  CU(c->tmpx.ensure((size_t)n * d * sizeof(double) + 16));
+  CU(c->tmpo.ensure((size_t)n * sizeof(double) + 16));
+  CU(c->ld.ensure((size_t)n * K * sizeof(double) + 16));
+  CU(cudaMemcpyAsync(c->tmpx.p, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_target_log_pdf(target_view(c), d, n, c->tmpx.as<double>(), c->tmpo.as<double>(), c->ld.as<double>(), K, c->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, c->tmpo.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int pmcgpu_normalize(pmcgpu_ctx *c, double maxW, double *logSum, long *count) {
+  if (!c || c->N <= 0) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  double S = 0.0;
+  long cnt = 0;
+  int rc = normalize_impl(c, maxW, &S, &cnt, false);
+  if (rc) return rc;
+  if (count) *count = cnt;
+  if (cnt == 0) return fail(c, kErrNoSample, "Not a single point in sample with flag=ok.");
+  if (S <= 0) return fail(c, kErrNegWeight, "Sum of weights <= 0 (got %g)", S);
+  launch_norm_scale(c->N, S, c->W.as<double>(), c->sm_count * 8, c->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  if (logSum) *logSum = std::log(S) + maxW - kDynMax;
+  return 0;
+}
+
+int pmcgpu_perplexity_ess(pmcgpu_ctx *c, double *perp, double *ess, long *n_flagged_out) {
+  if (!c || c->N <= 0) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  double H = 0, Q = 0;
+  long nexit = 0;
+  int rc = scale_perp_impl(c, 1.0, false, &H, &Q, &nexit, false);
+  if (rc) return rc;
+  if (n_flagged_out) *n_flagged_out = nexit;
+  if (nexit == c->N) return fail(c, kErrUndef, "all points are flagged");
+  if (ess) *ess = 1 / Q;
+  if (perp) *perp = std::exp(-H) / (double)(c->N - nexit);
+  return 0;
+}
+
+int pmcgpu_count_indices(pmcgpu_ctx *c, size_t *count) {
+  if (!c || !count || c->prop.K == 0) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  std::vector<size_t> cnt;
+  int rc = count_indices_impl(c, cnt, false);
+  if (rc) return rc;
+  memcpy(count, cnt.data(), cnt.size() * sizeof(size_t));
+  return 0;
+}
+
+static int update_common(pmcgpu_ctx *c, double maxR, long N_total, int hard, int *retry, double *o_wght,
+                         double *o_mean, double *o_L, double *o_detL, int *o_alive) {
+  int rc = check_ready(c, false);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  if (!retry) return PMCGPU_ERR_USAGE;
+  std::vector<size_t> count;
+  rc = count_indices_impl(c, count, true);
+  if (rc) return rc;
+  rc = update_two_pass(c, maxR, N_total > 0 ? N_total : c->N, hard, retry, count);
+  if (rc) return rc;
+  sanitize_dead(c->prop);
+  rc = install_proposal(c);
+  if (rc) return rc;
+  export_proposal(c, o_wght, o_mean, o_L, o_detL, o_alive);
+  return 0;
+}
+
+int pmcgpu_update_rb(pmcgpu_ctx *c, double maxR, long N_total, int *retry, double *o_wght, double *o_mean, double *o_L,
+                     double *o_detL, int *o_alive) {
+  return update_common(c, maxR, N_total, 0, retry, o_wght, o_mean, o_L, o_detL, o_alive);
+}
+int pmcgpu_update_hard(pmcgpu_ctx *c, long N_total, int *retry, double *o_wght, double *o_mean, double *o_L, double *o_detL,
+                       int *o_alive) {
+  if (c && c->prop.student) return fail(c, PMCGPU_ERR_USAGE, "update_prop with Student-t components yields NaN in the reference (pmc.c:1241-1258); not supported");
+  return update_common(c, 0.0, N_total, 1, retry, o_wght, o_mean, o_L, o_detL, o_alive);
+}
+
+int pmcgpu_ranindx(pmcgpu_ctx *c, long n, const double *z, size_t *idx) {
+  if (!c || c->prop.K == 0 || n < 0) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  CU(c->tmpx.ensure((size_t)n * sizeof(double) + 16));
+  CU(c->tmpo.ensure((size_t)n * sizeof(size_t) + 16));
+  CU(cudaMemcpyAsync(c->tmpx.p, z, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_ranindx(c->dprop.view.cw, c->prop.K, n, c->tmpx.as<double>(), c->tmpo.as<unsigned long long>(), c->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(idx, c->tmpo.p, (size_t)n * sizeof(size_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int pmcgpu_isinbox(pmcgpu_ctx *c, long n, const double *x, int *inside) {
+  if (!c || n < 0) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  if (c->nfaces == 0) { for (long i = 0; i < n; ++i) inside[i] = 1; return 0; }
+  const int d = c->box_d;
+  CU(c->tmpx.ensure((size_t)n * d * sizeof(double) + 16));
+  CU(c->tmpo.ensure((size_t)n * sizeof(int) + 16));
+  CU(cudaMemcpyAsync(c->tmpx.p, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_isinbox(BoxDev{c->nfaces, d, c->dfaces.as<double>()}, n, c->tmpx.as<double>(), c->tmpo.as<int>(), c->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(inside, c->tmpo.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- the iteration ------------------------------------------------------------------------------------------------
+static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, long first_index, long N_total,
+                     double t_temper, int do_update, int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean,
+                     double *o_L, double *o_detL, int *o_alive) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  if (c->tkind == PMCGPU_TGT_HOST) return fail(c, PMCGPU_ERR_USAGE, "host target: drive the phases separately (draw, download X, weights_host_post, ...)");
+  if (N_total <= 0) N_total = c->N;
+  int retry_local = retry ? *retry : 0;
+  pmcgpu_step_result r{};
+  if (do_draw) { rc = ensure_cwght_normalised(c); if (rc) return rc; }
+  const HostMix &m0 = c->prop;
+  const int K = m0.K, d = m0.d;
+  const FusedPlan p = plan_for(c);
+  WeightOut o;
+  const bool fused_stats = p.valid && do_update && !c->force_precise;
+  if (p.valid) {
+    rc = run_fused(c, p, do_draw, fused_stats ? 1 : 0, seed, iter, first_index, t_temper, nullptr, nullptr, o);
+    if (rc) return rc;
+  } else {
+    if (do_draw) {
+      long nrej = 0;
+      rc = pmcgpu_draw(c, seed, iter, first_index, &nrej);
+      if (rc) return rc;
+      o.counters[CNT_REJECT] = (unsigned long long)nrej;
+    }
+    const unsigned long long keep_rej = o.counters[CNT_REJECT];
+    rc = run_weights_generic(c, 0, nullptr, nullptr, t_temper, first_index, o);
+    if (rc) return rc;
+    o.counters[CNT_REJECT] = keep_rej;
+  }
+  // ---- global maxima (pmc_mpi.c:502-508 keeps the max over ranks) with the i==0 quirk carried as a flag
+  double mx[6];
+  mx[0] = o.counters[CNT_POSINF] ? INFINITY : o.M_all;
+  mx[1] = o.R_all;
+  mx[2] = (o.has_first && o.first[3] != 0.0 && std::isnan(o.first[2])) ? 1.0 : 0.0;  // maxW poisoned by NaN at i==0
+  mx[3] = (o.has_first && o.first[1] != 0.0 && std::isnan(o.first[0])) ? 1.0 : 0.0;
+  mx[4] = (o.has_first && o.first[3] != 0.0) ? 1.0 : 0.0;  // sample 0 reached the weight assignment
+  mx[5] = (o.has_first && o.first[1] != 0.0) ? 1.0 : 0.0;
+  const double M_local = o.M_all;
+  rc = allreduce_host(c, mx, 6, 1);
+  if (rc) return rc;
+  double maxW = mx[2] != 0.0 ? NAN : (mx[4] != 0.0 ? mx[0] : (mx[0] > kNegInit ? mx[0] : kNegInit));
+  double maxR = mx[3] != 0.0 ? NAN : (mx[5] != 0.0 ? mx[1] : (mx[1] > kNegInit ? mx[1] : kNegInit));
+  r.maxW = maxW;
+  r.maxR = maxR;
+  {
+    double cnt[2] = {(double)o.counters[CNT_REJECT], (double)o.counters[CNT_DRAWFAIL]};
+    rc = allreduce_host(c, cnt, 2, 0);
+    if (rc) return rc;
+    r.n_reject = (long)cnt[0];
+    if (do_draw && (cnt[1] > 0 || cnt[0] > 5.0 * (double)N_total))
+      return fail(c, kErrTooManySteps, "Too many points (%ld) outside of box", r.n_reject);
+  }
+  // ---- normalise (pmc.c:641-697), literally: S = sum exp(lw - maxW + 500)
+  double S = 0.0;
+  long cnt_ok = 0;
+  rc = normalize_impl(c, maxW, &S, &cnt_ok, true);
+  if (rc) return rc;
+  if (cnt_ok == 0) return fail(c, kErrNoSample, "Not a single point in sample with flag=ok.");
+  if (!(S > 0)) return fail(c, kErrNegWeight, "Sum of weights <= 0 (got %g)", S);
+  r.logSum = std::log(S) + maxW - kDynMax;
+  r.nok = cnt_ok;
+  double H = 0, Q = 0;
+  long nexit = 0;
+  rc = scale_perp_impl(c, S, true, &H, &Q, &nexit, true);
+  if (rc) return rc;
+  if (nexit == N_total) return fail(c, kErrUndef, "all points are flagged");
+  r.ess = 1 / Q;
+  r.perplexity = std::exp(-H) / (double)(N_total - nexit);
+  r.ln_evidence = r.logSum - std::log((double)(N_total - nexit));
+  // ---- update
+  if (do_update) {
+    bool precise = !fused_stats;
+    if (fused_stats) {
+      // reduce the statistics over ranks: rescale to the global maximum, then sum
+      const int E = 1 + d + d * (d + 1) / 2;
+      std::vector<double> st(o.stats);
+      const double Mg = mx[0];
+      const double sc = (M_local == -INFINITY) ? 0.0 : std::exp(M_local - Mg);
+      if (c->nranks > 1) for (double &v : st) v *= sc;
+      std::vector<double> cntk(K);
+      for (int k = 0; k < K; ++k) cntk[k] = (double)o.count_k[k];
+      rc = allreduce_host(c, st.data(), (long)st.size(), 0);
+      if (rc) return rc;
+      rc = allreduce_host(c, cntk.data(), K, 0);
+      if (rc) return rc;
+      std::vector<size_t> count(K);
+      for (int k = 0; k < K; ++k) count[k] = (size_t)cntk[k];
+      // unpack canonical statistics -> W (= G for Gaussian components), s1, S2 about the pivot
+      std::vector<double> W(K), s1((size_t)K * d), S2((size_t)K * d * d), pivot(d);
+      {
+        double sw = 0.0;
+        for (int k = 0; k < K; ++k) if (m0.wght[k] > 0) sw += m0.wght[k];
+        for (int j = 0; j < d; ++j) {
+          double s = 0.0;
+          for (int k = 0; k < K; ++k) if (m0.wght[k] > 0) s += m0.wght[k] * m0.mean[(size_t)k * d + j];
+          pivot[j] = s / sw;
+        }
+      }
+      for (int k = 0; k < K; ++k) {
+        const double *sk = st.data() + (size_t)k * E;
+        W[k] = sk[0];
+        for (int a = 0; a < d; ++a) s1[(size_t)k * d + a] = sk[1 + a];
+        int e = 1 + d;
+        for (int a = 0; a < d; ++a)
+          for (int b = a; b < d; ++b) { S2[(size_t)k * d * d + (size_t)a * d + b] = sk[e]; S2[(size_t)k * d * d + (size_t)b * d + a] = sk[e]; ++e; }
+      }
+      HostMix trial = c->prop;
+      int retry_trial = retry_local;
+      std::vector<int> alive(K);
+      rc = pmcgpu_finalize_update(K, d, W.data(), W.data(), s1.data(), S2.data(), pivot.data(), 0, count.data(), N_total,
+                                  trial.band.empty() ? nullptr : trial.band.data(), &retry_trial, trial.wght.data(),
+                                  trial.mean.data(), trial.L.data(), trial.detL.data(), alive.data());
+      // pivot guard: the one-pass covariance loses ~eps*(1 + r) relative accuracy, r = (mu'-pivot)^2 / Sigma'_aa
+      double worst = 0.0;
+      for (int k = 0; k < K && rc == 0; ++k) {
+        if (!(trial.wght[k] > 0.0)) continue;
+        for (int a = 0; a < d; ++a) {
+          double var = 0.0;  // Sigma'_aa = sum_j L_aj^2
+          for (int j = 0; j <= a; ++j) { const double l = trial.L[(size_t)k * d * d + (size_t)a * d + j]; var += l * l; }
+          const double dm = trial.mean[(size_t)k * d + a] - pivot[a];
+          const double ratio = dm * dm / var;
+          if (!(ratio <= worst)) worst = ratio;
+        }
+      }
+      if (rc != 0 || retry_trial != 0 || !(worst <= c->guard_ratio)) {
+        precise = true;  // anything unusual (failed factorisation, ill-conditioned pivot) goes through the literal path
+      } else {
+        c->prop = trial;
+        retry_local = retry_trial;
+      }
+    }
+    if (precise) {
+      std::vector<size_t> count;
+      rc = count_indices_impl(c, count, true);
+      if (rc) return rc;
+      rc = update_two_pass(c, maxR, N_total, 0, &retry_local, count);
+      if (rc) return rc;
+      r.used_precise_path = 1;
+    }
+    sanitize_dead(c->prop);
+    rc = install_proposal(c);
+    if (rc) return rc;
+  }
+  r.retry = retry_local;
+  r.n_alive = c->prop.n_alive();
+  if (retry) *retry = retry_local;
+  if (res) *res = r;
+  export_proposal(c, o_wght, o_mean, o_L, o_detL, o_alive);
+  return 0;
+}
+
+int pmcgpu_pmc_step(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, long N_total, int do_update,
+                    int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean, double *o_L, double *o_detL,
+                    int *o_alive) {
+  return step_impl(c, 1, seed, iter, first_index, N_total, 1.0, do_update, retry, res, o_wght, o_mean, o_L, o_detL, o_alive);
+}
+int pmcgpu_step_given(pmcgpu_ctx *c, long first_index, long N_total, double t_temper, int do_update, int *retry,
+                      pmcgpu_step_result *res, double *o_wght, double *o_mean, double *o_L, double *o_detL, int *o_alive) {
+  return step_impl(c, 0, 0, 0, first_index, N_total, t_temper, do_update, retry, res, o_wght, o_mean, o_L, o_detL, o_alive);
+}
+
+int pmcgpu_get_proposal(pmcgpu_ctx *c, double *o_wght, double *o_mean, double *o_L, double *o_detL, int *o_alive) {
+  if (!c || c->prop.K == 0) return PMCGPU_ERR_USAGE;
+  export_proposal(c, o_wght, o_mean, o_L, o_detL, o_alive);
+  return 0;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------
+void pmcgpu_shard_range(long N_total, int rank, int nranks, long *first, long *len) {
+  const long base = N_total / nranks, rem = N_total % nranks;
+  const long l = base + (rank < rem ? 1 : 0);
+  const long f = rank * base + (rank < rem ? rank : rem);
+  if (first) *first = f;
+  if (len) *len = l;
+}
+
+int pmcgpu_nccl_unique_id(void *id_out) {
+  std::string why;
+  if (!id_out) return PMCGPU_ERR_USAGE;
+  if (!load_nccl(why)) return PMCGPU_ERR_NCCL;
+  return g_nccl.GetUniqueId(id_out) == 0 ? 0 : PMCGPU_ERR_NCCL;
+}
+
+int pmcgpu_comm_init(pmcgpu_ctx *c, const void *id, int rank, int nranks) {
+  if (!c || !id || rank < 0 || rank >= nranks) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  std::string why;
+  if (!load_nccl(why)) return fail(c, PMCGPU_ERR_NCCL, "%s", why.c_str());
+  IdByValue idv;
+  memcpy(idv.internal, id, PMCGPU_NCCL_ID_BYTES);
+  void *comm = nullptr;
+  const int r = g_nccl.CommInitRank(&comm, nranks, idv, rank);
+  if (r != 0) return fail(c, PMCGPU_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  c->nccl_comm = comm;
+  c->rank = rank;
+  c->nranks = nranks;
+  c->cb = nullptr;
+  return 0;
+}
+
+int pmcgpu_comm_set_callback(pmcgpu_ctx *c, pmcgpu_allreduce_fn fn, void *user, int rank, int nranks) {
+  if (!c || rank < 0 || rank >= nranks) return PMCGPU_ERR_USAGE;
+  c->cb = fn;
+  c->cb_user = user;
+  c->rank = rank;
+  c->nranks = fn ? nranks : 1;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+// pmc_host.cpp — the O(K d^3) host side of the proposal update: from reduced sufficient statistics to the new
+// mixture.  This is deliberately NOT a kernel (4.5e7 flop at the largest config) and it follows
+// the reference's control flow literally, because component deaths, the retry flag and the weight floor are
+// integer/branch behaviour that must match exactly:
+//   mvdens_cholesky_decomp      mvdens.c:229-277  (+ gsl-1.14 gsl_linalg_cholesky_decomp semantics, un-vendored GSL)
+//   cleanup_after_update        pmc.c:1471-1533
+//   end of update_prop_rb       pmc.c:1409-1426, 1455-1462
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "../../include/pmcb200.h"
+#include "pmc_hostonly.h"
+
+namespace {
+
+constexpr int kMinCount = 20;  // pmc.h:71
+constexpr int kMvCholesky = -706;     // mv_cholesky, mvdens.h:60
+constexpr int kPmcNegWeight = -6005;  // pmc_negWeight, pmc.h:28
+
+// Euclidean norm the way the BLAS reference dnrm2 forms it (running scale and scaled sum of squares); GSL's
+// Cholesky uses it for the diagonal, so the pivots round the same way.
+double scaled_norm(const double *x, int n) {
+  if (n < 1) return 0.0;
+  if (n == 1) return std::fabs(x[0]);
+  double scale = 0.0, ssq = 1.0;
+  for (int i = 0; i < n; ++i) {
+    if (x[i] == 0.0) continue;
+    const double ax = std::fabs(x[i]);
+    if (scale < ax) {
+      const double r = scale / ax;
+      ssq = 1.0 + ssq * r * r;
+      scale = ax;
+    } else {
+      const double r = ax / scale;
+      ssq += r * r;
+    }
+  }
+  return scale * std::sqrt(ssq);
+}
+
+inline double sqrt_or_nan(double v) { return v >= 0 ? std::sqrt(v) : std::nan(""); }
+
+}  // namespace
+
+namespace pmcb200 {
+
+// Row-by-row factorisation; lower triangle receives L, upper triangle its mirror; any non-positive pivot -> failure
+// (after finishing the sweep, as GSL does), input restored.
+int host_cholesky(int d, double *a, double *detL) {
+  std::vector<double> keep(a, a + (size_t)d * d);
+  bool pd = true;
+  for (int r = 0; r < d; ++r) {
+    double *row = a + (size_t)r * d;
+    const double arr = row[r];
+    if (r == 1) {
+      // GSL treats the second row specially (explicit product instead of the norm)
+      const double l10 = row[0] / a[0];
+      const double piv = arr - l10 * l10;
+      row[0] = l10;
+      row[1] = sqrt_or_nan(piv);
+      if (piv <= 0) pd = false;
+      continue;
+    }
+    for (int c = 0; c < r; ++c) {
+      const double *rc = a + (size_t)c * d;
+      double dot = 0.0;
+      for (int j = 0; j < c; ++j) dot += rc[j] * row[j];
+      row[c] = (row[c] - dot) / rc[c];
+    }
+    const double nr = (r == 0) ? 0.0 : scaled_norm(row, r);
+    const double piv = (r == 0) ? arr : arr - nr * nr;
+    row[r] = sqrt_or_nan(piv);
+    if (piv <= 0) pd = false;
+  }
+  for (int r = 1; r < d; ++r)
+    for (int c = 0; c < r; ++c) a[(size_t)c * d + r] = a[(size_t)r * d + c];
+  if (!pd) {
+    std::memcpy(a, keep.data(), sizeof(double) * d * d);
+    return kMvCholesky;
+  }
+  if (detL) {
+    double det = 1.0;
+    for (int r = 0; r < d; ++r) det *= a[(size_t)r * d + r];  // determinant(), mvdens.c:204-213
+    *detL = det;
+  }
+  return 0;
+}
+
+// cleanup_after_update (pmc.c:1471-1533).  On entry L[k] holds the updated COVARIANCE of component k and wght the
+// un-normalised new weights; snapshot = the factors before the update (restored once on a failed factorisation).
+int host_cleanup_after_update(int K, int d, const size_t *count, double minwgt, int *retry, const double *snapshot,
+                              double *wght, double *mean, double *L, double *detL) {
+  const size_t dd = (size_t)d * d;
+  double total = 0.0;
+  for (int k = 0; k < K; ++k)
+    if (count[k] > (size_t)kMinCount) total += wght[k];
+  {
+    const double inv = 1.0 / total;
+    for (int k = 0; k < K; ++k) wght[k] *= inv;
+  }
+  int need_retry = 0;
+  for (int k = 0; k < K; ++k) {
+    if (!(wght[k] > minwgt)) continue;
+    if (host_cholesky(d, L + k * dd, &detL[k]) != 0) {
+      if (*retry == 0) {
+        std::memcpy(L + k * dd, snapshot + k * dd, sizeof(double) * dd);
+        need_retry = 1;
+      } else {
+        wght[k] = 0;
+      }
+    }
+  }
+  *retry = need_retry;
+  for (int k = 0; k < K; ++k) {
+    if (count[k] < (size_t)kMinCount || wght[k] < minwgt) {
+      wght[k] = 0.0;
+      std::memset(mean + (size_t)k * d, 0, sizeof(double) * d);
+      std::memset(L + k * dd, 0, sizeof(double) * dd);
+    }
+  }
+  total = 0.0;
+  for (int k = 0; k < K; ++k) total += wght[k];
+  if (total <= 0.0) return kPmcNegWeight;
+  {
+    const double inv = 1.0 / total;
+    for (int k = 0; k < K; ++k) wght[k] *= inv;
+  }
+  return 0;
+}
+
+}  // namespace pmcb200
+
+extern "C" {
+
+int pmcgpu_cholesky(int d, double *a, double *detL) { return pmcb200::host_cholesky(d, a, detL); }
+
+long pmcgpu_stats_len(int K, int d) { return (long)K * (2 + d + (long)d * d) + 8; }
+
+// New proposal from pivoted one-pass statistics:
+//   mu'_k = c + s1_k / G_k ;  Sigma'_k = (S2_k - s1_k s1_k^T / G_k) / W_k ;  alpha'_k = W_k (normalised in cleanup)
+// Components with count <= MINCOUNT get weight 0, mean 0, zero matrix exactly as pmc.c:1410-1425.
+int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const double *s1, const double *S2,
+                           const double *pivot, int pivot_per_component, const size_t *count, long N_total,
+                           const size_t *band_limit, int *retry, double *wght, double *mean, double *L, double *detL,
+                           int *alive) {
+  const size_t dd = (size_t)d * d;
+  std::vector<double> snapshot(L, L + K * dd);
+  for (int k = 0; k < K; ++k) {
+    double *cov = L + k * dd;
+    double *mu = mean + (size_t)k * d;
+    if (count[k] > (size_t)kMinCount) {
+      const double *c = pivot + (pivot_per_component ? (size_t)k * d : 0);
+      const double *s = s1 + (size_t)k * d;
+      const double *S = S2 + k * dd;
+      const size_t bl = band_limit ? band_limit[k] : (size_t)d;
+      wght[k] = W[k];
+      for (int a = 0; a < d; ++a) mu[a] = c[a] + s[a] / G[k];
+      const double invW = 1.0 / W[k];
+      for (int a = 0; a < d; ++a)
+        for (int b = a; b < d; ++b) {
+          double v = 0.0;
+          if ((size_t)(b - a) < bl) v = (S[(size_t)a * d + b] - s[a] * s[b] / G[k]) * invW;  // band cut, pmc.c:1444
+          cov[(size_t)a * d + b] = v;
+          cov[(size_t)b * d + a] = v;
+        }
+    } else {
+      wght[k] = 0.0;
+      std::memset(mu, 0, sizeof(double) * d);
+      std::memset(cov, 0, sizeof(double) * dd);
+    }
+  }
+  const int rc = pmcb200::host_cleanup_after_update(K, d, count, 1.0 / (double)N_total, retry, snapshot.data(), wght,
+                                                    mean, L, detL);
+  if (alive)
+    for (int k = 0; k < K; ++k) alive[k] = wght[k] > 0.0 ? 1 : 0;
+  return rc;
+}
+
+}  // extern "C"

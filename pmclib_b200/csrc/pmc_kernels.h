@@ -1,0 +1,113 @@
+// pmc_kernels.h — declarations shared by the kernel translation units and the C-ABI layer (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pmcb200.h"
+#include "pmc_dev.cuh"
+
+#ifndef PMCB200_MAXD
+#define PMCB200_MAXD 128  // largest dimension the generic kernels hold in per-thread local arrays
+#endif
+
+namespace pmcb200 {
+
+constexpr int GEN_WEIGHT_THREADS = 128;
+
+enum { CNT_REJECT = 0, CNT_DRAWFAIL = 1, CNT_NOK = 2, CNT_NORMCOUNT = 3, CNT_FLAGGED = 4, CNT_POSINF = 5, CNT_NUM = 8 };
+
+struct TargetDev {
+  int kind, d;  // d = dimension the density itself sees (nfull when a defaults map is set)
+  double b, sig1;
+  MixDev mix;
+  int nfull;  // 0 = no defaults map
+  const int *is_def;
+  const double *def_val;
+};
+
+// ---- generic kernels (pmc_generic.cu) ------------------------------------------------------------------------
+void launch_draw_generic(const MixDev &m, const BoxDev &bx, uint64_t seed, uint32_t iter, long first_index, long N,
+                         int max_attempts, double *X, unsigned long long *indices, short *flg,
+                         unsigned long long *counters, cudaStream_t s);
+void launch_weights_generic(const MixDev &m, const TargetDev &tg, int mode, const double *post_in, const short *ok_in,
+                            double t_temper, long first_index, long N, const double *X, double *lw, double *log_rho,
+                            short *flg, double *ldscratch, int ldstride, double *blk_maxw, double *blk_maxr,
+                            unsigned long long *counters, double *first_vals, cudaStream_t s);
+void launch_mix_log_pdf(const MixDev &m, long n, const double *X, double *out, double *ld, int ldstride, cudaStream_t s);
+void launch_target_log_pdf(const TargetDev &tg, int dfree, long n, const double *X, double *out, double *ld,
+                           int ldstride, cudaStream_t s);
+void launch_ranindx(const double *cw, int K, long n, const double *z, unsigned long long *idx, cudaStream_t s);
+void launch_isinbox(const BoxDev &bx, long n, const double *X, int *inside, cudaStream_t s);
+void launch_norm_exp_sum(long N, double maxW, double *w, short *flg, double *partial, int nblocks,
+                         unsigned long long *counters, cudaStream_t s);
+void launch_norm_scale(long N, double S, double *w, int nblocks, cudaStream_t s);
+void launch_perplexity(long N, const double *w, const short *flg, double *partial, int nblocks,
+                       unsigned long long *counters, cudaStream_t s);
+void launch_count_indices(long N, int K, const unsigned long long *indices, const short *flg,
+                          unsigned long long *count, int nblocks, cudaStream_t s);
+void launch_rb_resp(const MixDev &m, long n, long base, const double *X, const double *w, const double *log_rho,
+                    const short *flg, const unsigned long long *indices, const unsigned long long *count, double maxR,
+                    int hard, double *gw8, double *w8, cudaStream_t s);
+void launch_rb_reduce_mean(int K, int d, long n, long base, int nsplit, const double *X, const double *gw8,
+                           const double *w8, double *part, double *out, cudaStream_t s);
+void launch_rb_reduce_cov(int K, int d, long n, long base, int nsplit, const double *X, const double *gw8,
+                          const double *newmean, double *part, double *out, cudaStream_t s);
+void launch_norm_scale_perp(long N, double S, double *w, const short *flg, double *partial, int nblocks,
+                            unsigned long long *counters, cudaStream_t s);
+
+// ---- fused small-d iteration kernel (pmc_fused.cu) -----------------------------------------------------------
+constexpr int FUSED_MAXD = 16;
+
+struct FusedArgs {
+  // model (device pointers to packed parameter blocks, see pack_mixture_small())
+  const double *mixpack;
+  int mix_doubles, comp_stride, K;
+  const double *tgtpack;  // TGT_MIX / TGT_MVDENS: same packing, Kt components
+  int tgt_doubles, tgt_stride, Kt;
+  int tgt_kind;
+  double b, sig1, t_temper;
+  const double *post_in;  // TGT_HOST: target values evaluated by the caller
+  const short *ok_in;
+  // box in canonical slab form (thresholds of the -e_j and +e_j faces; +inf when absent)
+  int has_box;
+  double lo_thr[FUSED_MAXD], hi_thr[FUSED_MAXD];
+  double pivot[FUSED_MAXD];
+  // work
+  int do_draw, do_stats;
+  long N, first_index;
+  uint64_t seed;
+  uint32_t iter;
+  int max_attempts;
+  // sample store
+  double *X, *lw, *log_rho;
+  unsigned long long *indices;
+  short *flg;
+  // per-block outputs
+  double *partials;  // [grid][partial_len]
+  int partial_len;
+  unsigned long long *counters;  // CNT_*
+  unsigned long long *count_k;   // [K] histogram of indices over ok samples
+  double *first_vals;            // values of the sample with global index 0 (4 doubles)
+};
+
+struct FusedPlan {
+  int valid;
+  int D, RK, RE, NR, SPL;
+  int grid, threads;
+  size_t smem_bytes;
+  int partial_len;   // doubles per block partial: NR*32*RK*RE accumulators + 4 scalars (m, S, maxR, spare)
+  int nstat;         // K*E canonical statistics
+};
+
+// picks an instantiation for (d, K) or returns valid=0
+FusedPlan fused_plan(int d, int K, int Kt, int sm_count, int want_spl);
+// number of doubles of one packed component / whole packed mixture for dimension D
+int fused_comp_stride(int D);
+// host-side packing of a mixture (reference layout in, packed out); returns number of doubles written
+int fused_pack_mixture(int K, int D, const double *wght, const double *mean, const double *L, const double *logdet,
+                       double *out);
+int launch_fused(const FusedPlan &p, const FusedArgs &a, cudaStream_t s);
+// combines the block partials: stats_out[nstat + 4]: canonical statistics rescaled to the global max M, then
+// M (max log-weight over ok samples other than global sample 0), S = sum exp(lw - M), maxR-partial, spare
+int launch_fused_combine(const FusedPlan &p, const double *partials, int K, double *stats_out, cudaStream_t s);
+
+}  // namespace pmcb200

@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    """One PmcGpu context on cuda:0.  The CUDA extension must be the thing that runs: no fallback."""
+    from pmclib_b200 import PmcGpu
+    g = PmcGpu(0)
+    yield g
+    g.close()

@@ -1,0 +1,170 @@
+"""GPU parity: the CUDA path (through the pmcgpu_* C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerance: 1e-12 relative for floating point (BASELINE.json north_star), bit-exact for indices, flags and counts.
+Sizes are chosen so the oracle finishes in seconds; full-size behaviour is covered by test_gpu_properties.py.
+"""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from pmclib_b200 import workloads as W
+from util import RTOL, assert_close, compare_mixture, relerr
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: (workload factory, N)
+    "c1_banana_d10_K10": (lambda: W.banana(), 20000),
+    "c2_gmm_d5_K20": (lambda: W.gmm5(), 20000),
+    "c4_student_d30_K50": (lambda: W.student30(), 4000),
+    "c5_gauss_d128_K64": (lambda: W.gauss128(), 4000),
+    "shipped_d2_K9": (lambda: W.shipped_example(), 30000),
+    "ragged_d10_K10": (lambda: W.banana(seed=77), 1237),   # not a multiple of any tile size
+    "tiny_d10_K10": (lambda: W.banana(seed=78), 33),
+    "d3_K4_generic_only": (lambda: W.banana(d=3, K=4, seed=5, box=30.0), 5000),
+}
+PATHS = {"generic": 1, "fused": 0}
+
+
+def _setup(gpu, wl, X, idx, force_generic, spl=1):
+    gpu.set_option("force_generic", force_generic)
+    gpu.set_option("force_precise", 0)
+    gpu.set_option("spl", spl)
+    gpu.set_workload(wl)
+    gpu.resize(len(X), wl["d"])
+    gpu.upload(X=X, indices=idx, flg=np.ones(len(X), np.int16))
+
+
+@pytest.fixture(scope="module")
+def oracle_runs():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            f, N = CASES[name]
+            wl = f()
+            X, idx = O.orc_simulate(N, wl, seed=11)
+            o = O.orc_iteration(X, idx, wl, do_update=0 if wl["importance_only"] else 1)
+            cache[name] = (wl, X, idx, o)
+        return cache[name]
+    return get
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("name", list(CASES))
+def test_weights_normalise_perplexity(gpu, oracle_runs, name, path):
+    wl, X, idx, o = oracle_runs(name)
+    _setup(gpu, wl, X, idx, PATHS[path])
+    nok, maxW, maxR = gpu.weights(1.0)
+    got = gpu.download(X=False, indices=False)
+    assert nok == o["nok"]
+    assert np.array_equal(got["flg"], np.ones(len(X), np.int16))
+    big = max(np.max(np.abs(o["log_rho"])), 1.0)
+    assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho")
+    # a log-weight is a difference of two log-densities: the error is relative to their size, not to the difference
+    assert_close(got["weights"], o["logw"], RTOL, scale=big, what="log-weights")
+    assert_close(maxW, o["maxW"], RTOL, scale=big, what="maxW")
+    assert_close(maxR, o["maxR"], RTOL, what="maxR")
+    logSum, cnt = gpu.normalize(maxW)
+    assert cnt == o["nok"]
+    assert_close(logSum, o["logSum"], RTOL, scale=big, what="logSum")
+    got = gpu.download(X=False, indices=False, log_rho=False)
+    assert np.array_equal(got["flg"], o["flg"])
+    assert_close(got["weights"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
+    perp, ess, nfl = gpu.perplexity_ess()
+    assert nfl == int(np.sum(o["flg"] == 0))
+    assert_close(perp, o["perp"], 1e-11, what="perplexity")
+    assert_close(ess, o["ess"], 1e-11, what="ESS")
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if not CASES[n][0]()["importance_only"]])
+def test_update_rb_two_pass(gpu, oracle_runs, name):
+    """update_prop_rb on the oracle's own normalised sample (weights, log_rho, flags uploaded as the reference left them)."""
+    wl, X, idx, o = oracle_runs(name)
+    _setup(gpu, wl, X, idx, 1)
+    gpu.upload(weights=o["w_norm"], log_rho=o["log_rho"], flg=o["flg"])
+    if o["rc"] != 0:
+        with pytest.raises(Exception) as e:
+            gpu.update_rb(o["maxR"], len(X), 0)
+        assert str(o["rc"]) in str(e.value)
+        return
+    cnt = gpu.count_indices()
+    assert np.array_equal(cnt, np.bincount(idx[o["flg"] == 1].astype(np.int64), minlength=wl["K"]).astype(np.uint64))
+    u = gpu.update_rb(o["maxR"], len(X), 0)
+    assert u["retry"] == o["retry"]
+    errs = compare_mixture(u["wght"], u["mean"], u["L"], o["o_wght"], o["o_mean"], o["o_std"], what=name)
+    print(name, "two-pass update errors", errs)
+
+
+@pytest.mark.parametrize("spl", [1, 2])
+@pytest.mark.parametrize("name", ["c1_banana_d10_K10", "c2_gmm_d5_K20", "shipped_d2_K9", "ragged_d10_K10", "tiny_d10_K10"])
+def test_fused_iteration_given_samples(gpu, oracle_runs, name, spl):
+    """The one-pass fused kernel (weights + statistics) + host finalisation against the oracle's full iteration."""
+    wl, X, idx, o = oracle_runs(name)
+    _setup(gpu, wl, X, idx, 0, spl)
+    if o["rc"] != 0:
+        with pytest.raises(Exception):
+            gpu.step_given(0, len(X), 1.0, 1, 0)
+        return
+    r = gpu.step_given(0, len(X), 1.0, 1, 0)
+    big = max(np.max(np.abs(o["log_rho"])), 1.0)
+    assert r.nok == o["nok"]
+    assert_close(r.maxW, o["maxW"], RTOL, scale=big, what="maxW")
+    assert_close(r.maxR, o["maxR"], RTOL, what="maxR")
+    assert_close(r.logSum, o["logSum"], RTOL, scale=big, what="logSum")
+    assert_close(r.ln_evidence, o["ln_evidence"], RTOL, scale=big, what="ln evidence")
+    assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
+    assert_close(r.ess, o["ess"], 1e-11, what="ESS")
+    assert r.retry == o["retry"]
+    got = gpu.download(X=False, indices=False)
+    assert np.array_equal(got["flg"], o["flg"])
+    assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho")
+    assert_close(got["weights"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
+    errs = compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
+    print(name, f"spl={spl} precise={r.used_precise_path} one-pass update errors", errs)
+
+
+def test_importance_only_student(gpu, oracle_runs):
+    """configs[3] shape: weights + perplexity + evidence, no update (vanilla_importance.c:56-82)."""
+    wl, X, idx, o = oracle_runs("c4_student_d30_K50")
+    _setup(gpu, wl, X, idx, 0)
+    r = gpu.step_given(0, len(X), 1.0, 0, 0)
+    big = max(np.max(np.abs(o["log_rho"])), 1.0)
+    assert_close(r.logSum, o["logSum"], RTOL, scale=big, what="logSum")
+    assert_close(r.ln_evidence, o["ln_evidence"], RTOL, scale=big, what="ln evidence")
+    assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
+    assert_close(r.ess, o["ess"], 1e-11, what="ESS")
+
+
+def test_ranindx_and_box_bit_exact(gpu):
+    wl = W.banana()
+    gpu.set_option("force_generic", 0)
+    gpu.set_workload(wl)
+    rng = np.random.default_rng(3)
+    m = O.Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"])
+    cw = np.zeros(wl["K"])
+    O.orc().orc_cwght(wl["K"], O.P(m.wght), O.P(cw))
+    z = np.concatenate([rng.random(100000), cw, np.nextafter(cw, 0), np.nextafter(cw, 2), [0.0, 1.0 - 2**-53]])
+    ref = np.array([O.orc().orc_ranindx(O.P(cw), wl["K"], float(v)) for v in z], np.uint64)
+    assert np.array_equal(gpu.ranindx(z), ref)
+    # box: points on, just inside and just outside every face
+    d = wl["d"]
+    x = rng.normal(0, 25, (20000, d))
+    x[:2000, 0] = np.repeat([40.0, np.nextafter(40.0, 50), np.nextafter(40.0, 0), -40.0], 500)
+    faces = wl["faces"]
+    ref = np.array([O.orc().orc_isinbox(d, len(faces), O.P(faces), O.P(np.ascontiguousarray(r))) for r in x], np.int32)
+    assert np.array_equal(gpu.isinbox(x), ref)
+    # general (non axis-parallel) faces
+    gf = np.concatenate([faces, rng.normal(0, 1, (5, d + 1)) + np.r_[np.zeros(d), 30.0]])
+    gpu.set_box(gf)
+    ref = np.array([O.orc().orc_isinbox(d, len(gf), O.P(gf), O.P(np.ascontiguousarray(r))) for r in x], np.int32)
+    assert np.array_equal(gpu.isinbox(x), ref)
+
+
+def test_log_pdf_entry_points(gpu, oracle_runs):
+    for name in ("c1_banana_d10_K10", "c4_student_d30_K50"):
+        wl, X, idx, o = oracle_runs(name)
+        gpu.set_workload(wl)
+        assert_close(gpu.proposal_log_pdf(X[:3000]), o["log_rho"][:3000], RTOL, what="proposal_log_pdf")
+        post = gpu.target_log_pdf(X[:3000])
+        assert_close(post - o["log_rho"][:3000], o["logw"][:3000], RTOL, scale=np.max(np.abs(o["log_rho"])), what="target")
