@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — PMC samples/s per full iteration (draw + weight + RB update) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--samples S]
+
+A "step" is one full PMC iteration over one batch of S proposal samples per GPU: configs[2] of BASELINE.json
+(10-D banana target, 10-component Gaussian mixture proposal, 1e8 samples per iteration; at N GPUs every rank draws
+and weighs its own 1e8-sample shard -> weak scaling, and only the sufficient statistics cross NVLink).
+For N > 1 launch with torchrun (one rank per GPU); rank 0 prints ONE JSON line.
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/libpmcref.so = the reference's own C files compiled
+against the GSL shim) on the host cores, same metric/config, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from pmclib_b200 import workloads as W  # noqa: E402
+
+METRIC = "PMC samples/s per iteration (draw+weight+RB update)"
+UNIT = "samples/s"
+FLOP_PER_SAMPLE = 2987.0   # algorithmic flops per sample at d=10, K=10 (banana target)
+BYTES_PER_SAMPLE = 106.0   # compulsory HBM bytes per sample: X, weights, log_rho, indices, flg = 8d + 26
+FP64_PEAK_TFLOPS = 36.9    # measured DFMA peak on this pool's B200, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)
+
+
+def measured_hbm_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def workload():
+    return W.banana(d=10, K=10, seed=1234, mean_sigma=3.0, var=10.0, box=40.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "power_w_max": float(np.max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(N, niter, nworkers, seed=42):
+    """Times the compiled reference (vanilla_pmc loop; nworkers>1 = vanilla_pmc_mpi emulation) on the host."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+    import oracle_py as O
+    L = O.ref()
+    kind = "reference"
+    wl = workload()
+    K, d = wl["K"], wl["d"]
+    if L is None:
+        return None
+    tg = wl["target"]
+    tp = np.array([tg["b"], tg["sig1"]])
+    times = np.zeros(5 * niter); stats = np.zeros(3 * niter)
+    faces = wl["faces"]
+    t0 = time.time()
+    rc = L.ref_pmc_run(C.c_long(N), d, K, O.P(wl["wght"]), O.P(np.ascontiguousarray(wl["mean"])),
+                       O.P(np.ascontiguousarray(wl["cov"])), O.P(wl["df"]), tg["kind"], O.P(tp), 0, None, None, None, None,
+                       len(faces), O.P(faces), C.c_ulong(seed), niter, 1, nworkers, O.P(times), O.P(stats), None, None, None)
+    wall = time.time() - t0
+    if rc != 0:
+        raise RuntimeError(f"reference run failed rc={rc}")
+    per_iter = times.reshape(niter, 5).sum(1)
+    return dict(kind=kind, per_iter_s=per_iter, wall=wall, phase_s=times.reshape(niter, 5).sum(0), stats=stats.reshape(niter, 3))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    N = args.ref_samples
+    K, Wm = args.steps, args.warmup
+    r = cpu_reference_run(N, K + Wm, cores)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpmcref.so not built and /root/reference absent"}))
+        return
+    per = r["per_iter_s"][Wm:]
+    total = float(np.sum(per))
+    val = N * K / total
+    line = {
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
+        "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "configs[2]: 10-D banana (b=0.1, sig1^2=10), 10-component Gaussian mixture proposal, box +-40",
+                   "samples_per_step": N, "note": "bounded sample of the 1e8-sample iteration; throughput is per sample"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{N} samples/iteration x {K} iterations; vanilla_pmc_mpi emulation: weight loop forked over {cores} "
+                                   "workers on send_simulation's slices, draw/normalise/update on rank 0 as pmc_mpi.c does"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=100_000_000, help="proposal samples per GPU per iteration")
+    ap.add_argument("--ref-samples", type=int, default=1_000_000, help="samples per iteration for the CPU reference arm")
+    ap.add_argument("--cpu-baseline-samples", type=int, default=1_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spl", type=int, default=None)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pmclib_b200 import PmcGpu
+    from pmclib_b200.api import nccl_unique_id, shard_range
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = workload()
+    g = PmcGpu(local_rank)
+    if args.spl:
+        g.set_option("spl", args.spl)
+    g.set_workload(wl)
+    N_total = args.samples * world
+    first, n_local = shard_range(N_total, rank, world)
+    g.resize(n_local)
+    if world > 1:
+        ids = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        g.comm_init_nccl(ids[0], rank, world)
+    stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local_rank))
+    seed = 20261019
+
+    def reset():
+        g.set_workload(wl)
+
+    # ---- device-resident throughput -------------------------------------------------------------------------------
+    it = 0
+    retry = 0
+    for _ in range(args.warmup):
+        r = g.pmc_step(seed, it, first, N_total, 1, retry); retry = r.retry; it += 1
+    g.set_option("timing", 1)
+    _, _, launches0 = g.get_timing()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    perps = []
+    precise = 0
+    for _ in range(args.steps):
+        r = g.pmc_step(seed, it, first, N_total, 1, retry); retry = r.retry; it += 1
+        perps.append(r.perplexity); precise += r.used_precise_path
+    e1.record(stream)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    ev_ms = e0.elapsed_time(e1)
+    fused_ms, fused_n, launches1 = g.get_timing()
+    g.set_option("timing", 0)
+    t = torch.tensor([ev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ev_ms, wall_ms = float(t[0]), float(t[1])
+    value = N_total * args.steps / (ev_ms * 1e-3)
+    n_alive = r.n_alive
+
+    # ---- end to end: host buffers, H2D of the proposal and D2H of the whole sample inside the timed region ----------
+    e2e = None
+    if not args.no_e2e:
+        d, K = wl["d"], wl["K"]
+        host = dict(X=torch.empty((n_local, d), dtype=torch.float64).pin_memory().numpy(),
+                    indices=torch.empty(n_local, dtype=torch.int64).pin_memory().numpy().view(np.uint64),
+                    weights=torch.empty(n_local, dtype=torch.float64).pin_memory().numpy(),
+                    log_rho=torch.empty(n_local, dtype=torch.float64).pin_memory().numpy(),
+                    flg=torch.empty(n_local, dtype=torch.int16).pin_memory().numpy())
+        from pmclib_b200.api import _p
+        prop = g.get_proposal()
+
+        def e2e_step(it_, retry_):
+            # host -> device: the proposal the caller holds (reference layout), then the iteration, then the whole
+            # pmc_simu payload back to host memory, as pmc_simu_pmc_step's contract promises
+            g.set_proposal(prop["wght"], prop["mean"], prop["L"], prop["detL"], None)
+            rr = g.pmc_step(seed, it_, first, N_total, 1, retry_)
+            g._ck(g.lib.pmcgpu_download(g.h, _p(host["X"]), _p(host["indices"]), _p(host["weights"]), _p(host["log_rho"]), _p(host["flg"])))
+            prop.update(wght=rr.wght, mean=rr.mean, L=rr.L, detL=rr.detL)
+            return rr
+        rr = e2e_step(it, retry); it += 1
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        nst = max(1, min(args.steps, 5))
+        for _ in range(nst):
+            rr = e2e_step(it, rr.retry); it += 1
+        e1.record(stream)
+        barrier()
+        e_ms = 1e3 * (time.perf_counter() - t0)
+        t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d = K * (1 + d + d * d + 1) * 8 + K * 4
+        d2h = n_local * (8 * d + 8 + 8 + 8 + 2)
+        e2e = {"value": N_total * nst / (float(t[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": nst,
+               "path": "pmcgpu_set_proposal (host mixture) -> pmcgpu_pmc_step -> pmcgpu_download of X, indices, weights, log_rho, flg into pinned host buffers"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------------------
+    roof = None
+    if fused_n > 0:
+        ms = fused_ms / fused_n
+        tf = FLOP_PER_SAMPLE * n_local / (ms * 1e-3) * 1e-12
+        hbm_peak, which = measured_hbm_gbs()
+        roof = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
+                "traffic": None, "kernel": "k_fused<10,2,12,1,%d>" % (args.spl or 1), "kernel_ms": ms,
+                "kernel_share_of_step": fused_ms / ev_ms,
+                "peak_source": "measured DFMA peak, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)",
+                "algorithmic_flop_per_sample": FLOP_PER_SAMPLE,
+                "hbm": {"achieved": BYTES_PER_SAMPLE * n_local / (ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": BYTES_PER_SAMPLE * n_local / (ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": which + " MEASURED_PEAKS.json"}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            Nc, itc = args.cpu_baseline_samples, 4
+            rr = cpu_reference_run(Nc, itc, 1)
+            if rr is not None:
+                per = rr["per_iter_s"][1:]
+                cpu = {"value": Nc * len(per) / float(np.sum(per)), "unit": UNIT, "cores": 1, "kind": "reference",
+                       "sample": f"{Nc} samples/iteration x {len(per)} iterations of the compiled reference (vanilla_pmc loop), same workload",
+                       "phase_split_s": {k: float(v) for k, v in zip(["draw", "weight", "normalise", "update", "perplexity"], rr["phase_s"])}}
+        except Exception as ex:  # pragma: no cover
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {ex}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: 10-D banana (b=0.1, sig1^2=10), 10-component Gaussian mixture proposal, box +-40",
+                   "samples_per_gpu_per_step": n_local, "samples_per_step": N_total, "parallelism": f"sample shards x{world}",
+                   "cache": "inputs larger than L2 (10.6 GB of sample arrays per GPU per step)",
+                   "components_alive_at_end": int(n_alive), "perplexity_last": float(perps[-1]),
+                   "precise_path_steps": int(precise), "wall_ms_per_step": wall_ms / args.steps},
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": int(launches1 - launches0),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,8 +44,13 @@ void *pmcgpu_stream(pmcgpu_ctx *ctx);
 
 /* tuning / test knobs: "force_generic" (1 = never use the fused small-d kernel), "spl" (samples per lane of the fused
  * kernel, 1 or 2), "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass
- * update), "guard_ratio" (pivot guard threshold of the one-pass update) */
+ * update), "guard_ratio" (pivot guard threshold of the one-pass update), "timing" (see pmcgpu_get_timing) */
 int pmcgpu_set_option(pmcgpu_ctx *ctx, const char *name, double value);
+
+/* timing of the dominant (fused) kernel, measured with CUDA events on the launching stream while option "timing" = 1:
+ * accumulated milliseconds and launches since the option was set; total_launches = kernels launched by the library
+ * in this process */
+int pmcgpu_get_timing(pmcgpu_ctx *ctx, double *fused_ms, long *fused_launches, long *total_launches);
 
 /* ---- model: proposal, target, box ------------------------------------------------------------- */
 /* replaces the host-side mix_mvdens the reference passes around (mvdens.h:102-110) */

@@ -80,6 +80,11 @@ class PmcGpu:
     def set_option(self, name, value):
         self._ck(self.lib.pmcgpu_set_option(self.h, name.encode(), float(value)))
 
+    def get_timing(self):
+        ms, n, tot = C.c_double(), C.c_long(), C.c_long()
+        self._ck(self.lib.pmcgpu_get_timing(self.h, C.byref(ms), C.byref(n), C.byref(tot)))
+        return ms.value, n.value, tot.value
+
     @property
     def stream(self):
         return self.lib.pmcgpu_stream(self.h)

@@ -122,6 +122,11 @@ struct pmcgpu_ctx {
   DevBuf ld, blkmax, partials, stats, small, rbg, rbw, rbacc, rbpart, newmean, hostpost, hostok, tmpx, tmpo;
   double *hstage = nullptr;  // pinned
   size_t hstage_doubles = 0;
+  // timing of the dominant kernel (CUDA events on the launching stream)
+  int timing = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double fused_ms = 0.0;
+  long fused_launches = 0;
   // options
   int force_generic = 0, spl = 1, max_attempts = 10000, force_precise = 0;
   double guard_ratio = 200.0;
@@ -400,13 +405,24 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
   a.counters = sm + SM_COUNTERS;
   a.count_k = sm + SM_COUNTK;
   a.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
+  if (c->timing) {
+    if (!c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); }
+    CU(cudaEventRecord(c->ev0, c->stream));
+  }
   if (launch_fused(p, a, c->stream) != 0) return fail(c, PMCGPU_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
   if (launch_fused_combine(p, a.partials, c->prop.K, c->stats.as<double>(), c->stream) != 0)
     return fail(c, PMCGPU_ERR_CUDA, "combine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   RC(stage(c, (size_t)p.nstat + 4 + SM_LEN));
   CU(cudaMemcpyAsync(c->hstage, c->stats.p, (size_t)(p.nstat + 4) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->hstage + p.nstat + 4, c->small.p, SM_LEN * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->timing) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->fused_ms += ms;
+    c->fused_launches += 1;
+  }
   o.stats.assign(c->hstage, c->hstage + p.nstat);
   o.M_all = c->hstage[p.nstat];
   o.S = c->hstage[p.nstat + 1];
@@ -658,6 +674,7 @@ void pmcgpu_destroy(pmcgpu_ctx *c) {
                     &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll};
   for (DevBuf *b : bufs) b->release();
   if (c->hstage) cudaFreeHost(c->hstage);
+  if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -672,7 +689,16 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "max_attempts")) c->max_attempts = (int)value;
   else if (!strcmp(name, "force_precise")) c->force_precise = (int)value;
   else if (!strcmp(name, "guard_ratio")) c->guard_ratio = value;
+  else if (!strcmp(name, "timing")) { c->timing = (int)value; c->fused_ms = 0.0; c->fused_launches = 0; }
   else return fail(c, PMCGPU_ERR_USAGE, "unknown option %s", name);
+  return 0;
+}
+
+int pmcgpu_get_timing(pmcgpu_ctx *c, double *fused_ms, long *fused_launches, long *total_launches) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  if (fused_ms) *fused_ms = c->fused_ms;
+  if (fused_launches) *fused_launches = c->fused_launches;
+  if (total_launches) *total_launches = launch_count();
   return 0;
 }
 

@@ -542,6 +542,7 @@ static int launch_one(const FusedPlan &p, const FusedArgs &a, cudaStream_t s) {
     configured = p.smem_bytes;
   }
   kern<<<p.grid, p.threads, p.smem_bytes, s>>>(a);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -591,6 +592,7 @@ int launch_fused_combine(const FusedPlan &p, const double *partials, int K, doub
   const int NCH = (E + p.RE - 1) / p.RE;
   k_fused_combine<<<1, 256, p.grid * sizeof(double), s>>>(partials, p.grid, p.partial_len, p.partial_len - 4, K, E,
                                                             p.RK, p.RE, NCH, stats_out);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

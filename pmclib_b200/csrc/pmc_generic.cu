@@ -441,68 +441,71 @@ __global__ void k_norm_scale_perp(long N, double S, double *__restrict__ w, cons
 
 // ---- launch wrappers -----------------------------------------------------------------------------------------
 static inline int nblk(long n, int t) { return (int)((n + t - 1) / t); }
+static long g_launches = 0;
+long launch_count() { return g_launches; }
+void count_launch(int n) { g_launches += n; }
 
 void launch_draw_generic(const MixDev &m, const BoxDev &bx, uint64_t seed, uint32_t iter, long first_index, long N,
                          int max_attempts, double *X, unsigned long long *indices, short *flg,
                          unsigned long long *counters, cudaStream_t s) {
-  if (N > 0) k_draw_generic<<<nblk(N, 128), 128, 0, s>>>(m, bx, seed, iter, first_index, N, max_attempts, X, indices, flg, counters);
+  if (N > 0) { k_draw_generic<<<nblk(N, 128), 128, 0, s>>>(m, bx, seed, iter, first_index, N, max_attempts, X, indices, flg, counters); count_launch(); }
 }
 void launch_weights_generic(const MixDev &m, const TargetDev &tg, int mode, const double *post_in, const short *ok_in,
                             double t_temper, long first_index, long N, const double *X, double *lw, double *log_rho,
                             short *flg, double *ldscratch, int ldstride, double *blk_maxw, double *blk_maxr,
                             unsigned long long *counters, double *first_vals, cudaStream_t s) {
   if (N > 0)
-    k_weights_generic<<<nblk(N, GEN_WEIGHT_THREADS), GEN_WEIGHT_THREADS, 0, s>>>(m, tg, mode, post_in, ok_in, t_temper, first_index, N, X, lw, log_rho, flg,
-                                                 ldscratch, ldstride, blk_maxw, blk_maxr, counters, first_vals);
+    { k_weights_generic<<<nblk(N, GEN_WEIGHT_THREADS), GEN_WEIGHT_THREADS, 0, s>>>(m, tg, mode, post_in, ok_in, t_temper, first_index, N, X, lw, log_rho, flg,
+                                                 ldscratch, ldstride, blk_maxw, blk_maxr, counters, first_vals); count_launch(); }
 }
 void launch_mix_log_pdf(const MixDev &m, long n, const double *X, double *out, double *ld, int ldstride, cudaStream_t s) {
-  if (n > 0) k_mix_log_pdf<<<nblk(n, 128), 128, 0, s>>>(m, n, X, out, ld, ldstride);
+  if (n > 0) { k_mix_log_pdf<<<nblk(n, 128), 128, 0, s>>>(m, n, X, out, ld, ldstride); count_launch(); }
 }
 void launch_target_log_pdf(const TargetDev &tg, int dfree, long n, const double *X, double *out, double *ld, int ldstride, cudaStream_t s) {
-  if (n > 0) k_target_log_pdf<<<nblk(n, 128), 128, 0, s>>>(tg, dfree, n, X, out, ld, ldstride);
+  if (n > 0) { k_target_log_pdf<<<nblk(n, 128), 128, 0, s>>>(tg, dfree, n, X, out, ld, ldstride); count_launch(); }
 }
 void launch_ranindx(const double *cw, int K, long n, const double *z, unsigned long long *idx, cudaStream_t s) {
-  if (n > 0) k_ranindx<<<nblk(n, 256), 256, 0, s>>>(cw, K, n, z, idx);
+  if (n > 0) { k_ranindx<<<nblk(n, 256), 256, 0, s>>>(cw, K, n, z, idx); count_launch(); }
 }
 void launch_isinbox(const BoxDev &bx, long n, const double *X, int *inside, cudaStream_t s) {
-  if (n > 0) k_isinbox<<<nblk(n, 128), 128, 0, s>>>(bx, n, X, inside);
+  if (n > 0) { k_isinbox<<<nblk(n, 128), 128, 0, s>>>(bx, n, X, inside); count_launch(); }
 }
 void launch_norm_exp_sum(long N, double maxW, double *w, short *flg, double *partial, int nblocks,
                          unsigned long long *counters, cudaStream_t s) {
-  k_norm_exp_sum<<<nblocks, 256, 0, s>>>(N, maxW, w, flg, partial, counters);
+  { k_norm_exp_sum<<<nblocks, 256, 0, s>>>(N, maxW, w, flg, partial, counters); count_launch(); }
 }
 void launch_norm_scale(long N, double S, double *w, int nblocks, cudaStream_t s) {
-  k_norm_scale<<<nblocks, 256, 0, s>>>(N, S, w);
+  { k_norm_scale<<<nblocks, 256, 0, s>>>(N, S, w); count_launch(); }
 }
 void launch_perplexity(long N, const double *w, const short *flg, double *partial, int nblocks,
                        unsigned long long *counters, cudaStream_t s) {
-  k_perplexity<<<nblocks, 256, 0, s>>>(N, w, flg, partial, counters);
+  { k_perplexity<<<nblocks, 256, 0, s>>>(N, w, flg, partial, counters); count_launch(); }
 }
 void launch_count_indices(long N, int K, const unsigned long long *indices, const short *flg,
                           unsigned long long *count, int nblocks, cudaStream_t s) {
-  k_count_indices<<<nblocks, 256, K * sizeof(unsigned int), s>>>(N, K, indices, flg, count);
+  { k_count_indices<<<nblocks, 256, K * sizeof(unsigned int), s>>>(N, K, indices, flg, count); count_launch(); }
 }
 void launch_rb_resp(const MixDev &m, long n, long base, const double *X, const double *w, const double *log_rho,
                     const short *flg, const unsigned long long *indices, const unsigned long long *count, double maxR,
                     int hard, double *gw8, double *w8, cudaStream_t s) {
-  if (n > 0) k_rb_resp<<<nblk(n, 128), 128, 0, s>>>(m, n, base, X, w, log_rho, flg, indices, count, maxR, hard, gw8, w8);
+  if (n > 0) { k_rb_resp<<<nblk(n, 128), 128, 0, s>>>(m, n, base, X, w, log_rho, flg, indices, count, maxR, hard, gw8, w8); count_launch(); }
 }
 void launch_rb_reduce_mean(int K, int d, long n, long base, int nsplit, const double *X, const double *gw8,
                            const double *w8, double *part, double *out, cudaStream_t s) {
-  k_rb_reduce_mean<<<dim3(K, nsplit), ((d + 2 + 31) / 32) * 32, 0, s>>>(K, d, n, base, nsplit, X, gw8, w8, part);
+  { k_rb_reduce_mean<<<dim3(K, nsplit), ((d + 2 + 31) / 32) * 32, 0, s>>>(K, d, n, base, nsplit, X, gw8, w8, part); count_launch(); }
   const long len = (long)K * (d + 2);
-  k_rb_sum_splits<<<nblk(len, 256), 256, 0, s>>>(len, nsplit, part, out);
+  { k_rb_sum_splits<<<nblk(len, 256), 256, 0, s>>>(len, nsplit, part, out); count_launch(); }
 }
 void launch_rb_reduce_cov(int K, int d, long n, long base, int nsplit, const double *X, const double *gw8,
                           const double *newmean, double *part, double *out, cudaStream_t s) {
   cudaMemsetAsync(part, 0, sizeof(double) * (size_t)nsplit * K * d * d, s);
-  k_rb_reduce_cov<<<dim3(K, (d + RB_ROWS - 1) / RB_ROWS, nsplit), ((d + 31) / 32) * 32, 0, s>>>(K, d, n, base, nsplit, X, gw8, newmean, part);
+  { k_rb_reduce_cov<<<dim3(K, (d + RB_ROWS - 1) / RB_ROWS, nsplit), ((d + 31) / 32) * 32, 0, s>>>(K, d, n, base, nsplit, X, gw8, newmean, part); count_launch(); }
   const long len = (long)K * d * d;
-  k_rb_sum_splits<<<nblk(len, 256), 256, 0, s>>>(len, nsplit, part, out);
+  { k_rb_sum_splits<<<nblk(len, 256), 256, 0, s>>>(len, nsplit, part, out); count_launch(); }
 }
 void launch_norm_scale_perp(long N, double S, double *w, const short *flg, double *partial, int nblocks,
                             unsigned long long *counters, cudaStream_t s) {
-  k_norm_scale_perp<<<nblocks, 256, 0, s>>>(N, S, w, flg, partial, counters);
+  { k_norm_scale_perp<<<nblocks, 256, 0, s>>>(N, S, w, flg, partial, counters); count_launch(); }
 }
 
 }  // namespace pmcb200

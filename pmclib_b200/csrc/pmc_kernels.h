@@ -24,6 +24,10 @@ struct TargetDev {
   const double *def_val;
 };
 
+// number of kernels launched by this library in this process (bench.py reports it as gpu_launches)
+long launch_count();
+void count_launch(int n = 1);
+
 // ---- generic kernels (pmc_generic.cu) ------------------------------------------------------------------------
 void launch_draw_generic(const MixDev &m, const BoxDev &bx, uint64_t seed, uint32_t iter, long first_index, long N,
                          int max_attempts, double *X, unsigned long long *indices, short *flg,
