@@ -99,6 +99,7 @@ struct pmcgpu_ctx {
   DevMixBuf dprop;
   DevBuf dprop_pack;
   int prop_pack_doubles = 0;
+  std::vector<double> prop_pack_host, tgt_pack_host;
   int tkind = PMCGPU_TGT_NONE, td = 0;
   double tb = 0, tsig1 = 1;
   HostMix tmix;
@@ -128,6 +129,7 @@ struct pmcgpu_ctx {
   double fused_ms = 0.0;
   long fused_launches = 0;
   // options
+  int fused_version = 0;  // 0 = newest kernel that fits, 1 = pmc_fused.cu only, 2 = pmc_fused2.cu only
   int force_generic = 0, spl = 1, max_attempts = 10000, force_precise = 0;
   double guard_ratio = 200.0;
   // comm
@@ -230,13 +232,15 @@ int fill_mix(pmcgpu_ctx *c, HostMix &m, int K, int d, const double *wght, const 
   return 0;
 }
 
-int pack_small(pmcgpu_ctx *c, const HostMix &m, DevBuf &out, int &ndoubles) {
+int pack_small(pmcgpu_ctx *c, const HostMix &m, DevBuf &out, int &ndoubles, std::vector<double> &hostcopy) {
   ndoubles = 0;
+  hostcopy.clear();
   if (m.d > FUSED_MAXD || m.student) return 0;
   const int n = m.K * fused_comp_stride(m.d);
   CU(out.ensure((size_t)n * sizeof(double)));
   RC(stage(c, n));
   fused_pack_mixture(m.K, m.d, m.wght.data(), m.mean.data(), m.L.data(), m.logdet.data(), c->hstage);
+  hostcopy.assign(c->hstage, c->hstage + n);
   CU(cudaMemcpyAsync(out.p, c->hstage, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   ndoubles = n;
@@ -247,7 +251,7 @@ int install_proposal(pmcgpu_ctx *c) {
   derive_mix(c->prop);
   int rc = upload_mix(c, c->prop, c->dprop);
   if (rc) return rc;
-  return pack_small(c, c->prop, c->dprop_pack, c->prop_pack_doubles);
+  return pack_small(c, c->prop, c->dprop_pack, c->prop_pack_doubles, c->prop_pack_host);
 }
 
 TargetDev target_view(const pmcgpu_ctx *c) {
@@ -277,6 +281,10 @@ FusedPlan plan_for(const pmcgpu_ctx *c) {
     return none;
   }
   if (c->nfaces > 0 && !c->box_slab) return none;
+  if (c->fused_version != 1) {
+    const FusedPlan p2 = fused2_plan(c->prop.d, c->prop.K, Kt, c->tkind, c->sm_count, c->spl);
+    if (p2.valid || c->fused_version == 2) return p2;
+  }
   return fused_plan(c->prop.d, c->prop.K, Kt, c->sm_count, c->spl);
 }
 
@@ -409,9 +417,13 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
     if (!c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); }
     CU(cudaEventRecord(c->ev0, c->stream));
   }
-  if (launch_fused(p, a, c->stream) != 0) return fail(c, PMCGPU_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const int lrc = (p.valid == 2) ? launch_fused2(p, a, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), c->stream)
+                                 : launch_fused(p, a, c->stream);
+  if (lrc != 0) return fail(c, PMCGPU_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
-  if (launch_fused_combine(p, a.partials, c->prop.K, c->stats.as<double>(), c->stream) != 0)
+  const int crc = (p.valid == 2) ? launch_fused2_combine(p, a.partials, c->stats.as<double>(), c->stream)
+                                 : launch_fused_combine(p, a.partials, c->prop.K, c->stats.as<double>(), c->stream);
+  if (crc != 0)
     return fail(c, PMCGPU_ERR_CUDA, "combine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   RC(stage(c, (size_t)p.nstat + 4 + SM_LEN));
   CU(cudaMemcpyAsync(c->hstage, c->stats.p, (size_t)(p.nstat + 4) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -686,6 +698,7 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   if (!c || !name) return PMCGPU_ERR_USAGE;
   if (!strcmp(name, "force_generic")) c->force_generic = (int)value;
   else if (!strcmp(name, "spl")) c->spl = (int)value;
+  else if (!strcmp(name, "fused_version")) c->fused_version = (int)value;
   else if (!strcmp(name, "max_attempts")) c->max_attempts = (int)value;
   else if (!strcmp(name, "force_precise")) c->force_precise = (int)value;
   else if (!strcmp(name, "guard_ratio")) c->guard_ratio = value;
@@ -742,7 +755,7 @@ int pmcgpu_set_target_mix(pmcgpu_ctx *c, int kind, int K, int d, const double *w
   c->td = d;
   rc = upload_mix(c, c->tmix, c->dtmix);
   if (rc) return rc;
-  return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles);
+  return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles, c->tgt_pack_host);
 }
 
 int pmcgpu_set_target_host(pmcgpu_ctx *c, int d) {

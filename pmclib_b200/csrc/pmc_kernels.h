@@ -114,4 +114,10 @@ int launch_fused(const FusedPlan &p, const FusedArgs &a, cudaStream_t s);
 // M (max log-weight over ok samples other than global sample 0), S = sum exp(lw - M), maxR-partial, spare
 int launch_fused_combine(const FusedPlan &p, const double *partials, int K, double *stats_out, cudaStream_t s);
 
+// second-generation kernel (pmc_fused2.cu): (D, K) templated, mixture in constant memory, DMMA statistics.
+// plan.valid == 2; plan.RK / plan.RE carry K / KT.  h_mix / h_tgt are the host copies of the packed blocks.
+FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want_spl);
+int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, cudaStream_t s);
+int launch_fused2_combine(const FusedPlan &p, const double *partials, double *stats_out, cudaStream_t s);
+
 }  // namespace pmcb200

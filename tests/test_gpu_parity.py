@@ -23,11 +23,11 @@ CASES = {
     "tiny_d10_K10": (lambda: W.banana(seed=78), 33),
     "d3_K4_generic_only": (lambda: W.banana(d=3, K=4, seed=5, box=30.0), 5000),
 }
-PATHS = {"generic": 1, "fused": 0}
 
 
-def _setup(gpu, wl, X, idx, force_generic, spl=1):
+def _setup(gpu, wl, X, idx, force_generic, spl=1, ver=0):
     gpu.set_option("force_generic", force_generic)
+    gpu.set_option("fused_version", ver)
     gpu.set_option("force_precise", 0)
     gpu.set_option("spl", spl)
     gpu.set_workload(wl)
@@ -50,11 +50,14 @@ def oracle_runs():
     return get
 
 
+PATHS = {"generic": (1, 0), "fused_v1": (0, 1), "fused_v2": (0, 2)}
+
+
 @pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("name", list(CASES))
 def test_weights_normalise_perplexity(gpu, oracle_runs, name, path):
     wl, X, idx, o = oracle_runs(name)
-    _setup(gpu, wl, X, idx, PATHS[path])
+    _setup(gpu, wl, X, idx, PATHS[path][0], 1, PATHS[path][1])
     nok, maxW, maxR = gpu.weights(1.0)
     got = gpu.download(X=False, indices=False)
     assert nok == o["nok"]
@@ -96,12 +99,12 @@ def test_update_rb_two_pass(gpu, oracle_runs, name):
     print(name, "two-pass update errors", errs)
 
 
-@pytest.mark.parametrize("spl", [1, 2])
+@pytest.mark.parametrize("ver,spl", [(1, 1), (1, 2), (2, 1)])
 @pytest.mark.parametrize("name", ["c1_banana_d10_K10", "c2_gmm_d5_K20", "shipped_d2_K9", "ragged_d10_K10", "tiny_d10_K10"])
-def test_fused_iteration_given_samples(gpu, oracle_runs, name, spl):
+def test_fused_iteration_given_samples(gpu, oracle_runs, name, ver, spl):
     """The one-pass fused kernel (weights + statistics) + host finalisation against the oracle's full iteration."""
     wl, X, idx, o = oracle_runs(name)
-    _setup(gpu, wl, X, idx, 0, spl)
+    _setup(gpu, wl, X, idx, 0, spl, ver)
     if o["rc"] != 0:
         with pytest.raises(Exception):
             gpu.step_given(0, len(X), 1.0, 1, 0)
@@ -121,7 +124,7 @@ def test_fused_iteration_given_samples(gpu, oracle_runs, name, spl):
     assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho")
     assert_close(got["weights"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
     errs = compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
-    print(name, f"spl={spl} precise={r.used_precise_path} one-pass update errors", errs)
+    print(name, f"ver={ver} spl={spl} precise={r.used_precise_path} one-pass update errors", errs)
 
 
 def test_importance_only_student(gpu, oracle_runs):
