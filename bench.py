@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spl", type=int, default=None)
+    ap.add_argument("--opts", default="", help="comma separated pmcgpu_set_option pairs, e.g. k1_variant=1,split_stats=0")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
@@ -196,6 +197,9 @@ def main():
     g = PmcGpu(local_rank)
     if args.spl:
         g.set_option("spl", args.spl)
+    for kv in filter(None, args.opts.split(",")):
+        k_, v_ = kv.split("=")
+        g.set_option(k_, float(v_))
     g.set_workload(wl)
     N_total = args.samples * world
     first, n_local = shard_range(N_total, rank, world)
@@ -235,6 +239,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ev_ms = e0.elapsed_time(e1)
     fused_ms, fused_n, launches1 = g.get_timing()
+    stats_ms = g.get_stats_timing()
     g.set_option("timing", 0)
     t = torch.tensor([ev_ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -295,7 +300,7 @@ def main():
         hbm_peak, which = measured_hbm_gbs()
         roof = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
                 "traffic": None, "kernel": "k_fused<10,2,12,1,%d>" % (args.spl or 1), "kernel_ms": ms,
-                "kernel_share_of_step": fused_ms / ev_ms,
+                "kernel_share_of_step": fused_ms / ev_ms, "stats_kernel_ms": stats_ms / fused_n,
                 "peak_source": "measured DFMA peak, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flop_per_sample": FLOP_PER_SAMPLE,
                 "hbm": {"achieved": BYTES_PER_SAMPLE * n_local / (ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",

@@ -125,8 +125,10 @@ struct pmcgpu_ctx {
   size_t hstage_doubles = 0;
   // timing of the dominant kernel (CUDA events on the launching stream)
   int timing = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double fused_ms = 0.0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  double fused_ms = 0.0, stats_ms = 0.0;
+  int split_stats = 1, k1_variant = 0;
+  DevBuf resp, partials2, dscal, zig;
   long fused_launches = 0;
   // options
   int fused_version = 0;  // 0 = newest kernel that fits, 1 = pmc_fused.cu only, 2 = pmc_fused2.cu only
@@ -391,6 +393,7 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
       a.pivot[j] = s / sw;
     }
   }
+  a.zig = c->zig.as<double2>();
   a.do_draw = do_draw;
   a.do_stats = do_stats;
   a.N = c->N;
@@ -403,7 +406,8 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
   a.log_rho = c->R.as<double>();
   a.indices = c->Idx.as<unsigned long long>();
   a.flg = c->Flg.as<short>();
-  CU(c->partials.ensure((size_t)p.grid * p.partial_len * sizeof(double)));
+  const int maxblk = (p.valid == 2) ? fused2_max_blocks(p) : p.grid;
+  CU(c->partials.ensure((size_t)maxblk * p.partial_len * sizeof(double)));
   CU(c->stats.ensure((size_t)(p.nstat + 4) * sizeof(double)));
   a.partials = c->partials.as<double>();
   a.partial_len = p.partial_len;
@@ -413,32 +417,51 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
   a.counters = sm + SM_COUNTERS;
   a.count_k = sm + SM_COUNTK;
   a.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
+  const int mode = (p.valid == 2) ? (do_stats ? ((c->split_stats || p.SPL > 1) ? 1 : 2) : 0) : -1;
+  if (mode == 1) {
+    CU(c->resp.ensure((size_t)c->prop.K * c->N * sizeof(double)));
+    CU(c->partials2.ensure((size_t)p.grid * 2 * p.partial_len * sizeof(double)));
+    CU(c->dscal.ensure(4 * sizeof(double)));
+    a.resp = c->resp.as<double>();
+  }
   if (c->timing) {
-    if (!c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); }
+    if (!c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->ev2)); }
     CU(cudaEventRecord(c->ev0, c->stream));
   }
-  const int lrc = (p.valid == 2) ? launch_fused2(p, a, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), c->stream)
+  int nblk = p.grid;
+  const int lrc = (p.valid == 2) ? launch_fused2(p, a, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), mode, c->k1_variant, &nblk, c->stream)
                                  : launch_fused(p, a, c->stream);
   if (lrc != 0) return fail(c, PMCGPU_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
-  const int crc = (p.valid == 2) ? launch_fused2_combine(p, a.partials, c->stats.as<double>(), c->stream)
-                                 : launch_fused_combine(p, a.partials, c->prop.K, c->stats.as<double>(), c->stream);
+  int crc = 0;
+  if (mode == 1) {
+    crc = launch_fused2_max(p, a.partials, nblk, c->dscal.as<double>(), c->stream);
+    if (!crc) crc = launch_fused2_stats(p, a.X, a.lw, a.resp, a.flg, c->dscal.as<double>(), a.pivot, c->N, c->partials2.as<double>(), c->stream);
+    if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
+    if (!crc) crc = launch_fused2_combine(p, c->partials2.as<double>(), p.grid * 2, c->stats.as<double>(), c->stream);
+  } else if (p.valid == 2) {
+    crc = launch_fused2_combine(p, a.partials, nblk, c->stats.as<double>(), c->stream);
+  } else {
+    crc = launch_fused_combine(p, a.partials, c->prop.K, c->stats.as<double>(), c->stream);
+  }
   if (crc != 0)
     return fail(c, PMCGPU_ERR_CUDA, "combine launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-  RC(stage(c, (size_t)p.nstat + 4 + SM_LEN));
+  RC(stage(c, (size_t)p.nstat + 8 + SM_LEN));
   CU(cudaMemcpyAsync(c->hstage, c->stats.p, (size_t)(p.nstat + 4) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->hstage + p.nstat + 4, c->small.p, SM_LEN * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (mode == 1) CU(cudaMemcpyAsync(c->hstage + p.nstat + 4 + SM_LEN, c->dscal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (c->timing) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->fused_ms += ms;
     c->fused_launches += 1;
+    if (mode == 1) { CU(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats_ms += ms; }
   }
   o.stats.assign(c->hstage, c->hstage + p.nstat);
   o.M_all = c->hstage[p.nstat];
   o.S = c->hstage[p.nstat + 1];
-  o.R_all = c->hstage[p.nstat + 2];
+  o.R_all = (mode == 1) ? c->hstage[p.nstat + 4 + SM_LEN + 1] : c->hstage[p.nstat + 2];
   const unsigned long long *u = reinterpret_cast<const unsigned long long *>(c->hstage + p.nstat + 4);
   memcpy(o.counters, u + SM_COUNTERS, CNT_NUM * 8);
   memcpy(o.count_k, u + SM_COUNTK, 64 * 8);
@@ -670,6 +693,20 @@ int pmcgpu_create(int device, pmcgpu_ctx **out) {
   c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return PMCGPU_ERR_CUDA; }
   for (int j = 0; j < FUSED_MAXD; ++j) { c->lo_thr[j] = INFINITY; c->hi_thr[j] = INFINITY; }
+  {  // ziggurat table: x_0 = V/f(R), x_1 = R, x_i = sqrt(-2 ln(V/x_{i-1} + f(x_{i-1}))), x_256 = 0; entries (x_i, x_{i+1}/x_i)
+    std::vector<double> x(kZigLayers + 1), tab(2 * kZigLayers);
+    auto f = [](double v) { return std::exp(-0.5 * v * v); };
+    x[0] = kZigV / f(kZigR);
+    x[1] = kZigR;
+    for (int i = 2; i < kZigLayers; ++i) x[i] = std::sqrt(-2.0 * std::log(kZigV / x[i - 1] + f(x[i - 1])));
+    x[kZigLayers] = 0.0;
+    for (int i = 0; i < kZigLayers; ++i) { tab[2 * i] = x[i]; tab[2 * i + 1] = x[i + 1] / x[i]; }
+    if (c->zig.ensure(tab.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(c->zig.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+      pmcgpu_destroy(c);
+      return PMCGPU_ERR_CUDA;
+    }
+  }
   if (const char *e = getenv("PMCB200_FORCE_GENERIC")) c->force_generic = atoi(e);
   if (const char *e = getenv("PMCB200_SPL")) c->spl = atoi(e);
   *out = c;
@@ -683,10 +720,10 @@ void pmcgpu_destroy(pmcgpu_ctx *c) {
   if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
   DevBuf *bufs[] = {&c->dprop.buf, &c->dprop_pack, &c->dtmix.buf, &c->dt_pack, &c->ddef, &c->dfaces, &c->X, &c->W, &c->R,
                     &c->Idx, &c->Flg, &c->ld, &c->blkmax, &c->partials, &c->stats, &c->small, &c->rbg, &c->rbw, &c->rbacc,
-                    &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll};
+                    &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll, &c->resp, &c->partials2, &c->dscal, &c->zig};
   for (DevBuf *b : bufs) b->release();
   if (c->hstage) cudaFreeHost(c->hstage);
-  if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
+  if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -702,7 +739,9 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "max_attempts")) c->max_attempts = (int)value;
   else if (!strcmp(name, "force_precise")) c->force_precise = (int)value;
   else if (!strcmp(name, "guard_ratio")) c->guard_ratio = value;
-  else if (!strcmp(name, "timing")) { c->timing = (int)value; c->fused_ms = 0.0; c->fused_launches = 0; }
+  else if (!strcmp(name, "timing")) { c->timing = (int)value; c->fused_ms = 0.0; c->stats_ms = 0.0; c->fused_launches = 0; }
+  else if (!strcmp(name, "split_stats")) c->split_stats = (int)value;
+  else if (!strcmp(name, "k1_variant")) c->k1_variant = (int)value;
   else return fail(c, PMCGPU_ERR_USAGE, "unknown option %s", name);
   return 0;
 }
@@ -712,6 +751,12 @@ int pmcgpu_get_timing(pmcgpu_ctx *c, double *fused_ms, long *fused_launches, lon
   if (fused_ms) *fused_ms = c->fused_ms;
   if (fused_launches) *fused_launches = c->fused_launches;
   if (total_launches) *total_launches = launch_count();
+  return 0;
+}
+
+int pmcgpu_get_stats_timing(pmcgpu_ctx *c, double *stats_ms) {
+  if (!c || !stats_ms) return PMCGPU_ERR_USAGE;
+  *stats_ms = c->stats_ms;
   return 0;
 }
 

@@ -116,6 +116,123 @@ __device__ __forceinline__ bool in_box(const BoxDev &bx, const XT &x) {
   return true;
 }
 
+
+// ---- ziggurat normal sampler (Marsaglia & Tsang 2000 in Doornik's ZIGNOR form, 256 layers) --------------------------
+// A Box-Muller pair costs ~115 DFMA issue slots in double precision (log + sqrt + sincospi, profiles/r01_fp64_peak.md);
+// the ziggurat's fast path is one table lookup, one DADD, one DMUL and one compare and is taken 98.8 % of the time.
+// Table t[i] = (x_i, x_{i+1}/x_i), x_0 = V/f(R), x_1 = R, x_256 = 0 (built on the host by zig_build_table()).
+constexpr int kZigLayers = 256;
+constexpr double kZigR = 3.6541528853610088;
+constexpr double kZigV = 4.92867323399e-3;
+
+// candidate from 64 random bits: layer = bits 0..7, sign = bit 8, |u| = 52-bit mantissa in [0,1).  Returns true if the
+// rectangle test accepts; x holds the signed candidate either way.
+__device__ __forceinline__ bool zig_fast(uint32_t lo, uint32_t hi, const double2 *zt, double &x) {
+  const double2 t = zt[lo & 255u];
+  const double u = __hiloint2double(0x3ff00000 | (hi >> 12), (hi << 20) | (lo >> 12)) - 1.0;
+  const double ax = u * t.x;
+  x = (lo & 256u) ? -ax : ax;
+  return u < t.y;
+}
+
+// Slow path for a candidate whose rectangle test failed (wedge or tail), then fresh candidates until one is accepted.
+// Fresh randomness comes from Philox calls (cb | call) with call = 64, 65, ... of this sample/attempt.
+__device__ __forceinline__ double zig_finish(uint32_t lo, uint32_t hi, const double2 *zt, const Philox &ph, uint32_t ilo, uint32_t ihi,
+                             uint32_t cb, uint32_t iter, uint32_t &call) {
+  for (int guard = 0; guard < 1000; ++guard) {
+    const uint32_t layer = lo & 255u;
+    const double2 t = zt[layer];
+    const double u = __hiloint2double(0x3ff00000 | (hi >> 12), (hi << 20) | (lo >> 12)) - 1.0;
+    const bool neg = (lo & 256u) != 0;
+    const double ax = u * t.x;
+    if (u < t.y) return neg ? -ax : ax;
+    if (layer == 0) {  // tail beyond R (Marsaglia 1964)
+      for (int g2 = 0; g2 < 1000; ++g2) {
+        const uint4 r = ph(ilo, ihi, cb | call, iter);
+        ++call;
+        const double xx = log(u01_oc(r.x, r.y)) / kZigR, yy = log(u01_oc(r.z, r.w));
+        if (-2.0 * yy >= xx * xx) return neg ? xx - kZigR : kZigR - xx;
+      }
+      return neg ? -kZigR : kZigR;
+    }
+    {  // wedge between the rectangle and the density
+      const double xi = t.x, xi1 = t.x * t.y;
+      const double f0 = exp(-0.5 * (xi * xi - ax * ax)), f1 = exp(-0.5 * (xi1 * xi1 - ax * ax));
+      const uint4 r = ph(ilo, ihi, cb | call, iter);
+      ++call;
+      if (f1 + u01_co(r.x, r.y) * (f0 - f1) < 1.0) return neg ? -ax : ax;
+      lo = r.z;
+      hi = r.w;  // fresh candidate
+    }
+  }
+  return 0.0;
+}
+
+// D standard normals for (sample, attempt): Philox calls 1..ceil(D/2) feed the fast path, calls >= 64 the slow path
+template <int D>
+__device__ __forceinline__ void zig_normals(const Philox &ph, uint32_t ilo, uint32_t ihi, uint32_t cb, uint32_t iter,
+                                            const double2 *zt, double (&g)[D + 1]) {
+  uint32_t fail = 0;
+#pragma unroll
+  for (int j = 0; j < D; j += 2) {
+    const uint4 r = ph(ilo, ihi, cb | (1 + j / 2), iter);
+    if (!zig_fast(r.x, r.y, zt, g[j])) fail |= 1u << j;
+    if (j + 1 < D && !zig_fast(r.z, r.w, zt, g[j + 1])) fail |= 1u << (j + 1);
+  }
+  uint32_t call = 64;
+  while (fail) {  // 1.2 % of the candidates: regenerate the counter-based bits of the failed slot and finish it
+    const int j = __ffs(fail) - 1;
+    fail &= fail - 1;
+    const uint4 r = ph(ilo, ihi, cb | (1 + (j >> 1)), iter);
+    const double v = (j & 1) ? zig_finish(r.z, r.w, zt, ph, ilo, ihi, cb, iter, call)
+                             : zig_finish(r.x, r.y, zt, ph, ilo, ihi, cb, iter, call);
+#pragma unroll
+    for (int jj = 0; jj < D; ++jj)
+      if (jj == j) g[jj] = v;
+  }
+}
+
+// ---- batched exp ---------------------------------------------------------------------------------------------------
+// exp() for N independent arguments <= 709 with the Horner recurrences interleaved: each Taylor coefficient is
+// materialised once per batch instead of once per call and the N chains hide each other's latency.
+// Cody-Waite reduction x = n ln2 + r, |r| <= ln2/2; degree-13 Taylor polynomial (truncation 4e-18 relative);
+// 2^n applied by adding n to the exponent field.  Arguments below -708 (and -inf) give 0, NaN gives NaN; the caller
+// guarantees x <= 709.
+template <int N>
+__device__ __forceinline__ void exp_batch(const double (&x)[N], double (&out)[N]) {
+  constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer in the low word
+  constexpr double kL2e = 1.4426950408889634074, kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
+  double r[N], p[N];
+  int ni[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double xc = fmax(x[k], -800.0);  // keeps n in range (NaN -> -800, restored below)
+    const double t = fma(xc, kL2e, kMagic);
+    ni[k] = __double2loint(t);
+    const double n = t - kMagic;
+    r[k] = fma(n, -kLn2Lo, fma(n, -kLn2Hi, xc));
+  }
+  constexpr double c[14] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+                            1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
+#pragma unroll
+  for (int k = 0; k < N; ++k) p[k] = c[13];
+#pragma unroll
+  for (int j = 12; j >= 0; --j)
+#pragma unroll
+    for (int k = 0; k < N; ++k) p[k] = fma(p[k], r[k], c[j]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double v = __hiloint2double(__double2hiint(p[k]) + (ni[k] << 20), __double2loint(p[k]));
+    // x >= -708 -> v ; x < -708 or -inf -> 0 ; NaN -> NaN (x + v is NaN, and the comparison below is false for NaN)
+    out[k] = (x[k] >= -708.0) ? v : ((x[k] != x[k]) ? x[k] : 0.0);
+  }
+}
+__device__ __forceinline__ double exp_one(double x) {
+  double a[1] = {x}, o[1];
+  exp_batch<1>(a, o);
+  return o[0];
+}
+
 // warp reductions
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -44,6 +44,13 @@ int fused_pack_mixture(int K, int D, const double *wght, const double *mean, con
     double *o = out + (size_t)k * st;
     const double *Lk = L + (size_t)k * D * D;
     for (int i = 0; i < st; ++i) o[i] = 0.0;
+    if (!(wght[k] > 0.0)) {  // dead component: neutral, finite parameters (unit factor, weight 0); kernels skip it by weight
+      for (int a = 0; a < D; ++a) o[pk_oRinv(D) + a] = 1.0;
+      int e0 = pk_oLr(D);
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j <= i; ++j) o[e0++] = (i == j) ? 1.0 : 0.0;
+      continue;
+    }
     for (int a = 0; a < D; ++a) {
       o[a] = mean[(size_t)k * D + a];
       o[pk_oRinv(D) + a] = 1.0 / Lk[a * D + a];

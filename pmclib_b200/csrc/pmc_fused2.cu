@@ -18,7 +18,6 @@
 
 namespace pmcb200 {
 
-constexpr int F2_WARPS = 8;
 constexpr int F2_CMIX = 4096, F2_CTGT = 2048;
 __constant__ double c_mix[F2_CMIX];
 __constant__ double c_tgt[F2_CTGT];
@@ -86,9 +85,12 @@ struct F2Cfg {
   static constexpr int WARP_DOUBLES = 32 * PS + 32 * GS;
 };
 
-template <int D, int K, int KT, int SPL>
-__global__ void __launch_bounds__(F2_WARPS * 32, 1) k_fused2(const FusedArgs a) {
+// MODE 0: draw/weights only; 1: + responsibilities r[k][i] = alpha_k phi_k(x_i)/q(x_i) to global memory (for k_stats2);
+// 2: statistics fused in the same kernel (per-warp DMMA accumulators).
+template <int D, int K, int KT, int SPL, int MODE, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) {
   using C = F2Cfg<D, K, KT, SPL>;
+  constexpr int F2_WARPS = WARPS;
   constexpr int E = C::E, NT = C::NT, MT = C::MT, PS = C::PS, GS = C::GS, TS = C::TS, ST = C::ST;
   static_assert(K * ST <= F2_CMIX && KT * ST <= F2_CTGT, "constant memory budget");
   static_assert(TS * D <= 32 * PS, "X staging must fit in the P tile");
@@ -97,13 +99,16 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 1) k_fused2(const FusedArgs a) 
 
   double *mixs = smem;                      // copy of the packed mixture for the draw (per-lane component)
   double *cws = mixs + K * ST;
-  double *warp0 = cws + f2_ev2(K);
-  double *ptile = warp0 + (size_t)wid * C::WARP_DOUBLES;
+  double2 *zts = reinterpret_cast<double2 *>(cws + f2_ev2(K));  // ziggurat table (x_i, x_{i+1}/x_i), 4 KB
+  double *warp0 = cws + f2_ev2(K) + 2 * kZigLayers;
+  constexpr int WD = (MODE == 2) ? C::WARP_DOUBLES : f2_ev2(TS * D);
+  double *ptile = warp0 + (size_t)wid * WD;
   double *gtile = ptile + 32 * PS;
   __shared__ unsigned int s_count[64];
   __shared__ double s_m[F2_WARPS], s_S[F2_WARPS], s_r[F2_WARPS];
 
   for (int i = threadIdx.x; i < K * ST; i += blockDim.x) mixs[i] = c_mix[i];
+  for (int i = threadIdx.x; i < kZigLayers; i += blockDim.x) zts[i] = a.zig[i];
   if (threadIdx.x < 64) s_count[threadIdx.x] = 0;
   __syncthreads();
   if (threadIdx.x == 0) {  // cumulative weights exactly as mvdens.c:748-750 (sequential sum)
@@ -111,14 +116,15 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 1) k_fused2(const FusedArgs a) 
     for (int k = 0; k < K; ++k) { c = (k == 0) ? mixs[f2_oSc(D)] : c + mixs[k * ST + f2_oSc(D)]; cws[k] = c; }
   }
   // zero the padding rows/columns of this warp's tiles once (entries E..8NT-1, components K..8MT-1)
-  for (int i = lane; i < C::WARP_DOUBLES; i += 32) ptile[i] = 0.0;
+  for (int i = lane; i < WD; i += 32) ptile[i] = 0.0;
   __syncthreads();
 
-  double acc[MT][NT][2];
+  constexpr int AM = (MODE == 2) ? MT : 1, AN = (MODE == 2) ? NT : 1;
+  double acc[AM][AN][2];
 #pragma unroll
-  for (int m = 0; m < MT; ++m)
+  for (int m = 0; m < AM; ++m)
 #pragma unroll
-    for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+    for (int n = 0; n < AN; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
   double m_run = -INFINITY, S_lane = 0.0, maxr_lane = -INFINITY;
   unsigned int nok_lane = 0, rej_lane = 0, fail_lane = 0;
 
@@ -148,10 +154,13 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 1) k_fused2(const FusedArgs a) 
           for (int attempt = 0; attempt < a.max_attempts; ++attempt) {
             const uint32_t cb = (uint32_t)attempt << 12;
             const uint4 r0 = ph(ilo, ihi, cb, a.iter);
-            const int k = ranindx(cws, K, u01_co(r0.x, r0.y));
-            double g[D + 1];
+            // first index with cw >= z == number of entries below z (cw is non-decreasing), mvdens.c:776
+            const double zc = u01_co(r0.x, r0.y);
+            int k = 0;
 #pragma unroll
-            for (int j = 0; j < D; j += 2) box_muller(ph(ilo, ihi, cb | (1 + j / 2), a.iter), g[j], g[j + 1]);
+            for (int kk = 0; kk < K - 1; ++kk) k += (cws[kk] < zc) ? 1 : 0;
+            double g[D + 1];
+            zig_normals<D>(ph, ilo, ihi, cb, a.iter, zts, g);
             const double *cp = mixs + k * ST;
             bool inb = true;
 #pragma unroll
@@ -212,26 +221,29 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 1) k_fused2(const FusedArgs a) 
       for (int s = 0; s < SPL; ++s) post[s] = -0.5 * (D * kLn2Pi + q[s]) - c_tgt[f2_oSc(D) + 1];
     } else if (KT > 0 && a.tgt_kind == PMCGPU_TGT_MIX) {
       double tl[SPL][KT > 0 ? KT : 1], mx[SPL];
-      bool first = true;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) mx[s] = -INFINITY;
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
-        if (c_tgt[k * ST + f2_oSc(D)] > 0.0) {
-          double q[SPL];
-          whiten_c<D, SPL, true>(k * ST, x, q);
+        double q[SPL];
+        whiten_c<D, SPL, true>(k * ST, x, q);
+        const bool alive = c_tgt[k * ST + f2_oSc(D)] > 0.0;
 #pragma unroll
-          for (int s = 0; s < SPL; ++s) {
-            tl[s][k] = -0.5 * (D * kLn2Pi + q[s]) - c_tgt[k * ST + f2_oSc(D) + 1];
-            if (first || mx[s] < tl[s][k]) mx[s] = tl[s][k];
-          }
-          first = false;
+        for (int s = 0; s < SPL; ++s) {
+          tl[s][k] = -0.5 * (D * kLn2Pi + q[s]) - c_tgt[k * ST + f2_oSc(D) + 1];
+          if (alive && mx[s] < tl[s][k]) mx[s] = tl[s][k];
         }
       }
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
+        double arg[KT > 0 ? KT : 1], ex[KT > 0 ? KT : 1];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) arg[k] = (c_tgt[k * ST + f2_oSc(D)] > 0.0) ? tl[s][k] - mx[s] + kDynMax : -INFINITY;
+        exp_batch<(KT > 0 ? KT : 1)>(arg, ex);
         double lp = 0.0;
 #pragma unroll
         for (int k = 0; k < KT; ++k)
-          if (c_tgt[k * ST + f2_oSc(D)] > 0.0) lp = lp + exp(tl[s][k] - mx[s] + kDynMax) * c_tgt[k * ST + f2_oSc(D)];
+          if (c_tgt[k * ST + f2_oSc(D)] > 0.0) lp = lp + ex[k] * c_tgt[k * ST + f2_oSc(D)];
         post[s] = mx[s] + log(lp) - kDynMax;
       }
     } else if (a.tgt_kind == PMCGPU_TGT_HOST) {
@@ -243,29 +255,35 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 1) k_fused2(const FusedArgs a) 
     }
 
     // ---------------- proposal log-density (mvdens.c:784-825), component loop fully unrolled ----------------------
+    // One straight-line block for all K components: dead components (weight <= 0) carry neutral parameters in the
+    // pack (fused2 host packing) and are excluded by selects, so ptxas can schedule constant loads and FMA chains
+    // across component boundaries (a branch per component cost a constant-load latency bubble each, ncu r01_v4).
     double ev[SPL][K], mx[SPL], lpos[SPL];
     {
-      bool first = true;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) mx[s] = -INFINITY;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        if (c_mix[k * ST + f2_oSc(D)] > 0.0) {
-          double q[SPL];
-          whiten_c<D, SPL, false>(k * ST, x, q);
+        double q[SPL];
+        whiten_c<D, SPL, false>(k * ST, x, q);
+        const bool alive = c_mix[k * ST + f2_oSc(D)] > 0.0;
 #pragma unroll
-          for (int s = 0; s < SPL; ++s) {
-            ev[s][k] = -0.5 * (D * kLn2Pi + q[s]) - c_mix[k * ST + f2_oSc(D) + 1];
-            if (first || mx[s] < ev[s][k]) mx[s] = ev[s][k];
-          }
-          first = false;
+        for (int s = 0; s < SPL; ++s) {
+          ev[s][k] = -0.5 * (D * kLn2Pi + q[s]) - c_mix[k * ST + f2_oSc(D) + 1];
+          if (alive && mx[s] < ev[s][k]) mx[s] = ev[s][k];
         }
       }
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
+        double arg[K], ex[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) arg[k] = (c_mix[k * ST + f2_oSc(D)] > 0.0) ? ev[s][k] - mx[s] + kDynMax : -INFINITY;
+        exp_batch<K>(arg, ex);
         lpos[s] = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          double e = 0.0;
-          if (c_mix[k * ST + f2_oSc(D)] > 0.0) { e = exp(ev[s][k] - mx[s] + kDynMax) * c_mix[k * ST + f2_oSc(D)]; lpos[s] = lpos[s] + e; }
+          const double e = (c_mix[k * ST + f2_oSc(D)] > 0.0) ? ex[k] * c_mix[k * ST + f2_oSc(D)] : 0.0;
+          lpos[s] = lpos[s] + e;
           ev[s][k] = e;
         }
       }
@@ -299,21 +317,35 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 1) k_fused2(const FusedArgs a) 
     if (tmax > m_run) {  // online rescaling of everything accumulated so far
       const double sc = (m_run == -INFINITY) ? 0.0 : exp(m_run - tmax);
 #pragma unroll
-      for (int m = 0; m < MT; ++m)
+      for (int m = 0; m < AM; ++m)
 #pragma unroll
-        for (int n = 0; n < NT; ++n) { acc[m][n][0] *= sc; acc[m][n][1] *= sc; }
+        for (int n = 0; n < AN; ++n) { acc[m][n][0] *= sc; acc[m][n][1] *= sc; }
       S_lane *= sc;
       m_run = tmax;
     }
 #pragma unroll
     for (int s = 0; s < SPL; ++s) {
-      w[s] = (wfin[s] && lw[s] > -INFINITY) ? exp(lw[s] - m_run) : 0.0;
-      S_lane += w[s];
+      w[s] = 0.0;
+      if (MODE == 2) {
+        w[s] = (wfin[s] && lw[s] > -INFINITY) ? exp_one(lw[s] - m_run) : 0.0;
+        S_lane += w[s];
+      }
       if (wfin[s]) { ++nok_lane; atomicAdd(&s_count[kdraw[s] & 63], 1u); }
     }
 
+    if (MODE == 1) {  // responsibilities, component-major so that every store is one coalesced 256-byte row
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) {
+        const long i = tbase + s * 32 + lane;
+        if (i < a.N) {
+          const double rs = 1.0 / lpos[s];
+#pragma unroll
+          for (int k = 0; k < K; ++k) a.resp[(size_t)k * a.N + i] = ev[s][k] * rs;
+        }
+      }
+    }
     // ---------------- phase 2: statistics on the FP64 tensor path ---------------------------------------------------
-    if (a.do_stats) {
+    if (MODE == 2 && a.do_stats) {
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
         {
@@ -370,23 +402,28 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 1) k_fused2(const FusedArgs a) 
 #pragma unroll
   for (int w2 = 0; w2 < F2_WARPS; ++w2) { if (s_m[w2] > Mb) Mb = s_m[w2]; if (s_r[w2] > Rb) Rb = s_r[w2]; }
   const double scale = (m_run == -INFINITY) ? 0.0 : exp(m_run - Mb);
-  double *comb = warp0;
-  for (int w2 = 0; w2 < F2_WARPS; ++w2) {
-    if (wid == w2) {
-#pragma unroll
-      for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int n = 0; n < NT; ++n)
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int idx = ((m * NT + n) * 32 + lane) * 2 + c;
-            comb[idx] = (w2 == 0 ? 0.0 : comb[idx]) + acc[m][n][c] * scale;
-          }
-    }
-    __syncthreads();
-  }
   double *out = a.partials + (size_t)blockIdx.x * a.partial_len;
-  for (int idx = threadIdx.x; idx < C::ACC; idx += blockDim.x) out[idx] = comb[idx];
+  if (MODE == 2) {
+    double *comb = warp0;
+    for (int w2 = 0; w2 < F2_WARPS; ++w2) {
+      if (wid == w2) {
+#pragma unroll
+        for (int m = 0; m < AM; ++m)
+#pragma unroll
+          for (int n = 0; n < AN; ++n)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int idx = ((m * NT + n) * 32 + lane) * 2 + c;
+              comb[idx] = (w2 == 0 ? 0.0 : comb[idx]) + acc[m][n][c] * scale;
+            }
+      }
+      __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < C::ACC; idx += blockDim.x) out[idx] = comb[idx];
+  } else {
+    (void)scale;
+    for (int idx = threadIdx.x; idx < C::ACC; idx += blockDim.x) out[idx] = 0.0;
+  }
   if (threadIdx.x == 0) {
     double Sb = 0.0;
     for (int w2 = 0; w2 < F2_WARPS; ++w2) Sb += (s_m[w2] == -INFINITY) ? 0.0 : s_S[w2] * exp(s_m[w2] - Mb);
@@ -448,23 +485,215 @@ __global__ void k_fused2_combine(const double *__restrict__ partials, int nblock
   }
 }
 
+// ---- statistics kernel of the split pipeline ----------------------------------------------------------------------
+// C[k][e] += g[i][k] * P[i][e] over all samples, g = exp(lw_i - M) * r[k][i], P = products of the augmented vector
+// (1, x - pivot).  Pure DMMA work: per warp and 32-sample tile 8 k-steps x MT x NT mma.m8n8k4.f64; the B fragments are
+// formed on the fly from the 11-double augmented rows (two conflict-free LDS + one DMUL), so the tile is 7 KB per warp
+// and 16 warps fit per SM.
+struct StatsArgs {
+  const double *X, *lw, *resp;
+  const short *flg;
+  const double *M;  // device scalar: global maximum log-weight (this launch)
+  double pivot[FUSED_MAXD];
+  long N;
+  double *partials;
+  int partial_len;
+};
+
+template <int D, int K>
+__global__ void __launch_bounds__(256, 2) k_stats2(const StatsArgs a) {
+  using C = F2Cfg<D, K, 0, 1>;
+  constexpr int NT = C::NT, MT = C::MT, GS = C::GS;
+  constexpr int XS = (D + 1) | 1;  // odd stride of the augmented row (1, x~)
+  constexpr int WARPS = 8;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double *xh = smem + (size_t)wid * (32 * XS + 32 * GS);
+  double *gt = xh + 32 * XS;
+  __shared__ double s_S[WARPS];
+  for (int i = lane; i < 32 * XS + 32 * GS; i += 32) xh[i] = 0.0;
+  __syncwarp();
+  const int fr = lane >> 2, fc = lane & 3;
+  // which two augmented coordinates multiply to entry e = 8n + fr
+  int oa[NT], ob[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int e = 8 * n + fr;
+    int pa = 0, pb = 0;
+    if (e >= 1 && e <= D) pb = e;
+    else if (e > D && e < C::E) {
+      int q = e - 1 - D, r = 0;
+      while (q >= D - r) { q -= D - r; ++r; }
+      pa = 1 + r;
+      pb = 1 + r + q;
+    }
+    oa[n] = pa;
+    ob[n] = pb;
+  }
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+  double S_lane = 0.0;
+  const double M = a.M[0];
+  const long ntiles = (a.N + 31) / 32;
+  for (long tile = (long)blockIdx.x * WARPS + wid; tile < ntiles; tile += (long)gridDim.x * WARPS) {
+    const long i = tile * 32 + lane;
+    double w = 0.0;
+    double xr[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) xr[j] = 0.0;
+    if (i < a.N) {
+      const double lw = a.lw[i];
+      const bool wfin = a.flg[i] != 0 && !isnan(lw) && !(lw == INFINITY);
+      w = (wfin && lw > -INFINITY) ? exp_one(lw - M) : 0.0;
+      if (w != 0.0) {
+        if ((D & 1) == 0) {
+          const double2 *xp = reinterpret_cast<const double2 *>(a.X + (size_t)i * D);
+#pragma unroll
+          for (int j = 0; j < D / 2; ++j) { const double2 t = xp[j]; xr[2 * j] = t.x - a.pivot[2 * j]; xr[2 * j + 1] = t.y - a.pivot[2 * j + 1]; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < D; ++j) xr[j] = a.X[(size_t)i * D + j] - a.pivot[j];
+        }
+      }
+    }
+    S_lane += w;
+    double *xrow = xh + lane * XS, *grow = gt + lane * GS;
+    xrow[0] = 1.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) xrow[1 + j] = xr[j];
+#pragma unroll
+    for (int k = 0; k < K; ++k) grow[k] = (w != 0.0) ? w * a.resp[(size_t)k * a.N + i] : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int smp = 16 * h + t + 4 * fc;
+        double af[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) af[m] = gt[smp * GS + 8 * m + fr];
+        const double *xs = xh + smp * XS;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const double bf = xs[oa[n]] * xs[ob[n]];
+#pragma unroll
+          for (int m = 0; m < MT; ++m) dmma884(acc[m][n][0], acc[m][n][1], af[m], bf);
+        }
+      }
+    __syncwarp();
+  }
+  // block combine in warp order
+  __syncthreads();
+  {
+    const double Sw = warp_sum(S_lane);
+    if (lane == 0) s_S[wid] = Sw;
+  }
+  double *comb = smem;
+  for (int w2 = 0; w2 < WARPS; ++w2) {
+    __syncthreads();
+    if (wid == w2) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int idx = ((m * NT + n) * 32 + lane) * 2 + c;
+            comb[idx] = (w2 == 0 ? 0.0 : comb[idx]) + acc[m][n][c];
+          }
+    }
+  }
+  __syncthreads();
+  double *out = a.partials + (size_t)blockIdx.x * a.partial_len;
+  for (int idx = threadIdx.x; idx < C::ACC; idx += blockDim.x) out[idx] = comb[idx];
+  if (threadIdx.x == 0) {
+    double Sb = 0.0;
+    for (int w2 = 0; w2 < WARPS; ++w2) Sb += s_S[w2];
+    out[C::ACC + 0] = M;
+    out[C::ACC + 1] = Sb;
+    out[C::ACC + 2] = -INFINITY;
+    out[C::ACC + 3] = 0.0;
+  }
+}
+
+// global maxima from the block partials of a MODE 0/1 launch: out[0] = M, out[1] = maxR
+__global__ void k_f2_max(const double *__restrict__ partials, int nblocks, int partial_len, int acc_len, double *out) {
+  double M = -INFINITY, R = -INFINITY;
+  for (int b = threadIdx.x; b < nblocks; b += 32) {
+    const double mb = partials[(size_t)b * partial_len + acc_len], rb = partials[(size_t)b * partial_len + acc_len + 2];
+    if (mb > M) M = mb;
+    if (rb > R) R = rb;
+  }
+  M = warp_max_nan_ignoring(M);
+  R = warp_max_nan_ignoring(R);
+  if (threadIdx.x == 0) { out[0] = M; out[1] = R; }
+}
+
 // ---- instantiation table: (D, K, KT, SPL) ------------------------------------------------------------------------
 #define PMC_FUSED2_TABLE(X) \
   X(10, 10, 0, 1)           \
+  X(10, 10, 0, 2)           \
   X(5, 20, 4, 1)            \
+  X(5, 20, 4, 2)            \
   X(2, 9, 0, 1)
 
-template <int D, int K, int KT, int SPL>
-static int launch_one2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, cudaStream_t s) {
-  auto kern = k_fused2<D, K, KT, SPL>;
-  static size_t configured = 0;
-  if (p.smem_bytes > configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return -1;
-    configured = p.smem_bytes;
+// launch shapes of the draw/weights kernel (MODE 0/1): variant -> (warps per block, min blocks per SM)
+template <int D, int K, int KT, int SPL, int MODE, int WARPS, int MINB>
+static int launch_k1(const FusedPlan &p, const FusedArgs &a, int *nblocks_out, cudaStream_t s) {
+  auto kern = k_fused2<D, K, KT, SPL, MODE, WARPS, MINB>;
+  using C = F2Cfg<D, K, KT, SPL>;
+  const size_t wd = (MODE == 2) ? C::WARP_DOUBLES : f2_ev2(C::TS * D);
+  const size_t smem = ((size_t)K * C::ST + f2_ev2(K) + 2 * kZigLayers + (size_t)WARPS * wd) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
   }
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+  if (nb > 4) nb = 4;
+  *nblocks_out = p.grid * nb;
+  kern<<<p.grid * nb, WARPS * 32, smem, s>>>(a);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <int D, int K, int KT, int SPL>
+static int launch_one2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode,
+                       int variant, int *nb, cudaStream_t s) {
   if (h_mix && cudaMemcpyToSymbolAsync(c_mix, h_mix, sizeof(double) * K * f2_stride(D), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
   if (KT > 0 && h_tgt && cudaMemcpyToSymbolAsync(c_tgt, h_tgt, sizeof(double) * KT * f2_stride(D), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
-  kern<<<p.grid, p.threads, p.smem_bytes, s>>>(a);
+  if constexpr (SPL == 1) {
+    if (mode == 2) return launch_k1<D, K, KT, SPL, 2, 8, 1>(p, a, nb, s);
+    if (mode == 0) return launch_k1<D, K, KT, SPL, 0, 4, 3>(p, a, nb, s);
+    if (variant == 1) return launch_k1<D, K, KT, SPL, 1, 4, 4>(p, a, nb, s);
+    if (variant == 2) return launch_k1<D, K, KT, SPL, 1, 8, 1>(p, a, nb, s);
+    return launch_k1<D, K, KT, SPL, 1, 4, 3>(p, a, nb, s);
+  } else {  // two samples per lane: statistics always go through the split pipeline
+    if (mode == 2) return -1;
+    if (mode == 0) return launch_k1<D, K, KT, SPL, 0, 4, 2>(p, a, nb, s);
+    if (variant == 1) return launch_k1<D, K, KT, SPL, 1, 8, 1>(p, a, nb, s);
+    if (variant == 2) return launch_k1<D, K, KT, SPL, 1, 4, 3>(p, a, nb, s);
+    return launch_k1<D, K, KT, SPL, 1, 4, 2>(p, a, nb, s);
+  }
+}
+
+template <int D, int K>
+static int launch_stats2(const FusedPlan &p, const StatsArgs &a, cudaStream_t s) {
+  auto kern = k_stats2<D, K>;
+  using C = F2Cfg<D, K, 0, 1>;
+  constexpr int XS = (D + 1) | 1;
+  size_t smem = (size_t)8 * (32 * XS + 32 * C::GS) * sizeof(double);
+  if (smem < (size_t)C::ACC * sizeof(double)) smem = (size_t)C::ACC * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  kern<<<p.grid * 2, 256, smem, s>>>(a);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -476,10 +705,10 @@ FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want
 #define X(D_, K_, KT_, SPL_)                                                                             \
   if (!best.valid && d == D_ && K == K_ && (kt_needed == 0 || kt_needed == KT_) && SPL_ == want_spl) {   \
     using C = F2Cfg<D_, K_, KT_, SPL_>;                                                                  \
-    const size_t dbl = (size_t)K_ * C::ST + f2_ev2(K_) + (size_t)F2_WARPS * C::WARP_DOUBLES;             \
+    const size_t dbl = (size_t)K_ * C::ST + f2_ev2(K_) + 2 * kZigLayers + (size_t)8 * C::WARP_DOUBLES;   \
     if (dbl * 8 <= 227 * 1024) {                                                                         \
       best.valid = 2; best.D = D_; best.RK = K_; best.RE = KT_; best.NR = 0; best.SPL = SPL_;            \
-      best.grid = sm_count; best.threads = F2_WARPS * 32; best.smem_bytes = dbl * 8;                     \
+      best.grid = sm_count; best.threads = 256; best.smem_bytes = dbl * 8;                               \
       best.partial_len = C::ACC + 4; best.nstat = K_ * C::E;                                             \
     }                                                                                                    \
   }
@@ -488,18 +717,39 @@ FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want
   return best;
 }
 
-int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, cudaStream_t s) {
+int fused2_max_blocks(const FusedPlan &p) { return p.grid * 4; }
+
+int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode, int variant,
+                  int *nblocks_out, cudaStream_t s) {
 #define X(D_, K_, KT_, SPL_) \
-  if (p.D == D_ && p.RK == K_ && p.RE == KT_ && p.SPL == SPL_) return launch_one2<D_, K_, KT_, SPL_>(p, a, h_mix, h_tgt, s);
+  if (p.D == D_ && p.RK == K_ && p.RE == KT_ && p.SPL == SPL_) return launch_one2<D_, K_, KT_, SPL_>(p, a, h_mix, h_tgt, mode, variant, nblocks_out, s);
   PMC_FUSED2_TABLE(X)
 #undef X
   return -1;
 }
 
-int launch_fused2_combine(const FusedPlan &p, const double *partials, double *stats_out, cudaStream_t s) {
+int launch_fused2_max(const FusedPlan &p, const double *partials, int nblocks, double *out2, cudaStream_t s) {
+  k_f2_max<<<1, 32, 0, s>>>(partials, nblocks, p.partial_len, p.partial_len - 4, out2);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_fused2_stats(const FusedPlan &p, const double *X, const double *lw, const double *resp, const short *flg,
+                        const double *Mdev, const double *pivot, long N, double *partials, cudaStream_t s) {
+  StatsArgs a{};
+  a.X = X; a.lw = lw; a.resp = resp; a.flg = flg; a.M = Mdev; a.N = N; a.partials = partials; a.partial_len = p.partial_len;
+  for (int j = 0; j < FUSED_MAXD; ++j) a.pivot[j] = pivot[j];
+#define X(D_, K_, KT_, SPL_) \
+  if (p.D == D_ && p.RK == K_ && p.RE == KT_ && p.SPL == SPL_) return launch_stats2<D_, K_>(p, a, s);
+  PMC_FUSED2_TABLE(X)
+#undef X
+  return -1;
+}
+
+int launch_fused2_combine(const FusedPlan &p, const double *partials, int nblocks, double *stats_out, cudaStream_t s) {
   const int E = 1 + p.D + p.D * (p.D + 1) / 2;
   const int NT = (E + 7) / 8;
-  k_fused2_combine<<<1, 256, p.grid * sizeof(double), s>>>(partials, p.grid, p.partial_len, p.partial_len - 4, p.RK, E, NT, stats_out);
+  k_fused2_combine<<<1, 256, nblocks * sizeof(double), s>>>(partials, nblocks, p.partial_len, p.partial_len - 4, p.RK, E, NT, stats_out);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -91,6 +91,8 @@ struct FusedArgs {
   unsigned long long *counters;  // CNT_*
   unsigned long long *count_k;   // [K] histogram of indices over ok samples
   double *first_vals;            // values of the sample with global index 0 (4 doubles)
+  double *resp;                  // [K][N] responsibilities (split pipeline, MODE 1)
+  const double2 *zig;            // ziggurat table (pmc_fused2.cu draw)
 };
 
 struct FusedPlan {
@@ -117,7 +119,14 @@ int launch_fused_combine(const FusedPlan &p, const double *partials, int K, doub
 // second-generation kernel (pmc_fused2.cu): (D, K) templated, mixture in constant memory, DMMA statistics.
 // plan.valid == 2; plan.RK / plan.RE carry K / KT.  h_mix / h_tgt are the host copies of the packed blocks.
 FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want_spl);
-int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, cudaStream_t s);
-int launch_fused2_combine(const FusedPlan &p, const double *partials, double *stats_out, cudaStream_t s);
+int fused2_max_blocks(const FusedPlan &p);  // upper bound of the grid of any launch shape (size of the partials buffer)
+// mode 0: weights only, 1: weights + responsibilities (split pipeline), 2: statistics fused.  Returns blocks launched
+// through *nblocks_out.
+int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode, int variant,
+                  int *nblocks_out, cudaStream_t s);
+int launch_fused2_max(const FusedPlan &p, const double *partials, int nblocks, double *out2, cudaStream_t s);
+int launch_fused2_stats(const FusedPlan &p, const double *X, const double *lw, const double *resp, const short *flg,
+                        const double *Mdev, const double *pivot, long N, double *partials, cudaStream_t s);
+int launch_fused2_combine(const FusedPlan &p, const double *partials, int nblocks, double *stats_out, cudaStream_t s);
 
 }  // namespace pmcb200

@@ -1,0 +1,125 @@
+"""GPU draw (simulate_mix_mvdens, pmc.c:266-298): statistical validation, because the RNG stream (Philox + ziggurat /
+Box-Muller) cannot match the reference's gsl_rng stream; plus the exact properties the design promises."""
+import numpy as np
+import pytest
+from scipy import stats
+
+import oracle_py as O
+from pmclib_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _mix(rng, K, d):
+    cov = np.empty((K, d, d))
+    for k in range(K):
+        a = rng.normal(0, 1, (d, d))
+        cov[k] = a @ a.T / d + 0.5 * np.eye(d)
+    w = rng.random(K) + 0.2
+    return w / w.sum(), rng.normal(0, 2, (K, d)), cov
+
+
+@pytest.mark.parametrize("path,d,K", [("fused_v2", 10, 10), ("fused_v1", 10, 10), ("generic", 10, 10), ("fused_v2", 5, 20),
+                                      ("generic", 7, 3)])
+def test_draw_distribution(gpu, path, d, K):
+    rng = np.random.default_rng(100 + d + K)
+    w, mean, cov = _mix(rng, K, d)
+    gpu.set_option("force_generic", 1 if path == "generic" else 0)
+    gpu.set_option("fused_version", {"fused_v1": 1, "fused_v2": 2}.get(path, 0))
+    gpu.set_proposal_cov(w, mean, cov)
+    gpu.set_target_banana(d, 0.1, 10.0) if d >= 2 else None
+    gpu.set_box(None)
+    N = 1_000_000
+    gpu.resize(N, d)
+    if path == "generic":
+        gpu.draw(seed=777, it=3)
+    else:
+        gpu.pmc_step(seed=777, it=3, do_update=0)
+    got = gpu.download(weights=False, log_rho=False)
+    X, idx = got["X"], got["indices"].astype(np.int64)
+    assert np.all(got["flg"] == 1)
+    # component frequencies: chi-square against the mixture weights
+    cnt = np.bincount(idx, minlength=K)
+    chi2 = np.sum((cnt - N * w) ** 2 / (N * w))
+    assert stats.chi2.sf(chi2, K - 1) > 1e-4, f"component frequencies off (chi2={chi2:.1f})"
+    # whitened residuals of each component must be iid N(0, I)
+    zs = []
+    for k in range(K):
+        L = np.linalg.cholesky(cov[k])
+        zs.append(np.linalg.solve(L, (X[idx == k] - mean[k]).T).T)
+    z = np.concatenate(zs)
+    n = len(z)
+    assert np.all(np.abs(z.mean(0)) < 5 / np.sqrt(n))
+    assert np.all(np.abs(z.var(0) - 1) < 5 * np.sqrt(2 / n))
+    c = np.corrcoef(z.T) - np.eye(d)
+    assert np.max(np.abs(c)) < 5 / np.sqrt(n)
+    for j in range(d):
+        assert stats.kstest(z[:, j], "norm").pvalue > 1e-4, f"KS dim {j}"
+        assert abs(stats.kurtosis(z[:, j])) < 5 * np.sqrt(24 / n)
+    # tails (the ziggurat's slow path): P(|z| > 3.654) and P(|z| > 4.5)
+    flat = np.abs(z.ravel())
+    for t in (3.6541528853610088, 4.5):
+        p = 2 * stats.norm.sf(t)
+        m = flat.size
+        assert abs((flat > t).mean() - p) < 6 * np.sqrt(p / m), f"tail beyond {t}"
+    # chi-square of |z|^2
+    assert stats.kstest((z ** 2).sum(1), "chi2", args=(d,)).pvalue > 1e-4
+
+
+def test_draw_is_shard_invariant_and_reproducible(gpu):
+    """Philox is counted by the global sample index: drawing [0,N) at once or as two shards gives identical samples."""
+    wl = W.banana()
+    gpu.set_option("force_generic", 0)
+    gpu.set_option("fused_version", 0)
+    gpu.set_workload(wl)
+    N = 100_003
+    gpu.resize(N)
+    gpu.pmc_step(seed=5, it=2, first_index=0, N_total=N, do_update=0)
+    a = gpu.download()
+    gpu.pmc_step(seed=5, it=2, first_index=0, N_total=N, do_update=0)
+    b = gpu.download()
+    assert np.array_equal(a["X"], b["X"]) and np.array_equal(a["indices"], b["indices"])
+    n1 = 40_000
+    gpu.resize(n1)
+    gpu.pmc_step(seed=5, it=2, first_index=0, N_total=N, do_update=0)
+    s1 = gpu.download()
+    gpu.resize(N - n1)
+    gpu.pmc_step(seed=5, it=2, first_index=n1, N_total=N, do_update=0)
+    s2 = gpu.download()
+    assert np.array_equal(np.concatenate([s1["X"], s2["X"]]), a["X"])
+    assert np.array_equal(np.concatenate([s1["indices"], s2["indices"]]), a["indices"])
+    assert np.array_equal(np.concatenate([s1["log_rho"], s2["log_rho"]]), a["log_rho"])
+    gpu.resize(N)
+    gpu.pmc_step(seed=6, it=2, do_update=0)
+    c = gpu.download()
+    assert not np.array_equal(a["X"], c["X"])
+
+
+@pytest.mark.parametrize("path", ["fused", "generic"])
+def test_box_rejection(gpu, path):
+    """Samples are redrawn until inside the box (pmc.c:281-296): all returned points are inside, the accepted
+    distribution is the truncated proposal, and the rejection count matches the proposal mass outside."""
+    wl = W.banana(d=10, K=10, seed=9, mean_sigma=3.0, var=10.0, box=9.0)  # tight box: many rejections
+    gpu.set_option("force_generic", 1 if path == "generic" else 0)
+    gpu.set_option("fused_version", 0)
+    gpu.set_workload(wl)
+    N = 400_000
+    gpu.resize(N)
+    if path == "generic":
+        nrej = gpu.draw(seed=99, it=0)
+    else:
+        nrej = gpu.pmc_step(seed=99, it=0, do_update=0).n_reject
+    X = gpu.download(weights=False, log_rho=False)["X"]
+    assert np.all(np.abs(X) <= 9.0)
+    ins = gpu.isinbox(X)
+    assert np.all(ins == 1)
+    # acceptance probability estimated with the oracle's own draw (no box) and box test
+    wl2 = dict(wl, faces=None)
+    Xo, _ = O.orc_simulate(200_000, wl2, seed=1)
+    p_in = np.mean(np.all(np.abs(Xo) <= 9.0, axis=1))
+    expect = N * (1 - p_in) / p_in
+    assert abs(nrej - expect) < 6 * np.sqrt(expect / p_in) + 0.02 * expect, (nrej, expect)
+    # first moments of the truncated proposal agree with the oracle's rejection sampler
+    Xb, _ = O.orc_simulate(200_000, wl, seed=2)
+    se = np.sqrt(X.var(0) / len(X) + Xb.var(0) / len(Xb))
+    assert np.all(np.abs(X.mean(0) - Xb.mean(0)) < 5 * se)

@@ -99,7 +99,7 @@ def test_update_rb_two_pass(gpu, oracle_runs, name):
     print(name, "two-pass update errors", errs)
 
 
-@pytest.mark.parametrize("ver,spl", [(1, 1), (1, 2), (2, 1)])
+@pytest.mark.parametrize("ver,spl", [(1, 1), (1, 2), (2, 1), (2, 2)])
 @pytest.mark.parametrize("name", ["c1_banana_d10_K10", "c2_gmm_d5_K20", "shipped_d2_K9", "ragged_d10_K10", "tiny_d10_K10"])
 def test_fused_iteration_given_samples(gpu, oracle_runs, name, ver, spl):
     """The one-pass fused kernel (weights + statistics) + host finalisation against the oracle's full iteration."""
