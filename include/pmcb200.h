@@ -93,6 +93,9 @@ int pmcgpu_draw(pmcgpu_ctx *ctx, uint64_t seed, uint32_t iter, long first_index,
  * (log-weights t*post - log_rho), flg; returns the ok count and the running maxima exactly as the reference
  * defines them (the i==0 quirk applies to the sample whose global index is 0: pass first_index). */
 int pmcgpu_weights(pmcgpu_ctx *ctx, double t_temper, long first_index, long *nok, double *maxW, double *maxR);
+/* pmc_simu_importance (pmc.c:175-194) in one kernel: draw + weights; the log-weights are left un-normalised */
+int pmcgpu_draw_weights(pmcgpu_ctx *ctx, uint64_t seed, uint32_t iter, long first_index, double t_temper, long *nok,
+                        double *maxW, double *maxR, long *n_reject);
 /* same with the target evaluated by the caller on the host (PMCGPU_TGT_HOST): post[N]; ok[N] (may be NULL) = 0
  * where the callback raised an error (sample is flagged out, pmc.c:563) */
 int pmcgpu_weights_host_post(pmcgpu_ctx *ctx, const double *post, const short *ok, double t_temper,

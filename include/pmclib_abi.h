@@ -1,0 +1,271 @@
+/* pmclib_abi.h — the part of pmclib's public C API that libpmcb200.so implements as a drop-in.
+ *
+ * Existing pmclib callers are compiled against pmclib's own headers and only need to LINK against libpmcb200.so
+ * instead of libpmc / libmvdens / liberrorio for the PMC path: every struct below has the reference's layout and
+ * every function the reference's name, signature and error behaviour.  This header exists for new C callers, for the
+ * tests (tests/c/dropin_driver.c) and as the written contract; citations are file:line in CosmoStat/pmclib.
+ *
+ * What runs where: everything that loops over samples runs in CUDA kernels (see pmcb200.h); the functions here are
+ * host orchestration over the reference-layout host structs (psim->X etc. are HOST arrays, copied to and from the
+ * GPU inside each call, exactly the memory contract the reference offers).  There is no CPU implementation of the
+ * sample loops: without a CUDA device every compute entry point raises pmc_base-24 through the error chain.
+ */
+#ifndef PMCLIB_ABI_H
+#define PMCLIB_ABI_H
+#include <stddef.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- errorlist (pmctools/include/errorlist.h:20-53) -------------------------------------------------------- */
+#ifndef __ERRORLIST_H
+#define TXT_SZ 4192
+#define WHR_SZ 2048
+typedef struct _err {
+  char errWhere[WHR_SZ];
+  char errText[TXT_SZ];
+  int errValue;
+  struct _err *next;
+} error;
+#define forwardErr -123456789
+#define undefErr -987654321
+#define noErr 0
+#define placeHolderError 1020304050
+error *newError(int errV, char *where, char *text, error *linkTo, error *addErr);
+error *newErrorVA(int errV, const char *func, char *where, char *text, error *linkTo, error *addErr, ...);
+void stringError(char *str, error *err);
+void printError(FILE *flog, error *err);
+int getErrorValue(error *err);
+void purgeError(error **err);
+error *initError(void);
+void endError(error **err);
+int _isError(error *err);
+#define isError(err) (_isError(err))
+#endif
+
+/* ---- GSL types that appear by value in the ABI (mvdens.h:83-110, pmc.h:133) ---------------------------------- */
+#ifndef __GSL_BLOCK_DOUBLE_H__
+typedef struct { size_t size; double *data; } gsl_block;
+#endif
+#ifndef __GSL_VECTOR_DOUBLE_H__
+typedef struct { size_t size; size_t stride; double *data; gsl_block *block; int owner; } gsl_vector;
+typedef struct { gsl_vector vector; } gsl_vector_view;
+#endif
+#ifndef __GSL_MATRIX_DOUBLE_H__
+typedef struct { size_t size1; size_t size2; size_t tda; double *data; gsl_block *block; int owner; } gsl_matrix;
+typedef struct { gsl_matrix matrix; } gsl_matrix_view;
+#endif
+#ifndef __GSL_RNG_H__
+typedef struct {
+  const char *name;
+  unsigned long int max, min;
+  size_t size;
+  void (*set)(void *state, unsigned long int seed);
+  unsigned long int (*get)(void *state);
+  double (*get_double)(void *state);
+} gsl_rng_type;
+typedef struct { const gsl_rng_type *type; void *state; } gsl_rng;
+#endif
+
+/* ---- parabox (pmclib/include/parabox.h:22-26) ------------------------------------------------------------------ */
+#ifndef __PARABOX__
+typedef struct { int ndim; int nfaces; double *faces; } parabox;
+parabox *init_parabox(int parasize, error **err);
+int isinBox(const parabox *bx, double *pos, error **err);
+void add_lobound(parabox *bx, int coord, double vmin, error **err);
+void add_hibound(parabox *bx, int coord, double vmax, error **err);
+void add_slab(parabox *bx, int coord, double vmin, double vmax, error **err);
+void add_face(parabox *bx, double *dirvec, double threshold, error **err);
+void add_halfspace(parabox *bx, int coord, double sign, double val, error **err);
+void free_parabox(parabox **bx);
+#endif
+
+/* ---- mvdens / mix_mvdens (pmctools/include/mvdens.h:83-155) -------------------------------------------------------- */
+#ifndef __MVDENS_H
+typedef struct {
+  size_t ndim;
+  void *buf;
+  int own_buf;
+  double *mean;
+  double *std;
+  double *x_tmp;
+  gsl_vector_view mean_view_container;
+  gsl_vector *mean_view;
+  gsl_vector_view x_tmp_view_container;
+  gsl_vector *x_tmp_view;
+  gsl_matrix_view std_view_container;
+  gsl_matrix *std_view;
+  size_t band_limit;
+  int chol;
+  int df;
+  double detL;
+} mvdens;
+typedef struct {
+  size_t ncomp, ndim;
+  int init_cwght;
+  double *wght, *cwght;
+  gsl_vector_view wght_view_container, cwght_view_container;
+  gsl_vector *wght_view, *cwght_view;
+  mvdens **comp;
+  void *buf_comp;
+} mix_mvdens;
+mvdens *mvdens_alloc(size_t ndim, error **err);
+mvdens *mvdens_init(mvdens *g, size_t nndim, double *mn, double *std, error **err);
+void mvdens_empty(mvdens *g);
+void mvdens_free(mvdens **g);
+void mvdens_free_void(void **g);
+void mvdens_print(FILE *where, mvdens *what);
+void mvdens_dump(FILE *where, mvdens *what);
+void mvdens_set_band_limit(mvdens *self, size_t value);
+double determinant(const double *L, size_t ndim);
+void mvdens_cholesky_decomp(mvdens *self, error **err);
+double scalar_product(mvdens *g, const double *x, error **err);
+double mvdens_log_pdf(mvdens *g, const double *x, error **err);
+double mvdens_log_pdf_void(void *g, const double *x, error **err);
+mix_mvdens *mix_mvdens_alloc(size_t ncomp, size_t size, error **err);
+void mix_mvdens_free_void(void **m);
+void mix_mvdens_free(mix_mvdens **m);
+void mix_mvdens_print(FILE *where, mix_mvdens *what);
+void mix_mvdens_dump(FILE *where, mix_mvdens *what);
+mix_mvdens *mix_mvdens_dwnp(FILE *where, error **err);
+void mix_mvdens_set_band_limit(mix_mvdens *self, size_t value);
+void mix_mvdens_cholesky_decomp(mix_mvdens *self, error **err);
+size_t ranindx(double *cw, size_t nE, gsl_rng *r, error **err);
+double mix_mvdens_log_pdf(mix_mvdens *m, const double *x, error **err);
+double mix_mvdens_log_pdf_void(void *m, const double *x, error **err);
+#endif
+
+/* ---- plugin interface (pmclib/include/allmc.h:21-33, distribution.h:25-41) ------------------------------------------ */
+#ifndef __ALLMC_H
+struct _pmc_simu_struct_;
+typedef double posterior_log_pdf_func(void *, const double *, error **);
+typedef void retrieve_ded_func(const void *, double *, error **);
+typedef void(posterior_log_free)(void **);
+typedef long simulate_func(struct _pmc_simu_struct_ *, void *, gsl_rng *, parabox *, error **);
+typedef void filter_func(struct _pmc_simu_struct_ *, void *, error **);
+typedef void update_func(void *, struct _pmc_simu_struct_ *, error **);
+typedef void *mpi_exchange_func(void *, error **);
+typedef double first_derivative_func(void *, int, const double *, error **err);
+typedef double second_derivative_func(void *, int, int, const double *, error **err);
+#endif
+#ifndef __MC_DIST
+typedef char _char_name[1024];
+typedef struct _distribution_struct_ {
+  int ndim, n_ded, ndef;
+  double *pars;
+  int *def;
+  void *data;
+  posterior_log_pdf_func *log_pdf;
+  retrieve_ded_func *retrieve;
+  posterior_log_free *free;
+  simulate_func *simulate;
+  mpi_exchange_func *broadcast_mpi;
+  first_derivative_func *f_der;
+  second_derivative_func *d_der;
+  void *dlhandle;
+  _char_name *name;
+} distribution;
+distribution *init_distribution_full(int ndim, void *data, posterior_log_pdf_func *log_pdf, posterior_log_free *freef,
+                                     simulate_func *simulate, int nded, retrieve_ded_func *retrieve, error **err);
+distribution *init_simple_distribution(int ndim, void *data, posterior_log_pdf_func *log_pdf,
+                                       posterior_log_free *freef, error **err);
+distribution *init_distribution(int ndim, void *data, posterior_log_pdf_func *log_pdf, posterior_log_free *freef,
+                                simulate_func *simulate, error **err);
+void free_distribution(distribution **pdist);
+double distribution_lkl(void *pdist, const double *pars, error **err);
+void distribution_retrieve(const void *pdist, double *pars, error **err);
+void distribution_set_default(distribution *dist, int ndef, int *idef, double *vdef, error **err);
+#endif
+
+/* ---- pmc_simu (pmclib/include/pmc.h:76-205) --------------------------------------------------------------------------- */
+#ifndef __PMC_H
+#define MC_NORM 1
+#define MC_UNORM 0
+typedef struct _pmc_simu_struct_ {
+  long nsamples;
+  int ndim, n_ded;
+  void *data;
+  double *X, *X_ded, *weights;
+  double *log_rho;
+  short *flg;
+  size_t *indices;
+  int isLog;
+  double logSum;
+  double maxW, maxR;
+  parabox *pb;
+  distribution *target;
+  distribution *proposal;
+  int prop_print_step;
+  void *filter_data;
+  filter_func *pmc_filter;
+  update_func *pmc_update;
+  int retry;
+  int mpi_rank;
+  int mpi_size;
+} pmc_simu;
+pmc_simu *pmc_simu_init(long nsample, int ndim, error **err);
+pmc_simu *pmc_simu_init_plus_ded(long nsample, int ndim, int n_ded, error **err);
+void pmc_simu_free(pmc_simu **self);
+void pmc_simu_realloc(pmc_simu *psim, long newsamples, error **err);
+void pmc_simu_init_target(pmc_simu *psim, distribution *target, parabox *pb, error **err);
+void pmc_simu_init_proposal(pmc_simu *psim, distribution *proposal, int prop_print_step, error **err);
+void pmc_simu_init_pmc(pmc_simu *psim, void *filter_data, filter_func *pmc_filter, update_func *pmc_update);
+void pmc_simu_init_classic_importance(pmc_simu *psim, distribution *target, parabox *pb, void *prop_data,
+                                      int prop_print_step, error **err);
+void pmc_simu_init_classic_pmc(pmc_simu *psim, distribution *target, parabox *pb, void *prop_data, int prop_print_step,
+                               void *filter_data, filter_func *pmc_filter, error **err);
+size_t pmc_simu_importance(pmc_simu *psim, gsl_rng *r, error **err);
+double pmc_simu_pmc_step(pmc_simu *psim, gsl_rng *r, error **err);
+distribution *mix_mvdens_distribution(int ndim, void *mxmv, error **err);
+long simulate_mix_mvdens_void(struct _pmc_simu_struct_ *psim, void *proposal, gsl_rng *r, parabox *pb, error **err);
+long simulate_mix_mvdens(pmc_simu *psim, mix_mvdens *m, gsl_rng *r, parabox *pb, error **err);
+size_t get_importance_weight(pmc_simu *psim, mix_mvdens *m, posterior_log_pdf_func *posterior_log_pdf, void *extra,
+                             error **err);
+size_t generic_get_importance_weight(pmc_simu *psim, void *m, posterior_log_pdf_func *proposal_log_pdf,
+                                     posterior_log_pdf_func *posterior_log_pdf, void *extra, error **err);
+size_t get_importance_weight_plus_ded(pmc_simu *psim, mix_mvdens *m, posterior_log_pdf_func *posterior_log_pdf,
+                                      retrieve_ded_func *retrieve_ded, void *extra, error **err);
+size_t generic_get_importance_weight_and_deduced(pmc_simu *psim, void *m, posterior_log_pdf_func *proposal_log_pdf,
+                                                 posterior_log_pdf_func *posterior_log_pdf,
+                                                 retrieve_ded_func *retrieve_ded, void *extra, error **err);
+size_t generic_get_importance_weight_and_deduced_verb(pmc_simu *psim, void *proposal_data,
+                                                      posterior_log_pdf_func *proposal_log_pdf,
+                                                      posterior_log_pdf_func *posterior_log_pdf,
+                                                      retrieve_ded_func *retrieve_ded, void *target_data,
+                                                      double t_iter_tempered, int quiet, error **err);
+double normalize_importance_weight(pmc_simu *psim, error **err);
+void update_prop(mix_mvdens *m, pmc_simu *psim, error **err);
+void update_prop_rb_void(void *m, pmc_simu *psim, error **err);
+void update_prop_rb(mix_mvdens *m, pmc_simu *psim, error **err);
+double perplexity(pmc_simu *psim, int normalize, error **err);
+double perplexity_and_ess(pmc_simu *psim, int normalize, double *ess, error **err);
+double evidence(pmc_simu *psim, double *ln_evi, error **err);
+void pmc_simu_dump(FILE *where, pmc_simu *psim, error **err);
+#endif
+
+/* ---- example target shipped with the reference (examples/target/sampleTarget.h) ---------------------------------------- */
+#ifndef __SMP_TARGET__
+typedef struct { int ndim; double b, sig1; } bentGauss;
+bentGauss *init_bentGauss(int ndim, double b, double sig1, error **err);
+distribution *init_bentGauss_distribution(int ndim, double b, double sig1, error **err);
+double bentGauss_lkl(void *bg, double *pars, error **err);
+void bentGauss_free(void **bg);
+#endif
+
+/* ---- additions of this library (not in pmclib) ---------------------------------------------------------------------------- */
+/* Declare a distribution whose log_pdf is an opaque user function to be one of the densities the GPU evaluates itself
+ * (kind = PMCGPU_TGT_* of pmcb200.h; data must then be a bentGauss*, mvdens* or mix_mvdens*). */
+int pmcb200_register_target(distribution *dist, int kind);
+/* PMCB200_RESIDENT=1 (or this call) keeps X/weights/log_rho/indices/flg in HBM after pmc_simu_pmc_step; this call
+ * copies them into the host arrays of psim on demand. */
+void pmcb200_set_resident(int on);
+int pmcb200_sync_host(pmc_simu *psim, error **err);
+/* the pmcgpu context behind a psim (created on first use), for callers that mix both APIs */
+void *pmcb200_context(pmc_simu *psim, error **err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

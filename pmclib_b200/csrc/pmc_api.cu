@@ -971,6 +971,40 @@ int pmcgpu_weights_host_post(pmcgpu_ctx *c, const double *post, const short *ok,
   return weights_common(c, 1, post, ok, t_temper, first_index, nok, maxW, maxR);
 }
 
+int pmcgpu_draw_weights(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, double t_temper, long *nok,
+                        double *maxW, double *maxR, long *n_reject) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  if (c->tkind == PMCGPU_TGT_HOST) return fail(c, PMCGPU_ERR_USAGE, "host target: use pmcgpu_draw then pmcgpu_weights_host_post");
+  if (t_temper < 0) return fail(c, -6019, "t_iter_tempered=%g should be > 0", t_temper);
+  rc = ensure_cwght_normalised(c);
+  if (rc) return rc;
+  const FusedPlan p = plan_for(c);
+  WeightOut o;
+  if (p.valid) {
+    rc = run_fused(c, p, 1, 0, seed, iter, first_index, t_temper, nullptr, nullptr, o);
+    if (rc) return rc;
+  } else {
+    long nrej = 0;
+    rc = pmcgpu_draw(c, seed, iter, first_index, &nrej);
+    if (rc) return rc;
+    rc = run_weights_generic(c, 0, nullptr, nullptr, t_temper, first_index, o);
+    if (rc) return rc;
+    o.counters[CNT_REJECT] = (unsigned long long)nrej;
+    o.counters[CNT_DRAWFAIL] = 0;
+  }
+  if (n_reject) *n_reject = (long)o.counters[CNT_REJECT];
+  if (o.counters[CNT_DRAWFAIL] || (long)o.counters[CNT_REJECT] > 5 * c->N)
+    return fail(c, kErrTooManySteps, "Too many points (%llu) outside of box", o.counters[CNT_REJECT]);
+  if (nok) *nok = (long)o.counters[CNT_NOK];
+  double mw = o.M_all;
+  if (o.counters[CNT_POSINF]) mw = INFINITY;
+  if (maxW) *maxW = fold_max(mw, o.has_first, o.first[3] != 0.0, o.first[2]);
+  if (maxR) *maxR = fold_max(o.R_all, o.has_first, o.first[1] != 0.0, o.first[0]);
+  return 0;
+}
+
 int pmcgpu_proposal_log_pdf(pmcgpu_ctx *c, long n, const double *x, double *out) {
   if (!c || c->prop.K == 0 || n < 0) return PMCGPU_ERR_USAGE;
   cudaSetDevice(c->device);
@@ -1176,8 +1210,9 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   r.ln_evidence = r.logSum - std::log((double)(N_total - nexit));
   // ---- update
   if (do_update) {
-    bool precise = !fused_stats;
-    if (fused_stats) {
+    // a NaN maximum (the i==0 quirk) poisons the reference's responsibilities: only the literal path reproduces that
+    bool precise = !fused_stats || std::isnan(maxR) || std::isnan(maxW);
+    if (fused_stats && !precise) {
       // reduce the statistics over ranks: rescale to the global maximum, then sum
       const int E = 1 + d + d * (d + 1) / 2;
       std::vector<double> st(o.stats);

@@ -154,12 +154,16 @@ int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const
       const double *S = S2 + k * dd;
       const size_t bl = band_limit ? band_limit[k] : (size_t)d;
       wght[k] = W[k];
-      for (int a = 0; a < d; ++a) mu[a] = c[a] + s[a] / G[k];
+      // scale-free form: the statistics may carry any common factor (the reference's exp(maxR-500) is ~1e-217), so
+      // never multiply two of them: shift = s1/G is O(1), S2/W is O(1), G/W is O(1)
+      std::vector<double> shift(d);
+      for (int a = 0; a < d; ++a) { shift[a] = s[a] / G[k]; mu[a] = c[a] + shift[a]; }
       const double invW = 1.0 / W[k];
+      const double gw = G[k] * invW;
       for (int a = 0; a < d; ++a)
         for (int b = a; b < d; ++b) {
           double v = 0.0;
-          if ((size_t)(b - a) < bl) v = (S[(size_t)a * d + b] - s[a] * s[b] / G[k]) * invW;  // band cut, pmc.c:1444
+          if ((size_t)(b - a) < bl) v = S[(size_t)a * d + b] * invW - (shift[a] * shift[b]) * gw;  // band cut, pmc.c:1444
           cov[(size_t)a * d + b] = v;
           cov[(size_t)b * d + a] = v;
         }

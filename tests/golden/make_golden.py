@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures from the UNMODIFIED reference (oracle/_ref/libpmcref.so, i.e. /root/reference's own C
+files compiled against the GSL shim).  Run where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or golden vectors of its own for the PMC path, so these files are the pin:
+inputs (X, indices, proposal, target) and every output of one iteration as the reference computed it.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle_py as O  # noqa: E402
+from pmclib_b200 import workloads as W  # noqa: E402
+
+CASES = {
+    "c1_banana_d10_K10": (W.banana, 1500, 101),
+    "c2_gmm_d5_K20": (W.gmm5, 2500, 102),
+    "c4_student_d30_K50": (W.student30, 600, 103),
+    "c5_gauss_d128_K64": (W.gauss128, 250, 104),
+    "shipped_d2_K9": (W.shipped_example, 4000, 105),
+}
+
+
+def main():
+    assert O.ref() is not None, "the compiled reference is needed"
+    for name, (f, N, seed) in CASES.items():
+        wl = f()
+        X, idx = O.ref_simulate(N, wl, seed=seed)
+        upd = 0 if wl["importance_only"] else 1
+        r = O.ref_iteration(X, idx, wl, do_update=upd)
+        out = dict(X=X, indices=idx, rc=r["rc"], nok=r["nok"], maxW=r["maxW"], maxR=r["maxR"], logSum=r["logSum"],
+                   perp=r["perp"], ess=r["ess"], ln_evidence=r["ln_evidence"], retry=r["retry"], log_rho=r["log_rho"],
+                   logw=r["logw"], w_norm=r["w_norm"], flg=r["flg"], do_update=upd)
+        if upd:
+            out.update(o_wght=r["o_wght"], o_mean=r["o_mean"], o_std=r["o_std"], o_detL=r["o_detL"])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "rc", r["rc"], "perp", r["perp"], "ess", r["ess"], os.path.getsize(os.path.join(HERE, name + ".npz")))
+    # ranindx / isinBox / Cholesky known answers
+    rng = np.random.default_rng(7)
+    wl = W.banana()
+    cw = np.cumsum(wl["wght"])
+    z = np.concatenate([rng.random(2000), cw, np.nextafter(cw, 0), np.nextafter(cw, 2)])
+    idx = np.zeros(len(z), np.uint64)
+    O.ref().ref_ranindx(O.C.c_long(len(z)), wl["K"], O.P(cw), O.P(z), O.P(idx))
+    xb = rng.normal(0, 25, (2000, wl["d"]))
+    xb[:40, 0] = np.repeat([40.0, np.nextafter(40.0, 50), np.nextafter(40.0, 0), -40.0], 10)
+    ins = np.zeros(len(xb), np.int32)
+    O.ref().ref_isinbox(O.C.c_long(len(xb)), wl["d"], len(wl["faces"]), O.P(wl["faces"]), O.P(xb), O.P(ins))
+    a = rng.normal(0, 1, (12, 12))
+    spd = a @ a.T + 0.5 * np.eye(12)
+    L = spd.copy()
+    det = O.C.c_double()
+    rc = O.ref().ref_cholesky(12, O.P(L), O.C.byref(det))
+    bad = spd.copy(); bad[3, 3] = -1.0
+    Lb = bad.copy()
+    rcb = O.ref().ref_cholesky(12, O.P(Lb), O.C.byref(O.C.c_double()))
+    np.savez_compressed(os.path.join(HERE, "misc.npz"), cw=cw, z=z, ranindx=idx, box_x=xb, box_in=ins, faces=wl["faces"],
+                        spd=spd, chol=L, chol_det=det.value, chol_rc=rc, bad=bad, bad_rc=rcb, bad_after=Lb)
+    print("misc", rc, rcb)
+
+
+if __name__ == "__main__":
+    main()

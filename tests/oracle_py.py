@@ -100,7 +100,15 @@ def orc_iteration(X, indices, wl, t=1.0, do_update=1, in_retry=0):
     L = orc()
     X = np.ascontiguousarray(X, np.float64)
     N, d = X.shape
-    m = Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"])
+    if wl.get("is_chol"):  # wl["cov"] already holds Cholesky factors (e.g. the proposal a previous update produced)
+        m = Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"], factorise=False)
+        for k in range(m.K):
+            det = 1.0
+            for a in range(d):
+                det *= m.L[k, a, a]
+            m.detL[k] = det
+    else:
+        m = Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"])
     tgt, keep = make_target(wl["target"])
     w = np.zeros(N); lr = np.zeros(N); flg = np.zeros(N, np.int16)
     mw, mr = C.c_double(), C.c_double()

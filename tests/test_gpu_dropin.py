@@ -1,0 +1,85 @@
+"""GPU: pmclib's own C API (include/pmclib_abi.h) implemented by libpmcb200.so, driven by a C program that is written like
+a pmclib user (tests/c/dropin_driver.c).  Every iteration the driver records is re-computed by the oracle from the
+recorded samples and the proposal that was in force, and must agree."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from pmclib_b200 import workloads as W
+from pmclib_b200.lib import LIB_PATH
+from util import RTOL, assert_close, compare_mixture
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("drv") / "dropin_driver")
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "dropin_driver.c"),
+                    "-o", exe, "-L" + os.path.dirname(LIB_PATH), "-lpmcb200", "-Wl,-rpath," + os.path.dirname(LIB_PATH), "-lm"], check=True)
+    return exe
+
+
+def _run(driver, tmp_path, wl, N, niter, mode, seed=4242):
+    K, d = wl["K"], wl["d"]
+    faces = wl["faces"]
+    cfg, out = tmp_path / f"in{mode}.bin", tmp_path / f"out{mode}.bin"
+    with open(cfg, "wb") as f:
+        f.write(np.array([K, d, N, niter, 0 if faces is None else len(faces), seed], np.int64).tobytes())
+        f.write(np.array([wl["target"]["b"], wl["target"]["sig1"]]).tobytes())
+        f.write(np.ascontiguousarray(wl["wght"]).tobytes()); f.write(np.ascontiguousarray(wl["mean"]).tobytes())
+        f.write(np.ascontiguousarray(wl["cov"]).tobytes())
+        if faces is not None:
+            f.write(np.ascontiguousarray(faces).tobytes())
+    r = subprocess.run([driver, str(cfg), str(out), str(mode)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out, np.uint8)
+    rec = []
+    pos = 0
+
+    def take(dt, n):
+        nonlocal pos
+        a = raw[pos:pos + n * np.dtype(dt).itemsize].view(dt).copy()
+        pos += n * np.dtype(dt).itemsize
+        return a
+    for _ in range(niter):
+        sc = take(np.float64, 8)
+        rec.append(dict(perp=sc[0], ess=sc[1], lne=sc[2], logSum=sc[3], maxW=sc[4], maxR=sc[5], retry=int(sc[6]), isLog=int(sc[7]),
+                        X=take(np.float64, N * d).reshape(N, d), idx=take(np.uint64, N), w=take(np.float64, N),
+                        lr=take(np.float64, N), flg=take(np.int16, N), wght=take(np.float64, K),
+                        mean=take(np.float64, K * d).reshape(K, d), L=take(np.float64, K * d * d).reshape(K, d, d)))
+    assert pos == len(raw)
+    return rec, r.stdout
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_c_driver_iterations_match_oracle(driver, tmp_path, mode):
+    wl = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
+    N, niter = 40000, 3
+    rec, stdout = _run(driver, tmp_path, wl, N, niter, mode)
+    cur = dict(wl)
+    for it, r in enumerate(rec):
+        assert np.all(np.abs(r["X"]) <= 40.0)
+        o = O.orc_iteration(r["X"], r["idx"], cur, do_update=1, in_retry=0 if it == 0 else rec[it - 1]["retry"])
+        assert o["rc"] == 0
+        big = max(np.max(np.abs(o["log_rho"])), 1.0)
+        assert r["isLog"] == 0 and np.array_equal(r["flg"], o["flg"])
+        assert_close(r["lr"], o["log_rho"], RTOL, what=f"it{it} log_rho")
+        assert_close(r["w"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
+        assert_close(r["perp"], o["perp"], 1e-11, what="perplexity")
+        assert_close(r["ess"], o["ess"], 1e-11, what="ess")
+        assert_close(r["lne"], o["ln_evidence"], RTOL, scale=big, what="ln evidence")
+        assert_close(r["logSum"], o["logSum"], RTOL, scale=big, what="logSum")
+        assert_close(r["maxW"], o["maxW"], RTOL, scale=big, what="maxW")
+        assert_close(r["maxR"], o["maxR"], RTOL, what="maxR")
+        assert r["retry"] == o["retry"]
+        errs = compare_mixture(r["wght"], r["mean"], r["L"], o["o_wght"], o["o_mean"], o["o_std"], what=f"mode{mode} it{it}")
+        print(f"mode {mode} iteration {it}: perp {r['perp']:.4f} update errors {errs}")
+        # the next iteration starts from the proposal the library produced (factors)
+        cur = dict(wl, wght=r["wght"], mean=r["mean"], cov=r["L"], is_chol=True)
+    if mode == 2:
+        assert f"user callback calls {N * niter}" in stdout  # the opaque target really ran on the host, once per sample

@@ -1,0 +1,130 @@
+"""GPU at (close to) BASELINE.json's full sizes, through properties that do not need the oracle to run at that size:
+self-consistency of the fused pass with the literal two-pass kernels, normalisation identities, determinism,
+permutation/shard invariance of the reductions, and a spot check of a random sub-sample against the oracle."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from pmclib_b200 import workloads as W
+from util import RTOL, assert_close, compare_mixture
+
+pytestmark = pytest.mark.gpu
+
+
+def _adapted(gpu, wl, N, iters=3):
+    gpu.set_option("force_generic", 0); gpu.set_option("fused_version", 0); gpu.set_option("spl", 1)
+    gpu.set_option("force_precise", 0)
+    gpu.set_workload(wl)
+    gpu.resize(N)
+    r = None
+    for it in range(iters):
+        r = gpu.pmc_step(seed=2026, it=it, retry=0 if r is None else r.retry)
+    return r
+
+
+def test_full_size_iteration_invariants(gpu):
+    """configs[2] shape at 2e7 samples on one GPU."""
+    wl = W.banana()
+    N = 20_000_000
+    r = _adapted(gpu, wl, N, iters=3)
+    prop = gpu.get_proposal()
+    assert r.n_alive == wl["K"] and r.nok == N
+    assert 0.0 < r.perplexity <= 1.0 and 1.0 <= r.ess <= N
+    # analytic evidence of the banana: ln Z = 0.5 ln(sig1^2) + d ln sqrt(2 pi)  
+    lnZ = 0.5 * np.log(10.0) + wl["d"] * 0.5 * np.log(2 * np.pi)
+    assert abs(r.ln_evidence - lnZ) < 0.02
+    got = gpu.download(X=False, indices=True)
+    w = got["weights"]
+    assert np.all(got["flg"] == 1) and np.all(w >= 0)
+    assert abs(w.sum() - 1.0) < 1e-9                      # normalised (tree sums vs sequential: ~sqrt(N) eps)
+    H = -(w[w >= 1e-20] * np.log(w[w >= 1e-20])).sum()
+    assert_close(r.perplexity, np.exp(H) / N, 1e-9, what="perplexity identity")
+    assert_close(r.ess, 1.0 / (w ** 2).sum(), 1e-9, what="ESS identity")
+    cnt = np.bincount(got["indices"].astype(np.int64), minlength=wl["K"])
+    assert np.array_equal(gpu.count_indices(), cnt.astype(np.uint64))   # integer histogram: bit-exact
+    # determinism: the same call twice gives bit-identical results
+    gpu.set_proposal(prop["wght"], prop["mean"], prop["L"], prop["detL"])
+    a = gpu.pmc_step(seed=7, it=9, retry=0)
+    wa = gpu.download(X=False, indices=False, log_rho=False, flg=False)["weights"]
+    gpu.set_proposal(prop["wght"], prop["mean"], prop["L"], prop["detL"])
+    b = gpu.pmc_step(seed=7, it=9, retry=0)
+    wb = gpu.download(X=False, indices=False, log_rho=False, flg=False)["weights"]
+    assert np.array_equal(wa, wb) and a.perplexity == b.perplexity
+    assert np.array_equal(a.mean, b.mean) and np.array_equal(a.L, b.L) and np.array_equal(a.wght, b.wght)
+
+
+def test_fused_update_equals_two_pass_at_scale(gpu):
+    """The one-pass pivoted statistics (fused / DMMA path) and the literal two-pass update agree at 5e6 samples."""
+    wl = W.banana()
+    N = 5_000_000
+    _adapted(gpu, wl, N, iters=2)
+    prop = gpu.get_proposal()
+    one = gpu.pmc_step(seed=11, it=5, retry=0)
+    assert one.used_precise_path == 0
+    gpu.set_proposal(prop["wght"], prop["mean"], prop["L"], prop["detL"])
+    gpu.set_option("force_precise", 1)
+    two = gpu.pmc_step(seed=11, it=5, retry=0)
+    gpu.set_option("force_precise", 0)
+    assert two.used_precise_path == 1
+    assert one.perplexity == two.perplexity and one.logSum == two.logSum
+    errs = compare_mixture(one.wght, one.mean, one.L, two.wght, two.mean, two.L, rtol=1e-11, what="one-pass vs two-pass")
+    print("one-pass vs two-pass at 5e6:", errs)
+
+
+def test_subsample_against_oracle_at_scale(gpu):
+    """A random 20k sub-sample of a 1e7-sample iteration: log_rho and log-weights re-computed by the oracle."""
+    wl = W.gmm5()
+    N = 10_000_000
+    gpu.set_option("force_generic", 0); gpu.set_option("fused_version", 0); gpu.set_option("spl", 1)
+    gpu.set_workload(wl)
+    gpu.resize(N)
+    r = gpu.pmc_step(seed=3, it=0, do_update=0)
+    got = gpu.download()
+    sel = np.random.default_rng(0).choice(N, 20000, replace=False)
+    o = O.orc_iteration(got["X"][sel], got["indices"][sel], wl, do_update=0)
+    assert_close(got["log_rho"][sel], o["log_rho"], RTOL, what="log_rho")
+    # normalised weights differ by the global normaliser only: compare ratios to the sub-sample maximum
+    j = np.argmax(o["logw"])
+    lw_gpu = np.log(got["weights"][sel] / got["weights"][sel][j])
+    big = np.max(np.abs(o["log_rho"]))
+    keep = got["weights"][sel] > 1e-250
+    assert_close(lw_gpu[keep], (o["logw"] - o["logw"][j])[keep], 1e-11, scale=big, what="log-weight differences")
+    assert r.nok == N
+
+
+def test_nan_and_flag_semantics_on_gpu(gpu):
+    """Per-sample failure handling (pmc.c:546-583, 663-669): NaN inputs are flagged out, -inf log-weights count with
+    weight 0, and all-flagged input raises pmc_nosamplep — on every path."""
+    wl = W.banana()
+    X, idx = O.orc_simulate(2000, wl, seed=3)
+    X = X.copy()
+    X[5, 2] = np.nan
+    X[9, 0] = 1e6
+    o = O.orc_iteration(X, idx, wl, do_update=1)
+    X0 = X.copy()
+    X0[0, 1] = np.nan   # global sample 0: the unconditional i==0 assignment poisons maxR with NaN (pmc.c:552)
+    o0 = O.orc_iteration(X0, idx, wl, do_update=0)
+    assert o["rc"] == 0 and np.isnan(o0["maxR"])
+    for fg, ver in [(1, 0), (0, 1), (0, 2)]:
+        gpu.set_option("force_generic", fg); gpu.set_option("fused_version", ver); gpu.set_option("spl", 1)
+        gpu.set_workload(wl)
+        gpu.resize(len(X))
+        gpu.upload(X=X, indices=idx, flg=np.ones(len(X), np.int16))
+        r = gpu.step_given(0, len(X), 1.0, 1, 0)
+        got = gpu.download(X=False, indices=False)
+        assert np.array_equal(got["flg"], o["flg"]) and r.nok == o["nok"]
+        assert got["weights"][9] == 0.0 and got["flg"][9] == 1 and got["flg"][5] == 0
+        assert_close(r.maxR, o["maxR"], RTOL, what="maxR")
+        compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=f"nan case path {fg},{ver}")
+        gpu.set_workload(wl)
+        gpu.upload(X=X0, indices=idx, flg=np.ones(len(X), np.int16))
+        nok, maxW, maxR = gpu.weights(1.0)
+        assert nok == o0["nok"] and np.isnan(maxR)
+        assert_close(maxW, o0["maxW"], RTOL, scale=np.nanmax(np.abs(o0["log_rho"])), what="maxW")
+        assert np.array_equal(gpu.download(X=False, indices=False)["flg"], o0["flg"])
+    Xn = np.full((64, wl["d"]), np.nan)
+    gpu.resize(64)
+    gpu.upload(X=Xn, indices=idx[:64], flg=np.ones(64, np.int16))
+    with pytest.raises(Exception) as e:
+        gpu.step_given(0, 64, 1.0, 0, 0)
+    assert "-6017" in str(e.value)
