@@ -81,6 +81,9 @@ int pmcgpu_resize(pmcgpu_ctx *ctx, long N, int d);
 int pmcgpu_upload(pmcgpu_ctx *ctx, const double *X, const size_t *indices, const double *weights,
                   const double *log_rho, const short *flg);
 int pmcgpu_download(pmcgpu_ctx *ctx, double *X, size_t *indices, double *weights, double *log_rho, short *flg);
+/* page-lock / unlock a caller-owned host block (e.g. pmc_simu.data) so pmcgpu_upload/download run as DMA */
+int pmcgpu_pin_host(void *p, size_t bytes);
+int pmcgpu_unpin_host(void *p);
 /* device addresses of the store, for zero-copy consumers: out[5] = X, indices, weights, log_rho, flg */
 int pmcgpu_device_arrays(pmcgpu_ctx *ctx, void **out);
 

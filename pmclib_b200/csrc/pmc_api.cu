@@ -1307,6 +1307,20 @@ int pmcgpu_get_proposal(pmcgpu_ctx *c, double *o_wght, double *o_mean, double *o
   return 0;
 }
 
+// page-lock / unlock a caller-owned host block so that upload/download run as DMA at PCIe speed
+int pmcgpu_pin_host(void *p, size_t bytes) {
+  if (!p || !bytes) return PMCGPU_ERR_USAGE;
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return PMCGPU_ERR_CUDA; }
+  return 0;
+}
+int pmcgpu_unpin_host(void *p) {
+  if (!p) return PMCGPU_ERR_USAGE;
+  const cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { cudaGetLastError(); return PMCGPU_ERR_CUDA; }
+  return 0;
+}
+
 // ---- multi-GPU ---------------------------------------------------------------------------------------------------
 void pmcgpu_shard_range(long N_total, int rank, int nranks, long *first, long *len) {
   const long base = N_total / nranks, rem = N_total % nranks;

@@ -56,6 +56,7 @@ struct Side {
   int d = 0;
   uint32_t iter = 0;
   bool host_stale = false;  // resident mode: HBM holds newer sample arrays than the host
+  void *pinned = nullptr;   // psim->data while it is page-locked
 };
 std::map<const pmc_simu *, Side> g_side;
 std::map<const distribution *, int> g_registered;
@@ -83,6 +84,11 @@ Side *side_for(pmc_simu *psim, error **err) {
     }
     s.N = psim->nsamples;
     s.d = psim->ndim;
+  }
+  if (s.pinned != psim->data) {  // page-lock the caller's sample block once (it is re-allocated by pmc_simu_realloc)
+    const size_t bytes = (size_t)psim->nsamples * ((psim->ndim + 2 + psim->n_ded) * sizeof(double) + sizeof(short) + sizeof(size_t));
+    s.pinned = (pmcgpu_pin_host(psim->data, bytes) == 0) ? psim->data : nullptr;
+    if (!s.pinned) s.pinned = psim->data;  // pageable copies still work; do not retry every call
   }
   return &s;
 }
@@ -747,6 +753,7 @@ void pmc_simu_free(pmc_simu **melf) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_side.find(s);
     if (it != g_side.end()) {
+      if (it->second.pinned) pmcgpu_unpin_host(it->second.pinned);
       if (it->second.ctx) pmcgpu_destroy(it->second.ctx);
       g_side.erase(it);
     }
@@ -759,6 +766,11 @@ void pmc_simu_free(pmc_simu **melf) {
 }
 void pmc_simu_realloc(pmc_simu *psim, long newsamples, error **err) {
   if (psim->nsamples == newsamples) return;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_side.find(psim);
+    if (it != g_side.end() && it->second.pinned) { pmcgpu_unpin_host(it->second.pinned); it->second.pinned = nullptr; }
+  }
   psim->nsamples = newsamples;
   free(psim->data);
   psim->data = xmalloc((size_t)newsamples * ((psim->ndim + 2) * sizeof(double) + psim->n_ded * sizeof(double) + sizeof(short) + sizeof(size_t)), err);

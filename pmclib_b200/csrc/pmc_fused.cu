@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 1) k_fused(const FusedArgs a
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
         const double rs = (w[s] != 0.0) ? w[s] / lpos[s] : 0.0;
-        for (int k = 0; k < K; ++k) grow[s][k] = grow[s][k] * rs;  // g_ik = w_i * alpha_k phi_k(x_i) / q(x_i)
+        for (int k = 0; k < K; ++k) grow[s][k] = (rs != 0.0) ? grow[s][k] * rs : 0.0;  // g_ik = w_i alpha_k phi_k(x_i)/q(x_i); NaN densities of flagged-out samples must not leak
         for (int k = K; k < GS; ++k) grow[s][k] = 0.0;
       }
 

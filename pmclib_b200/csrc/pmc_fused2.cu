@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
           const double rs = (w[s] != 0.0) ? w[s] / lpos[s] : 0.0;
           double *grow = gtile + lane * GS;
 #pragma unroll
-          for (int k = 0; k < K; ++k) grow[k] = ev[s][k] * rs;  // g_ik = w_i alpha_k phi_k(x_i) / q(x_i)
+          for (int k = 0; k < K; ++k) grow[k] = (rs != 0.0) ? ev[s][k] * rs : 0.0;  // g_ik = w_i alpha_k phi_k(x_i) / q(x_i)
           double xc[D];
 #pragma unroll
           for (int i2 = 0; i2 < D; ++i2) xc[i2] = (w[s] != 0.0) ? x[s][i2] - a.pivot[i2] : 0.0;

@@ -31,7 +31,9 @@ def test_iteration_matches_reference_golden(gpu, name, path):
         with pytest.raises(Exception) as e:
             gpu.step_given(0, len(X), 1.0, upd, 0)
         assert str(int(g["rc"])) in str(e.value)   # same reference error code (pmc_negWeight for the tiny c5 sample)
-        # the importance part is still well defined
+        # the importance part is still well defined (the failed update has consumed the proposal, as in the reference)
+        gpu.set_workload(wl)
+        gpu.upload(X=X, indices=idx, flg=np.ones(len(X), np.int16))
         r = gpu.step_given(0, len(X), 1.0, 0, 0)
     else:
         r = gpu.step_given(0, len(X), 1.0, upd, 0)

@@ -105,8 +105,9 @@ def test_nan_and_flag_semantics_on_gpu(gpu):
     X0[0, 1] = np.nan   # global sample 0: the unconditional i==0 assignment poisons maxR with NaN (pmc.c:552)
     o0 = O.orc_iteration(X0, idx, wl, do_update=0)
     assert o["rc"] == 0 and np.isnan(o0["maxR"])
-    for fg, ver in [(1, 0), (0, 1), (0, 2)]:
+    for fg, ver, split in [(1, 0, 1), (0, 1, 1), (0, 2, 1), (0, 2, 0)]:
         gpu.set_option("force_generic", fg); gpu.set_option("fused_version", ver); gpu.set_option("spl", 1)
+        gpu.set_option("split_stats", split)
         gpu.set_workload(wl)
         gpu.resize(len(X))
         gpu.upload(X=X, indices=idx, flg=np.ones(len(X), np.int16))
@@ -122,6 +123,7 @@ def test_nan_and_flag_semantics_on_gpu(gpu):
         assert nok == o0["nok"] and np.isnan(maxR)
         assert_close(maxW, o0["maxW"], RTOL, scale=np.nanmax(np.abs(o0["log_rho"])), what="maxW")
         assert np.array_equal(gpu.download(X=False, indices=False)["flg"], o0["flg"])
+    gpu.set_option("split_stats", 1)
     Xn = np.full((64, wl["d"]), np.nan)
     gpu.resize(64)
     gpu.upload(X=Xn, indices=idx[:64], flg=np.ones(64, np.int16))
