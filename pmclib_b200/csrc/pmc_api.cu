@@ -693,7 +693,7 @@ int pmcgpu_create(int device, pmcgpu_ctx **out) {
   c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return PMCGPU_ERR_CUDA; }
   for (int j = 0; j < FUSED_MAXD; ++j) { c->lo_thr[j] = INFINITY; c->hi_thr[j] = INFINITY; }
-  {  // ziggurat table: x_0 = V/f(R), x_1 = R, x_i = sqrt(-2 ln(V/x_{i-1} + f(x_{i-1}))), x_256 = 0; entries (x_i, x_{i+1}/x_i)
+  {  // ziggurat table: x_0 = V/f(R), x_1 = R, x_i = sqrt(-2 ln(V/x_{i-1} + f(x_{i-1}))), x_C = 0; entries (x_i, x_{i+1}/x_i)
     std::vector<double> x(kZigLayers + 1), tab(2 * kZigLayers);
     auto f = [](double v) { return std::exp(-0.5 * v * v); };
     x[0] = kZigV / f(kZigR);

@@ -18,6 +18,10 @@ constexpr double kNegInit = -1.0e30;         // pmc.c:535
 struct Philox {
   uint32_t k0, k1;
   __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+#ifdef PMC_EXP_CHEAP_RNG  // timing experiment only: NOT a usable generator
+    const uint32_t h = (c0 * 0x9E3779B9u) ^ (c2 * 0x85EBCA6Bu) ^ c3 ^ k0;
+    return make_uint4(h * 0xC2B2AE35u, h ^ (h >> 15), (h + c1) * 0x27D4EB2Fu, h * 0x165667B1u);
+#endif
     uint32_t a = k0, b = k1;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -117,33 +121,44 @@ __device__ __forceinline__ bool in_box(const BoxDev &bx, const XT &x) {
 }
 
 
-// ---- ziggurat normal sampler (Marsaglia & Tsang 2000 in Doornik's ZIGNOR form, 256 layers) --------------------------
+// ---- ziggurat normal sampler (Marsaglia & Tsang 2000 in Doornik's ZIGNOR form, 1024 layers) -------------------------
 // A Box-Muller pair costs ~115 DFMA issue slots in double precision (log + sqrt + sincospi, profiles/r01_fp64_peak.md);
-// the ziggurat's fast path is one table lookup, one DADD, one DMUL and one compare and is taken 98.8 % of the time.
-// Table t[i] = (x_i, x_{i+1}/x_i), x_0 = V/f(R), x_1 = R, x_256 = 0 (built on the host by zig_build_table()).
-constexpr int kZigLayers = 256;
-constexpr double kZigR = 3.6541528853610088;
-constexpr double kZigV = 4.92867323399e-3;
+// the ziggurat's fast path is one table lookup, one DADD, one DMUL and one compare.  With 1024 layers it is taken
+// 99.7 % of the time, which matters on a GPU because one slow lane stalls its whole warp (the 256-layer version
+// spent 27 % of the draw/weights kernel in the slow path, measured by A/B builds).
+// Table t[i] = (x_i, x_{i+1}/x_i), x_0 = V/f(R), x_1 = R, x_C = 0 (built on the host by the C-ABI layer).
+// R and V solve the closing condition x_{C-1} (1 - f(x_{C-1})) = V; the solver reproduces the published constants
+// for C = 128 and 256.
+constexpr int kZigLayers = 1024;
+constexpr double kZigR = 4.038849846109505;
+constexpr double kZigV = 0.0012263246463530852;
 
-// candidate from 64 random bits: layer = bits 0..7, sign = bit 8, |u| = 52-bit mantissa in [0,1).  Returns true if the
-// rectangle test accepts; x holds the signed candidate either way.
+// candidate from 64 random bits (hi:lo): layer = lo[0..9], sign = lo[10], lo[11..13] are left for the caller,
+// |u| = the top 50 bits as a fraction in [0,1)
+__device__ __forceinline__ double zig_u(uint32_t lo, uint32_t hi) {
+  return __hiloint2double(0x3ff00000 | (hi >> 12), ((hi << 20) | (lo >> 12)) & ~3u) - 1.0;
+}
 __device__ __forceinline__ bool zig_fast(uint32_t lo, uint32_t hi, const double2 *zt, double &x) {
-  const double2 t = zt[lo & 255u];
-  const double u = __hiloint2double(0x3ff00000 | (hi >> 12), (hi << 20) | (lo >> 12)) - 1.0;
+  const double2 t = zt[lo & (kZigLayers - 1)];
+  const double u = zig_u(lo, hi);
   const double ax = u * t.x;
-  x = (lo & 256u) ? -ax : ax;
+  x = (lo & kZigLayers) ? -ax : ax;
   return u < t.y;
 }
 
+// exp() of two arguments at once (defined below)
+template <int N>
+__device__ __forceinline__ void exp_batch(const double (&x)[N], double (&out)[N]);
+
 // Slow path for a candidate whose rectangle test failed (wedge or tail), then fresh candidates until one is accepted.
 // Fresh randomness comes from Philox calls (cb | call) with call = 64, 65, ... of this sample/attempt.
-__device__ __forceinline__ double zig_finish(uint32_t lo, uint32_t hi, const double2 *zt, const Philox &ph, uint32_t ilo, uint32_t ihi,
-                             uint32_t cb, uint32_t iter, uint32_t &call) {
+__device__ __forceinline__ double zig_finish(uint32_t lo, uint32_t hi, const double2 *zt, const Philox &ph, uint32_t ilo,
+                                             uint32_t ihi, uint32_t cb, uint32_t iter, uint32_t &call) {
   for (int guard = 0; guard < 1000; ++guard) {
-    const uint32_t layer = lo & 255u;
+    const uint32_t layer = lo & (kZigLayers - 1);
     const double2 t = zt[layer];
-    const double u = __hiloint2double(0x3ff00000 | (hi >> 12), (hi << 20) | (lo >> 12)) - 1.0;
-    const bool neg = (lo & 256u) != 0;
+    const double u = zig_u(lo, hi);
+    const bool neg = (lo & kZigLayers) != 0;
     const double ax = u * t.x;
     if (u < t.y) return neg ? -ax : ax;
     if (layer == 0) {  // tail beyond R (Marsaglia 1964)
@@ -157,10 +172,12 @@ __device__ __forceinline__ double zig_finish(uint32_t lo, uint32_t hi, const dou
     }
     {  // wedge between the rectangle and the density
       const double xi = t.x, xi1 = t.x * t.y;
-      const double f0 = exp(-0.5 * (xi * xi - ax * ax)), f1 = exp(-0.5 * (xi1 * xi1 - ax * ax));
+      const double arg[2] = {-0.5 * (xi * xi - ax * ax), -0.5 * (xi1 * xi1 - ax * ax)};
+      double f[2];
+      exp_batch<2>(arg, f);
       const uint4 r = ph(ilo, ihi, cb | call, iter);
       ++call;
-      if (f1 + u01_co(r.x, r.y) * (f0 - f1) < 1.0) return neg ? -ax : ax;
+      if (f[1] + u01_co(r.x, r.y) * (f[0] - f[1]) < 1.0) return neg ? -ax : ax;
       lo = r.z;
       hi = r.w;  // fresh candidate
     }
@@ -168,24 +185,45 @@ __device__ __forceinline__ double zig_finish(uint32_t lo, uint32_t hi, const dou
   return 0.0;
 }
 
-// D standard normals for (sample, attempt): Philox calls 1..ceil(D/2) feed the fast path, calls >= 64 the slow path
+// D standard normals for (sample, attempt): Philox calls 1..ceil(D/2) feed the fast path, calls >= 64 the slow path.
+// spare receives the 3 unused bits of every candidate (3*D bits, candidate j in bits 3j..3j+2).
 template <int D>
 __device__ __forceinline__ void zig_normals(const Philox &ph, uint32_t ilo, uint32_t ihi, uint32_t cb, uint32_t iter,
-                                            const double2 *zt, double (&g)[D + 1]) {
-  uint32_t fail = 0;
+                                            const double2 *zt, double (&g)[D + 1], uint32_t &spare) {
+  uint32_t fail = 0, slo = 0, shi = 0;
+  spare = 0;
 #pragma unroll
   for (int j = 0; j < D; j += 2) {
     const uint4 r = ph(ilo, ihi, cb | (1 + j / 2), iter);
-    if (!zig_fast(r.x, r.y, zt, g[j])) fail |= 1u << j;
-    if (j + 1 < D && !zig_fast(r.z, r.w, zt, g[j + 1])) fail |= 1u << (j + 1);
+    spare |= ((r.x >> 11) & 7u) << ((3 * j) & 31);
+    if (!zig_fast(r.x, r.y, zt, g[j])) {
+      if (!fail) { slo = r.x; shi = r.y; }
+      fail |= 1u << j;
+    }
+    if (j + 1 < D) {
+      spare |= ((r.z >> 11) & 7u) << ((3 * (j + 1)) & 31);
+      if (!zig_fast(r.z, r.w, zt, g[j + 1])) {
+        if (!fail) { slo = r.z; shi = r.w; }
+        fail |= 1u << (j + 1);
+      }
+    }
   }
+#ifdef PMC_EXP_NO_SLOW  // timing experiment only
+  fail = 0;
+#endif
   uint32_t call = 64;
-  while (fail) {  // 1.2 % of the candidates: regenerate the counter-based bits of the failed slot and finish it
+  bool first = true;
+  while (fail) {  // 0.3 % of the candidates; the bits of the first failed slot were kept, later ones are regenerated
     const int j = __ffs(fail) - 1;
     fail &= fail - 1;
-    const uint4 r = ph(ilo, ihi, cb | (1 + (j >> 1)), iter);
-    const double v = (j & 1) ? zig_finish(r.z, r.w, zt, ph, ilo, ihi, cb, iter, call)
-                             : zig_finish(r.x, r.y, zt, ph, ilo, ihi, cb, iter, call);
+    uint32_t lo = slo, hi = shi;
+    if (!first) {
+      const uint4 r = ph(ilo, ihi, cb | (1 + (j >> 1)), iter);
+      lo = (j & 1) ? r.z : r.x;
+      hi = (j & 1) ? r.w : r.y;
+    }
+    first = false;
+    const double v = zig_finish(lo, hi, zt, ph, ilo, ihi, cb, iter, call);
 #pragma unroll
     for (int jj = 0; jj < D; ++jj)
       if (jj == j) g[jj] = v;

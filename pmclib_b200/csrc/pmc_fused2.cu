@@ -38,8 +38,13 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 // |L^-1 (x - mu)|^2 with every parameter read from a constant bank at a compile-time offset
 template <int D, int SPL, bool TGT>
-__device__ __forceinline__ void whiten_c(int base, const double (&x)[SPL][D], double (&q)[SPL]) {
+__device__ __forceinline__ void whiten_c(int base, const double (&x)[SPL][D], double (&q)[SPL], const double *smem_mix = nullptr) {
+#ifdef PMC_F2_SMEM_PARAMS
+  const double *cp = TGT ? c_tgt : smem_mix;
+#else
   const double *cp = TGT ? c_tgt : c_mix;
+  (void)smem_mix;
+#endif
   double v[SPL][D];
 #pragma unroll
   for (int a = 0; a < D; ++a) {
@@ -134,11 +139,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
 
   for (long tile = (long)blockIdx.x * F2_WARPS + wid; tile < ntiles; tile += (long)gridDim.x * F2_WARPS) {
     const long tbase = tile * TS;
-    const int tn = (a.N - tbase) < TS ? (int)(a.N - tbase) : TS;
     double x[SPL][D];
     bool valid[SPL];
     int kdraw[SPL];
-    double *xt = ptile;  // X staging aliases the P tile
 
     // ---------------- draw or load --------------------------------------------------------------------------
     if (a.do_draw) {
@@ -153,25 +156,39 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
           const uint32_t ilo = (uint32_t)gi, ihi = (uint32_t)(gi >> 32);
           for (int attempt = 0; attempt < a.max_attempts; ++attempt) {
             const uint32_t cb = (uint32_t)attempt << 12;
-            const uint4 r0 = ph(ilo, ihi, cb, a.iter);
+            double g[D + 1];
+            uint32_t spare;
+            zig_normals<D>(ph, ilo, ihi, cb, a.iter, zts, g, spare);
+            // uniform for the component pick: the 3 spare bits of each of the D candidates when that gives >= 30 bits
+            // (the reference's own gsl_rng_uniform has 32-bit resolution), else one more Philox call
+            double zc;
+            if (3 * D >= 30) {
+              zc = (double)(spare & 0x3fffffffu) * (1.0 / 1073741824.0);
+            } else {
+              const uint4 r0 = ph(ilo, ihi, cb, a.iter);
+              zc = u01_co(r0.x, r0.y);
+            }
             // first index with cw >= z == number of entries below z (cw is non-decreasing), mvdens.c:776
-            const double zc = u01_co(r0.x, r0.y);
             int k = 0;
 #pragma unroll
             for (int kk = 0; kk < K - 1; ++kk) k += (cws[kk] < zc) ? 1 : 0;
-            double g[D + 1];
-            zig_normals<D>(ph, ilo, ihi, cb, a.iter, zts, g);
             const double *cp = mixs + k * ST;
             bool inb = true;
 #pragma unroll
             for (int i2 = 0; i2 < D; ++i2) {
               double t = 0.0;
 #pragma unroll
+#ifdef PMC_EXP_NO_LG  // timing experiment only
+              t = g[i2];
+#else
               for (int j = 0; j <= i2; ++j) t = fma(g[j], cp[f2_oLr(D) + i2 * (i2 + 1) / 2 + j], t);
+#endif
               const double xv = t + cp[i2];
               x[s][i2] = xv;
               inb = inb && isfinite(xv);
-              if (a.has_box) inb = inb && !(a.lo_thr[i2] + xv < 0) && !(a.hi_thr[i2] - xv < 0);
+              // thr - c*x < 0 (parabox.c:125-131) for c = -1 / +1: IEEE addition keeps the sign of the exact sum, so the
+              // decision equals a direct comparison with the (negated) threshold
+              if (a.has_box) inb = inb && !(xv < -a.lo_thr[i2]) && !(xv > a.hi_thr[i2]);
             }
             kdraw[s] = k;
             if (inb) { ok = true; break; }
@@ -185,25 +202,36 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
         valid[s] = valid[s] && ok;
         if (i < a.N) {
           a.indices[i] = (unsigned long long)kdraw[s];
+          if ((D & 1) == 0) {
+            double2 *xo = reinterpret_cast<double2 *>(a.X + (size_t)i * D);
 #pragma unroll
-          for (int i2 = 0; i2 < D; ++i2) xt[(s * 32 + lane) * D + i2] = x[s][i2];
+            for (int i2 = 0; i2 < D; i2 += 2) xo[i2 / 2] = make_double2(x[s][i2], x[s][i2 + 1]);
+          } else {
+#pragma unroll
+            for (int i2 = 0; i2 < D; ++i2) a.X[(size_t)i * D + i2] = x[s][i2];
+          }
         }
       }
-      __syncwarp();
-      for (int idx = lane; idx < tn * D; idx += 32) a.X[(size_t)tbase * D + idx] = xt[idx];
-      __syncwarp();
     } else {
-      for (int idx = lane; idx < tn * D; idx += 32) xt[idx] = a.X[(size_t)tbase * D + idx];
-      __syncwarp();
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
         const long i = tbase + s * 32 + lane;
         valid[s] = i < a.N;
+        kdraw[s] = 0;
 #pragma unroll
-        for (int i2 = 0; i2 < D; ++i2) x[s][i2] = valid[s] ? xt[(s * 32 + lane) * D + i2] : 0.0;
-        kdraw[s] = valid[s] ? (int)a.indices[i] : 0;
+        for (int i2 = 0; i2 < D; ++i2) x[s][i2] = 0.0;
+        if (valid[s]) {  // each lane owns 8D contiguous bytes of X
+          if ((D & 1) == 0) {
+            const double2 *xi = reinterpret_cast<const double2 *>(a.X + (size_t)i * D);
+#pragma unroll
+            for (int i2 = 0; i2 < D; i2 += 2) { const double2 t = xi[i2 / 2]; x[s][i2] = t.x; x[s][i2 + 1] = t.y; }
+          } else {
+#pragma unroll
+            for (int i2 = 0; i2 < D; ++i2) x[s][i2] = a.X[(size_t)i * D + i2];
+          }
+          kdraw[s] = (int)a.indices[i];
+        }
       }
-      __syncwarp();
     }
 
     // ---------------- target ------------------------------------------------------------------------------------
@@ -265,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         double q[SPL];
-        whiten_c<D, SPL, false>(k * ST, x, q);
+        whiten_c<D, SPL, false>(k * ST, x, q, mixs);
         const bool alive = c_mix[k * ST + f2_oSc(D)] > 0.0;
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
@@ -463,7 +491,7 @@ __global__ void k_fused2_combine(const double *__restrict__ partials, int nblock
   }
   __syncthreads();
   const int nstat = K * E;
-  for (int t = threadIdx.x; t < nstat; t += blockDim.x) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nstat; t += gridDim.x * blockDim.x) {
     const int k = t / E, e = t - k * E;
     const int m = k >> 3, r = k & 7, n = e >> 3, cc = e & 7;
     const int idx = ((m * NT + n) * 32 + (r * 4 + (cc >> 1))) * 2 + (cc & 1);  // C fragment: row = lane/4, cols 2(lane%4)+{0,1}
@@ -471,7 +499,7 @@ __global__ void k_fused2_combine(const double *__restrict__ partials, int nblock
     for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * partial_len + idx] * sc[b];
     out[t] = s;
   }
-  if (threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     double S = 0.0, R = -INFINITY;
     for (int b = 0; b < nblocks; ++b) {
       S += partials[(size_t)b * partial_len + acc_len + 1] * sc[b];
@@ -500,18 +528,40 @@ struct StatsArgs {
   int partial_len;
 };
 
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
+template <int D, int K>
+struct S2Cfg {
+  static constexpr int XS = (D + 1) | 1;                          // odd stride of the augmented row (1, x~)
+  static constexpr int GS = F2Cfg<D, K, 0, 1>::GS;
+  static constexpr int STAGE = 32 * D + 32 * K + 32 + 8;          // raw X rows | resp rows (k-major) | lw | flg (32 shorts)
+  static constexpr int WARP_DOUBLES = 32 * XS + 32 * GS + STAGE;  // compute tiles + one prefetch stage
+};
+
 template <int D, int K>
 __global__ void __launch_bounds__(256, 2) k_stats2(const StatsArgs a) {
   using C = F2Cfg<D, K, 0, 1>;
-  constexpr int NT = C::NT, MT = C::MT, GS = C::GS;
-  constexpr int XS = (D + 1) | 1;  // odd stride of the augmented row (1, x~)
+  using S2 = S2Cfg<D, K>;
+  constexpr int NT = C::NT, MT = C::MT, GS = C::GS, XS = S2::XS;
   constexpr int WARPS = 8;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *xh = smem + (size_t)wid * (32 * XS + 32 * GS);
+  double *xh = smem + (size_t)wid * S2::WARP_DOUBLES;
   double *gt = xh + 32 * XS;
+  double *stx = gt + 32 * GS;        // [32][D] raw sample rows of the NEXT tile (LDGSTS prefetch)
+  double *str = stx + 32 * D;        // [K][32] responsibilities
+  double *stw = str + 32 * K;        // [32] log-weights
+  short *stf = reinterpret_cast<short *>(stw + 32);  // [32] flags
   __shared__ double s_S[WARPS];
-  for (int i = lane; i < 32 * XS + 32 * GS; i += 32) xh[i] = 0.0;
+  for (int i = lane; i < S2::WARP_DOUBLES; i += 32) xh[i] = 0.0;
   __syncwarp();
   const int fr = lane >> 2, fc = lane & 3;
   // which two augmented coordinates multiply to entry e = 8n + fr
@@ -538,25 +588,44 @@ __global__ void __launch_bounds__(256, 2) k_stats2(const StatsArgs a) {
   double S_lane = 0.0;
   const double M = a.M[0];
   const long ntiles = (a.N + 31) / 32;
-  for (long tile = (long)blockIdx.x * WARPS + wid; tile < ntiles; tile += (long)gridDim.x * WARPS) {
+  const long tstep = (long)gridDim.x * WARPS;
+
+  // asynchronous copy of one tile's inputs into the stage (cp.async = SASS LDGSTS): overlaps with the DMMA loop
+  auto prefetch = [&](long tile) {
+    const long base = tile * 32;
+    const int tn = (a.N - base) < 32 ? (int)(a.N - base) : 32;
+    if ((D & 1) == 0) {
+      for (int c = lane; c < tn * D / 2; c += 32) cp_async16(stx + 2 * c, a.X + (size_t)base * D + 2 * c);
+    } else {
+      for (int c = lane; c < tn * D; c += 32) cp_async8(stx + c, a.X + (size_t)base * D + c);
+    }
+    if (lane < tn) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) cp_async8(str + k * 32 + lane, a.resp + (size_t)k * a.N + base + lane);
+      cp_async8(stw + lane, a.lw + base + lane);
+    }
+    if (2 * lane + 1 < tn) cp_async4(stf + 2 * lane, a.flg + base + 2 * lane);
+    else if (2 * lane < tn) stf[2 * lane] = a.flg[base + 2 * lane];
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  long tile = (long)blockIdx.x * WARPS + wid;
+  if (tile < ntiles) prefetch(tile);
+  for (; tile < ntiles; tile += tstep) {
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncwarp();
     const long i = tile * 32 + lane;
     double w = 0.0;
     double xr[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) xr[j] = 0.0;
     if (i < a.N) {
-      const double lw = a.lw[i];
-      const bool wfin = a.flg[i] != 0 && !isnan(lw) && !(lw == INFINITY);
+      const double lw = stw[lane];
+      const bool wfin = stf[lane] != 0 && !isnan(lw) && !(lw == INFINITY);
       w = (wfin && lw > -INFINITY) ? exp_one(lw - M) : 0.0;
       if (w != 0.0) {
-        if ((D & 1) == 0) {
-          const double2 *xp = reinterpret_cast<const double2 *>(a.X + (size_t)i * D);
 #pragma unroll
-          for (int j = 0; j < D / 2; ++j) { const double2 t = xp[j]; xr[2 * j] = t.x - a.pivot[2 * j]; xr[2 * j + 1] = t.y - a.pivot[2 * j + 1]; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < D; ++j) xr[j] = a.X[(size_t)i * D + j] - a.pivot[j];
-        }
+        for (int j = 0; j < D; ++j) xr[j] = stx[lane * D + j] - a.pivot[j];
       }
     }
     S_lane += w;
@@ -565,8 +634,9 @@ __global__ void __launch_bounds__(256, 2) k_stats2(const StatsArgs a) {
 #pragma unroll
     for (int j = 0; j < D; ++j) xrow[1 + j] = xr[j];
 #pragma unroll
-    for (int k = 0; k < K; ++k) grow[k] = (w != 0.0) ? w * a.resp[(size_t)k * a.N + i] : 0.0;
-    __syncwarp();
+    for (int k = 0; k < K; ++k) grow[k] = (w != 0.0) ? w * str[k * 32 + lane] : 0.0;
+    __syncwarp();  // tiles complete, stage consumed
+    if (tile + tstep < ntiles) prefetch(tile + tstep);
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -685,8 +755,7 @@ template <int D, int K>
 static int launch_stats2(const FusedPlan &p, const StatsArgs &a, cudaStream_t s) {
   auto kern = k_stats2<D, K>;
   using C = F2Cfg<D, K, 0, 1>;
-  constexpr int XS = (D + 1) | 1;
-  size_t smem = (size_t)8 * (32 * XS + 32 * C::GS) * sizeof(double);
+  size_t smem = (size_t)8 * S2Cfg<D, K>::WARP_DOUBLES * sizeof(double);
   if (smem < (size_t)C::ACC * sizeof(double)) smem = (size_t)C::ACC * sizeof(double);
   static bool configured = false;
   if (!configured) {
@@ -749,7 +818,8 @@ int launch_fused2_stats(const FusedPlan &p, const double *X, const double *lw, c
 int launch_fused2_combine(const FusedPlan &p, const double *partials, int nblocks, double *stats_out, cudaStream_t s) {
   const int E = 1 + p.D + p.D * (p.D + 1) / 2;
   const int NT = (E + 7) / 8;
-  k_fused2_combine<<<1, 256, nblocks * sizeof(double), s>>>(partials, nblocks, p.partial_len, p.partial_len - 4, p.RK, E, NT, stats_out);
+  const int nstat = p.RK * E;
+  k_fused2_combine<<<(nstat + 63) / 64, 64, nblocks * sizeof(double), s>>>(partials, nblocks, p.partial_len, p.partial_len - 4, p.RK, E, NT, stats_out);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

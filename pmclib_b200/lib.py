@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpmcb200.so")
+LIB_PATH = os.environ.get("PMCB200_LIB", os.path.join(HERE, "libpmcb200.so"))  # the override is for A/B kernel experiments
 
 
 class PmcError(RuntimeError):
