@@ -31,6 +31,8 @@ from pmclib_b200 import workloads as W  # noqa: E402
 METRIC = "PMC samples/s per iteration (draw+weight+RB update)"
 UNIT = "samples/s"
 FLOP_PER_SAMPLE = 2987.0   # algorithmic flops per sample at d=10, K=10 (banana target)
+FLOP_K1 = 1547.0           # of which the draw/weights kernel: draw 140 + mixture log-density 1371 + target 28 + weight 8
+FLOP_K2 = 1440.0           # and the statistics kernel: RB update 10 x 144
 BYTES_PER_SAMPLE = 106.0   # compulsory HBM bytes per sample: X, weights, log_rho, indices, flg = 8d + 26
 FP64_PEAK_TFLOPS = 36.9    # measured DFMA peak on this pool's B200, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)
 
@@ -296,15 +298,36 @@ def main():
     roof = None
     if fused_n > 0:
         ms = fused_ms / fused_n
-        tf = FLOP_PER_SAMPLE * n_local / (ms * 1e-3) * 1e-12
+        ms2 = stats_ms / fused_n
+        split = ms2 > 0
+        flop = FLOP_K1 if split else FLOP_PER_SAMPLE
+        tf = flop * n_local / (ms * 1e-3) * 1e-12
         hbm_peak, which = measured_hbm_gbs()
+        # compulsory bytes of the dominant kernel: the five pmc_simu arrays (+ the responsibilities it hands to the
+        # statistics kernel in the split pipeline)
+        bytes_k1 = BYTES_PER_SAMPLE + (8.0 * wl["K"] if split else 0.0)
         roof = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
-                "traffic": None, "kernel": "k_fused<10,2,12,1,%d>" % (args.spl or 1), "kernel_ms": ms,
-                "kernel_share_of_step": fused_ms / ev_ms, "stats_kernel_ms": stats_ms / fused_n,
+                "traffic": None, "kernel": "k_fused2 (draw + mixture log-density + target + log-weights)" if split else "k_fused2 (single pass)",
+                "kernel_ms": ms, "kernel_share_of_step": fused_ms / ev_ms, "algorithmic_flop_per_sample": flop,
                 "peak_source": "measured DFMA peak, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)",
-                "algorithmic_flop_per_sample": FLOP_PER_SAMPLE,
-                "hbm": {"achieved": BYTES_PER_SAMPLE * n_local / (ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": BYTES_PER_SAMPLE * n_local / (ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": which + " MEASURED_PEAKS.json"}}
+                "hbm": {"achieved": bytes_k1 * n_local / (ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bytes_k1 * n_local / (ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": which + " MEASURED_PEAKS.json",
+                        "algorithmic_bytes_per_sample": bytes_k1}}
+        if split:
+            tf2 = FLOP_K2 * n_local / (ms2 * 1e-3) * 1e-12
+            tfp = FLOP_PER_SAMPLE * n_local / ((ms + ms2) * 1e-3) * 1e-12
+            roof["stats_kernel"] = {"kernel": "k_stats2 (DMMA sufficient statistics)", "kernel_ms": ms2, "achieved": tf2,
+                                    "frac": tf2 / FP64_PEAK_TFLOPS, "algorithmic_flop_per_sample": FLOP_K2,
+                                    "kernel_share_of_step": stats_ms / ev_ms}
+            roof["pipeline"] = {"achieved": tfp, "frac": tfp / FP64_PEAK_TFLOPS, "algorithmic_flop_per_sample": FLOP_PER_SAMPLE,
+                                "note": "both FP64 kernels together, (k_fused2 + k_stats2) time"}
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f)
+            if tr.get("samples") == n_local:
+                roof["traffic"] = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
 
     cpu = None
     if not args.no_cpu_baseline:

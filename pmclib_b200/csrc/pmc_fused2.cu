@@ -36,6 +36,9 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem);
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem);
+
 // |L^-1 (x - mu)|^2 with every parameter read from a constant bank at a compile-time offset
 template <int D, int SPL, bool TGT>
 __device__ __forceinline__ void whiten_c(int base, const double (&x)[SPL][D], double (&q)[SPL], const double *smem_mix = nullptr) {
@@ -91,7 +94,7 @@ struct F2Cfg {
 };
 
 // MODE 0: draw/weights only; 1: + responsibilities r[k][i] = alpha_k phi_k(x_i)/q(x_i) to global memory (for k_stats2);
-// 2: statistics fused in the same kernel (per-warp DMMA accumulators).
+// 2: statistics fused in the same kernel (per-warp DMMA accumulators); 3: draw only (X, indices; integer-heavy, small code).
 template <int D, int K, int KT, int SPL, int MODE, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) {
   using C = F2Cfg<D, K, KT, SPL>;
@@ -137,6 +140,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
   const Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
   const int fr = lane >> 2, fc = lane & 3;  // fragment row (component / entry within a tile), k-step column (sample)
 
+  // asynchronous copy (cp.async = LDGSTS) of one tile of X rows into this warp's stage
+  auto prefetch_x = [&](long nt) {
+    if (nt < ntiles) {
+      const long nb = nt * TS;
+      const int tn = (a.N - nb) < TS ? (int)(a.N - nb) : TS;
+      if ((D & 1) == 0) { for (int c = lane; c < tn * D / 2; c += 32) cp_async16(ptile + 2 * c, a.X + (size_t)nb * D + 2 * c); }
+      else { for (int c = lane; c < tn * D; c += 32) cp_async8(ptile + c, a.X + (size_t)nb * D + c); }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+#ifdef PMC_XPREFETCH  // measured 6 % slower than plain per-lane loads on B200 (A/B build, r01): off by default
+  if (MODE != 3 && !a.do_draw) prefetch_x((long)blockIdx.x * F2_WARPS + wid);  // prologue of the X prefetch pipeline
+#endif
   for (long tile = (long)blockIdx.x * F2_WARPS + wid; tile < ntiles; tile += (long)gridDim.x * F2_WARPS) {
     const long tbase = tile * TS;
     double x[SPL][D];
@@ -213,6 +229,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
         }
       }
     } else {
+      // samples already in HBM: the tile was prefetched into this warp's stage with cp.async (LDGSTS) while the previous
+      // tile was being computed, so the first FP64 instruction does not wait for a global load
+#ifdef PMC_XPREFETCH  // measured 6 % slower than plain per-lane loads on B200 (A/B build, r01): off by default
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) {
+        const long i = tbase + s * 32 + lane;
+        valid[s] = i < a.N;
+        kdraw[s] = 0;
+#pragma unroll
+        for (int i2 = 0; i2 < D; ++i2) x[s][i2] = valid[s] ? ptile[(s * 32 + lane) * D + i2] : 0.0;
+        if (valid[s]) kdraw[s] = (int)a.indices[i];
+      }
+      __syncwarp();
+      if (MODE != 2) prefetch_x(tile + (long)gridDim.x * F2_WARPS);  // MODE 2 re-uses the stage as its P tile: prefetch after phase 2
+#else
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
         const long i = tbase + s * 32 + lane;
@@ -220,19 +253,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
         kdraw[s] = 0;
 #pragma unroll
         for (int i2 = 0; i2 < D; ++i2) x[s][i2] = 0.0;
-        if (valid[s]) {  // each lane owns 8D contiguous bytes of X
-          if ((D & 1) == 0) {
-            const double2 *xi = reinterpret_cast<const double2 *>(a.X + (size_t)i * D);
+        if (valid[s]) {
+          const double2 *xi = reinterpret_cast<const double2 *>(a.X + (size_t)i * D);
 #pragma unroll
-            for (int i2 = 0; i2 < D; i2 += 2) { const double2 t = xi[i2 / 2]; x[s][i2] = t.x; x[s][i2 + 1] = t.y; }
-          } else {
-#pragma unroll
-            for (int i2 = 0; i2 < D; ++i2) x[s][i2] = a.X[(size_t)i * D + i2];
-          }
+          for (int i2 = 0; i2 + 1 < D; i2 += 2) { const double2 t = xi[i2 / 2]; x[s][i2] = t.x; x[s][i2 + 1] = t.y; }
           kdraw[s] = (int)a.indices[i];
         }
       }
+#endif
     }
+
+    if (MODE == 3) continue;  // draw-only kernel: the FP64 part runs as a second launch on the stored samples
 
     // ---------------- target ------------------------------------------------------------------------------------
     double post[SPL];
@@ -415,6 +446,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
         __syncwarp();
       }
     }
+#ifdef PMC_XPREFETCH  // measured 6 % slower than plain per-lane loads on B200 (A/B build, r01): off by default
+    if (MODE == 2 && !a.do_draw) prefetch_x(tile + (long)gridDim.x * F2_WARPS);
+#endif
   }
 
   // ---------------- block combine (fixed order -> deterministic) ----------------------------------------------
@@ -725,6 +759,7 @@ static int launch_k1(const FusedPlan &p, const FusedArgs &a, int *nblocks_out, c
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
   if (nb > 4) nb = 4;
+  if (MODE == 3 && nb > 2) nb = nb;  // the draw kernel writes no partials that matter
   *nblocks_out = p.grid * nb;
   kern<<<p.grid * nb, WARPS * 32, smem, s>>>(a);
   count_launch();
@@ -736,6 +771,11 @@ static int launch_one2(const FusedPlan &p, const FusedArgs &a, const double *h_m
                        int variant, int *nb, cudaStream_t s) {
   if (h_mix && cudaMemcpyToSymbolAsync(c_mix, h_mix, sizeof(double) * K * f2_stride(D), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
   if (KT > 0 && h_tgt && cudaMemcpyToSymbolAsync(c_tgt, h_tgt, sizeof(double) * KT * f2_stride(D), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+  if (mode == 3) {
+    if (variant == 1) return launch_k1<D, K, KT, SPL, 3, 8, 3>(p, a, nb, s);
+    if (variant == 2) return launch_k1<D, K, KT, SPL, 3, 8, 4>(p, a, nb, s);
+    return launch_k1<D, K, KT, SPL, 3, 8, 2>(p, a, nb, s);
+  }
   if constexpr (SPL == 1) {
     if (mode == 2) return launch_k1<D, K, KT, SPL, 2, 8, 1>(p, a, nb, s);
     if (mode == 0) return launch_k1<D, K, KT, SPL, 0, 4, 3>(p, a, nb, s);

@@ -277,13 +277,27 @@ __global__ void k_norm_exp_sum(long N, double maxW, double *__restrict__ w, shor
                                double *__restrict__ partial, unsigned long long *counters) {
   double v[1] = {0.0};
   unsigned int cnt = 0;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
-    if (flg[i] == 1) {
-      const double e = exp(w[i] - maxW + kDynMax);
-      w[i] = e;
-      if (!isfinite(e)) { flg[i] = 0; continue; }
-      v[0] += e;
-      ++cnt;
+  const long stride = (long)gridDim.x * blockDim.x;
+  constexpr int U = 4;  // four independent loads in flight per thread (HBM-bound pass: memory-level parallelism)
+  for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < N; i0 += U * stride) {
+    double lw[U];
+    short f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * stride;
+      f[u] = (i < N) ? flg[i] : (short)0;
+      lw[u] = (i < N) ? w[i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * stride;
+      if (i < N && f[u] == 1) {
+        const double e = exp(lw[u] - maxW + kDynMax);
+        w[i] = e;
+        if (!isfinite(e)) { flg[i] = 0; continue; }
+        v[0] += e;
+        ++cnt;
+      }
     }
   }
   block_sum_store<1>(v, partial);
@@ -426,13 +440,28 @@ __global__ void k_norm_scale_perp(long N, double S, double *__restrict__ w, cons
                                   double *__restrict__ partial, unsigned long long *counters) {
   double v[2] = {0.0, 0.0};
   unsigned int nexit = 0;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
-    const double wi = w[i] / S;
-    w[i] = wi;
-    if (flg[i] == 0) { ++nexit; continue; }
-    if (wi < kPerpZero) continue;
-    v[0] += wi * log(wi);
-    v[1] += wi * wi;
+  const long stride = (long)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < N; i0 += U * stride) {
+    double wu[U];
+    short f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * stride;
+      f[u] = (i < N) ? flg[i] : (short)1;
+      wu[u] = (i < N) ? w[i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * stride;
+      if (i >= N) continue;
+      const double wi = wu[u] / S;
+      w[i] = wi;
+      if (f[u] == 0) { ++nexit; continue; }
+      if (wi < kPerpZero) continue;
+      v[0] += wi * log(wi);
+      v[1] += wi * wi;
+    }
   }
   block_sum_store<2>(v, partial);
   const unsigned int c = (unsigned int)warp_sum_ll(nexit);
