@@ -31,7 +31,8 @@ from pmclib_b200 import workloads as W  # noqa: E402
 METRIC = "PMC samples/s per iteration (draw+weight+RB update)"
 UNIT = "samples/s"
 FLOP_PER_SAMPLE = 2987.0   # algorithmic flops per sample at d=10, K=10 (banana target)
-FLOP_K1 = 1547.0           # of which the draw/weights kernel: draw 140 + mixture log-density 1371 + target 28 + weight 8
+FLOP_DRAW = 140.0          # of which the draw kernel
+FLOP_K1 = 1407.0           # the weights kernel (dominant): mixture log-density 1371 + target 28 + weight 8
 FLOP_K2 = 1440.0           # and the statistics kernel: RB update 10 x 144
 BYTES_PER_SAMPLE = 106.0   # compulsory HBM bytes per sample: X, weights, log_rho, indices, flg = 8d + 26
 FP64_PEAK_TFLOPS = 36.9    # measured DFMA peak on this pool's B200, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)
@@ -242,6 +243,7 @@ def main():
     ev_ms = e0.elapsed_time(e1)
     fused_ms, fused_n, launches1 = g.get_timing()
     stats_ms = g.get_stats_timing()
+    draw_ms = g.get_draw_timing()
     g.set_option("timing", 0)
     t = torch.tensor([ev_ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -300,14 +302,17 @@ def main():
         ms = fused_ms / fused_n
         ms2 = stats_ms / fused_n
         split = ms2 > 0
-        flop = FLOP_K1 if split else FLOP_PER_SAMPLE
+        msd = draw_ms / fused_n
+        flop = (FLOP_K1 + (0.0 if msd > 0 else FLOP_DRAW)) if split else FLOP_PER_SAMPLE
         tf = flop * n_local / (ms * 1e-3) * 1e-12
         hbm_peak, which = measured_hbm_gbs()
         # compulsory bytes of the dominant kernel: the five pmc_simu arrays (+ the responsibilities it hands to the
         # statistics kernel in the split pipeline)
         bytes_k1 = BYTES_PER_SAMPLE + (8.0 * wl["K"] if split else 0.0)
+        if split and msd > 0:
+            bytes_k1 = 8.0 * wl["d"] + 8 + 18 + 8.0 * wl["K"]   # reads X and indices, writes weights, log_rho, flg, responsibilities
         roof = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
-                "traffic": None, "kernel": "k_fused2 (draw + mixture log-density + target + log-weights)" if split else "k_fused2 (single pass)",
+                "traffic": None, "kernel": ("k_fused2<MODE 1> (mixture log-density + target + log-weights)" if msd > 0 else "k_fused2 (draw + mixture log-density + target + log-weights)") if split else "k_fused2 (single pass)",
                 "kernel_ms": ms, "kernel_share_of_step": fused_ms / ev_ms, "algorithmic_flop_per_sample": flop,
                 "peak_source": "measured DFMA peak, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm": {"achieved": bytes_k1 * n_local / (ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
@@ -315,12 +320,16 @@ def main():
                         "algorithmic_bytes_per_sample": bytes_k1}}
         if split:
             tf2 = FLOP_K2 * n_local / (ms2 * 1e-3) * 1e-12
-            tfp = FLOP_PER_SAMPLE * n_local / ((ms + ms2) * 1e-3) * 1e-12
+            tfp = FLOP_PER_SAMPLE * n_local / ((ms + ms2 + msd) * 1e-3) * 1e-12
+            if msd > 0:
+                roof["draw_kernel"] = {"kernel": "k_fused2<MODE 3> (Philox + ziggurat + L g + box)", "kernel_ms": msd,
+                                       "kernel_share_of_step": draw_ms / ev_ms,
+                                       "hbm_gbs": (8.0 * wl["d"] + 8) * n_local / (msd * 1e-3) * 1e-9}
             roof["stats_kernel"] = {"kernel": "k_stats2 (DMMA sufficient statistics)", "kernel_ms": ms2, "achieved": tf2,
                                     "frac": tf2 / FP64_PEAK_TFLOPS, "algorithmic_flop_per_sample": FLOP_K2,
                                     "kernel_share_of_step": stats_ms / ev_ms}
             roof["pipeline"] = {"achieved": tfp, "frac": tfp / FP64_PEAK_TFLOPS, "algorithmic_flop_per_sample": FLOP_PER_SAMPLE,
-                                "note": "both FP64 kernels together, (k_fused2 + k_stats2) time"}
+                                "note": "all three kernels of the iteration together (draw + weights + statistics)"}
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tr = json.load(f)

@@ -53,6 +53,8 @@ int pmcgpu_set_option(pmcgpu_ctx *ctx, const char *name, double value);
 int pmcgpu_get_timing(pmcgpu_ctx *ctx, double *fused_ms, long *fused_launches, long *total_launches);
 /* accumulated milliseconds of the statistics kernel (split pipeline) over the same launches */
 int pmcgpu_get_stats_timing(pmcgpu_ctx *ctx, double *stats_ms);
+/* accumulated milliseconds of the draw kernel when it runs as its own launch (option "split_draw") */
+int pmcgpu_get_draw_timing(pmcgpu_ctx *ctx, double *draw_ms);
 
 /* ---- model: proposal, target, box ------------------------------------------------------------- */
 /* replaces the host-side mix_mvdens the reference passes around (mvdens.h:102-110) */

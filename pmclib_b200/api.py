@@ -85,6 +85,11 @@ class PmcGpu:
         self._ck(self.lib.pmcgpu_get_timing(self.h, C.byref(ms), C.byref(n), C.byref(tot)))
         return ms.value, n.value, tot.value
 
+    def get_draw_timing(self):
+        ms = C.c_double()
+        self._ck(self.lib.pmcgpu_get_draw_timing(self.h, C.byref(ms)))
+        return ms.value
+
     def get_stats_timing(self):
         ms = C.c_double()
         self._ck(self.lib.pmcgpu_get_stats_timing(self.h, C.byref(ms)))
