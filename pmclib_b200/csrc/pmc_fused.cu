@@ -553,12 +553,22 @@ static int launch_one(const FusedPlan &p, const FusedArgs &a, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// (D, RK, RE, NR, SPL): E = 1 + D + D(D+1)/2 statistics per component are cut into chunks of RE; a lane owns RK
+// components x one chunk; NR rounds of 32 lanes must cover ceil(K/RK) * ceil(E/RE) units.
 #define PMC_FUSED_TABLE(X) \
   X(10, 2, 12, 1, 1)       \
   X(10, 2, 12, 1, 2)       \
   X(10, 2, 12, 2, 1)       \
+  X(8, 2, 12, 1, 1)        \
+  X(8, 2, 12, 2, 1)        \
+  X(6, 2, 10, 1, 1)        \
+  X(6, 2, 10, 2, 1)        \
   X(5, 2, 8, 1, 1)         \
   X(5, 2, 8, 1, 2)         \
+  X(4, 2, 8, 1, 1)         \
+  X(4, 2, 8, 2, 1)         \
+  X(3, 2, 6, 1, 1)         \
+  X(3, 2, 6, 2, 1)         \
   X(2, 2, 6, 1, 1)         \
   X(2, 2, 6, 1, 2)
 

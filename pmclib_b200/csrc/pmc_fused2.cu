@@ -253,10 +253,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
         kdraw[s] = 0;
 #pragma unroll
         for (int i2 = 0; i2 < D; ++i2) x[s][i2] = 0.0;
-        if (valid[s]) {
-          const double2 *xi = reinterpret_cast<const double2 *>(a.X + (size_t)i * D);
+        if (valid[s]) {  // each lane owns 8D contiguous bytes of X (16-byte aligned rows when D is even)
+          if ((D & 1) == 0) {
+            const double2 *xi = reinterpret_cast<const double2 *>(a.X + (size_t)i * D);
 #pragma unroll
-          for (int i2 = 0; i2 + 1 < D; i2 += 2) { const double2 t = xi[i2 / 2]; x[s][i2] = t.x; x[s][i2 + 1] = t.y; }
+            for (int i2 = 0; i2 < D; i2 += 2) { const double2 t = xi[i2 / 2]; x[s][i2] = t.x; x[s][i2 + 1] = t.y; }
+          } else {
+#pragma unroll
+            for (int i2 = 0; i2 < D; ++i2) x[s][i2] = a.X[(size_t)i * D + i2];
+          }
           kdraw[s] = (int)a.indices[i];
         }
       }

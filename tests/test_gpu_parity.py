@@ -21,7 +21,11 @@ CASES = {
     "shipped_d2_K9": (lambda: W.shipped_example(), 30000),
     "ragged_d10_K10": (lambda: W.banana(seed=77), 1237),   # not a multiple of any tile size
     "tiny_d10_K10": (lambda: W.banana(seed=78), 33),
-    "d3_K4_generic_only": (lambda: W.banana(d=3, K=4, seed=5, box=30.0), 5000),
+    "d3_K4": (lambda: W.banana(d=3, K=4, seed=5, box=30.0), 5000),
+    "d4_K6": (lambda: W.banana(d=4, K=6, seed=6, mean_sigma=2.0, var=6.0, box=30.0), 6000),
+    "d6_K12": (lambda: W.banana(d=6, K=12, seed=7, mean_sigma=2.0, var=6.0, box=30.0), 12000),
+    "d8_K20": (lambda: W.banana(d=8, K=20, seed=8, mean_sigma=2.0, var=6.0, box=30.0), 20000),
+    "d7_K3_generic_only": (lambda: W.banana(d=7, K=3, seed=9, mean_sigma=2.0, var=6.0, box=30.0), 3000),
 }
 
 
@@ -100,7 +104,8 @@ def test_update_rb_two_pass(gpu, oracle_runs, name):
 
 
 @pytest.mark.parametrize("ver,spl", [(1, 1), (1, 2), (2, 1), (2, 2)])
-@pytest.mark.parametrize("name", ["c1_banana_d10_K10", "c2_gmm_d5_K20", "shipped_d2_K9", "ragged_d10_K10", "tiny_d10_K10"])
+@pytest.mark.parametrize("name", ["c1_banana_d10_K10", "c2_gmm_d5_K20", "shipped_d2_K9", "ragged_d10_K10", "tiny_d10_K10",
+                                  "d3_K4", "d4_K6", "d6_K12", "d8_K20", "d7_K3_generic_only"])
 def test_fused_iteration_given_samples(gpu, oracle_runs, name, ver, spl):
     """The one-pass fused kernel (weights + statistics) + host finalisation against the oracle's full iteration."""
     wl, X, idx, o = oracle_runs(name)
