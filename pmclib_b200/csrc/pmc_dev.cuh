@@ -18,10 +18,6 @@ constexpr double kNegInit = -1.0e30;         // pmc.c:535
 struct Philox {
   uint32_t k0, k1;
   __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
-#ifdef PMC_EXP_CHEAP_RNG  // timing experiment only: NOT a usable generator
-    const uint32_t h = (c0 * 0x9E3779B9u) ^ (c2 * 0x85EBCA6Bu) ^ c3 ^ k0;
-    return make_uint4(h * 0xC2B2AE35u, h ^ (h >> 15), (h + c1) * 0x27D4EB2Fu, h * 0x165667B1u);
-#endif
     uint32_t a = k0, b = k1;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -208,9 +204,6 @@ __device__ __forceinline__ void zig_normals(const Philox &ph, uint32_t ilo, uint
       }
     }
   }
-#ifdef PMC_EXP_NO_SLOW  // timing experiment only
-  fail = 0;
-#endif
   uint32_t call = 64;
   bool first = true;
   while (fail) {  // 0.3 % of the candidates; the bits of the first failed slot were kept, later ones are regenerated

@@ -194,11 +194,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
             for (int i2 = 0; i2 < D; ++i2) {
               double t = 0.0;
 #pragma unroll
-#ifdef PMC_EXP_NO_LG  // timing experiment only
-              t = g[i2];
-#else
               for (int j = 0; j <= i2; ++j) t = fma(g[j], cp[f2_oLr(D) + i2 * (i2 + 1) / 2 + j], t);
-#endif
               const double xv = t + cp[i2];
               x[s][i2] = xv;
               inb = inb && isfinite(xv);
