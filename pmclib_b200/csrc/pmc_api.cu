@@ -418,7 +418,7 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
   a.counters = sm + SM_COUNTERS;
   a.count_k = sm + SM_COUNTK;
   a.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
-  const int mode = (p.valid == 2) ? (do_stats ? ((c->split_stats || p.SPL > 1) ? 1 : 2) : 0) : -1;
+  const int mode = (p.valid == 2) ? (do_stats ? ((c->split_stats || p.SPL > 1 || p.NR == 0) ? 1 : 2) : 0) : -1;
   if (mode == 1) {
     CU(c->resp.ensure((size_t)c->prop.K * c->N * sizeof(double)));
     CU(c->partials2.ensure((size_t)p.grid * 2 * p.partial_len * sizeof(double)));

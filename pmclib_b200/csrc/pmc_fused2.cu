@@ -335,14 +335,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
       }
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
-        double arg[K], ex[K];
+        // exponentials in sub-batches of EB: each batch keeps 7 registers per element live, so the batch size sets the
+        // register peak of the kernel (EB = 5: fits 128 registers without spills, enough chains to hide the FMA latency)
+        constexpr int EB = (K % 5 == 0) ? 5 : ((K % 4 == 0) ? 4 : ((K % 3 == 0) ? 3 : 1));
 #pragma unroll
-        for (int k = 0; k < K; ++k) arg[k] = (c_mix[k * ST + f2_oSc(D)] > 0.0) ? ev[s][k] - mx[s] + kDynMax : -INFINITY;
-        exp_batch<K>(arg, ex);
+        for (int k0 = 0; k0 < K; k0 += EB) {
+          double arg[EB], ex[EB];
+#pragma unroll
+          for (int j = 0; j < EB; ++j)
+            arg[j] = (c_mix[(k0 + j) * ST + f2_oSc(D)] > 0.0) ? ev[s][k0 + j] - mx[s] + kDynMax : -INFINITY;
+          exp_batch<EB>(arg, ex);
+#pragma unroll
+          for (int j = 0; j < EB; ++j) ev[s][k0 + j] = ex[j];
+        }
         lpos[s] = 0.0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const double e = (c_mix[k * ST + f2_oSc(D)] > 0.0) ? ex[k] * c_mix[k * ST + f2_oSc(D)] : 0.0;
+        for (int k = 0; k < K; ++k) {  // same summation order as mvdens.c:814-819
+          const double e = (c_mix[k * ST + f2_oSc(D)] > 0.0) ? ev[s][k] * c_mix[k * ST + f2_oSc(D)] : 0.0;
           lpos[s] = lpos[s] + e;
           ev[s][k] = e;
         }
@@ -740,9 +749,10 @@ __global__ void k_f2_max(const double *__restrict__ partials, int nblocks, int p
 // ---- instantiation table: (D, K, KT, SPL) ------------------------------------------------------------------------
 #define PMC_FUSED2_TABLE(X) \
   X(10, 10, 0, 1)           \
-  X(10, 10, 0, 2)           \
+  X(10, 20, 0, 1)           \
+  X(10, 5, 0, 1)            \
   X(5, 20, 4, 1)            \
-  X(5, 20, 4, 2)            \
+  X(5, 10, 0, 1)            \
   X(2, 9, 0, 1)
 
 // launch shapes of the draw/weights kernel (MODE 0/1): variant -> (warps per block, min blocks per SM)
@@ -759,7 +769,7 @@ static int launch_k1(const FusedPlan &p, const FusedArgs &a, int *nblocks_out, c
   }
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
-  if (nb > 4) nb = 4;
+  if (nb > 5) nb = 5;
   if (MODE == 3 && nb > 2) nb = nb;  // the draw kernel writes no partials that matter
   *nblocks_out = p.grid * nb;
   kern<<<p.grid * nb, WARPS * 32, smem, s>>>(a);
@@ -772,24 +782,13 @@ static int launch_one2(const FusedPlan &p, const FusedArgs &a, const double *h_m
                        int variant, int *nb, cudaStream_t s) {
   if (h_mix && cudaMemcpyToSymbolAsync(c_mix, h_mix, sizeof(double) * K * f2_stride(D), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
   if (KT > 0 && h_tgt && cudaMemcpyToSymbolAsync(c_tgt, h_tgt, sizeof(double) * KT * f2_stride(D), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
-  if (mode == 3) {
-    if (variant == 1) return launch_k1<D, K, KT, SPL, 3, 8, 3>(p, a, nb, s);
-    if (variant == 2) return launch_k1<D, K, KT, SPL, 3, 8, 4>(p, a, nb, s);
-    return launch_k1<D, K, KT, SPL, 3, 8, 2>(p, a, nb, s);
-  }
-  if constexpr (SPL == 1) {
-    if (mode == 2) return launch_k1<D, K, KT, SPL, 2, 8, 1>(p, a, nb, s);
-    if (mode == 0) return launch_k1<D, K, KT, SPL, 0, 4, 3>(p, a, nb, s);
-    if (variant == 1) return launch_k1<D, K, KT, SPL, 1, 4, 4>(p, a, nb, s);
-    if (variant == 2) return launch_k1<D, K, KT, SPL, 1, 8, 1>(p, a, nb, s);
-    return launch_k1<D, K, KT, SPL, 1, 4, 3>(p, a, nb, s);
-  } else {  // two samples per lane: statistics always go through the split pipeline
-    if (mode == 2) return -1;
-    if (mode == 0) return launch_k1<D, K, KT, SPL, 0, 4, 2>(p, a, nb, s);
-    if (variant == 1) return launch_k1<D, K, KT, SPL, 1, 8, 1>(p, a, nb, s);
-    if (variant == 2) return launch_k1<D, K, KT, SPL, 1, 4, 3>(p, a, nb, s);
-    return launch_k1<D, K, KT, SPL, 1, 4, 2>(p, a, nb, s);
-  }
+  // launch shapes (warps per block, min blocks per SM) chosen by A/B timing on B200; `variant` selects alternatives for experiments
+  (void)variant;
+  static_assert(SPL == 1, "two samples per lane measured slower (register spills); only SPL = 1 is instantiated");
+  if (mode == 3) return launch_k1<D, K, KT, SPL, 3, 8, 2>(p, a, nb, s);
+  if (mode == 2) return launch_k1<D, K, KT, SPL, 2, 8, 1>(p, a, nb, s);
+  if (mode == 0) return launch_k1<D, K, KT, SPL, 0, 4, 4>(p, a, nb, s);
+  return launch_k1<D, K, KT, SPL, 1, 4, 4>(p, a, nb, s);
 }
 
 template <int D, int K>
@@ -816,18 +815,17 @@ FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want
   if (!best.valid && d == D_ && K == K_ && (kt_needed == 0 || kt_needed == KT_) && SPL_ == want_spl) {   \
     using C = F2Cfg<D_, K_, KT_, SPL_>;                                                                  \
     const size_t dbl = (size_t)K_ * C::ST + f2_ev2(K_) + 2 * kZigLayers + (size_t)8 * C::WARP_DOUBLES;   \
-    if (dbl * 8 <= 227 * 1024) {                                                                         \
-      best.valid = 2; best.D = D_; best.RK = K_; best.RE = KT_; best.NR = 0; best.SPL = SPL_;            \
-      best.grid = sm_count; best.threads = 256; best.smem_bytes = dbl * 8;                               \
-      best.partial_len = C::ACC + 4; best.nstat = K_ * C::E;                                             \
-    }                                                                                                    \
+    best.valid = 2; best.D = D_; best.RK = K_; best.RE = KT_; best.SPL = SPL_;                           \
+    best.NR = (dbl * 8 <= 227 * 1024) ? 1 : 0; /* does the single-kernel mode (MODE 2) fit in shared memory? */ \
+    best.grid = sm_count; best.threads = 256; best.smem_bytes = dbl * 8;                                 \
+    best.partial_len = C::ACC + 4; best.nstat = K_ * C::E;                                               \
   }
   PMC_FUSED2_TABLE(X)
 #undef X
   return best;
 }
 
-int fused2_max_blocks(const FusedPlan &p) { return p.grid * 4; }
+int fused2_max_blocks(const FusedPlan &p) { return p.grid * 5; }
 
 int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode, int variant,
                   int *nblocks_out, cudaStream_t s) {

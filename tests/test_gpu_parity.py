@@ -25,6 +25,9 @@ CASES = {
     "d4_K6": (lambda: W.banana(d=4, K=6, seed=6, mean_sigma=2.0, var=6.0, box=30.0), 6000),
     "d6_K12": (lambda: W.banana(d=6, K=12, seed=7, mean_sigma=2.0, var=6.0, box=30.0), 12000),
     "d8_K20": (lambda: W.banana(d=8, K=20, seed=8, mean_sigma=2.0, var=6.0, box=30.0), 20000),
+    "d10_K20": (lambda: W.banana(d=10, K=20, seed=10, mean_sigma=2.0, var=6.0, box=40.0), 30000),
+    "d10_K5": (lambda: W.banana(d=10, K=5, seed=11, mean_sigma=2.0, var=6.0, box=40.0), 8000),
+    "d5_K10": (lambda: W.banana(d=5, K=10, seed=12, mean_sigma=2.0, var=6.0, box=30.0), 10000),
     "d7_K3_generic_only": (lambda: W.banana(d=7, K=3, seed=9, mean_sigma=2.0, var=6.0, box=30.0), 3000),
 }
 
@@ -105,7 +108,7 @@ def test_update_rb_two_pass(gpu, oracle_runs, name):
 
 @pytest.mark.parametrize("ver,spl", [(1, 1), (1, 2), (2, 1), (2, 2)])
 @pytest.mark.parametrize("name", ["c1_banana_d10_K10", "c2_gmm_d5_K20", "shipped_d2_K9", "ragged_d10_K10", "tiny_d10_K10",
-                                  "d3_K4", "d4_K6", "d6_K12", "d8_K20", "d7_K3_generic_only"])
+                                  "d3_K4", "d4_K6", "d6_K12", "d8_K20", "d10_K20", "d10_K5", "d5_K10", "d7_K3_generic_only"])
 def test_fused_iteration_given_samples(gpu, oracle_runs, name, ver, spl):
     """The one-pass fused kernel (weights + statistics) + host finalisation against the oracle's full iteration."""
     wl, X, idx, o = oracle_runs(name)
