@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 #include <dlfcn.h>
 #include "pmc_kernels.h"
@@ -135,6 +137,13 @@ struct pmcgpu_ctx {
   int fused_version = 0;  // 0 = newest kernel that fits, 1 = pmc_fused.cu only, 2 = pmc_fused2.cu only
   int force_generic = 0, spl = 1, max_attempts = 10000, force_precise = 0;
   double guard_ratio = 200.0;
+  // large-d tensor path (pmc_mma.cu)
+  struct MmaMix { DevBuf pack, kmap; int J = 0; bool valid = false; };
+  MmaMix mprop, mtgt;
+  DevBuf Q, Qt, mpart, mstats, mpivot;
+  long q_stride = 0;
+  bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
+  int use_mma = 1, mma_min_d = 17;
   // comm
   int rank = 0, nranks = 1;
   void *nccl_comm = nullptr;
@@ -250,9 +259,39 @@ int pack_small(pmcgpu_ctx *c, const HostMix &m, DevBuf &out, int &ndoubles, std:
   return 0;
 }
 
+// inverse factors of the live components in DMMA fragment order (pmc_mma.cu); the O(K d^3) inversion runs on a few
+// host threads because at d = 128, K = 64 it is 22 MFLOP of extended-precision work per iteration
+int pack_mma(pmcgpu_ctx *c, const HostMix &m, pmcgpu_ctx::MmaMix &o) {
+  o.valid = false;
+  o.J = 0;
+  c->q_resident = false;
+  if (!c->use_mma || c->force_generic || m.K == 0 || m.d < c->mma_min_d || mma_nt(m.d) == 0) return 0;
+  std::vector<int> alive;
+  for (int k = 0; k < m.K; ++k) if (m.wght[k] > 0.0) alive.push_back(k);
+  if (alive.empty()) return 0;
+  const int J = (int)alive.size(), d = m.d;
+  const size_t cs = mma_comp_stride(d), nd = (size_t)J * cs;
+  RC(stage(c, nd + (J + 1) / 2));
+  double *h = c->hstage;
+  parallel_components(J, (double)d * d * d / 3.0, [&](int j) {
+    mma_pack_component(d, m.mean.data() + (size_t)alive[j] * d, m.L.data() + (size_t)alive[j] * d * d, h + (size_t)j * cs);
+  });
+  memcpy(h + nd, alive.data(), J * sizeof(int));
+  CU(o.pack.ensure(nd * sizeof(double)));
+  CU(o.kmap.ensure(J * sizeof(int)));
+  CU(cudaMemcpyAsync(o.pack.p, h, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(o.kmap.p, h + nd, J * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  o.J = J;
+  o.valid = true;
+  return 0;
+}
+
 int install_proposal(pmcgpu_ctx *c) {
   derive_mix(c->prop);
   int rc = upload_mix(c, c->prop, c->dprop);
+  if (rc) return rc;
+  rc = pack_mma(c, c->prop, c->mprop);
   if (rc) return rc;
   return pack_small(c, c->prop, c->dprop_pack, c->prop_pack_doubles, c->prop_pack_host);
 }
@@ -484,8 +523,128 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
 
 constexpr long GEN_CHUNK = 1L << 18;
 
+// can the large-d tensor path evaluate this configuration?  (mode 1 = target values supplied by the host)
+bool mma_usable(const pmcgpu_ctx *c, int mode) {
+  if (!c->use_mma || c->force_generic || !c->mprop.valid || c->nfull != 0) return false;
+  if (mode == 1 || c->tkind == PMCGPU_TGT_HOST) return true;
+  if (c->tkind == PMCGPU_TGT_BANANA) return c->td == c->prop.d;
+  if (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX) return c->mtgt.valid && c->tmix.d == c->prop.d;
+  return false;
+}
+
+// weights through pmc_mma.cu: DMMA whitening of every (sample, component) pair, then the literal tail
+int run_weights_mma(pmcgpu_ctx *c, int mode, const double *post_in, const short *ok_in, double t_temper,
+                    long first_index, WeightOut &o) {
+  const long N = c->N;
+  const int K = c->prop.K, d = c->prop.d;
+  const bool tq = mode == 0 && (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX);
+  const int Kt = tq ? c->tmix.K : 0;
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t have = c->Q.cap + c->Qt.cap;
+  const size_t budget = std::min<size_t>((free_b + have) / 2, (size_t)64 << 30);
+  long chunk = (long)(budget / (sizeof(double) * (size_t)(K + Kt)));
+  chunk = std::max<long>(1024, (chunk / 1024) * 1024);
+  if (chunk > N) chunk = N;
+  const long qs = chunk;
+  CU(c->Q.ensure((size_t)K * qs * sizeof(double)));
+  if (tq) CU(c->Qt.ensure((size_t)Kt * qs * sizeof(double)));
+  const int nb = (int)((chunk + GEN_WEIGHT_THREADS - 1) / GEN_WEIGHT_THREADS);
+  CU(c->blkmax.ensure((size_t)2 * nb * sizeof(double)));
+  int rc = zero_small(c);
+  if (rc) return rc;
+  unsigned long long *sm = c->small.as<unsigned long long>();
+  const TargetDev tv = target_view(c);
+  RC(stage(c, (size_t)2 * nb + SM_LEN));
+  if (c->timing) {
+    if (!c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->ev2)); CU(cudaEventCreate(&c->evd)); }
+    CU(cudaEventRecord(c->ev0, c->stream));
+  }
+  for (long base = 0; base < N; base += chunk) {
+    const long n = (N - base) < chunk ? (N - base) : chunk;
+    const int nbc = (int)((n + GEN_WEIGHT_THREADS - 1) / GEN_WEIGHT_THREADS);
+    const double *Xb = c->X.as<double>() + (size_t)base * d;
+    if (launch_q_mma(Xb, n, d, c->mprop.pack.as<double>(), c->mprop.J, c->mprop.kmap.as<int>(), c->Q.as<double>(), qs, c->sm_count, c->stream))
+      return fail(c, PMCGPU_ERR_CUDA, "whitening kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (tq && launch_q_mma(Xb, n, d, c->mtgt.pack.as<double>(), c->mtgt.J, c->mtgt.kmap.as<int>(), c->Qt.as<double>(), qs, c->sm_count, c->stream))
+      return fail(c, PMCGPU_ERR_CUDA, "whitening kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (c->timing && base == 0) CU(cudaEventRecord(c->ev1, c->stream));
+    launch_weights_q(c->dprop.view, tv, mode, post_in ? post_in + base : nullptr, ok_in ? ok_in + base : nullptr, t_temper,
+                     first_index + base, n, Xb, c->Q.as<double>(), c->Qt.as<double>(), qs, c->W.as<double>() + base,
+                     c->R.as<double>() + base, c->Flg.as<short>() + base, c->blkmax.as<double>(), c->blkmax.as<double>() + nb,
+                     sm + SM_COUNTERS, reinterpret_cast<double *>(sm + SM_FIRST), c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->hstage, c->blkmax.p, (size_t)2 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < nbc; ++b) {
+      if (c->hstage[b] > o.M_all) o.M_all = c->hstage[b];
+      if (c->hstage[nb + b] > o.R_all) o.R_all = c->hstage[nb + b];
+    }
+    if (c->timing && base == 0) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));  // the whitening kernel(s) of the first chunk
+      c->fused_ms += ms;
+      c->fused_launches += 1;
+    }
+  }
+  c->q_stride = qs;
+  c->q_resident = (chunk == N);
+  rc = read_small(c, o.counters, nullptr, o.first);
+  o.has_first = (first_index == 0);
+  return rc;
+}
+
+// one-pass pivoted statistics on the tensor path (Gaussian components; Q still holds ld_k for the whole store and the
+// weights are normalised).  Outputs in the layout pmcgpu_finalize_update expects.
+int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector<double> &pivot, std::vector<double> &W,
+              std::vector<double> &s1, std::vector<double> &S2) {
+  const HostMix &m = c->prop;
+  const int K = m.K, d = m.d, J = c->mprop.J;
+  const long N = c->N;
+  const size_t len = 1 + d + (size_t)d * d;
+  CU(c->tmpo.ensure((size_t)K * 8));
+  CU(c->mpivot.ensure((size_t)d * sizeof(double)));
+  RC(stage(c, (size_t)K + d));
+  unsigned long long *hc = reinterpret_cast<unsigned long long *>(c->hstage);
+  for (int k = 0; k < K; ++k) hc[k] = count[k];
+  memcpy(c->hstage + K, pivot.data(), d * sizeof(double));
+  CU(cudaMemcpyAsync(c->tmpo.p, hc, (size_t)K * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->mpivot.p, c->hstage + K, d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const int nchunk = mma_stats_chunks(N, J, c->sm_count);
+  CU(c->mpart.ensure(mma_stats_partial_doubles(d, J, nchunk) * sizeof(double)));
+  CU(c->mstats.ensure((size_t)K * len * sizeof(double)));
+  CU(cudaMemsetAsync(c->mstats.p, 0, (size_t)K * len * sizeof(double), c->stream));
+  if (c->timing && c->ev1) CU(cudaEventRecord(c->ev1, c->stream));
+  launch_resp_q(c->dprop.view, N, c->W.as<double>(), c->R.as<double>(), c->Flg.as<short>(), c->tmpo.as<unsigned long long>(),
+                c->Q.as<double>(), c->q_stride, c->stream);
+  if (launch_stats_mma(c->X.as<double>(), N, d, c->Q.as<double>(), c->q_stride, J, c->mprop.kmap.as<int>(),
+                       c->mpivot.as<double>(), nchunk, c->mpart.as<double>(), c->mstats.as<double>(), c->stream))
+    return fail(c, PMCGPU_ERR_CUDA, "statistics kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (c->timing && c->ev1) CU(cudaEventRecord(c->ev2, c->stream));
+  c->q_resident = false;  // Q now holds responsibilities
+  RC(stage(c, (size_t)K * len));
+  CU(cudaMemcpyAsync(c->hstage, c->mstats.p, (size_t)K * len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->timing && c->ev1) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats_ms += ms; }
+  std::vector<double> st(c->hstage, c->hstage + (size_t)K * len);
+  int rc = allreduce_host(c, st.data(), (long)st.size(), 0);
+  if (rc) return rc;
+  W.assign(K, 0.0);
+  s1.assign((size_t)K * d, 0.0);
+  S2.assign((size_t)K * d * d, 0.0);
+  for (int k = 0; k < K; ++k) {
+    const double *sk = st.data() + (size_t)k * len;
+    W[k] = sk[0];
+    memcpy(s1.data() + (size_t)k * d, sk + 1, d * sizeof(double));
+    memcpy(S2.data() + (size_t)k * d * d, sk + 1 + d, (size_t)d * d * sizeof(double));
+  }
+  return 0;
+}
+
 int run_weights_generic(pmcgpu_ctx *c, int mode, const double *post_in, const short *ok_in, double t_temper,
                         long first_index, WeightOut &o) {
+  if (mma_usable(c, mode)) return run_weights_mma(c, mode, post_in, ok_in, t_temper, first_index, o);
+  c->q_resident = false;
   const long N = c->N;
   const int Kmax = c->prop.K > c->tmix.K ? c->prop.K : c->tmix.K;
   const long chunk = N < GEN_CHUNK ? N : GEN_CHUNK;
@@ -743,6 +902,12 @@ void pmcgpu_destroy(pmcgpu_ctx *c) {
 const char *pmcgpu_last_error(const pmcgpu_ctx *c) { return c ? c->err.c_str() : "null context"; }
 void *pmcgpu_stream(pmcgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
+static int repack_mma(pmcgpu_ctx *c) {
+  if (c->prop.K) RC(pack_mma(c, c->prop, c->mprop));
+  if (c->tmix.K && (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX)) RC(pack_mma(c, c->tmix, c->mtgt));
+  return 0;
+}
+
 int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   if (!c || !name) return PMCGPU_ERR_USAGE;
   if (!strcmp(name, "force_generic")) c->force_generic = (int)value;
@@ -756,6 +921,8 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "split_draw")) c->split_draw = (int)value;
   else if (!strcmp(name, "draw_variant")) c->draw_variant = (int)value;
   else if (!strcmp(name, "k1_variant")) c->k1_variant = (int)value;
+  else if (!strcmp(name, "mma")) { c->use_mma = (int)value; return repack_mma(c); }
+  else if (!strcmp(name, "mma_min_d")) { c->mma_min_d = (int)value; return repack_mma(c); }
   else return fail(c, PMCGPU_ERR_USAGE, "unknown option %s", name);
   return 0;
 }
@@ -804,6 +971,7 @@ int pmcgpu_set_target_banana(pmcgpu_ctx *c, int d, double b, double sig1) {
   c->tb = b;
   c->tsig1 = sig1;
   c->tmix = HostMix();
+  c->mtgt.valid = false;
   return 0;
 }
 
@@ -819,6 +987,8 @@ int pmcgpu_set_target_mix(pmcgpu_ctx *c, int kind, int K, int d, const double *w
   c->td = d;
   rc = upload_mix(c, c->tmix, c->dtmix);
   if (rc) return rc;
+  rc = pack_mma(c, c->tmix, c->mtgt);
+  if (rc) return rc;
   return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles, c->tgt_pack_host);
 }
 
@@ -827,6 +997,7 @@ int pmcgpu_set_target_host(pmcgpu_ctx *c, int d) {
   c->tkind = PMCGPU_TGT_HOST;
   c->td = d;
   c->tmix = HostMix();
+  c->mtgt.valid = false;
   return 0;
 }
 
@@ -1230,25 +1401,12 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   // ---- update
   if (do_update) {
     // a NaN maximum (the i==0 quirk) poisons the reference's responsibilities: only the literal path reproduces that
-    bool precise = !fused_stats || std::isnan(maxR) || std::isnan(maxW);
-    if (fused_stats && !precise) {
-      // reduce the statistics over ranks: rescale to the global maximum, then sum
-      const int E = 1 + d + d * (d + 1) / 2;
-      std::vector<double> st(o.stats);
-      const double Mg = mx[0];
-      const double sc = (M_local == -INFINITY) ? 0.0 : std::exp(M_local - Mg);
-      if (c->nranks > 1) for (double &v : st) v *= sc;
-      std::vector<double> cntk(K);
-      for (int k = 0; k < K; ++k) cntk[k] = (double)o.count_k[k];
-      rc = allreduce_host(c, st.data(), (long)st.size(), 0);
-      if (rc) return rc;
-      rc = allreduce_host(c, cntk.data(), K, 0);
-      if (rc) return rc;
+    const bool mma_stats = !p.valid && !c->force_precise && !m0.student && c->q_resident && mma_usable(c, 0);
+    bool precise = !(fused_stats || mma_stats) || std::isnan(maxR) || std::isnan(maxW);
+    if (!precise) {
+      std::vector<double> W, s1, S2, pivot(d);
       std::vector<size_t> count(K);
-      for (int k = 0; k < K; ++k) count[k] = (size_t)cntk[k];
-      // unpack canonical statistics -> W (= G for Gaussian components), s1, S2 about the pivot
-      std::vector<double> W(K), s1((size_t)K * d), S2((size_t)K * d * d), pivot(d);
-      {
+      {  // pivot = mixture mean (weights of live components)
         double sw = 0.0;
         for (int k = 0; k < K; ++k) if (m0.wght[k] > 0) sw += m0.wght[k];
         for (int j = 0; j < d; ++j) {
@@ -1257,13 +1415,37 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
           pivot[j] = s / sw;
         }
       }
-      for (int k = 0; k < K; ++k) {
-        const double *sk = st.data() + (size_t)k * E;
-        W[k] = sk[0];
-        for (int a = 0; a < d; ++a) s1[(size_t)k * d + a] = sk[1 + a];
-        int e = 1 + d;
-        for (int a = 0; a < d; ++a)
-          for (int b = a; b < d; ++b) { S2[(size_t)k * d * d + (size_t)a * d + b] = sk[e]; S2[(size_t)k * d * d + (size_t)b * d + a] = sk[e]; ++e; }
+      if (fused_stats) {
+        // reduce the statistics over ranks: rescale to the global maximum, then sum
+        const int E = 1 + d + d * (d + 1) / 2;
+        std::vector<double> st(o.stats);
+        const double Mg = mx[0];
+        const double sc = (M_local == -INFINITY) ? 0.0 : std::exp(M_local - Mg);
+        if (c->nranks > 1) for (double &v : st) v *= sc;
+        std::vector<double> cntk(K);
+        for (int k = 0; k < K; ++k) cntk[k] = (double)o.count_k[k];
+        rc = allreduce_host(c, st.data(), (long)st.size(), 0);
+        if (rc) return rc;
+        rc = allreduce_host(c, cntk.data(), K, 0);
+        if (rc) return rc;
+        for (int k = 0; k < K; ++k) count[k] = (size_t)cntk[k];
+        // unpack canonical statistics -> W (= G for Gaussian components), s1, S2 about the pivot
+        W.resize(K);
+        s1.resize((size_t)K * d);
+        S2.resize((size_t)K * d * d);
+        for (int k = 0; k < K; ++k) {
+          const double *sk = st.data() + (size_t)k * E;
+          W[k] = sk[0];
+          for (int a = 0; a < d; ++a) s1[(size_t)k * d + a] = sk[1 + a];
+          int e = 1 + d;
+          for (int a = 0; a < d; ++a)
+            for (int b = a; b < d; ++b) { S2[(size_t)k * d * d + (size_t)a * d + b] = sk[e]; S2[(size_t)k * d * d + (size_t)b * d + a] = sk[e]; ++e; }
+        }
+      } else {
+        rc = count_indices_impl(c, count, true);
+        if (rc) return rc;
+        rc = stats_mma(c, count, pivot, W, s1, S2);
+        if (rc) return rc;
       }
       HostMix trial = c->prop;
       int retry_trial = retry_local;

@@ -99,15 +99,18 @@ int host_cleanup_after_update(int K, int d, const size_t *count, double minwgt, 
     for (int k = 0; k < K; ++k) wght[k] *= inv;
   }
   int need_retry = 0;
+  std::vector<int> failed(K, 0);
+  parallel_components(K, (double)d * d * d / 3.0, [&](int k) {
+    if (!(wght[k] > minwgt)) return;
+    failed[k] = host_cholesky(d, L + k * dd, &detL[k]) != 0;
+  });
   for (int k = 0; k < K; ++k) {
-    if (!(wght[k] > minwgt)) continue;
-    if (host_cholesky(d, L + k * dd, &detL[k]) != 0) {
-      if (*retry == 0) {
-        std::memcpy(L + k * dd, snapshot + k * dd, sizeof(double) * dd);
-        need_retry = 1;
-      } else {
-        wght[k] = 0;
-      }
+    if (!failed[k]) continue;
+    if (*retry == 0) {
+      std::memcpy(L + k * dd, snapshot + k * dd, sizeof(double) * dd);
+      need_retry = 1;
+    } else {
+      wght[k] = 0;
     }
   }
   *retry = need_retry;
@@ -145,7 +148,7 @@ int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const
                            int *alive) {
   const size_t dd = (size_t)d * d;
   std::vector<double> snapshot(L, L + K * dd);
-  for (int k = 0; k < K; ++k) {
+  pmcb200::parallel_components(K, (double)d * d, [&](int k) {
     double *cov = L + k * dd;
     double *mu = mean + (size_t)k * d;
     if (count[k] > (size_t)kMinCount) {
@@ -172,7 +175,7 @@ int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const
       std::memset(mu, 0, sizeof(double) * d);
       std::memset(cov, 0, sizeof(double) * dd);
     }
-  }
+  });
   const int rc = pmcb200::host_cleanup_after_update(K, d, count, 1.0 / (double)N_total, retry, snapshot.data(), wght,
                                                     mean, L, detL);
   if (alive)

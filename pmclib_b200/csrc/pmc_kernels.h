@@ -129,4 +129,24 @@ int launch_fused2_stats(const FusedPlan &p, const double *X, const double *lw, c
                         const double *Mdev, const double *pivot, long N, double *partials, cudaStream_t s);
 int launch_fused2_combine(const FusedPlan &p, const double *partials, int nblocks, double *stats_out, cudaStream_t s);
 
+// ---- large-d tensor-path kernels (pmc_mma.cu): DMMA whitening and DMMA sufficient statistics, 16 < d <= 128 --------
+int mma_nt(int d);                    // number of 8-row tiles the dimension is padded to (0 = not supported)
+size_t mma_comp_stride(int d);        // doubles of one packed component
+void mma_pack_component(int d, const double *mean, const double *L, double *out);  // host: inverse factor in fragment order
+// q[kmap[j]][i] = |L_j^-1 (x_i - mu_j)|^2 for the J packed components, i < n; Q row stride qs
+int launch_q_mma(const double *X, long n, int d, const double *pack, int J, const int *kmap, double *Q, long qs,
+                 int sm_count, cudaStream_t s);
+void launch_weights_q(const MixDev &m, const TargetDev &tg, int mode, const double *post_in, const short *ok_in,
+                      double t_temper, long first_index, long N, const double *X, double *Q, double *Qt,
+                      long qs, double *lw, double *log_rho, short *flg, double *blk_maxw, double *blk_maxr,
+                      unsigned long long *counters, double *first_vals, cudaStream_t s);
+void launch_lse_q(const MixDev &m, long n, double *Q, long qs, double *out, cudaStream_t s);
+void launch_resp_q(const MixDev &m, long N, const double *w, const double *log_rho, const short *flg,
+                   const unsigned long long *count, double *Q, long qs, cudaStream_t s);
+int mma_stats_chunks(long n, int J, int sm_count);
+size_t mma_stats_partial_doubles(int d, int J, int nchunk);
+// out[k] = { W_k, s1_k[d], S2_k[d*d] } for the J packed components (rows of other components untouched)
+int launch_stats_mma(const double *X, long n, int d, const double *G, long qs, int J, const int *kmap,
+                     const double *pivot, int nchunk, double *part, double *out, cudaStream_t s);
+
 }  // namespace pmcb200

@@ -1,0 +1,545 @@
+// pmc_mma.cu — the large-d path (16 < d <= 128): whitening and Rao-Blackwell statistics as dense FP64 contractions on
+// the tensor path (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4).
+//
+// Why a separate path: with one sample per lane (pmc_fused2.cu) a d x d triangular factor no longer fits the constant
+// bank / registers, and the generic kernels (one thread per sample, factor streamed from L2) run at ~4 % of the FP64
+// peak.  For large d the whitening  y = L_k^-1 (x - mu_k)  of MANY samples against ONE component is a true matrix
+// product, so it is tiled the GEMM way:
+//
+//   k_q_mma<NT>      q[k][i] = | Linv_k (x_i - mu_k) |^2 .  M = 8 samples per DMMA, N = 8 output rows, K = 4 input
+//                    columns; only the tiles on or below the diagonal of Linv_k are issued (NT(NT+1) of 2 NT^2).  The
+//                    sample fragments stay in registers for all components; one component's factor (already laid out
+//                    in B-fragment order by the host) is staged in shared memory by cp.async while the previous one is
+//                    being used, so every LDS is a conflict-free 256-byte row.
+//   k_weights_q      literal mix_mvdens_log_pdf / importance-weight tail (mvdens.c:784-825, pmc.c:528-590) from q.
+//   k_resp_q         responsibilities g[k][i] = w_i alpha_k phi_k(x_i) / q(x_i)   (pmc.c:1384-1390, scale-free form)
+//   k_stats_mma<NT>  S_k = sum_i g[k][i] (x_i - c)(x_i - c)^T, s_k = sum_i g[k][i] (x_i - c), W_k = sum_i g[k][i]
+//                    about one pivot c: per component a (d x n)(n x d) product, lower tiles only, warps own row-tile
+//                    pairs (r, NT-1-r) so every warp issues NT+1 DMMAs per 4 samples.
+//
+// The inverse factors are formed on the host in extended precision (mma_pack_mixture); a product with Linv differs from
+// the reference's forward substitution (mvdens.c:341) by O(eps cond(L)) — inside the 1e-12 parity tolerance for the
+// well-conditioned factors a PMC proposal has (tests/test_gpu_mma.py measures it against the oracle).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "pmc_kernels.h"
+
+namespace pmcb200 {
+
+namespace {
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cpa8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cpa16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cpa_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__host__ __device__ constexpr int q_tiles(int NT) {  // tiles (nt, ks) with 4 ks <= 8 nt + 7
+  int t = 0;
+  for (int ks = 0; ks < 2 * NT; ++ks) t += NT - ks / 2;
+  return t;
+}
+__host__ __device__ constexpr int q_comp_stride(int NT) { return 8 * NT + 32 * q_tiles(NT); }
+__host__ __device__ constexpr int q_mt(int NT) { return NT <= 4 ? 4 : (NT <= 8 ? 2 : 1); }
+
+// ---- whitening ----------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+k_q_mma(const double *__restrict__ X, long n, int d, const double *__restrict__ pack, int J,
+        const int *__restrict__ kmap, double *__restrict__ Q, long qs) {
+  constexpr int KS = 2 * NT, MT = q_mt(NT), CS = q_comp_stride(NT), TS = 64 * MT;
+  extern __shared__ double sm[];  // [2][CS]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+  const long ntile = (n + TS - 1) / TS;
+  if ((long)blockIdx.x >= ntile) return;
+  auto issue = [&](int buf, int j) {
+    const double *src = pack + (size_t)j * CS;
+    double *dst = sm + (size_t)buf * CS;
+    for (int c = threadIdx.x; c < CS / 2; c += 256) cpa16(dst + 2 * c, src + 2 * c);
+    cpa_commit();
+  };
+  issue(0, 0);
+  unsigned s = 0;
+  for (long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const long base = tile * TS + warp * (8 * MT);
+    double xa[MT][KS];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const long row = base + mt * 8 + g;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int col = 4 * ks + t4;
+        xa[mt][ks] = (row < n && col < d) ? X[(size_t)row * d + col] : 0.0;
+      }
+    }
+    const bool last_tile = tile + gridDim.x >= ntile;
+    for (int j = 0; j < J; ++j, ++s) {
+      cpa_wait0();
+      __syncthreads();
+      if (!(last_tile && j == J - 1)) issue((s + 1) & 1, (j + 1 == J) ? 0 : j + 1);
+      const double *cb = sm + (size_t)(s & 1) * CS;
+      double C[MT][NT][2];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { C[mt][nt][0] = 0.0; C[mt][nt][1] = 0.0; }
+      const double *tp = cb + 8 * NT + lane;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const double mu = cb[4 * ks + t4];
+        double a[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) a[mt] = xa[mt][ks] - mu;
+#pragma unroll
+        for (int nt = ks / 2; nt < NT; ++nt) {
+          const double b = *tp;
+          tp += 32;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) dmma(C[mt][nt][0], C[mt][nt][1], a[mt], b);
+        }
+      }
+      const int k = kmap[j];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        double q = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { q = fma(C[mt][nt][0], C[mt][nt][0], q); q = fma(C[mt][nt][1], C[mt][nt][1], q); }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        const long row = base + mt * 8 + g;
+        if (t4 == 0 && row < n) Q[(size_t)k * qs + row] = q;
+      }
+    }
+  }
+}
+
+// ---- literal weight tail from q ---------------------------------------------------------------------------------------
+// mix_mvdens_log_pdf (mvdens.c:784-825) with ld_k = tail(q_k).  The column of q values is overwritten by the
+// component log-densities ld_k (k_resp_q reads them back; the Student-t tail costs a log, so it is evaluated once).
+__device__ __forceinline__ double mix_lse_q(const MixDev &m, double *__restrict__ Q, long qs, long i) {
+  int iloc = 0;
+  while (iloc < m.K && m.alpha[iloc] <= 0) iloc++;
+  if (iloc >= m.K) return nan("");
+  double mx = logpdf_from_q(Q[(size_t)iloc * qs + i], m.d, m.logdet[iloc], m.df[iloc], m.gam[iloc], m.norm[iloc]);
+  Q[(size_t)iloc * qs + i] = mx;
+  for (int k = iloc + 1; k < m.K; ++k)
+    if (m.alpha[k] > 0.0) {
+      const double v = logpdf_from_q(Q[(size_t)k * qs + i], m.d, m.logdet[k], m.df[k], m.gam[k], m.norm[k]);
+      Q[(size_t)k * qs + i] = v;
+      if (mx < v) mx = v;
+    }
+  double lpos = 0.0;
+  for (int k = 0; k < m.K; ++k)
+    if (m.alpha[k] > 0.0) lpos = lpos + exp(Q[(size_t)k * qs + i] - mx + kDynMax) * m.alpha[k];
+  return mx + log(lpos) - kDynMax;
+}
+
+// same outputs and flag/maximum semantics as k_weights_generic (pmc.c:528-590)
+__global__ void k_weights_q(MixDev m, TargetDev tg, int mode, const double *__restrict__ post_in,
+                            const short *__restrict__ ok_in, double t_temper, long first_index, long N,
+                            const double *__restrict__ X, double *__restrict__ Q, double *__restrict__ Qt,
+                            long qs, double *__restrict__ lw, double *__restrict__ log_rho, short *__restrict__ flg,
+                            double *blk_maxw, double *blk_maxr, unsigned long long *counters, double *first_vals) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  double my_w = -INFINITY, my_r = -INFINITY;
+  bool okflag = false;
+  if (i < N) {
+    flg[i] = 0;
+    lw[i] = 0;
+    const double rloc = mix_lse_q(m, Q, qs, i);
+    my_r = rloc;
+    log_rho[i] = rloc;
+    bool reached_w = false;
+    double w = 0.0;
+    if (!(isnan(rloc) || isinf(rloc))) {
+      bool tok = true;
+      double post;
+      if (mode == 0) {
+        if (tg.kind == PMCGPU_TGT_BANANA) post = bent_gauss(X + (size_t)i * m.d, tg.d, tg.b, tg.sig1);
+        else if (tg.kind == PMCGPU_TGT_MVDENS)
+          post = logpdf_from_q(Qt[i], tg.mix.d, tg.mix.logdet[0], tg.mix.df[0], tg.mix.gam[0], tg.mix.norm[0]);
+        else post = mix_lse_q(tg.mix, Qt, qs, i);
+      } else {
+        post = post_in[i];
+        tok = ok_in ? (ok_in[i] != 0) : true;
+      }
+      if (tok) {
+        w = t_temper * post - rloc;
+        reached_w = true;
+        lw[i] = w;
+        flg[i] = 1;
+        okflag = true;
+        my_w = w;
+        if (w == INFINITY) atomicAdd(&counters[CNT_POSINF], 1ull);
+      }
+    }
+    if (first_index + i == 0) {
+      first_vals[0] = rloc;
+      first_vals[1] = 1.0;
+      first_vals[2] = w;
+      first_vals[3] = reached_w ? 1.0 : 0.0;
+    }
+  }
+  if (my_w != my_w) my_w = -INFINITY;
+  if (my_r != my_r) my_r = -INFINITY;
+  my_w = warp_max_nan_ignoring(my_w);
+  my_r = warp_max_nan_ignoring(my_r);
+  __shared__ double sw[32], sr[32];
+  __shared__ unsigned int scnt;
+  if (threadIdx.x == 0) scnt = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sw[wid] = my_w; sr[wid] = my_r; }
+  const unsigned int nok = __popc(__ballot_sync(0xffffffffu, okflag));
+  if (lane == 0 && nok) atomicAdd(&scnt, nok);
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double a = lane < nw ? sw[lane] : -INFINITY, b = lane < nw ? sr[lane] : -INFINITY;
+    a = warp_max_nan_ignoring(a);
+    b = warp_max_nan_ignoring(b);
+    if (lane == 0) {
+      blk_maxw[blockIdx.x] = a;
+      blk_maxr[blockIdx.x] = b;
+      if (scnt) atomicAdd(&counters[CNT_NOK], (unsigned long long)scnt);
+    }
+  }
+}
+
+// mixture log-density only (pmcgpu_proposal_log_pdf on the large-d path)
+__global__ void k_lse_q(MixDev m, long n, double *__restrict__ Q, long qs, double *__restrict__ out) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mix_lse_q(m, Q, qs, i);
+}
+
+// responsibilities in place of ld: g[k][i] = w_i alpha_k exp(ld_k(x_i) - log_rho_i) for ok samples and components with
+// count > MINCOUNT (pmc.c:1382-1390; the reference's common factor exp(maxR - 500) is dropped, it cancels)
+__global__ void k_resp_q(MixDev m, long N, const double *__restrict__ w, const double *__restrict__ log_rho,
+                         const short *__restrict__ flg, const unsigned long long *__restrict__ count,
+                         double *__restrict__ Q, long qs) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const bool ok = flg[i] != 0;
+  const double wi = w[i], lr = log_rho[i];
+  for (int k = 0; k < m.K; ++k) {
+    if (!(m.alpha[k] > 0.0)) continue;
+    double g = 0.0;
+    if (ok && count[k] > kMinCount) {
+      g = wi * (m.alpha[k] * exp(Q[(size_t)k * qs + i] - lr));  // the column holds ld_k since k_weights_q
+      if (!(g == g) || isinf(g)) g = 0.0;
+    }
+    Q[(size_t)k * qs + i] = g;
+  }
+}
+
+// ---- statistics ------------------------------------------------------------------------------------------------------
+constexpr int ST_SS = 64;  // samples per shared-memory stage
+__host__ __device__ constexpr int st_tw(int NT) { return NT / 2; }
+__host__ __device__ constexpr int st_sw(int NT) { return 8 / st_tw(NT) < 1 ? 1 : 8 / st_tw(NT); }
+__host__ __device__ constexpr int st_warps(int NT) { return st_tw(NT) * st_sw(NT); }
+__host__ __device__ constexpr int st_dpad(int NT) { return 8 * NT + 4; }
+// doubles one block writes: per warp (NT+1) tiles x 64, two s1 fragments x 32, one W fragment x 32
+__host__ __device__ constexpr int st_warp_len(int NT) { return (NT + 1) * 64 + 96; }
+__host__ __device__ constexpr int st_unit_len(int NT) { return st_warps(NT) * st_warp_len(NT); }
+
+template <int NT>
+__global__ void __launch_bounds__(32 * st_warps(NT), 1)
+k_stats_mma(const double *__restrict__ X, long n, int d, const double *__restrict__ G, long qs,
+            const int *__restrict__ kmap, const double *__restrict__ pivot, int nchunk, long chunk_len,
+            double *__restrict__ part) {
+  constexpr int TW = st_tw(NT), SW = st_sw(NT), NWARP = TW * SW, NTHR = 32 * NWARP, DPAD = st_dpad(NT), SS = ST_SS;
+  extern __shared__ double sm[];
+  double *xs = sm;                       // [2][SS][DPAD]
+  double *gs = sm + 2 * SS * DPAD;       // [2][SS]
+  double *pv = gs + 2 * SS;              // [8 NT]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+  const int tw = warp % TW, sw = warp / TW;
+  const int r0 = tw, r1 = NT - 1 - tw;
+  const int j = blockIdx.x / nchunk, ch = blockIdx.x % nchunk;
+  const int k = kmap[j];
+  const long lo = ch * chunk_len, hi = (lo + chunk_len < n) ? lo + chunk_len : n;
+  const double *Gk = G + (size_t)k * qs;
+  for (int c = threadIdx.x; c < 2 * SS * DPAD; c += NTHR) xs[c] = 0.0;
+  for (int c = threadIdx.x; c < 8 * NT; c += NTHR) pv[c] = (c < d) ? pivot[c] : 0.0;
+  __syncthreads();
+  const bool even = (d & 1) == 0;
+  auto issue = [&](int buf, long s0) {
+    double *dx = xs + (size_t)buf * SS * DPAD;
+    const int rows = (int)((hi - s0) < SS ? (hi - s0) : SS);
+    if (even) {
+      const int per = d / 2;
+      for (int c = threadIdx.x; c < rows * per; c += NTHR) {
+        const int r = c / per, q2 = c - r * per;
+        cpa16(dx + r * DPAD + 2 * q2, X + (size_t)(s0 + r) * d + 2 * q2);
+      }
+    } else {
+      for (int c = threadIdx.x; c < rows * d; c += NTHR) {
+        const int r = c / d, q1 = c - r * d;
+        cpa8(dx + r * DPAD + q1, X + (size_t)(s0 + r) * d + q1);
+      }
+    }
+    for (int r = threadIdx.x; r < rows; r += NTHR) cpa8(gs + buf * SS + r, Gk + s0 + r);
+    cpa_commit();
+  };
+  double C[NT + 1][2];
+#pragma unroll
+  for (int t = 0; t <= NT; ++t) { C[t][0] = 0.0; C[t][1] = 0.0; }
+  double s1a = 0.0, s1b = 0.0, wacc = 0.0;
+  if (lo < hi) issue(0, lo);
+  unsigned st = 0;
+  for (long s0 = lo; s0 < hi; s0 += SS, ++st) {
+    const int buf = st & 1;
+    cpa_wait0();
+    __syncthreads();  // stage st landed; everybody is done with stage st-1 (the other buffer)
+    if (s0 + SS < hi) issue(buf ^ 1, s0 + SS);
+    double *dx = xs + (size_t)buf * SS * DPAD;
+    double *dg = gs + buf * SS;
+    const int rows = (int)((hi - s0) < SS ? (hi - s0) : SS);
+    if (threadIdx.x < SS && threadIdx.x >= rows) dg[threadIdx.x] = 0.0;
+    // centre on the pivot; rows without weight (flagged out, tail) become exact zeros so that 0 * NaN never appears
+    for (int c = threadIdx.x; c < SS * 8 * NT; c += NTHR) {
+      const int r = c / (8 * NT), a = c - r * (8 * NT);
+      const double gv = (r < rows) ? dg[r] : 0.0;
+      const double v = dx[r * DPAD + a];
+      dx[r * DPAD + a] = (gv != 0.0 && a < d) ? v - pv[a] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ks = sw; ks < SS / 4; ks += SW) {
+      const int srow = 4 * ks + t4;
+      const double gv = dg[srow];
+      const double *xr = dx + srow * DPAD + g;
+      const double a0 = gv * xr[8 * r0], a1 = gv * xr[8 * r1];
+      s1a += a0;
+      s1b += a1;
+      wacc += gv;
+#pragma unroll
+      for (int t = 0; t <= NT; ++t) {
+        const bool first = t <= r0;
+        const int bt = first ? t : t - r0 - 1;
+        dmma(C[t][0], C[t][1], first ? a0 : a1, xr[8 * bt]);
+      }
+    }
+  }
+  double *o = part + (size_t)blockIdx.x * st_unit_len(NT) + (size_t)warp * st_warp_len(NT);
+#pragma unroll
+  for (int t = 0; t <= NT; ++t) { o[t * 64 + 2 * lane] = C[t][0]; o[t * 64 + 2 * lane + 1] = C[t][1]; }
+  o[(NT + 1) * 64 + lane] = s1a;
+  o[(NT + 1) * 64 + 32 + lane] = s1b;
+  o[(NT + 1) * 64 + 64 + lane] = wacc;
+}
+
+// partials -> canonical statistics  out[k] = { W, s1[d], S2[d*d] (full symmetric) }, fixed summation order
+template <int NT>
+__global__ void k_stats_mma_combine(const double *__restrict__ part, int J, const int *__restrict__ kmap, int nchunk,
+                                    int d, double *__restrict__ out) {
+  constexpr int TW = st_tw(NT), SW = st_sw(NT), WL = st_warp_len(NT), UL = st_unit_len(NT);
+  const int j = blockIdx.y;
+  const int k = kmap[j];
+  const long len = 1 + d + (long)d * d;
+  double *ok = out + (size_t)k * len;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < 1 + d + (long)d * (d + 1) / 2; e += (long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    if (e == 0) {  // W: warps with tw == 0, lanes g == 0 (t4 = 0..3 carry distinct samples)
+      for (int c = 0; c < nchunk; ++c)
+        for (int sw = 0; sw < SW; ++sw) {
+          const double *p = part + (size_t)(j * nchunk + c) * UL + (size_t)(sw * TW) * WL + (NT + 1) * 64 + 64;
+          acc += (p[0] + p[1]) + (p[2] + p[3]);
+        }
+      ok[0] = acc;
+    } else if (e <= d) {
+      const int a = (int)e - 1, rt = a >> 3, g = a & 7;
+      const bool first = rt < TW;
+      const int tw = first ? rt : NT - 1 - rt;
+      for (int c = 0; c < nchunk; ++c)
+        for (int sw = 0; sw < SW; ++sw) {
+          const double *p = part + (size_t)(j * nchunk + c) * UL + (size_t)(sw * TW + tw) * WL + (NT + 1) * 64 + (first ? 0 : 32) + 4 * g;
+          acc += (p[0] + p[1]) + (p[2] + p[3]);
+        }
+      ok[1 + a] = acc;
+    } else {
+      // lower-triangle element (a >= b), enumerated row by row
+      long t = e - 1 - d;
+      int a = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while ((long)(a + 1) * (a + 2) / 2 <= t) ++a;
+      while ((long)a * (a + 1) / 2 > t) --a;
+      const int b = (int)(t - (long)a * (a + 1) / 2);
+      const int rt = a >> 3, bt = b >> 3, g = a & 7, col = b & 7;
+      const bool first = rt < TW;
+      const int tw = first ? rt : NT - 1 - rt;
+      const int slot = first ? bt : tw + 1 + bt;
+      const int off = slot * 64 + 2 * (g * 4 + (col >> 1)) + (col & 1);
+      for (int c = 0; c < nchunk; ++c)
+        for (int sw = 0; sw < SW; ++sw)
+          acc += part[(size_t)(j * nchunk + c) * UL + (size_t)(sw * TW + tw) * WL + off];
+      ok[1 + d + (size_t)a * d + b] = acc;
+      ok[1 + d + (size_t)b * d + a] = acc;
+    }
+  }
+}
+
+template <int NT>
+int launch_q(const double *X, long n, int d, const double *pack, int J, const int *kmap, double *Q, long qs, int sm_count,
+             cudaStream_t s) {
+  constexpr int TS = 64 * q_mt(NT);
+  const size_t smem = (size_t)2 * q_comp_stride(NT) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_q_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    attr_done = true;
+  }
+  const long ntile = (n + TS - 1) / TS;
+  const int grid = (int)(ntile < sm_count ? ntile : sm_count);
+  k_q_mma<NT><<<grid, 256, smem, s>>>(X, n, d, pack, J, kmap, Q, qs);
+  count_launch();
+  return cudaGetLastError() != cudaSuccess;
+}
+
+template <int NT>
+int launch_stats(const double *X, long n, int d, const double *G, long qs, int J, const int *kmap, const double *pivot,
+                 int nchunk, double *part, double *out, cudaStream_t s) {
+  const size_t smem = ((size_t)2 * ST_SS * st_dpad(NT) + 2 * ST_SS + 8 * NT) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_stats_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    attr_done = true;
+  }
+  long chunk_len = (n + nchunk - 1) / nchunk;
+  chunk_len = ((chunk_len + ST_SS - 1) / ST_SS) * ST_SS;
+  k_stats_mma<NT><<<J * nchunk, 32 * st_warps(NT), smem, s>>>(X, n, d, G, qs, kmap, pivot, nchunk, chunk_len, part);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return 1;
+  k_stats_mma_combine<NT><<<dim3(8, J), 256, 0, s>>>(part, J, kmap, nchunk, d, out);
+  count_launch();
+  return cudaGetLastError() != cudaSuccess;
+}
+
+}  // namespace
+
+// ---- host interface ----------------------------------------------------------------------------------------------------
+int mma_nt(int d) { return d <= 16 ? 2 : (d <= 32 ? 4 : (d <= 64 ? 8 : (d <= 128 ? 16 : 0))); }
+size_t mma_comp_stride(int d) {
+  switch (mma_nt(d)) {
+    case 2: return q_comp_stride(2);
+    case 4: return q_comp_stride(4);
+    case 8: return q_comp_stride(8);
+    case 16: return q_comp_stride(16);
+  }
+  return 0;
+}
+
+// One component in kernel order: mu[8 NT] (zero padded), then for ks ascending, nt = ks/2 .. NT-1, the 32 B-fragment
+// values  Linv[8 nt + lane/4][4 ks + lane%4].  Linv is formed column by column in extended precision.
+void mma_pack_component(int d, const double *mean, const double *L, double *out) {
+  const int NT = mma_nt(d), DP = 8 * NT;
+  // Linv L = I, row r of Linv from the diagonal leftwards: inv[r][c] = -(sum_{m=c+1..r} inv[r][m] L[m][c]) / L[c][c];
+  // Lt holds L transposed so that both operands of the dot product are contiguous
+  std::vector<double> Lt((size_t)d * d, 0.0);
+  for (int r = 0; r < d; ++r)
+    for (int c = 0; c <= r; ++c) Lt[(size_t)c * d + r] = L[(size_t)r * d + c];
+  std::vector<long double> inv((size_t)d * d, 0.0L);
+  for (int r = 0; r < d; ++r) {
+    long double *ir = inv.data() + (size_t)r * d;
+    ir[r] = 1.0L / (long double)L[(size_t)r * d + r];
+    for (int c = r - 1; c >= 0; --c) {
+      const double *lc = Lt.data() + (size_t)c * d;
+      long double acc0 = 0.0L, acc1 = 0.0L;
+      int m = c + 1;
+      for (; m + 1 <= r; m += 2) { acc0 += ir[m] * (long double)lc[m]; acc1 += ir[m + 1] * (long double)lc[m + 1]; }
+      if (m <= r) acc0 += ir[m] * (long double)lc[m];
+      ir[c] = -(acc0 + acc1) / (long double)lc[c];
+    }
+  }
+  for (int a = 0; a < DP; ++a) out[a] = a < d ? mean[a] : 0.0;
+  double *tp = out + DP;
+  for (int ks = 0; ks < 2 * NT; ++ks)
+    for (int nt = ks / 2; nt < NT; ++nt) {
+      for (int lane = 0; lane < 32; ++lane) {
+        const int r = 8 * nt + lane / 4, c = 4 * ks + lane % 4;
+        tp[lane] = (r < d && c < d && c <= r) ? (double)inv[(size_t)r * d + c] : 0.0;
+      }
+      tp += 32;
+    }
+}
+
+int launch_q_mma(const double *X, long n, int d, const double *pack, int J, const int *kmap, double *Q, long qs,
+                 int sm_count, cudaStream_t s) {
+  if (n <= 0 || J <= 0) return 0;
+  switch (mma_nt(d)) {
+    case 2: return launch_q<2>(X, n, d, pack, J, kmap, Q, qs, sm_count, s);
+    case 4: return launch_q<4>(X, n, d, pack, J, kmap, Q, qs, sm_count, s);
+    case 8: return launch_q<8>(X, n, d, pack, J, kmap, Q, qs, sm_count, s);
+    case 16: return launch_q<16>(X, n, d, pack, J, kmap, Q, qs, sm_count, s);
+  }
+  return 1;
+}
+
+void launch_weights_q(const MixDev &m, const TargetDev &tg, int mode, const double *post_in, const short *ok_in,
+                      double t_temper, long first_index, long N, const double *X, double *Q, double *Qt,
+                      long qs, double *lw, double *log_rho, short *flg, double *blk_maxw, double *blk_maxr,
+                      unsigned long long *counters, double *first_vals, cudaStream_t s) {
+  if (N <= 0) return;
+  const int nb = (int)((N + GEN_WEIGHT_THREADS - 1) / GEN_WEIGHT_THREADS);
+  k_weights_q<<<nb, GEN_WEIGHT_THREADS, 0, s>>>(m, tg, mode, post_in, ok_in, t_temper, first_index, N, X, Q, Qt, qs, lw,
+                                                log_rho, flg, blk_maxw, blk_maxr, counters, first_vals);
+  count_launch();
+}
+
+void launch_lse_q(const MixDev &m, long n, double *Q, long qs, double *out, cudaStream_t s) {
+  if (n <= 0) return;
+  k_lse_q<<<(int)((n + 127) / 128), 128, 0, s>>>(m, n, Q, qs, out);
+  count_launch();
+}
+
+void launch_resp_q(const MixDev &m, long N, const double *w, const double *log_rho, const short *flg,
+                   const unsigned long long *count, double *Q, long qs, cudaStream_t s) {
+  if (N <= 0) return;
+  k_resp_q<<<(int)((N + 127) / 128), 128, 0, s>>>(m, N, w, log_rho, flg, count, Q, qs);
+  count_launch();
+}
+
+size_t mma_stats_partial_doubles(int d, int J, int nchunk) {
+  size_t ul = 0;
+  switch (mma_nt(d)) {
+    case 2: ul = st_unit_len(2); break;
+    case 4: ul = st_unit_len(4); break;
+    case 8: ul = st_unit_len(8); break;
+    case 16: ul = st_unit_len(16); break;
+  }
+  return ul * (size_t)J * nchunk;
+}
+
+// number of sample chunks per component: fill whole waves of the grid, at least four stages per block
+int mma_stats_chunks(long n, int J, int sm_count) {
+  const long max_c = std::max<long>(1, n / (4 * ST_SS));
+  int best = 1;
+  double best_eff = 0.0;
+  for (int c = 1; c <= 64 && c <= max_c; ++c) {
+    const double waves = (double)J * c / sm_count;
+    const double eff = waves / std::ceil(waves);
+    if (eff > best_eff + 1e-3) { best_eff = eff; best = c; }
+  }
+  return best;
+}
+
+int launch_stats_mma(const double *X, long n, int d, const double *G, long qs, int J, const int *kmap,
+                     const double *pivot, int nchunk, double *part, double *out, cudaStream_t s) {
+  if (n <= 0 || J <= 0) return 0;
+  switch (mma_nt(d)) {
+    case 2: return launch_stats<2>(X, n, d, G, qs, J, kmap, pivot, nchunk, part, out, s);
+    case 4: return launch_stats<4>(X, n, d, G, qs, J, kmap, pivot, nchunk, part, out, s);
+    case 8: return launch_stats<8>(X, n, d, G, qs, J, kmap, pivot, nchunk, part, out, s);
+    case 16: return launch_stats<16>(X, n, d, G, qs, J, kmap, pivot, nchunk, part, out, s);
+  }
+  return 1;
+}
+
+}  // namespace pmcb200

@@ -1,0 +1,166 @@
+"""GPU parity of the large-d tensor path (pmc_mma.cu: DMMA whitening + DMMA statistics) against the CPU oracle.
+
+The whitening multiplies by host-inverted Cholesky factors instead of the reference's forward substitution
+(mvdens.c:341); the tolerance stays the north-star 1e-12 relative, flags / counts bit-exact.
+"""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from pmclib_b200 import workloads as W
+from util import RTOL, assert_close, compare_mixture
+
+pytestmark = pytest.mark.gpu
+
+
+def _gmix_target(d, seed):
+    """Gaussian-mixture target with two correlated components (exercises the target whitening on the tensor path)."""
+    rng = np.random.default_rng(seed)
+    cov = np.empty((2, d, d))
+    for k in range(2):
+        u = rng.normal(0.0, 1.0, (d, 3)) / np.sqrt(d)
+        cov[k] = np.eye(d) + 0.3 * (u @ u.T) * d / 3
+    mean = np.zeros((2, d))
+    mean[0, 0], mean[1, 0] = 0.6, -0.6
+    return W._target(W.TGT_MIX, d, K=2, wght=np.array([0.4, 0.6]), mean=mean, cov=cov, df=np.full(2, -1, np.int32))
+
+
+def _case(d, K, seed, target="mvdens", df=-1):
+    wl = W.gauss128(d=d, K=K, seed=seed)
+    wl["name"] = f"mma_d{d}_K{K}_{target}"
+    if target == "banana":
+        wl["target"] = W._target(W.TGT_BANANA, d, b=0.05, sig1=1.5)
+    elif target == "mix":
+        wl["target"] = _gmix_target(d, seed + 1)
+    if df != -1:
+        wl["df"] = np.full(K, df, np.int32)
+        wl["importance_only"] = True
+    return wl
+
+
+CASES = {
+    # name: (workload factory, N)    padded tile counts NT = 4, 8, 16; odd d; d == tile edge; dead component
+    "d17_K5_banana": (lambda: _case(17, 5, 21, "banana"), 6000),
+    "d20_K8_mix": (lambda: _case(20, 8, 22, "mix"), 8000),
+    "d32_K6": (lambda: _case(32, 6, 23), 8000),
+    "d33_K4_banana": (lambda: _case(33, 4, 24, "banana"), 6000),
+    "d64_K5_mix": (lambda: _case(64, 5, 25, "mix"), 9000),
+    "d100_K3": (lambda: _case(100, 3, 26), 7001),
+    "d128_K64_c5": (lambda: W.gauss128(), 12000),
+    "d30_K50_student_c4": (lambda: W.student30(), 4000),
+    "d24_K6_student5": (lambda: _case(24, 6, 27, "mix", df=5), 3000),
+}
+
+
+@pytest.fixture(scope="module")
+def oracle_runs():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            f, N = CASES[name]
+            wl = f()
+            X, idx = O.orc_simulate(N, wl, seed=13)
+            o = O.orc_iteration(X, idx, wl, do_update=0 if wl["importance_only"] else 1)
+            cache[name] = (wl, X, idx, o)
+        return cache[name]
+    return get
+
+
+def _setup(gpu, wl, X, idx, mma=1):
+    gpu.set_option("force_generic", 0)
+    gpu.set_option("fused_version", 0)
+    gpu.set_option("force_precise", 0)
+    gpu.set_option("mma", mma)
+    gpu.set_workload(wl)
+    gpu.resize(len(X), wl["d"])
+    gpu.upload(X=X, indices=idx, flg=np.ones(len(X), np.int16))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_mma_weights(gpu, oracle_runs, name):
+    wl, X, idx, o = oracle_runs(name)
+    _setup(gpu, wl, X, idx)
+    gpu.set_option("timing", 1)
+    nok, maxW, maxR = gpu.weights(1.0)
+    ms, launches, _ = gpu.get_timing()
+    gpu.set_option("timing", 0)
+    assert launches >= 1, "the tensor-path whitening kernel did not run"
+    got = gpu.download(X=False, indices=False)
+    assert nok == o["nok"]
+    assert np.array_equal(got["flg"], np.ones(len(X), np.int16))
+    big = max(np.max(np.abs(o["log_rho"])), 1.0)
+    assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho")
+    assert_close(got["weights"], o["logw"], RTOL, scale=big, what="log-weights")
+    assert_close(maxW, o["maxW"], RTOL, scale=big, what="maxW")
+    assert_close(maxR, o["maxR"], RTOL, what="maxR")
+    logSum, cnt = gpu.normalize(maxW)
+    assert cnt == o["nok"]
+    assert_close(logSum, o["logSum"], RTOL, scale=big, what="logSum")
+    got = gpu.download(X=False, indices=False, log_rho=False)
+    assert np.array_equal(got["flg"], o["flg"])
+    assert_close(got["weights"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
+    perp, ess, nfl = gpu.perplexity_ess()
+    assert_close(perp, o["perp"], 1e-11, what="perplexity")
+    assert_close(ess, o["ess"], 1e-11, what="ESS")
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if not CASES[n][0]()["importance_only"]])
+def test_mma_iteration_given_samples(gpu, oracle_runs, name):
+    """Weights + normalisation + one-pass DMMA statistics + host finalisation against the oracle's full iteration."""
+    wl, X, idx, o = oracle_runs(name)
+    _setup(gpu, wl, X, idx)
+    if o["rc"] != 0:
+        with pytest.raises(Exception):
+            gpu.step_given(0, len(X), 1.0, 1, 0)
+        return
+    r = gpu.step_given(0, len(X), 1.0, 1, 0)
+    big = max(np.max(np.abs(o["log_rho"])), 1.0)
+    assert r.nok == o["nok"]
+    assert_close(r.logSum, o["logSum"], RTOL, scale=big, what="logSum")
+    assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
+    assert_close(r.ess, o["ess"], 1e-11, what="ESS")
+    assert r.retry == o["retry"]
+    errs = compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
+    print(name, f"precise={r.used_precise_path} one-pass DMMA update errors", errs)
+    if o["retry"] == 0:
+        assert r.used_precise_path == 0, "the tensor-path statistics were expected to pass the pivot guard"
+
+
+def test_mma_matches_generic_with_dead_component_and_flags(gpu):
+    """A dead component, a sample outside the support (flagged) and a NaN row: tensor path == literal kernels."""
+    wl = _case(40, 6, 31, "mix")
+    wl["wght"] = np.array([0.3, 0.0, 0.2, 0.25, 0.25, 0.0])
+    N = 5000
+    X, idx = O.orc_simulate(N, wl, seed=3)
+    X = X.copy()
+    X[7, :] = 1e200    # |L^-1 (x - mu)|^2 overflows -> log-density -inf -> flagged out by the weight pass
+    X[11, 3] = np.nan  # NaN row
+    res = {}
+    for mma in (0, 1):
+        _setup(gpu, wl, X, idx, mma)
+        r = gpu.step_given(0, N, 1.0, 1, 0)
+        res[mma] = (r, gpu.download(X=False, indices=False))
+    (r0, g0), (r1, g1) = res[0], res[1]
+    assert np.array_equal(g0["flg"], g1["flg"])
+    assert g1["flg"][7] == 0 and g1["flg"][11] == 0
+    ok = g0["flg"] == 1
+    assert_close(g1["log_rho"][ok], g0["log_rho"][ok], RTOL, what="log_rho")
+    assert_close(g1["weights"][ok], g0["weights"][ok], 2e-12, scale=np.max(g0["weights"][ok]) * 1e-3, what="weights")
+    assert r0.n_alive == r1.n_alive
+    assert np.array_equal(r0.alive, r1.alive)
+    compare_mixture(r1.wght, r1.mean, r1.L, r0.wght, r0.mean, r0.L, what="mma vs generic")
+
+
+def test_mma_full_step_draw(gpu):
+    """Draw + weights + update on the tensor path: self-consistency (finite, normalised, sane perplexity) at c5 shape."""
+    wl = W.gauss128()
+    gpu.set_option("mma", 1)
+    gpu.set_option("force_generic", 0)
+    gpu.set_workload(wl)
+    gpu.resize(30000, wl["d"])
+    r = gpu.pmc_step(5, 0)
+    assert 0.0 < r.perplexity <= 1.0 and r.ess > 1.0
+    assert abs(np.sum(r.wght) - 1.0) < 1e-12
+    got = gpu.download(X=False, indices=False, log_rho=False)
+    assert abs(np.sum(got["weights"]) - 1.0) < 1e-10
