@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -138,9 +139,9 @@ struct pmcgpu_ctx {
   int force_generic = 0, spl = 1, max_attempts = 10000, force_precise = 0;
   double guard_ratio = 200.0;
   // large-d tensor path (pmc_mma.cu)
-  struct MmaMix { DevBuf pack, kmap; int J = 0; bool valid = false; };
+  struct MmaMix { DevBuf pack, lpack, kmap, dfj; int J = 0; bool valid = false; std::vector<int> alive; };
   MmaMix mprop, mtgt;
-  DevBuf Q, Qt, mpart, mstats, mpivot;
+  DevBuf Q, Qt, mpart, mstats, mpivot, dperm, dtiles, dcnt, xc;
   long q_stride = 0;
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 17;
@@ -271,17 +272,25 @@ int pack_mma(pmcgpu_ctx *c, const HostMix &m, pmcgpu_ctx::MmaMix &o) {
   if (alive.empty()) return 0;
   const int J = (int)alive.size(), d = m.d;
   const size_t cs = mma_comp_stride(d), nd = (size_t)J * cs;
-  RC(stage(c, nd + (J + 1) / 2));
+  RC(stage(c, 2 * nd + J + 2));
   double *h = c->hstage;
   parallel_components(J, (double)d * d * d / 3.0, [&](int j) {
-    mma_pack_component(d, m.mean.data() + (size_t)alive[j] * d, m.L.data() + (size_t)alive[j] * d * d, h + (size_t)j * cs);
+    const double *mu = m.mean.data() + (size_t)alive[j] * d, *Lk = m.L.data() + (size_t)alive[j] * d * d;
+    mma_pack_component(d, mu, Lk, 1, h + (size_t)j * cs);        // whitening: inverse factor
+    mma_pack_component(d, mu, Lk, 0, h + nd + (size_t)j * cs);   // draw: the factor itself
   });
-  memcpy(h + nd, alive.data(), J * sizeof(int));
+  int *hi = reinterpret_cast<int *>(h + 2 * nd);
+  for (int j = 0; j < J; ++j) { hi[j] = alive[j]; hi[J + j] = m.df[alive[j]]; }
   CU(o.pack.ensure(nd * sizeof(double)));
+  CU(o.lpack.ensure(nd * sizeof(double)));
   CU(o.kmap.ensure(J * sizeof(int)));
+  CU(o.dfj.ensure(J * sizeof(int)));
   CU(cudaMemcpyAsync(o.pack.p, h, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(o.kmap.p, h + nd, J * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(o.lpack.p, h + nd, nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(o.kmap.p, hi, J * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(o.dfj.p, hi + J, J * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  o.alive = alive;
   o.J = J;
   o.valid = true;
   return 0;
@@ -613,12 +622,14 @@ int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector
   const int nchunk = mma_stats_chunks(N, J, c->sm_count);
   CU(c->mpart.ensure(mma_stats_partial_doubles(d, J, nchunk) * sizeof(double)));
   CU(c->mstats.ensure((size_t)K * len * sizeof(double)));
+  if (c->xc.ensure((size_t)N * d * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return 1; }  // no room for the centred copy: literal path
   CU(cudaMemsetAsync(c->mstats.p, 0, (size_t)K * len * sizeof(double), c->stream));
   if (c->timing && c->ev1) CU(cudaEventRecord(c->ev1, c->stream));
   launch_resp_q(c->dprop.view, N, c->W.as<double>(), c->R.as<double>(), c->Flg.as<short>(), c->tmpo.as<unsigned long long>(),
                 c->Q.as<double>(), c->q_stride, c->stream);
-  if (launch_stats_mma(c->X.as<double>(), N, d, c->Q.as<double>(), c->q_stride, J, c->mprop.kmap.as<int>(),
-                       c->mpivot.as<double>(), nchunk, c->mpart.as<double>(), c->mstats.as<double>(), c->stream))
+  if (launch_stats_mma(c->X.as<double>(), c->Flg.as<short>(), N, d, c->Q.as<double>(), c->q_stride, J, c->mprop.kmap.as<int>(),
+                       c->mpivot.as<double>(), nchunk, c->xc.as<double>(), c->mpart.as<double>(), c->mstats.as<double>(),
+                       c->sm_count, c->stream))
     return fail(c, PMCGPU_ERR_CUDA, "statistics kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (c->timing && c->ev1) CU(cudaEventRecord(c->ev2, c->stream));
   c->q_resident = false;  // Q now holds responsibilities
@@ -1094,6 +1105,68 @@ int pmcgpu_device_arrays(pmcgpu_ctx *c, void **out) {
   return 0;
 }
 
+// Grouped draw on the tensor path (no box): returns 1 if the configuration is not covered (caller uses the generic kernel)
+static int draw_mma(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index) {
+  const pmcgpu_ctx::MmaMix &mm = c->mprop;
+  if (!c->use_mma || c->force_generic || !mm.valid || c->nfaces > 0 || c->N >= (1L << 31)) return 1;
+  const int K = c->prop.K, d = c->prop.d, J = mm.J;
+  const long N = c->N;
+  CU(c->dcnt.ensure((size_t)2 * K * sizeof(unsigned int)));
+  CU(c->dperm.ensure((size_t)N * sizeof(unsigned int)));
+  CU(cudaMemsetAsync(c->dcnt.p, 0, (size_t)K * sizeof(unsigned int), c->stream));
+  if (c->timing) {
+    if (!c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->ev2)); CU(cudaEventCreate(&c->evd)); }
+    CU(cudaEventRecord(c->ev0, c->stream));
+  }
+  launch_draw_pick(c->dprop.view.cw, K, seed, iter, first_index, N, c->Idx.as<unsigned long long>(), c->dcnt.as<unsigned int>(), c->sm_count * 4, c->stream);
+  CU(cudaGetLastError());
+  RC(stage(c, K + 2));
+  unsigned int *hc = reinterpret_cast<unsigned int *>(c->hstage);
+  CU(cudaMemcpyAsync(hc, c->dcnt.p, (size_t)K * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::vector<unsigned int> cnt(hc, hc + K), off(K, 0);
+  std::vector<int> jof(K, -1);
+  for (int j = 0; j < J; ++j) jof[mm.alive[j]] = j;
+  unsigned int acc = 0;
+  for (int k = 0; k < K; ++k) {
+    off[k] = acc;
+    acc += cnt[k];
+    if (cnt[k] && jof[k] < 0) return 1;  // a zero-weight component was picked (z == 0 exactly): literal kernel handles it
+  }
+  const int TS = mma_draw_tile_samples(d);
+  std::vector<int> tiles;
+  for (int k = 0; k < K; ++k)
+    for (unsigned int s0 = 0; s0 < cnt[k]; s0 += TS) {
+      tiles.push_back(jof[k]);
+      tiles.push_back((int)(off[k] + s0));
+      tiles.push_back((int)std::min<unsigned int>(TS, cnt[k] - s0));
+      tiles.push_back(0);
+    }
+  const int ntiles = (int)(tiles.size() / 4);
+  CU(c->dtiles.ensure(tiles.size() * sizeof(int) + 16));
+  RC(stage(c, (tiles.size() + K) / 2 + 2));
+  int *ht = reinterpret_cast<int *>(c->hstage);
+  memcpy(ht, tiles.data(), tiles.size() * sizeof(int));
+  memcpy(ht + tiles.size(), off.data(), K * sizeof(unsigned int));
+  CU(cudaMemcpyAsync(c->dtiles.p, ht, tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  unsigned int *cursor = c->dcnt.as<unsigned int>() + K;
+  CU(cudaMemcpyAsync(cursor, ht + tiles.size(), (size_t)K * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
+  launch_draw_perm(N, c->Idx.as<unsigned long long>(), cursor, c->dperm.as<unsigned int>(), c->sm_count * 4, c->stream);
+  CU(cudaGetLastError());
+  if (launch_draw_mma(mm.lpack.as<double>(), c->dtiles.p, ntiles, c->dperm.as<unsigned int>(), mm.dfj.as<int>(), d, seed, iter,
+                      first_index, c->X.as<double>(), c->Flg.as<short>(), c->small.as<unsigned long long>() + SM_COUNTERS,
+                      c->sm_count, c->stream))
+    return fail(c, PMCGPU_ERR_CUDA, "draw kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (c->timing) {
+    CU(cudaEventRecord(c->evd, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->evd));
+    c->draw_ms += ms;
+  }
+  return 0;
+}
+
 int pmcgpu_draw(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, long *n_reject) {
   int rc = check_ready(c, false);
   if (rc) return rc;
@@ -1102,6 +1175,16 @@ int pmcgpu_draw(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, l
   if (rc) return rc;
   rc = zero_small(c);
   if (rc) return rc;
+  rc = draw_mma(c, seed, iter, first_index);
+  if (rc == 0) {
+    unsigned long long cnt[CNT_NUM];
+    rc = read_small(c, cnt, nullptr, nullptr);
+    if (rc) return rc;
+    if (n_reject) *n_reject = 0;
+    if (cnt[CNT_DRAWFAIL]) return fail(c, kErrTooManySteps, "Too many points (%llu) outside of box", cnt[CNT_DRAWFAIL]);
+    return 0;
+  }
+  if (rc != 1) return rc;
   BoxDev bx{c->nfaces, c->box_d, c->dfaces.as<double>()};
   if (c->nfaces > 0 && c->box_d != c->d) return fail(c, PMCGPU_ERR_USAGE, "box dimension %d != %d", c->box_d, c->d);
   launch_draw_generic(c->dprop.view, bx, seed, iter, first_index, c->N, c->max_attempts, c->X.as<double>(),
@@ -1333,6 +1416,15 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   int rc = check_ready(c, true);
   if (rc) return rc;
   cudaSetDevice(c->device);
+  // PMCB200_TRACE=1: wall-clock of the phases of one iteration on stderr (host finalisation included)
+  static const bool trace = getenv("PMCB200_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pmcb200] %-22s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   if (c->tkind == PMCGPU_TGT_HOST) return fail(c, PMCGPU_ERR_USAGE, "host target: drive the phases separately (draw, download X, weights_host_post, ...)");
   if (N_total <= 0) N_total = c->N;
   int retry_local = retry ? *retry : 0;
@@ -1358,6 +1450,7 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
     if (rc) return rc;
     o.counters[CNT_REJECT] = keep_rej;
   }
+  tick("draw+weights");
   // ---- global maxima (pmc_mpi.c:502-508 keeps the max over ranks) with the i==0 quirk carried as a flag
   double mx[6];
   mx[0] = o.counters[CNT_POSINF] ? INFINITY : o.M_all;
@@ -1398,14 +1491,15 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   r.ess = 1 / Q;
   r.perplexity = std::exp(-H) / (double)(N_total - nexit);
   r.ln_evidence = r.logSum - std::log((double)(N_total - nexit));
+  tick("normalise+perplexity");
   // ---- update
   if (do_update) {
     // a NaN maximum (the i==0 quirk) poisons the reference's responsibilities: only the literal path reproduces that
     const bool mma_stats = !p.valid && !c->force_precise && !m0.student && c->q_resident && mma_usable(c, 0);
     bool precise = !(fused_stats || mma_stats) || std::isnan(maxR) || std::isnan(maxW);
+    std::vector<double> W, s1, S2, pivot(d);
+    std::vector<size_t> count(K);
     if (!precise) {
-      std::vector<double> W, s1, S2, pivot(d);
-      std::vector<size_t> count(K);
       {  // pivot = mixture mean (weights of live components)
         double sw = 0.0;
         for (int k = 0; k < K; ++k) if (m0.wght[k] > 0) sw += m0.wght[k];
@@ -1445,8 +1539,12 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
         rc = count_indices_impl(c, count, true);
         if (rc) return rc;
         rc = stats_mma(c, count, pivot, W, s1, S2);
-        if (rc) return rc;
+        if (rc == 1) precise = true;
+        else if (rc) return rc;
       }
+      tick("statistics");
+    }
+    if (!precise) {
       HostMix trial = c->prop;
       int retry_trial = retry_local;
       std::vector<int> alive(K);
@@ -1465,6 +1563,7 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
           if (!(ratio <= worst)) worst = ratio;
         }
       }
+      tick("finalise+guard");
       if (rc != 0 || retry_trial != 0 || !(worst <= c->guard_ratio)) {
         precise = true;  // anything unusual (failed factorisation, ill-conditioned pivot) goes through the literal path
       } else {
@@ -1483,12 +1582,14 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
     sanitize_dead(c->prop);
     rc = install_proposal(c);
     if (rc) return rc;
+    tick("install proposal");
   }
   r.retry = retry_local;
   r.n_alive = c->prop.n_alive();
   if (retry) *retry = retry_local;
   if (res) *res = r;
   export_proposal(c, o_wght, o_mean, o_L, o_detL, o_alive);
+  tick("export");
   return 0;
 }
 

@@ -284,4 +284,39 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   return v;
 }
 
+// per-sample Philox stream of the draw: counter = (global sample index, attempt << 12 | call, iteration)
+struct DrawStream {
+  Philox ph;
+  uint32_t i_lo, i_hi, iter, attempt, call;
+  __device__ __forceinline__ uint4 next() {
+    const uint4 r = ph(i_lo, i_hi, (attempt << 12) | call, iter);
+    ++call;
+    return r;
+  }
+};
+
+static __device__ double chisq_mt(DrawStream &st, double nu) {  // 2*Gamma(nu/2,1), Marsaglia-Tsang (as gsl_ran_chisq)
+  double a = nu * 0.5, boost = 1.0;
+  if (a < 1.0) {
+    const uint4 r = st.next();
+    boost = pow(u01_oc(r.x, r.y), 1.0 / a);
+    a += 1.0;
+  }
+  const double dd = a - 1.0 / 3.0, c = (1.0 / 3.0) / sqrt(dd);
+  for (int guard = 0; guard < 1000; ++guard) {
+    double x, v, g1;
+    do {
+      box_muller(st.next(), x, g1);
+      v = 1.0 + c * x;
+    } while (v <= 0);
+    v = v * v * v;
+    const uint4 r = st.next();
+    const double u = u01_oc(r.x, r.y);
+    if (u < 1 - 0.0331 * x * x * x * x) return 2.0 * dd * v * boost;
+    if (log(u) < 0.5 * x * x + dd * (1 - v + log(v))) return 2.0 * dd * v * boost;
+  }
+  return 2.0 * dd * boost;
+}
+
+
 }  // namespace pmcb200

@@ -65,39 +65,6 @@ __device__ double target_log_pdf_generic(const TargetDev &t, const double *xfree
 }
 
 // ---- draw (pmc.c:266-298, mvdens.c:730-782, 279-317) ---------------------------------------------------------
-struct DrawStream {
-  Philox ph;
-  uint32_t i_lo, i_hi, iter, attempt, call;
-  __device__ __forceinline__ uint4 next() {
-    const uint4 r = ph(i_lo, i_hi, (attempt << 12) | call, iter);
-    ++call;
-    return r;
-  }
-};
-
-__device__ double chisq_mt(DrawStream &st, double nu) {  // 2*Gamma(nu/2,1), Marsaglia-Tsang (as gsl_ran_chisq)
-  double a = nu * 0.5, boost = 1.0;
-  if (a < 1.0) {
-    const uint4 r = st.next();
-    boost = pow(u01_oc(r.x, r.y), 1.0 / a);
-    a += 1.0;
-  }
-  const double dd = a - 1.0 / 3.0, c = (1.0 / 3.0) / sqrt(dd);
-  for (int guard = 0; guard < 1000; ++guard) {
-    double x, v, g1;
-    do {
-      box_muller(st.next(), x, g1);
-      v = 1.0 + c * x;
-    } while (v <= 0);
-    v = v * v * v;
-    const uint4 r = st.next();
-    const double u = u01_oc(r.x, r.y);
-    if (u < 1 - 0.0331 * x * x * x * x) return 2.0 * dd * v * boost;
-    if (log(u) < 0.5 * x * x + dd * (1 - v + log(v))) return 2.0 * dd * v * boost;
-  }
-  return 2.0 * dd * boost;
-}
-
 __global__ void k_draw_generic(MixDev m, BoxDev bx, uint64_t seed, uint32_t iter, long first_index, long N,
                                int max_attempts, double *__restrict__ X, unsigned long long *__restrict__ indices,
                                short *__restrict__ flg, unsigned long long *counters) {

@@ -132,7 +132,8 @@ int launch_fused2_combine(const FusedPlan &p, const double *partials, int nblock
 // ---- large-d tensor-path kernels (pmc_mma.cu): DMMA whitening and DMMA sufficient statistics, 16 < d <= 128 --------
 int mma_nt(int d);                    // number of 8-row tiles the dimension is padded to (0 = not supported)
 size_t mma_comp_stride(int d);        // doubles of one packed component
-void mma_pack_component(int d, const double *mean, const double *L, double *out);  // host: inverse factor in fragment order
+// host: mean + (invert ? inverse factor : factor) of one component in B-fragment order
+void mma_pack_component(int d, const double *mean, const double *L, int invert, double *out);
 // q[kmap[j]][i] = |L_j^-1 (x_i - mu_j)|^2 for the J packed components, i < n; Q row stride qs
 int launch_q_mma(const double *X, long n, int d, const double *pack, int J, const int *kmap, double *Q, long qs,
                  int sm_count, cudaStream_t s);
@@ -143,10 +144,21 @@ void launch_weights_q(const MixDev &m, const TargetDev &tg, int mode, const doub
 void launch_lse_q(const MixDev &m, long n, double *Q, long qs, double *out, cudaStream_t s);
 void launch_resp_q(const MixDev &m, long N, const double *w, const double *log_rho, const short *flg,
                    const unsigned long long *count, double *Q, long qs, cudaStream_t s);
+// grouped draw: component pick + histogram, permutation, then x = mu + L g tile by tile (tiles: int4 {packed comp, first
+// position in perm, samples, 0})
+int mma_draw_tile_samples(int d);
+void launch_draw_pick(const double *cw, int K, uint64_t seed, uint32_t iter, long first_index, long N,
+                      unsigned long long *indices, unsigned int *cnt, int nblocks, cudaStream_t s);
+void launch_draw_perm(long N, const unsigned long long *indices, unsigned int *cursor, unsigned int *perm, int nblocks,
+                      cudaStream_t s);
+int launch_draw_mma(const double *pack, const void *tiles, int ntiles, const unsigned int *perm, const int *dfj, int d,
+                    uint64_t seed, uint32_t iter, long first_index, double *X, short *flg, unsigned long long *counters,
+                    int sm_count, cudaStream_t s);
 int mma_stats_chunks(long n, int J, int sm_count);
 size_t mma_stats_partial_doubles(int d, int J, int nchunk);
-// out[k] = { W_k, s1_k[d], S2_k[d*d] } for the J packed components (rows of other components untouched)
-int launch_stats_mma(const double *X, long n, int d, const double *G, long qs, int J, const int *kmap,
-                     const double *pivot, int nchunk, double *part, double *out, cudaStream_t s);
+// out[k] = { W_k, s1_k[d], S2_k[d*d] } for the J packed components (rows of other components untouched).  Xc is a
+// scratch of n*d doubles that receives the centred sample (zero rows where flg == 0).
+int launch_stats_mma(const double *X, const short *flg, long n, int d, const double *G, long qs, int J, const int *kmap,
+                     const double *pivot, int nchunk, double *Xc, double *part, double *out, int sm_count, cudaStream_t s);
 
 }  // namespace pmcb200

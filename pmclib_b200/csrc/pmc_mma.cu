@@ -242,33 +242,80 @@ __global__ void k_resp_q(MixDev m, long N, const double *__restrict__ w, const d
 
 // ---- statistics ------------------------------------------------------------------------------------------------------
 constexpr int ST_SS = 64;  // samples per shared-memory stage
+constexpr int ST_CK = 2;   // components per block: the centred tile and its B fragments are shared by both
 __host__ __device__ constexpr int st_tw(int NT) { return NT / 2; }
 __host__ __device__ constexpr int st_sw(int NT) { return 8 / st_tw(NT) < 1 ? 1 : 8 / st_tw(NT); }
 __host__ __device__ constexpr int st_warps(int NT) { return st_tw(NT) * st_sw(NT); }
 __host__ __device__ constexpr int st_dpad(int NT) { return 8 * NT + 4; }
-// doubles one block writes: per warp (NT+1) tiles x 64, two s1 fragments x 32, one W fragment x 32
+// doubles one (warp, component) writes: (NT+1) tiles x 64, two s1 fragments x 32, one W fragment x 32
 __host__ __device__ constexpr int st_warp_len(int NT) { return (NT + 1) * 64 + 96; }
-__host__ __device__ constexpr int st_unit_len(int NT) { return st_warps(NT) * st_warp_len(NT); }
+__host__ __device__ constexpr int st_unit_len(int NT) { return st_warps(NT) * ST_CK * st_warp_len(NT); }
+
+// The DMMA loop of one warp that owns row tiles R0 = TWI and R1 = NT-1-TWI (compile-time, so every accumulator and
+// fragment index is static): per 4 samples R1+1 B-fragment loads feed CK (NT+1) DMMAs.
+template <int NT, int TWI>
+__device__ __forceinline__ void stats_warp(const double *__restrict__ dx, const double *__restrict__ dg, int sw, int g,
+                                           int t4, double (&C)[ST_CK][NT + 1][2], double (&s1)[ST_CK][2],
+                                           double (&wacc)[ST_CK]) {
+  constexpr int SW = st_sw(NT), DPAD = st_dpad(NT), SS = ST_SS, R0 = TWI, R1 = NT - 1 - TWI;
+#pragma unroll 2
+  for (int ks = sw; ks < SS / 4; ks += SW) {
+    const int srow = 4 * ks + t4;
+    const double *xr = dx + srow * DPAD + g;
+    double bf[R1 + 1];
+#pragma unroll
+    for (int bt = 0; bt <= R1; ++bt) bf[bt] = xr[8 * bt];
+    double a0[ST_CK], a1[ST_CK];
+#pragma unroll
+    for (int c = 0; c < ST_CK; ++c) {
+      const double gv = dg[c * SS + srow];
+      a0[c] = gv * bf[R0];
+      a1[c] = gv * bf[R1];
+      s1[c][0] += a0[c];
+      s1[c][1] += a1[c];
+      wacc[c] += gv;
+    }
+#pragma unroll
+    for (int bt = 0; bt <= R1; ++bt) {
+#pragma unroll
+      for (int c = 0; c < ST_CK; ++c) {
+        dmma(C[c][R0 + 1 + bt][0], C[c][R0 + 1 + bt][1], a1[c], bf[bt]);
+        if (bt <= R0) dmma(C[c][bt][0], C[c][bt][1], a0[c], bf[bt]);
+      }
+    }
+  }
+}
+
+// Xc = X - pivot for samples that carry weight, exact zeros otherwise (so that 0 * NaN never reaches a DMMA)
+__global__ void k_centre(const double *__restrict__ X, const short *__restrict__ flg, const double *__restrict__ pivot,
+                         long n, int d, double *__restrict__ Xc) {
+  const long tot = n * d;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < tot; e += (long)gridDim.x * blockDim.x) {
+    const long i = e / d;
+    const int a = (int)(e - i * d);
+    Xc[e] = flg[i] != 0 ? X[e] - pivot[a] : 0.0;
+  }
+}
 
 template <int NT>
 __global__ void __launch_bounds__(32 * st_warps(NT), 1)
-k_stats_mma(const double *__restrict__ X, long n, int d, const double *__restrict__ G, long qs,
-            const int *__restrict__ kmap, const double *__restrict__ pivot, int nchunk, long chunk_len,
+k_stats_mma(const double *__restrict__ X /* centred, rows without weight zeroed (k_centre) */, long n, int d,
+            const double *__restrict__ G, long qs, int J, const int *__restrict__ kmap, int nchunk, long chunk_len,
             double *__restrict__ part) {
-  constexpr int TW = st_tw(NT), SW = st_sw(NT), NWARP = TW * SW, NTHR = 32 * NWARP, DPAD = st_dpad(NT), SS = ST_SS;
+  constexpr int TW = st_tw(NT), SW = st_sw(NT), NWARP = TW * SW, NTHR = 32 * NWARP, DPAD = st_dpad(NT), SS = ST_SS,
+                CK = ST_CK;
   extern __shared__ double sm[];
   double *xs = sm;                       // [2][SS][DPAD]
-  double *gs = sm + 2 * SS * DPAD;       // [2][SS]
-  double *pv = gs + 2 * SS;              // [8 NT]
+  double *gs = sm + 2 * SS * DPAD;       // [2][CK][SS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
   const int tw = warp % TW, sw = warp / TW;
-  const int r0 = tw, r1 = NT - 1 - tw;
-  const int j = blockIdx.x / nchunk, ch = blockIdx.x % nchunk;
-  const int k = kmap[j];
+  const int jg = blockIdx.x / nchunk, ch = blockIdx.x % nchunk;
+  const double *Gk[CK];
+#pragma unroll
+  for (int c = 0; c < CK; ++c) Gk[c] = (jg * CK + c < J) ? G + (size_t)kmap[jg * CK + c] * qs : nullptr;
   const long lo = ch * chunk_len, hi = (lo + chunk_len < n) ? lo + chunk_len : n;
-  const double *Gk = G + (size_t)k * qs;
   for (int c = threadIdx.x; c < 2 * SS * DPAD; c += NTHR) xs[c] = 0.0;
-  for (int c = threadIdx.x; c < 8 * NT; c += NTHR) pv[c] = (c < d) ? pivot[c] : 0.0;
+  for (int c = threadIdx.x; c < 2 * CK * SS; c += NTHR) gs[c] = 0.0;
   __syncthreads();
   const bool even = (d & 1) == 0;
   auto issue = [&](int buf, long s0) {
@@ -286,13 +333,21 @@ k_stats_mma(const double *__restrict__ X, long n, int d, const double *__restric
         cpa8(dx + r * DPAD + q1, X + (size_t)(s0 + r) * d + q1);
       }
     }
-    for (int r = threadIdx.x; r < rows; r += NTHR) cpa8(gs + buf * SS + r, Gk + s0 + r);
+    for (int c = threadIdx.x; c < CK * SS; c += NTHR) {
+      const int cc = c / SS, r = c - cc * SS;
+      if (r < rows && Gk[cc]) cpa8(gs + (buf * CK + cc) * SS + r, Gk[cc] + s0 + r);
+      else gs[(buf * CK + cc) * SS + r] = 0.0;  // tail rows carry no weight (their tile rows keep older, finite data)
+    }
     cpa_commit();
   };
-  double C[NT + 1][2];
+  double C[CK][NT + 1][2];
+  double s1[CK][2], wacc[CK];
 #pragma unroll
-  for (int t = 0; t <= NT; ++t) { C[t][0] = 0.0; C[t][1] = 0.0; }
-  double s1a = 0.0, s1b = 0.0, wacc = 0.0;
+  for (int c = 0; c < CK; ++c) {
+#pragma unroll
+    for (int t = 0; t <= NT; ++t) { C[c][t][0] = 0.0; C[c][t][1] = 0.0; }
+    s1[c][0] = s1[c][1] = wacc[c] = 0.0;
+  }
   if (lo < hi) issue(0, lo);
   unsigned st = 0;
   for (long s0 = lo; s0 < hi; s0 += SS, ++st) {
@@ -300,58 +355,47 @@ k_stats_mma(const double *__restrict__ X, long n, int d, const double *__restric
     cpa_wait0();
     __syncthreads();  // stage st landed; everybody is done with stage st-1 (the other buffer)
     if (s0 + SS < hi) issue(buf ^ 1, s0 + SS);
-    double *dx = xs + (size_t)buf * SS * DPAD;
-    double *dg = gs + buf * SS;
-    const int rows = (int)((hi - s0) < SS ? (hi - s0) : SS);
-    if (threadIdx.x < SS && threadIdx.x >= rows) dg[threadIdx.x] = 0.0;
-    // centre on the pivot; rows without weight (flagged out, tail) become exact zeros so that 0 * NaN never appears
-    for (int c = threadIdx.x; c < SS * 8 * NT; c += NTHR) {
-      const int r = c / (8 * NT), a = c - r * (8 * NT);
-      const double gv = (r < rows) ? dg[r] : 0.0;
-      const double v = dx[r * DPAD + a];
-      dx[r * DPAD + a] = (gv != 0.0 && a < d) ? v - pv[a] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll 2
-    for (int ks = sw; ks < SS / 4; ks += SW) {
-      const int srow = 4 * ks + t4;
-      const double gv = dg[srow];
-      const double *xr = dx + srow * DPAD + g;
-      const double a0 = gv * xr[8 * r0], a1 = gv * xr[8 * r1];
-      s1a += a0;
-      s1b += a1;
-      wacc += gv;
-#pragma unroll
-      for (int t = 0; t <= NT; ++t) {
-        const bool first = t <= r0;
-        const int bt = first ? t : t - r0 - 1;
-        dmma(C[t][0], C[t][1], first ? a0 : a1, xr[8 * bt]);
-      }
+    const double *dx = xs + (size_t)buf * SS * DPAD;
+    const double *dg = gs + buf * CK * SS;
+    switch (tw) {
+      case 0: stats_warp<NT, 0>(dx, dg, sw, g, t4, C, s1, wacc); break;
+      case 1: if constexpr (TW > 1) stats_warp<NT, 1>(dx, dg, sw, g, t4, C, s1, wacc); break;
+      case 2: if constexpr (TW > 2) stats_warp<NT, 2>(dx, dg, sw, g, t4, C, s1, wacc); break;
+      case 3: if constexpr (TW > 3) stats_warp<NT, 3>(dx, dg, sw, g, t4, C, s1, wacc); break;
+      case 4: if constexpr (TW > 4) stats_warp<NT, 4>(dx, dg, sw, g, t4, C, s1, wacc); break;
+      case 5: if constexpr (TW > 5) stats_warp<NT, 5>(dx, dg, sw, g, t4, C, s1, wacc); break;
+      case 6: if constexpr (TW > 6) stats_warp<NT, 6>(dx, dg, sw, g, t4, C, s1, wacc); break;
+      case 7: if constexpr (TW > 7) stats_warp<NT, 7>(dx, dg, sw, g, t4, C, s1, wacc); break;
     }
   }
-  double *o = part + (size_t)blockIdx.x * st_unit_len(NT) + (size_t)warp * st_warp_len(NT);
 #pragma unroll
-  for (int t = 0; t <= NT; ++t) { o[t * 64 + 2 * lane] = C[t][0]; o[t * 64 + 2 * lane + 1] = C[t][1]; }
-  o[(NT + 1) * 64 + lane] = s1a;
-  o[(NT + 1) * 64 + 32 + lane] = s1b;
-  o[(NT + 1) * 64 + 64 + lane] = wacc;
+  for (int c = 0; c < CK; ++c) {
+    double *o = part + (size_t)blockIdx.x * st_unit_len(NT) + (size_t)(warp * CK + c) * st_warp_len(NT);
+#pragma unroll
+    for (int t = 0; t <= NT; ++t) { o[t * 64 + 2 * lane] = C[c][t][0]; o[t * 64 + 2 * lane + 1] = C[c][t][1]; }
+    o[(NT + 1) * 64 + lane] = s1[c][0];
+    o[(NT + 1) * 64 + 32 + lane] = s1[c][1];
+    o[(NT + 1) * 64 + 64 + lane] = wacc[c];
+  }
 }
 
 // partials -> canonical statistics  out[k] = { W, s1[d], S2[d*d] (full symmetric) }, fixed summation order
 template <int NT>
 __global__ void k_stats_mma_combine(const double *__restrict__ part, int J, const int *__restrict__ kmap, int nchunk,
                                     int d, double *__restrict__ out) {
-  constexpr int TW = st_tw(NT), SW = st_sw(NT), WL = st_warp_len(NT), UL = st_unit_len(NT);
+  constexpr int TW = st_tw(NT), SW = st_sw(NT), WL = st_warp_len(NT), UL = st_unit_len(NT), CK = ST_CK;
   const int j = blockIdx.y;
   const int k = kmap[j];
+  const int jg = j / CK, cc = j % CK;
   const long len = 1 + d + (long)d * d;
   double *ok = out + (size_t)k * len;
+  auto blk = [&](int c, int w) { return part + (size_t)(jg * nchunk + c) * UL + (size_t)(w * CK + cc) * WL; };
   for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < 1 + d + (long)d * (d + 1) / 2; e += (long)gridDim.x * blockDim.x) {
     double acc = 0.0;
     if (e == 0) {  // W: warps with tw == 0, lanes g == 0 (t4 = 0..3 carry distinct samples)
       for (int c = 0; c < nchunk; ++c)
         for (int sw = 0; sw < SW; ++sw) {
-          const double *p = part + (size_t)(j * nchunk + c) * UL + (size_t)(sw * TW) * WL + (NT + 1) * 64 + 64;
+          const double *p = blk(c, sw * TW) + (NT + 1) * 64 + 64;
           acc += (p[0] + p[1]) + (p[2] + p[3]);
         }
       ok[0] = acc;
@@ -361,7 +405,7 @@ __global__ void k_stats_mma_combine(const double *__restrict__ part, int J, cons
       const int tw = first ? rt : NT - 1 - rt;
       for (int c = 0; c < nchunk; ++c)
         for (int sw = 0; sw < SW; ++sw) {
-          const double *p = part + (size_t)(j * nchunk + c) * UL + (size_t)(sw * TW + tw) * WL + (NT + 1) * 64 + (first ? 0 : 32) + 4 * g;
+          const double *p = blk(c, sw * TW + tw) + (NT + 1) * 64 + (first ? 0 : 32) + 4 * g;
           acc += (p[0] + p[1]) + (p[2] + p[3]);
         }
       ok[1 + a] = acc;
@@ -378,12 +422,157 @@ __global__ void k_stats_mma_combine(const double *__restrict__ part, int J, cons
       const int slot = first ? bt : tw + 1 + bt;
       const int off = slot * 64 + 2 * (g * 4 + (col >> 1)) + (col & 1);
       for (int c = 0; c < nchunk; ++c)
-        for (int sw = 0; sw < SW; ++sw)
-          acc += part[(size_t)(j * nchunk + c) * UL + (size_t)(sw * TW + tw) * WL + off];
+        for (int sw = 0; sw < SW; ++sw) acc += blk(c, sw * TW + tw)[off];
       ok[1 + d + (size_t)a * d + b] = acc;
       ok[1 + d + (size_t)b * d + a] = acc;
     }
   }
+}
+
+// ---- draw ------------------------------------------------------------------------------------------------------------
+// simulate_mix_mvdens without a box (pmc.c:266-298): x = mu_k + L_k g.  Samples are grouped by their component so that
+// L_k g is a product of one factor with many normal vectors.  The Philox counters are those of k_draw_generic
+// (call 0: component, calls 1..ceil(d/2): Box-Muller pairs, then the chi-square of a Student-t component), so both
+// kernels produce the same sample up to the rounding of the different summation order.
+__global__ void k_draw_pick(const double *__restrict__ cw, int K, uint64_t seed, uint32_t iter, long first_index, long N,
+                            unsigned long long *__restrict__ indices, unsigned int *__restrict__ cnt) {
+  extern __shared__ unsigned int sc[];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sc[k] = 0;
+  __syncthreads();
+  const Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
+    const uint64_t gi = (uint64_t)(first_index + i);
+    const uint4 r0 = ph((uint32_t)gi, (uint32_t)(gi >> 32), 0u, iter);
+    const int k = ranindx(cw, K, u01_co(r0.x, r0.y));
+    indices[i] = (unsigned long long)k;
+    atomicAdd(&sc[k], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    if (sc[k]) atomicAdd(&cnt[k], sc[k]);
+}
+// perm = sample ids grouped by component (order inside a group is irrelevant: every sample is computed from its own id)
+__global__ void k_draw_perm(long N, const unsigned long long *__restrict__ indices, unsigned int *__restrict__ cursor,
+                            unsigned int *__restrict__ perm) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x)
+    perm[atomicAdd(&cursor[indices[i]], 1u)] = (unsigned int)i;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+k_draw_mma(const double *__restrict__ pack, const int4 *__restrict__ tiles, int ntiles, const unsigned int *__restrict__ perm,
+           const int *__restrict__ dfj, int d, uint64_t seed, uint32_t iter, long first_index, double *__restrict__ X,
+           short *__restrict__ flg, unsigned long long *counters) {
+  constexpr int KS = 2 * NT, MT = q_mt(NT), CS = q_comp_stride(NT);
+  extern __shared__ double sm[];  // [CS]: mean and factor tiles of the current component
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+  const int per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int tb = blockIdx.x * per, te = min(ntiles, tb + per);
+  const Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  int cur = -1;
+  for (int t = tb; t < te; ++t) {
+    const int4 td = tiles[t];  // x = packed component, y = first position in perm, z = samples in this tile
+    if (td.x != cur) {
+      __syncthreads();
+      const double *src = pack + (size_t)td.x * CS;
+      for (int c = threadIdx.x; c < CS / 2; c += 256) cpa16(sm + 2 * c, src + 2 * c);
+      cpa_commit();
+      cur = td.x;
+    }
+    // standard normals in A-fragment order: over a pair of k-steps (8 columns) each lane of a quad evaluates one
+    // Box-Muller pair, the quad exchanges them by shuffles
+    double xa[MT][KS];
+    long sid[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int pos = warp * (8 * MT) + mt * 8 + g;
+      sid[mt] = pos < td.z ? (long)perm[td.y + pos] : -1;
+      const uint64_t gi = (uint64_t)(first_index + (sid[mt] < 0 ? 0 : sid[mt]));
+#pragma unroll
+      for (int m = 0; m < NT; ++m) {
+        const int c0 = 8 * m + 2 * t4;  // this lane's pair of columns
+        double g0 = 0.0, g1 = 0.0;
+        if (c0 < d) box_muller(ph((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)(1 + 4 * m + t4), iter), g0, g1);
+        const int qb = lane & ~3;
+        const double e0 = __shfl_sync(0xffffffffu, g0, qb + (t4 >> 1)), e1 = __shfl_sync(0xffffffffu, g1, qb + (t4 >> 1));
+        const double f0 = __shfl_sync(0xffffffffu, g0, qb + 2 + (t4 >> 1)), f1 = __shfl_sync(0xffffffffu, g1, qb + 2 + (t4 >> 1));
+        const double va = (t4 & 1) ? e1 : e0, vb = (t4 & 1) ? f1 : f0;
+        xa[mt][2 * m] = (8 * m + t4 < d) ? va : 0.0;
+        xa[mt][2 * m + 1] = (8 * m + 4 + t4 < d) ? vb : 0.0;
+      }
+    }
+    cpa_wait0();
+    __syncthreads();
+    double C[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) { C[mt][nt][0] = 0.0; C[mt][nt][1] = 0.0; }
+    const double *tp = sm + 8 * NT + lane;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int nt = ks / 2; nt < NT; ++nt) {
+        const double b = *tp;
+        tp += 32;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) dmma(C[mt][nt][0], C[mt][nt][1], xa[mt][ks], b);
+      }
+    }
+    const int df = dfj[td.x];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      double corr = 1.0;
+      if (df != -1) {  // Student-t: y *= sqrt(df / chi2_df)  (mvdens.c:306-312)
+        if (t4 == 0 && sid[mt] >= 0) {
+          const uint64_t gi = (uint64_t)(first_index + sid[mt]);
+          DrawStream st{ph, (uint32_t)gi, (uint32_t)(gi >> 32), iter, 0u, (uint32_t)(1 + (d + 1) / 2)};
+          corr = sqrt(df / chisq_mt(st, (double)df));
+        }
+        corr = __shfl_sync(0xffffffffu, corr, lane & ~3);
+      }
+      bool fin = true;
+      if (sid[mt] >= 0) {
+        double *xr = X + (size_t)sid[mt] * d;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int a = 8 * nt + 2 * t4;
+          if (a < d) {
+            const double v = C[mt][nt][0] * corr + sm[a];
+            fin = fin && isfinite(v);
+            xr[a] = v;
+          }
+          if (a + 1 < d) {
+            const double v = C[mt][nt][1] * corr + sm[a + 1];
+            fin = fin && isfinite(v);
+            xr[a + 1] = v;
+          }
+        }
+      }
+      const unsigned bad = __ballot_sync(0xffffffffu, !fin);
+      if (t4 == 0 && sid[mt] >= 0) {
+        const bool ok = ((bad >> (lane & ~3)) & 0xfu) == 0;
+        flg[sid[mt]] = ok ? 1 : 0;
+        if (!ok) atomicAdd(&counters[CNT_DRAWFAIL], 1ull);
+      }
+    }
+  }
+}
+
+template <int NT>
+int launch_draw_t(const double *pack, const int4 *tiles, int ntiles, const unsigned int *perm, const int *dfj, int d,
+                  uint64_t seed, uint32_t iter, long first_index, double *X, short *flg, unsigned long long *counters,
+                  int sm_count, cudaStream_t s) {
+  const size_t smem = (size_t)q_comp_stride(NT) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_draw_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    attr_done = true;
+  }
+  const int grid = ntiles < sm_count ? ntiles : sm_count;
+  k_draw_mma<NT><<<grid, 256, smem, s>>>(pack, tiles, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters);
+  count_launch();
+  return cudaGetLastError() != cudaSuccess;
 }
 
 template <int NT>
@@ -404,9 +593,9 @@ int launch_q(const double *X, long n, int d, const double *pack, int J, const in
 }
 
 template <int NT>
-int launch_stats(const double *X, long n, int d, const double *G, long qs, int J, const int *kmap, const double *pivot,
-                 int nchunk, double *part, double *out, cudaStream_t s) {
-  const size_t smem = ((size_t)2 * ST_SS * st_dpad(NT) + 2 * ST_SS + 8 * NT) * sizeof(double);
+int launch_stats(const double *X, long n, int d, const double *G, long qs, int J, const int *kmap, int nchunk,
+                 double *part, double *out, cudaStream_t s) {
+  const size_t smem = ((size_t)2 * ST_SS * st_dpad(NT) + 2 * ST_CK * ST_SS) * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(k_stats_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
@@ -414,7 +603,7 @@ int launch_stats(const double *X, long n, int d, const double *G, long qs, int J
   }
   long chunk_len = (n + nchunk - 1) / nchunk;
   chunk_len = ((chunk_len + ST_SS - 1) / ST_SS) * ST_SS;
-  k_stats_mma<NT><<<J * nchunk, 32 * st_warps(NT), smem, s>>>(X, n, d, G, qs, kmap, pivot, nchunk, chunk_len, part);
+  k_stats_mma<NT><<<((J + ST_CK - 1) / ST_CK) * nchunk, 32 * st_warps(NT), smem, s>>>(X, n, d, G, qs, J, kmap, nchunk, chunk_len, part);
   count_launch();
   if (cudaGetLastError() != cudaSuccess) return 1;
   k_stats_mma_combine<NT><<<dim3(8, J), 256, 0, s>>>(part, J, kmap, nchunk, d, out);
@@ -438,7 +627,7 @@ size_t mma_comp_stride(int d) {
 
 // One component in kernel order: mu[8 NT] (zero padded), then for ks ascending, nt = ks/2 .. NT-1, the 32 B-fragment
 // values  Linv[8 nt + lane/4][4 ks + lane%4].  Linv is formed column by column in extended precision.
-void mma_pack_component(int d, const double *mean, const double *L, double *out) {
+void mma_pack_component(int d, const double *mean, const double *L, int invert, double *out) {
   const int NT = mma_nt(d), DP = 8 * NT;
   // Linv L = I, row r of Linv from the diagonal leftwards: inv[r][c] = -(sum_{m=c+1..r} inv[r][m] L[m][c]) / L[c][c];
   // Lt holds L transposed so that both operands of the dot product are contiguous
@@ -446,7 +635,9 @@ void mma_pack_component(int d, const double *mean, const double *L, double *out)
   for (int r = 0; r < d; ++r)
     for (int c = 0; c <= r; ++c) Lt[(size_t)c * d + r] = L[(size_t)r * d + c];
   std::vector<long double> inv((size_t)d * d, 0.0L);
-  for (int r = 0; r < d; ++r) {
+  for (int r = 0; r < d && !invert; ++r)
+    for (int c = 0; c <= r; ++c) inv[(size_t)r * d + c] = (long double)L[(size_t)r * d + c];  // the factor itself (draw)
+  for (int r = 0; r < d && invert; ++r) {
     long double *ir = inv.data() + (size_t)r * d;
     ir[r] = 1.0L / (long double)L[(size_t)r * d + r];
     for (int c = r - 1; c >= 0; --c) {
@@ -514,7 +705,7 @@ size_t mma_stats_partial_doubles(int d, int J, int nchunk) {
     case 8: ul = st_unit_len(8); break;
     case 16: ul = st_unit_len(16); break;
   }
-  return ul * (size_t)J * nchunk;
+  return ul * (size_t)((J + ST_CK - 1) / ST_CK) * nchunk;
 }
 
 // number of sample chunks per component: fill whole waves of the grid, at least four stages per block
@@ -523,21 +714,56 @@ int mma_stats_chunks(long n, int J, int sm_count) {
   int best = 1;
   double best_eff = 0.0;
   for (int c = 1; c <= 64 && c <= max_c; ++c) {
-    const double waves = (double)J * c / sm_count;
+    const double waves = (double)((J + ST_CK - 1) / ST_CK) * c / sm_count;
     const double eff = waves / std::ceil(waves);
     if (eff > best_eff + 1e-3) { best_eff = eff; best = c; }
   }
   return best;
 }
 
-int launch_stats_mma(const double *X, long n, int d, const double *G, long qs, int J, const int *kmap,
-                     const double *pivot, int nchunk, double *part, double *out, cudaStream_t s) {
-  if (n <= 0 || J <= 0) return 0;
+int mma_draw_tile_samples(int d) {
   switch (mma_nt(d)) {
-    case 2: return launch_stats<2>(X, n, d, G, qs, J, kmap, pivot, nchunk, part, out, s);
-    case 4: return launch_stats<4>(X, n, d, G, qs, J, kmap, pivot, nchunk, part, out, s);
-    case 8: return launch_stats<8>(X, n, d, G, qs, J, kmap, pivot, nchunk, part, out, s);
-    case 16: return launch_stats<16>(X, n, d, G, qs, J, kmap, pivot, nchunk, part, out, s);
+    case 2: return 64 * q_mt(2);
+    case 4: return 64 * q_mt(4);
+    case 8: return 64 * q_mt(8);
+    case 16: return 64 * q_mt(16);
+  }
+  return 0;
+}
+void launch_draw_pick(const double *cw, int K, uint64_t seed, uint32_t iter, long first_index, long N,
+                      unsigned long long *indices, unsigned int *cnt, int nblocks, cudaStream_t s) {
+  k_draw_pick<<<nblocks, 256, K * sizeof(unsigned int), s>>>(cw, K, seed, iter, first_index, N, indices, cnt);
+  count_launch();
+}
+void launch_draw_perm(long N, const unsigned long long *indices, unsigned int *cursor, unsigned int *perm, int nblocks,
+                      cudaStream_t s) {
+  k_draw_perm<<<nblocks, 256, 0, s>>>(N, indices, cursor, perm);
+  count_launch();
+}
+int launch_draw_mma(const double *pack, const void *tiles, int ntiles, const unsigned int *perm, const int *dfj, int d,
+                    uint64_t seed, uint32_t iter, long first_index, double *X, short *flg, unsigned long long *counters,
+                    int sm_count, cudaStream_t s) {
+  if (ntiles <= 0) return 0;
+  const int4 *t4 = reinterpret_cast<const int4 *>(tiles);
+  switch (mma_nt(d)) {
+    case 2: return launch_draw_t<2>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, sm_count, s);
+    case 4: return launch_draw_t<4>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, sm_count, s);
+    case 8: return launch_draw_t<8>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, sm_count, s);
+    case 16: return launch_draw_t<16>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, sm_count, s);
+  }
+  return 1;
+}
+
+int launch_stats_mma(const double *X, const short *flg, long n, int d, const double *G, long qs, int J, const int *kmap,
+                     const double *pivot, int nchunk, double *Xc, double *part, double *out, int sm_count, cudaStream_t s) {
+  if (n <= 0 || J <= 0) return 0;
+  k_centre<<<sm_count * 8, 256, 0, s>>>(X, flg, pivot, n, d, Xc);
+  count_launch();
+  switch (mma_nt(d)) {
+    case 2: return launch_stats<2>(Xc, n, d, G, qs, J, kmap, nchunk, part, out, s);
+    case 4: return launch_stats<4>(Xc, n, d, G, qs, J, kmap, nchunk, part, out, s);
+    case 8: return launch_stats<8>(Xc, n, d, G, qs, J, kmap, nchunk, part, out, s);
+    case 16: return launch_stats<16>(Xc, n, d, G, qs, J, kmap, nchunk, part, out, s);
   }
   return 1;
 }

@@ -1,0 +1,8 @@
+import os, sys
+sys.path.insert(0, "/root/repo")
+from pmclib_b200 import PmcGpu, workloads as W
+N = int(os.environ.get("N5", 200000))
+g = PmcGpu(0); wl = W.gauss128(); g.set_workload(wl); g.resize(N, wl["d"])
+for it in range(int(os.environ.get("ITERS", 2))):
+    r = g.pmc_step(1, it)
+    print("iter", it, r.perplexity, r.n_alive, r.used_precise_path, file=sys.stderr)
