@@ -142,6 +142,8 @@ struct pmcgpu_ctx {
   struct MmaMix { DevBuf pack, lpack, kmap, dfj; int J = 0; bool valid = false; std::vector<int> alive; };
   MmaMix mprop, mtgt;
   DevBuf Q, Qt, mpart, mstats, mpivot, dperm, dtiles, dcnt, xc;
+  HostMix trial;  // scratch of the update (kept to reuse its storage)
+  std::vector<double> hW, hs1, hS2;
   long q_stride = 0;
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 17;
@@ -637,14 +639,13 @@ int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector
   CU(cudaMemcpyAsync(c->hstage, c->mstats.p, (size_t)K * len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (c->timing && c->ev1) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats_ms += ms; }
-  std::vector<double> st(c->hstage, c->hstage + (size_t)K * len);
-  int rc = allreduce_host(c, st.data(), (long)st.size(), 0);
+  int rc = allreduce_host(c, c->hstage, (long)((size_t)K * len), 0);  // in place in the pinned staging buffer
   if (rc) return rc;
-  W.assign(K, 0.0);
-  s1.assign((size_t)K * d, 0.0);
-  S2.assign((size_t)K * d * d, 0.0);
+  W.resize(K);
+  s1.resize((size_t)K * d);
+  S2.resize((size_t)K * d * d);
   for (int k = 0; k < K; ++k) {
-    const double *sk = st.data() + (size_t)k * len;
+    const double *sk = c->hstage + (size_t)k * len;
     W[k] = sk[0];
     memcpy(s1.data() + (size_t)k * d, sk + 1, d * sizeof(double));
     memcpy(S2.data() + (size_t)k * d * d, sk + 1 + d, (size_t)d * d * sizeof(double));
@@ -1497,7 +1498,8 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
     // a NaN maximum (the i==0 quirk) poisons the reference's responsibilities: only the literal path reproduces that
     const bool mma_stats = !p.valid && !c->force_precise && !m0.student && c->q_resident && mma_usable(c, 0);
     bool precise = !(fused_stats || mma_stats) || std::isnan(maxR) || std::isnan(maxW);
-    std::vector<double> W, s1, S2, pivot(d);
+    std::vector<double> &W = c->hW, &s1 = c->hs1, &S2 = c->hS2;
+    std::vector<double> pivot(d);
     std::vector<size_t> count(K);
     if (!precise) {
       {  // pivot = mixture mean (weights of live components)
@@ -1545,7 +1547,8 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
       tick("statistics");
     }
     if (!precise) {
-      HostMix trial = c->prop;
+      HostMix &trial = c->trial;
+      trial = c->prop;
       int retry_trial = retry_local;
       std::vector<int> alive(K);
       rc = pmcgpu_finalize_update(K, d, W.data(), W.data(), s1.data(), S2.data(), pivot.data(), 0, count.data(), N_total,
@@ -1567,7 +1570,7 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
       if (rc != 0 || retry_trial != 0 || !(worst <= c->guard_ratio)) {
         precise = true;  // anything unusual (failed factorisation, ill-conditioned pivot) goes through the literal path
       } else {
-        c->prop = trial;
+        std::swap(c->prop, trial);
         retry_local = retry_trial;
       }
     }

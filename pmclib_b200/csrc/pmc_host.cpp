@@ -5,7 +5,10 @@
 //   mvdens_cholesky_decomp      mvdens.c:229-277  (+ gsl-1.14 gsl_linalg_cholesky_decomp semantics, un-vendored GSL)
 //   cleanup_after_update        pmc.c:1471-1533
 //   end of update_prop_rb       pmc.c:1409-1426, 1455-1462
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "../../include/pmcb200.h"
@@ -147,8 +150,21 @@ int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const
                            const size_t *band_limit, int *retry, double *wght, double *mean, double *L, double *detL,
                            int *alive) {
   const size_t dd = (size_t)d * d;
-  std::vector<double> snapshot(L, L + K * dd);
-  pmcb200::parallel_components(K, (double)d * d, [&](int k) {
+  static const bool trace = getenv("PMCB200_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pmcb200]   finalize: %-16s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+  // old factors, restored by cleanup_after_update on a first failed factorisation; the buffer persists across calls
+  // (a fresh 8 MB vector per iteration costs more in page faults than the copy itself)
+  static thread_local std::vector<double> snapshot;
+  snapshot.resize(K * dd);
+  double *const snap = snapshot.data();  // (the worker threads must not name the thread_local object itself)
+  pmcb200::parallel_components(K, (double)d * d * 16.0, [&, snap](int k) {
+    std::memcpy(snap + k * dd, L + k * dd, sizeof(double) * dd);
     double *cov = L + k * dd;
     double *mu = mean + (size_t)k * d;
     if (count[k] > (size_t)kMinCount) {
@@ -176,8 +192,10 @@ int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const
       std::memset(cov, 0, sizeof(double) * dd);
     }
   });
-  const int rc = pmcb200::host_cleanup_after_update(K, d, count, 1.0 / (double)N_total, retry, snapshot.data(), wght,
+  tick("covariances");
+  const int rc = pmcb200::host_cleanup_after_update(K, d, count, 1.0 / (double)N_total, retry, snap, wght,
                                                     mean, L, detL);
+  tick("cleanup+cholesky");
   if (alive)
     for (int k = 0; k < K; ++k) alive[k] = wght[k] > 0.0 ? 1 : 0;
   return rc;

@@ -18,12 +18,13 @@ from util import compare_mixture  # noqa: E402
 rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lrank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
-wl = W.banana()
-N = 4_000_003
+cfg = os.environ.get("MGPU_CONFIG", "c3")   # c3: fused small-d kernels; c5: large-d tensor path (pmc_mma.cu)
+wl = W.gauss128() if cfg == "c5" else W.banana()
+N = int(os.environ.get("MGPU_N", 400_003 if cfg == "c5" else 4_000_003))
 g = PmcGpu(lrank)
 g.set_workload(wl)
 first, n = shard_range(N, rank, world)
-g.resize(n)
+g.resize(n, wl["d"])
 ids = [nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 g.comm_init_nccl(ids[0], rank, world)
@@ -43,7 +44,7 @@ ok = same
 if rank == 0:
     s = PmcGpu(lrank)
     s.set_workload(wl)
-    s.resize(N)
+    s.resize(N, wl["d"])
     retry = 0
     for it in range(3):
         q = s.pmc_step(seed=99, it=it, first_index=0, N_total=N, do_update=1, retry=retry)
