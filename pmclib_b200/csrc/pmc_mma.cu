@@ -520,17 +520,22 @@ k_draw_mma(const double *__restrict__ pack, const int4 *__restrict__ tiles, int 
       }
     }
     const int df = dfj[td.x];
+    // Student-t: y *= sqrt(df / chi2_df)  (mvdens.c:306-312).  The rejection sampler is divergent scalar work: lane t4
+    // of a quad draws the factor of the quad's sample mt == t4, the quad then exchanges the factors.
+    double corr_mine = 1.0;
+    if (df != -1) {
+      long mysid = -1;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) if (t4 == mt) mysid = sid[mt];
+      if (mysid >= 0) {
+        const uint64_t gi = (uint64_t)(first_index + mysid);
+        DrawStream st{ph, (uint32_t)gi, (uint32_t)(gi >> 32), iter, 0u, (uint32_t)(1 + (d + 1) / 2)};
+        corr_mine = sqrt(df / chisq_mt(st, (double)df));
+      }
+    }
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      double corr = 1.0;
-      if (df != -1) {  // Student-t: y *= sqrt(df / chi2_df)  (mvdens.c:306-312)
-        if (t4 == 0 && sid[mt] >= 0) {
-          const uint64_t gi = (uint64_t)(first_index + sid[mt]);
-          DrawStream st{ph, (uint32_t)gi, (uint32_t)(gi >> 32), iter, 0u, (uint32_t)(1 + (d + 1) / 2)};
-          corr = sqrt(df / chisq_mt(st, (double)df));
-        }
-        corr = __shfl_sync(0xffffffffu, corr, lane & ~3);
-      }
+      const double corr = (df != -1) ? __shfl_sync(0xffffffffu, corr_mine, (lane & ~3) + (mt & 3)) : 1.0;
       bool fin = true;
       if (sid[mt] >= 0) {
         double *xr = X + (size_t)sid[mt] * d;
