@@ -169,6 +169,40 @@ def test_finalize_kills_small_components_and_reports_negweight():
     assert rc == 0 and retry.value == 0 and wght[0] == 0 and alive[0] == 0
 
 
+def test_finalize_threaded_large_shape_matches_numpy():
+    """At d = 128, K = 64 the host finalisation runs on several threads (pmc_hostonly.h): same result as a plain numpy
+    evaluation of mu' = c + s/W, Sigma' = S/W - (s/W)(s/W)^T, L = chol(Sigma'), one failed component restored + retry."""
+    lib = load_library()
+    wl = W.gauss128()
+    K, d = wl["K"], wl["d"]
+    rng = np.random.default_rng(5)
+    W_ = rng.uniform(0.5, 1.5, K) / K
+    shift = rng.normal(0.0, 0.05, (K, d))
+    s1 = shift * W_[:, None]
+    S2 = np.array([W_[k] * (wl["cov"][k] + np.outer(shift[k], shift[k])) for k in range(K)])
+    S2[7] = -S2[7]   # not positive definite: first failure restores the old factor and raises retry
+    pivot = rng.normal(0.0, 0.1, d)
+    count = np.full(K, 1000, np.uint64)
+    m = O.Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"])
+    for _ in range(2):  # twice: the scratch buffers persist across calls
+        wght, mean, L, detL = m.wght.copy(), m.mean.copy(), m.L.copy(), m.detL.copy()
+        alive = np.zeros(K, np.int32)
+        retry = C.c_int(0)
+        rc = lib.pmcgpu_finalize_update(K, d, O.P(W_), O.P(W_), O.P(np.ascontiguousarray(s1)), O.P(np.ascontiguousarray(S2)),
+                                        O.P(pivot), 0, O.P(count), 100000, None, C.byref(retry), O.P(wght), O.P(mean), O.P(L),
+                                        O.P(detL), O.P(alive))
+        assert rc == 0 and retry.value == 1 and alive.all()
+        assert np.array_equal(L[7], m.L[7])
+        assert relerr(wght, W_ / W_.sum()) < 1e-14
+        for k in range(K):
+            if k == 7:
+                continue
+            assert relerr(mean[k], pivot + shift[k]) < 1e-12
+            Lk = np.linalg.cholesky(wl["cov"][k])
+            assert relerr(np.tril(L[k]), Lk) < 1e-11
+            assert relerr(detL[k], np.prod(np.diag(Lk))) < 1e-11
+
+
 def test_shard_range_partitions_like_send_simulation():
     from pmclib_b200.api import shard_range
     for N, P in [(100, 8), (101, 8), (7, 8), (10**8, 3), (1, 1)]:

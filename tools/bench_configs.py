@@ -41,6 +41,35 @@ def flops(wl, upd):
                 stats=(K * (d * d + 4 * d + 4)) if upd else 0)
 
 
+CPU_SAMPLE = {"c2": (1_000_000, 3), "c4": (100_000, 3), "c5": (2_000, 1)}  # (samples/iteration, iterations); c5: the reference's update runs at ~80 samples/s (denormals)
+
+
+def cpu_reference(cfg, wl, upd, nworkers=1):
+    """The compiled reference (oracle/_ref, vanilla_pmc loop) on the host cores, bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+    import oracle_py as O
+    L = O.ref()
+    if L is None:
+        return None
+    N, niter = CPU_SAMPLE[cfg]
+    K, d, tg = wl["K"], wl["d"], wl["target"]
+    tp = np.array([tg["b"], tg["sig1"]])
+    times = np.zeros(5 * niter); stats = np.zeros(3 * niter)
+    faces = wl["faces"]
+    ca = lambda a, t=np.float64: None if a is None else np.ascontiguousarray(a, t)
+    tw, tm, tc, tdf = ca(tg["wght"]), ca(tg["mean"]), ca(tg["cov"]), ca(tg["df"], np.int32)
+    rc = L.ref_pmc_run(C.c_long(N), d, K, O.P(ca(wl["wght"])), O.P(ca(wl["mean"])), O.P(ca(wl["cov"])), O.P(ca(wl["df"], np.int32)),
+                       tg["kind"], O.P(tp), tg["K"], O.P(tw), O.P(tm), O.P(tc), O.P(tdf),
+                       0 if faces is None else len(faces), O.P(ca(faces)), C.c_ulong(42), niter, upd, nworkers,
+                       O.P(times), O.P(stats), None, None, None)
+    per = times.reshape(niter, 5).sum(1)
+    per = per[1:] if niter > 1 else per
+    return {"value": N * len(per) / float(np.sum(per)), "unit": "samples/s", "cores": nworkers, "kind": "reference", "rc": int(rc),
+            "sample": f"{N} samples/iteration x {len(per)} timed iteration(s) of the compiled reference, same workload",
+            "phase_split_s": {k: float(v) for k, v in zip(["draw", "weight", "normalise", "update", "perplexity"], times.reshape(niter, 5).sum(0))}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c5", choices=list(CFG))
@@ -48,6 +77,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--opts", default="")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -108,7 +138,11 @@ def main():
         step_ms = wall_ms / args.steps  # host finalisation is part of an iteration: wall clock between barriers
         value = N_total * args.steps / (wall_ms * 1e-3)
         kern = {}
-        if q_n > 0:
+        if q_n > 0 and wl["d"] <= 16:   # fused small-d kernels (pmc_fused2.cu): same timers, other kernels
+            kern["weights kernel k_fused2"] = {"ms": q_ms / q_n, "share_of_step": q_ms / q_n / step_ms}
+            if s_ms > 0: kern["statistics kernel k_stats2"] = {"ms": s_ms / q_n, "share_of_step": s_ms / q_n / step_ms}
+            if d_ms > 0: kern["draw kernel k_fused2<MODE 3>"] = {"ms": d_ms / q_n, "share_of_step": d_ms / q_n / step_ms}
+        elif q_n > 0:
             ms = q_ms / q_n
             tf = (F["density"] + (F["target"] if wl["target"]["kind"] != W.TGT_BANANA else 0)) * n_local / (ms * 1e-3) * 1e-12
             kern["whitening k_q_mma (proposal + target densities)"] = {"ms": ms, "share_of_step": ms / step_ms, "algorithmic_tflops": tf, "frac_of_fp64_peak": tf / FP64_PEAK_TFLOPS}
@@ -118,6 +152,12 @@ def main():
                 kern["statistics k_resp_q + k_centre + k_stats_mma"] = {"ms": ms2, "share_of_step": ms2 / step_ms, "algorithmic_tflops": tf2, "frac_of_fp64_peak": tf2 / FP64_PEAK_TFLOPS}
             if d_ms > 0:
                 kern["draw k_draw_pick/perm/mma"] = {"ms": d_ms / q_n, "share_of_step": d_ms / q_n / step_ms}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                cpu = cpu_reference(args.config, wl, upd)
+            except Exception as ex:  # pragma: no cover
+                cpu = {"value": None, "sample": f"failed: {ex}"}
         print(json.dumps({
             "metric": "PMC samples/s per iteration (draw+weight" + ("+RB update)" if upd else ", importance only)"),
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -129,7 +169,7 @@ def main():
             "roofline": {"bound": "fp64", "algorithmic_flop_per_sample": Ftot, "achieved": value / world * Ftot * 1e-12,
                          "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": value / world * Ftot * 1e-12 / FP64_PEAK_TFLOPS,
                          "kernels": kern},
-            "gpu_launches": int(l1 - l0)}))
+            "cpu_baseline": cpu, "gpu_launches": int(l1 - l0)}))
     if world > 1:
         dist.destroy_process_group()
 
