@@ -197,9 +197,9 @@ def test_finalize_threaded_large_shape_matches_numpy():
         for k in range(K):
             if k == 7:
                 continue
-            assert relerr(mean[k], pivot + shift[k]) < 1e-12
+            assert relerr(mean[k], pivot + shift[k], scale=0.1) < 1e-13
             Lk = np.linalg.cholesky(wl["cov"][k])
-            assert relerr(np.tril(L[k]), Lk) < 1e-11
+            assert relerr(np.tril(L[k]), Lk, scale=1.0) < 1e-12   # error relative to the size of the factor
             assert relerr(detL[k], np.prod(np.diag(Lk))) < 1e-11
 
 
