@@ -113,6 +113,16 @@ int pmcgpu_target_log_pdf(pmcgpu_ctx *ctx, long n, const double *x, double *out)
 int pmcgpu_normalize(pmcgpu_ctx *ctx, double maxW, double *logSum, long *count);
 /* perplexity_and_ess (pmc.c:1041-1077, MC_UNORM) and the flagged-out count evidence() needs (pmc.c:1088-1105) */
 int pmcgpu_perplexity_ess(pmcgpu_ctx *ctx, double *perp, double *ess, long *n_flagged_out);
+/* filter_histogram (pmc.c:709-770), the shipped pmc_filter hook of pmc_simu_pmc_step (pmc.c:203-206), on the resident
+ * log-weights: ok samples whose weight lies in the clipleft lowest or clipright highest of nbins equal bins between the
+ * minimum and maximum are flagged out.  Reproduces the reference's initialisation of min/max with weights[0] (whatever
+ * its flag).  With ranks attached, min/max are reduced over all ranks (first_index = global index of local sample 0). */
+int pmcgpu_filter_histogram(pmcgpu_ctx *ctx, int nbins, int clipleft, int clipright, long first_index, long *n_filtered);
+/* the same filter applied inside pmcgpu_pmc_step / pmcgpu_step_given between the weights and the normalisation
+ * (nbins <= 0 switches it off).  With the fused small-d kernels the update then runs through the literal two-pass path. */
+int pmcgpu_set_filter_histogram(pmcgpu_ctx *ctx, int nbins, int clipleft, int clipright);
+/* mean_from_psim (pmc.c:1108-1120): sum over flg != 0 of weights[i] * X[i][a] */
+int pmcgpu_weighted_mean(pmcgpu_ctx *ctx, int a, double *mean);
 /* prepare_update's histogram (pmc.c:1559-1564): count[K] of indices over flg==1 */
 int pmcgpu_count_indices(pmcgpu_ctx *ctx, size_t *count);
 /* update_prop_rb (pmc.c:1323-1469) + prepare_update + cleanup_after_update on the resident, normalised sample:

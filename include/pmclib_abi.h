@@ -243,6 +243,10 @@ double perplexity(pmc_simu *psim, int normalize, error **err);
 double perplexity_and_ess(pmc_simu *psim, int normalize, double *ess, error **err);
 double evidence(pmc_simu *psim, double *ln_evi, error **err);
 void pmc_simu_dump(FILE *where, pmc_simu *psim, error **err);
+void out_pmc_simu(const char *name, const pmc_simu *psim, error **err);                 /* pmc.c:306-325 */
+int *filter_histogram_init(int nbins, int clipleft, int clipright, error **err);       /* pmc.c:699-707 */
+void filter_histogram(pmc_simu *psim, void *filter_data, error **err);                  /* pmc.c:709-770 */
+double mean_from_psim(double *X, double *w, short *flg, int nsamples, int ndim, int a); /* pmc.c:1108-1120 */
 #endif
 
 /* ---- example target shipped with the reference (examples/target/sampleTarget.h) ---------------------------------------- */

@@ -523,3 +523,36 @@ long orc_simulate(long N, orc_mix *m, int nfaces, const double *faces, unsigned 
   free(g);
   return i;
 }
+
+/* filter_histogram (pmc.c:709-770): the shipped pmc_filter hook.  min and max start from weights[0] (not from the
+ * first ok sample, pmc.c:734-735) as soon as any sample is ok; returns the number of samples flagged out. */
+long orc_filter_histogram(long N, const double *weights, short *flg, int nbins, int cl, int cr) {
+  double minW = 0, maxW = 0;
+  long i, nfilt = 0;
+  for (i = 0; i < N; i++)
+    if (flg[i] == 1) { minW = weights[0]; maxW = weights[0]; break; }
+  for (; i < N; i++)
+    if (flg[i] == 1) {
+      const double w = weights[i];
+      if (w > maxW) maxW = w;
+      if (w < minW) minW = w;
+    }
+  const double step = (maxW - minW) * 1. / nbins;
+  const double bl = minW + step * cl, br = maxW - step * cr;
+  for (i = 0; i < N; i++)
+    if (flg[i] == 1) {
+      const double w = weights[i];
+      if (w < bl || br < w) { flg[i] = 0; nfilt++; }
+    }
+  return nfilt;
+}
+
+/* mean_from_psim (pmc.c:1108-1120) */
+double orc_mean_from_psim(const double *X, const double *w, const short *flg, long N, int d, int a) {
+  double m = 0.0;
+  for (long i = 0; i < N; i++) {
+    if (flg[i] == 0) continue;
+    m += w[i] * X[i * d + a];
+  }
+  return m;
+}

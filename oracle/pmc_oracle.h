@@ -102,6 +102,10 @@ int orc_cleanup_after_update(orc_mix *m, const size_t *count, double minwgt, int
 long orc_simulate(long N, orc_mix *m, int nfaces, const double *faces, unsigned long long seed,
                   double *X, size_t *indices, short *flg, double *cw_scratch);
 
+/* filter_histogram (pmc.c:709-770), mean_from_psim (pmc.c:1108-1120) */
+long orc_filter_histogram(long N, const double *weights, short *flg, int nbins, int cl, int cr);
+double orc_mean_from_psim(const double *X, const double *w, const short *flg, long N, int d, int a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -373,3 +373,21 @@ int ref_pmc_run(long N, int d, int K, const double *wght, const double *mean, co
   endError(err);
   return rc;
 }
+
+/* filter_histogram / mean_from_psim of the compiled reference on plain arrays */
+long ref_filter_histogram(long N, double *weights, short *flg, int nbins, int cl, int cr) {
+  error *e = initError(), **err = &e;
+  pmc_simu ps;
+  memset(&ps, 0, sizeof ps);
+  ps.nsamples = N; ps.weights = weights; ps.flg = flg; ps.isLog = 1;
+  int *fil = filter_histogram_init(nbins, cl, cr, err);
+  long before = 0, after = 0;
+  for (long i = 0; i < N; ++i) before += flg[i] == 1;
+  filter_histogram(&ps, fil, err);
+  int rc = take_err(err);
+  for (long i = 0; i < N; ++i) after += flg[i] == 1;
+  free(fil);
+  endError(err);
+  return rc ? rc : before - after;
+}
+double ref_mean_from_psim(double *X, double *w, short *flg, int N, int d, int a) { return mean_from_psim(X, w, flg, N, d, a); }

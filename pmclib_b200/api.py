@@ -219,6 +219,22 @@ class PmcGpu:
         self._ck(self.lib.pmcgpu_perplexity_ess(self.h, C.byref(p), C.byref(e), C.byref(n)))
         return p.value, e.value, n.value
 
+    def filter_histogram(self, nbins, clipleft, clipright, first_index=0):
+        """filter_histogram (pmc.c:709-770) on the resident log-weights; returns the number of samples flagged out."""
+        n = C.c_long()
+        self._ck(self.lib.pmcgpu_filter_histogram(self.h, nbins, clipleft, clipright, first_index, C.byref(n)))
+        return n.value
+
+    def set_filter_histogram(self, nbins, clipleft=0, clipright=0):
+        """Apply filter_histogram inside pmc_step / step_given (the pmc_filter hook, pmc.c:203-206); nbins=0: off."""
+        self._ck(self.lib.pmcgpu_set_filter_histogram(self.h, nbins, clipleft, clipright))
+
+    def weighted_mean(self, a):
+        """mean_from_psim (pmc.c:1108-1120) of coordinate a."""
+        m = C.c_double()
+        self._ck(self.lib.pmcgpu_weighted_mean(self.h, a, C.byref(m)))
+        return m.value
+
     def count_indices(self):
         c = np.zeros(self.K, np.uint64)
         self._ck(self.lib.pmcgpu_count_indices(self.h, _p(c)))

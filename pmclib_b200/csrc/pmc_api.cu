@@ -147,6 +147,7 @@ struct pmcgpu_ctx {
   long q_stride = 0;
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 17;
+  int filt_nbins = 0, filt_cl = 0, filt_cr = 0;  // filter_histogram inside the iteration (0 = off)
   // comm
   int rank = 0, nranks = 1;
   void *nccl_comm = nullptr;
@@ -730,6 +731,59 @@ int scale_perp_impl(pmcgpu_ctx *c, double S, bool scale, double *H, double *Q, l
   *H = red[0];
   *Q = red[1];
   *nexit = (long)red[2];
+  return 0;
+}
+
+// filter_histogram (pmc.c:709-770) on the resident weights
+int filter_histogram_impl(pmcgpu_ctx *c, int nbins, int cl, int cr, long first_index, bool reduce_ranks, long *n_filtered) {
+  const int nb = c->sm_count * 8;
+  CU(c->blkmax.ensure((size_t)2 * nb * sizeof(double)));
+  int rc = zero_small(c);
+  if (rc) return rc;
+  unsigned long long *sm = c->small.as<unsigned long long>();
+  launch_minmax_ok(c->N, c->W.as<double>(), c->Flg.as<short>(), c->blkmax.as<double>(), nb, sm + SM_COUNTERS + CNT_NOK, c->stream);
+  CU(cudaGetLastError());
+  RC(stage(c, (size_t)2 * nb + SM_LEN + 1));
+  CU(cudaMemcpyAsync(c->hstage, c->blkmax.p, (size_t)2 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->hstage + 2 * nb, c->small.p, SM_LEN * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->hstage + 2 * nb + SM_LEN, c->W.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  // red[0] = max, red[1] = -min over ok samples; red[2], red[3] = w0, -w0 from the rank that owns global sample 0;
+  // red[4] = 1 if that w0 is NaN (then every comparison of the reference is false and nothing is filtered)
+  double red[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0};
+  for (int b = 0; b < nb; ++b) {
+    if (c->hstage[2 * b] > red[0]) red[0] = c->hstage[2 * b];
+    if (c->hstage[2 * b + 1] > red[1]) red[1] = c->hstage[2 * b + 1];
+  }
+  double cnt = (double)reinterpret_cast<const unsigned long long *>(c->hstage + 2 * nb)[SM_COUNTERS + CNT_NOK];
+  if (first_index == 0) {
+    const double w0 = c->hstage[2 * nb + SM_LEN];
+    if (std::isnan(w0)) red[4] = 1.0;
+    else { red[2] = w0; red[3] = -w0; }
+  }
+  if (reduce_ranks) {
+    rc = allreduce_host(c, red, 5, 1);
+    if (rc) return rc;
+    rc = allreduce_host(c, &cnt, 1, 0);
+    if (rc) return rc;
+  }
+  if (n_filtered) *n_filtered = 0;
+  if (cnt == 0.0 || red[4] != 0.0) return 0;  // no ok sample: min = max = 0 and the last loop has nothing to test
+  double maxW = red[2], minW = -red[3];        // both start from weights[0] (pmc.c:734-735)
+  if (red[0] > maxW) maxW = red[0];
+  if (-red[1] < minW) minW = -red[1];
+  const double step = (maxW - minW) * 1. / nbins;
+  const double bl = minW + step * cl, br = maxW - step * cr;
+  rc = zero_small(c);
+  if (rc) return rc;
+  launch_flag_outside(c->N, c->W.as<double>(), c->Flg.as<short>(), bl, br, nb, sm + SM_COUNTERS + CNT_FLAGGED, c->stream);
+  CU(cudaGetLastError());
+  unsigned long long counters[CNT_NUM];
+  rc = read_small(c, counters, nullptr, nullptr);
+  if (rc) return rc;
+  double nf = (double)counters[CNT_FLAGGED];
+  if (reduce_ranks) { rc = allreduce_host(c, &nf, 1, 0); if (rc) return rc; }
+  if (n_filtered) *n_filtered = (long)nf;
   return 0;
 }
 
@@ -1344,6 +1398,36 @@ int pmcgpu_perplexity_ess(pmcgpu_ctx *c, double *perp, double *ess, long *n_flag
   return 0;
 }
 
+int pmcgpu_filter_histogram(pmcgpu_ctx *c, int nbins, int clipleft, int clipright, long first_index, long *n_filtered) {
+  if (!c || c->N <= 0 || nbins <= 0) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  return filter_histogram_impl(c, nbins, clipleft, clipright, first_index, true, n_filtered);
+}
+int pmcgpu_set_filter_histogram(pmcgpu_ctx *c, int nbins, int clipleft, int clipright) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  c->filt_nbins = nbins > 0 ? nbins : 0;
+  c->filt_cl = clipleft;
+  c->filt_cr = clipright;
+  return 0;
+}
+int pmcgpu_weighted_mean(pmcgpu_ctx *c, int a, double *mean) {
+  if (!c || c->N <= 0 || a < 0 || a >= c->d || !mean) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  const int nb = c->sm_count * 8;
+  CU(c->blkmax.ensure((size_t)2 * nb * sizeof(double)));
+  launch_weighted_coord(c->N, c->d, a, c->X.as<double>(), c->W.as<double>(), c->Flg.as<short>(), c->blkmax.as<double>(), nb, c->stream);
+  CU(cudaGetLastError());
+  RC(stage(c, nb));
+  CU(cudaMemcpyAsync(c->hstage, c->blkmax.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double s = 0.0;
+  for (int b = 0; b < nb; ++b) s += c->hstage[b];
+  int rc = allreduce_host(c, &s, 1, 0);
+  if (rc) return rc;
+  *mean = s;
+  return 0;
+}
+
 int pmcgpu_count_indices(pmcgpu_ctx *c, size_t *count) {
   if (!c || !count || c->prop.K == 0) return PMCGPU_ERR_USAGE;
   cudaSetDevice(c->device);
@@ -1435,7 +1519,7 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   const int K = m0.K, d = m0.d;
   const FusedPlan p = plan_for(c);
   WeightOut o;
-  const bool fused_stats = p.valid && do_update && !c->force_precise;
+  const bool fused_stats = p.valid && do_update && !c->force_precise && c->filt_nbins == 0;  // a filter changes the flags between weights and statistics
   if (p.valid) {
     rc = run_fused(c, p, do_draw, fused_stats ? 1 : 0, seed, iter, first_index, t_temper, nullptr, nullptr, o);
     if (rc) return rc;
@@ -1474,6 +1558,12 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
     r.n_reject = (long)cnt[0];
     if (do_draw && (cnt[1] > 0 || cnt[0] > 5.0 * (double)N_total))
       return fail(c, kErrTooManySteps, "Too many points (%ld) outside of box", r.n_reject);
+  }
+  // ---- pmc_filter hook (pmc.c:203-206): filter_histogram on the log-weights
+  if (c->filt_nbins > 0) {
+    long nf = 0;
+    rc = filter_histogram_impl(c, c->filt_nbins, c->filt_cl, c->filt_cr, first_index, true, &nf);
+    if (rc) return rc;
   }
   // ---- normalise (pmc.c:641-697), literally: S = sum exp(lw - maxW + 500)
   double S = 0.0;

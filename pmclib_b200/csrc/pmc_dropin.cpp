@@ -22,7 +22,7 @@ namespace {
 
 // reference error codes (pmc.h:23-43, mvdens.h:54-68, parabox.h:9-11, distribution.h:115-117, errorlist.h:147-149)
 constexpr int pmc_base = -6000, pmc_allocate = pmc_base - 1, pmc_io = pmc_base - 10, pmc_incompat = pmc_base - 16,
-              pmc_undef = pmc_base - 8, pmc_infinite = pmc_base - 19;
+              pmc_undef = pmc_base - 8, pmc_infinite = pmc_base - 19, pmc_isLog = pmc_base - 20;
 constexpr int mv_base = -700, mv_negative = mv_base - 7, mv_io = mv_base - 10;
 constexpr int pb_infnan = -12002, dist_undef = -6701, err_allocate = -102;
 
@@ -62,6 +62,11 @@ std::map<const pmc_simu *, Side> g_side;
 std::map<const distribution *, int> g_registered;
 std::mutex g_mu;
 uint64_t g_seed_counter = 0x9E3779B97F4A7C15ull;
+
+int device_ordinal() {
+  if (const char *e = getenv("PMCB200_DEVICE")) return atoi(e);
+  return 0;
+}
 
 Side *side_for(pmc_simu *psim, error **err) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -1054,7 +1059,8 @@ double pmc_simu_pmc_step(pmc_simu *psim, gsl_rng *r, error **err) {
   if (!psim->pmc_update) { ERR_HERE(*err, pmc_allocate, "update function undefined", *err, nullptr); return 0; }
   const bool fast = psim->proposal && psim->target && psim->proposal->simulate == &simulate_mix_mvdens_void &&
                     psim->proposal->log_pdf == &mix_mvdens_log_pdf_void && device_kind(psim->target) != PMCGPU_TGT_HOST &&
-                    psim->pmc_filter == nullptr && psim->pmc_update == &update_prop_rb_void;
+                    (psim->pmc_filter == nullptr || psim->pmc_filter == &filter_histogram) &&
+                    psim->pmc_update == &update_prop_rb_void;
   if (!fast) {  // the reference's own sequence, phase by phase (opaque target, user filter or user update)
     pmc_simu_importance(psim, r, err);
     FWD(*err, 0);
@@ -1076,8 +1082,11 @@ double pmc_simu_pmc_step(pmc_simu *psim, gsl_rng *r, error **err) {
   std::vector<int> alive(K);
   int retry = psim->retry;
   pmcgpu_step_result res;
+  const int *fil = psim->pmc_filter ? (const int *)psim->filter_data : nullptr;  // the shipped filter runs on the device
+  pmcgpu_set_filter_histogram(s->ctx, fil ? fil[0] : 0, fil ? fil[1] : 0, fil ? fil[2] : 0);
   const int rc = pmcgpu_pmc_step(s->ctx, seed_from(r), s->iter++, 0, psim->nsamples, 1, &retry, &res, w.data(), mean.data(),
                                  L.data(), detL.data(), alive.data());
+  pmcgpu_set_filter_histogram(s->ctx, 0, 0, 0);
   if (rc) { gpu_fail(s, rc, err, __func__); return 0; }
   psim->maxW = res.maxW;
   psim->maxR = res.maxR;
@@ -1105,6 +1114,49 @@ void pmc_simu_dump(FILE *where, pmc_simu *psim, error **err) {
        fwrite(psim->X, sizeof(double), N * psim->ndim, where) == N * psim->ndim &&
        fwrite(psim->X_ded, sizeof(double), N * psim->n_ded, where) == N * psim->n_ded;
   if (!ok) ERR_HERE(*err, pmc_io, "Cannot write to file", *err, nullptr);
+}
+
+// ---- weight post-processing either side of the iteration (pmc.c:699-770, 1108-1120, 306-325) -------------------------------------
+int *filter_histogram_init(int nbins, int clipleft, int clipright, error **err) {
+  int *self = (int *)malloc(sizeof(int) * 3);
+  if (!self) { ERR_HERE(*err, pmc_allocate, "Cannot allocate the filter", *err, nullptr); return nullptr; }
+  self[0] = nbins;
+  self[1] = clipleft;
+  self[2] = clipright;
+  return self;
+}
+void filter_histogram(pmc_simu *psim, void *filter_data, error **err) {
+  const int *fil = (const int *)filter_data;
+  if (psim->isLog == 0) { ERR_HERE(*err, pmc_isLog, "can only filter un-normalized data", *err, nullptr); return; }
+  Side *s = side_for(psim, err);
+  if (!s) return;
+  if (!push_samples(s, psim, false, false, true, false, true, err)) return;
+  long nf = 0;
+  const int rc = pmcgpu_filter_histogram(s->ctx, fil[0], fil[1], fil[2], 0, &nf);
+  if (rc) { gpu_fail(s, rc, err, __func__); return; }
+  if (!s->host_stale) pull_samples(s, psim, false, false, false, false, true, err);
+}
+// mean of the a-th parameter; the arrays are plain host arrays (no pmc_simu), so they go through a scratch context
+double mean_from_psim(double *X, double *w, short *flg, int nsamples, int ndim, int a) {
+  static pmcgpu_ctx *scratch = nullptr;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!scratch && pmcgpu_create(device_ordinal(), &scratch) != 0) return std::nan("");
+  double m = std::nan("");
+  if (pmcgpu_resize(scratch, nsamples, ndim) == 0 && pmcgpu_upload(scratch, X, nullptr, w, nullptr, flg) == 0)
+    pmcgpu_weighted_mean(scratch, a, &m);
+  return m;
+}
+void out_pmc_simu(const char *name, const pmc_simu *psim, error **err) {
+  if (pmcb200_sync_host(const_cast<pmc_simu *>(psim), err) != 0) return;
+  FILE *out = fopen(name, "w");
+  if (!out) { ERR_HERE(*err, pmc_io, "Cannot open file", *err, nullptr); return; }
+  for (long i = 0; i < psim->nsamples; ++i) {
+    if (psim->flg[i] == 0) continue;
+    for (int j = 0; j < psim->ndim; ++j) fprintf(out, "% .5e ", psim->X[j + i * psim->ndim]);
+    for (int j = 0; j < psim->n_ded; ++j) fprintf(out, "% .5e ", psim->X_ded[j + i * psim->n_ded]);
+    fprintf(out, "% .5e\n", psim->weights[i]);
+  }
+  fclose(out);
 }
 
 // ---- additions ------------------------------------------------------------------------------------------------------------------

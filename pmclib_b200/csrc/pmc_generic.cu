@@ -435,6 +435,54 @@ __global__ void k_norm_scale_perp(long N, double S, double *__restrict__ w, cons
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counters[CNT_FLAGGED], (unsigned long long)c);
 }
 
+
+// ---- weight post-processing hooks (pmc.c:699-770, 1108-1120) -----------------------------------------------------------
+// filter_histogram, step 1: minimum and maximum of the weights of ok samples ("w > max" / "w < min": NaN never wins)
+__global__ void k_minmax_ok(long N, const double *__restrict__ w, const short *__restrict__ flg,
+                            double *__restrict__ partial /* [2*gridDim.x]: max, -min */, unsigned long long *cnt) {
+  double mx = -INFINITY, mn = INFINITY;
+  unsigned int n = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x)
+    if (flg[i] == 1) {
+      const double v = w[i];
+      if (v > mx) mx = v;
+      if (v < mn) mn = v;
+      ++n;
+    }
+  double a = warp_max_nan_ignoring(mx), b = warp_max_nan_ignoring(-mn);
+  __shared__ double sa[32], sb[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { sa[wid] = a; sb[wid] = b; }
+  __syncthreads();
+  if (wid == 0) {
+    a = warp_max_nan_ignoring(lane < nw ? sa[lane] : -INFINITY);
+    b = warp_max_nan_ignoring(lane < nw ? sb[lane] : -INFINITY);
+    if (lane == 0) { partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b; }
+  }
+  const unsigned int c = (unsigned int)warp_sum_ll(n);
+  if (lane == 0 && c) atomicAdd(cnt, (unsigned long long)c);
+}
+// step 2: ok samples outside [bl, br] are flagged out (pmc.c:756-765)
+__global__ void k_flag_outside(long N, const double *__restrict__ w, short *__restrict__ flg, double bl, double br,
+                               unsigned long long *cnt) {
+  unsigned int n = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x)
+    if (flg[i] == 1) {
+      const double v = w[i];
+      if (v < bl || br < v) { flg[i] = 0; ++n; }
+    }
+  const unsigned int c = (unsigned int)warp_sum_ll(n);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(cnt, (unsigned long long)c);
+}
+// mean_from_psim (pmc.c:1108-1120): sum over ok samples of w_i X[i][a]
+__global__ void k_weighted_coord(long N, int d, int a, const double *__restrict__ X, const double *__restrict__ w,
+                                 const short *__restrict__ flg, double *__restrict__ partial) {
+  double v[1] = {0.0};
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x)
+    if (flg[i] != 0) v[0] += w[i] * X[(size_t)i * d + a];
+  block_sum_store<1>(v, partial);
+}
+
 // ---- launch wrappers -----------------------------------------------------------------------------------------
 static inline int nblk(long n, int t) { return (int)((n + t - 1) / t); }
 static long g_launches = 0;
@@ -502,6 +550,19 @@ void launch_rb_reduce_cov(int K, int d, long n, long base, int nsplit, const dou
 void launch_norm_scale_perp(long N, double S, double *w, const short *flg, double *partial, int nblocks,
                             unsigned long long *counters, cudaStream_t s) {
   { k_norm_scale_perp<<<nblocks, 256, 0, s>>>(N, S, w, flg, partial, counters); count_launch(); }
+}
+
+void launch_minmax_ok(long N, const double *w, const short *flg, double *partial, int nblocks, unsigned long long *cnt,
+                      cudaStream_t s) {
+  { k_minmax_ok<<<nblocks, 256, 0, s>>>(N, w, flg, partial, cnt); count_launch(); }
+}
+void launch_flag_outside(long N, const double *w, short *flg, double bl, double br, int nblocks, unsigned long long *cnt,
+                         cudaStream_t s) {
+  { k_flag_outside<<<nblocks, 256, 0, s>>>(N, w, flg, bl, br, cnt); count_launch(); }
+}
+void launch_weighted_coord(long N, int d, int a, const double *X, const double *w, const short *flg, double *partial,
+                           int nblocks, cudaStream_t s) {
+  { k_weighted_coord<<<nblocks, 256, 0, s>>>(N, d, a, X, w, flg, partial); count_launch(); }
 }
 
 }  // namespace pmcb200

@@ -58,6 +58,13 @@ void launch_rb_reduce_cov(int K, int d, long n, long base, int nsplit, const dou
 void launch_norm_scale_perp(long N, double S, double *w, const short *flg, double *partial, int nblocks,
                             unsigned long long *counters, cudaStream_t s);
 
+void launch_minmax_ok(long N, const double *w, const short *flg, double *partial, int nblocks, unsigned long long *cnt,
+                      cudaStream_t s);
+void launch_flag_outside(long N, const double *w, short *flg, double bl, double br, int nblocks, unsigned long long *cnt,
+                         cudaStream_t s);
+void launch_weighted_coord(long N, int d, int a, const double *X, const double *w, const short *flg, double *partial,
+                           int nblocks, cudaStream_t s);
+
 // ---- fused small-d iteration kernel (pmc_fused.cu) -----------------------------------------------------------
 constexpr int FUSED_MAXD = 16;
 

@@ -85,7 +85,13 @@ int main(int argc, char **argv) {
     for (int f = 0; f < nfaces; ++f) { add_face(pb, faces + (size_t)f * (d + 1), faces[(size_t)f * (d + 1) + d], err); CHECK(err, "add_face"); }
   }
   pmc_simu *psim = pmc_simu_init(N, d, err); CHECK(err, "pmc_simu_init");
-  pmc_simu_init_classic_pmc(psim, tgt, pb, m, 0, NULL, NULL, err); CHECK(err, "init_classic_pmc");
+  if (mode == 4) { /* the shipped pmc_filter hook (pmc.c:203-206): histogram clipping of the log-weights */
+    int *fil = filter_histogram_init(20, 1, 2, err); CHECK(err, "filter_histogram_init");
+    pmc_simu_init_classic_pmc(psim, tgt, pb, m, 0, fil, &filter_histogram, err);
+  } else {
+    pmc_simu_init_classic_pmc(psim, tgt, pb, m, 0, NULL, NULL, err);
+  }
+  CHECK(err, "init_classic_pmc");
   sm_state st = {(uint64_t)hdr[5]};
   gsl_rng rng = {&sm_type, &st};
 
@@ -133,6 +139,12 @@ int main(int argc, char **argv) {
     for (int k = 0; k < K; ++k) fwrite(m->comp[k]->mean, sizeof(double), d, out);
     for (int k = 0; k < K; ++k) fwrite(m->comp[k]->std, sizeof(double), (size_t)d * d, out);
     printf("iteration %d perplexity %g effectiveSampleSize %g evidence %g\n", it, perp, ess, exp(lne));
+  }
+  if (mode == 4) { /* post-processing either side of the path: ASCII dump and per-coordinate mean */
+    char name[4096];
+    snprintf(name, sizeof name, "%s.txt", argv[2]);
+    out_pmc_simu(name, psim, err); CHECK(err, "out_pmc_simu");
+    for (int a = 0; a < d; ++a) printf("mean %d %.17g\n", a, mean_from_psim(psim->X, psim->weights, psim->flg, (int)N, d, a));
   }
   if (ut) printf("user callback calls %ld\n", ut->calls);
   fclose(out);

@@ -51,6 +51,8 @@ def orc():
         L.orc_ranindx.argtypes = [vp, C.c_size_t, C.c_double]
         L.orc_weights.restype = C.c_long
         L.orc_simulate.restype = C.c_long
+        L.orc_filter_histogram.restype = C.c_long
+        L.orc_mean_from_psim.restype = C.c_double
         _orc = L
     return _orc
 
@@ -95,7 +97,7 @@ def make_target(t):
     return OrcTarget(t["kind"], t["d"], 0.0, 0.0, m.c), m
 
 
-def orc_iteration(X, indices, wl, t=1.0, do_update=1, in_retry=0):
+def orc_iteration(X, indices, wl, t=1.0, do_update=1, in_retry=0, filt=None):
     """Restatement of one iteration on given samples; mirrors ref_iteration's outputs."""
     L = orc()
     X = np.ascontiguousarray(X, np.float64)
@@ -118,6 +120,9 @@ def orc_iteration(X, indices, wl, t=1.0, do_update=1, in_retry=0):
     if nok < 0:
         out["rc"] = nok
         return out
+    if filt is not None:  # the pmc_filter hook between weights and normalisation (pmc.c:203-206)
+        L.orc_filter_histogram.restype = C.c_long
+        out["n_filtered"] = L.orc_filter_histogram(C.c_long(N), P(w), P(flg), *[int(f) for f in filt])
     ls = C.c_double()
     rc = L.orc_normalize(C.c_long(N), P(w), P(flg), mw, C.byref(ls))
     out.update(rc=rc, logSum=ls.value, w_norm=w.copy(), flg=flg.copy())

@@ -107,3 +107,50 @@ def test_oracle_draw_statistics():
 
 def test_golden_files_present():
     assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 6
+
+
+@pytest.mark.parametrize("case", ["plain", "first_flagged", "w0_extreme", "none_ok", "nan_inside"])
+def test_filter_histogram_restatement_equals_reference(case):
+    """filter_histogram (pmc.c:709-770): flags bit-exact, including the weights[0] initialisation quirk."""
+    import ctypes as C
+    R = O.ref()
+    if R is None:
+        pytest.skip("compiled reference not available")
+    L = O.orc()
+    rng = np.random.default_rng(17)
+    N = 5000
+    w = rng.normal(-300.0, 25.0, N)
+    flg = (rng.uniform(size=N) > 0.05).astype(np.int16)
+    if case == "first_flagged":
+        flg[:5] = 0
+    if case == "w0_extreme":
+        flg[0] = 0
+        w[0] = 1e6   # not ok, yet it seeds min and max (pmc.c:734-735)
+    if case == "none_ok":
+        flg[:] = 0
+    if case == "nan_inside":
+        w[100] = np.nan
+    for nb, cl, cr in [(10, 1, 1), (50, 0, 3), (7, 2, 0)]:
+        f1, f2 = flg.copy(), flg.copy()
+        w1, w2 = w.copy(), w.copy()
+        R.ref_filter_histogram.restype = C.c_long
+        n1 = R.ref_filter_histogram(C.c_long(N), O.P(w1), O.P(f1), nb, cl, cr)
+        n2 = L.orc_filter_histogram(C.c_long(N), O.P(w2), O.P(f2), nb, cl, cr)
+        assert n1 == n2 and np.array_equal(f1, f2)
+        if case == "plain":
+            assert 0 < n1 < N
+
+
+def test_mean_from_psim_restatement_equals_reference():
+    import ctypes as C
+    R = O.ref()
+    if R is None:
+        pytest.skip("compiled reference not available")
+    L = O.orc()
+    rng = np.random.default_rng(3)
+    N, d = 4000, 6
+    X = rng.normal(size=(N, d)); w = rng.uniform(size=N); w /= w.sum()
+    flg = (rng.uniform(size=N) > 0.1).astype(np.int16)
+    R.ref_mean_from_psim.restype = C.c_double
+    for a in range(d):
+        assert R.ref_mean_from_psim(O.P(X), O.P(w), O.P(flg), N, d, a) == L.orc_mean_from_psim(O.P(X), O.P(w), O.P(flg), C.c_long(N), d, a)

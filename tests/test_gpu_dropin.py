@@ -83,3 +83,32 @@ def test_c_driver_iterations_match_oracle(driver, tmp_path, mode):
         cur = dict(wl, wght=r["wght"], mean=r["mean"], cov=r["L"], is_chol=True)
     if mode == 2:
         assert f"user callback calls {N * niter}" in stdout  # the opaque target really ran on the host, once per sample
+
+
+def test_c_driver_with_histogram_filter(driver, tmp_path):
+    """pmc_simu_init_classic_pmc(..., filter_histogram_init(20,1,2), &filter_histogram): the filter runs on the device inside
+    pmc_simu_pmc_step; afterwards out_pmc_simu (byte format of pmc.c:306-325) and mean_from_psim."""
+    wl = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
+    N, niter = 30000, 2
+    rec, stdout = _run(driver, tmp_path, wl, N, niter, 4)
+    cur = dict(wl)
+    for it, r in enumerate(rec):
+        o = O.orc_iteration(r["X"], r["idx"], cur, do_update=1, in_retry=0 if it == 0 else rec[it - 1]["retry"], filt=(20, 1, 2))
+        assert o["rc"] == 0 and o["n_filtered"] > 0
+        assert np.array_equal(r["flg"], o["flg"])
+        assert_close(r["w"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
+        assert_close(r["perp"], o["perp"], 1e-11, what="perplexity")
+        assert r["retry"] == o["retry"]
+        compare_mixture(r["wght"], r["mean"], r["L"], o["o_wght"], o["o_mean"], o["o_std"], what=f"filter it{it}")
+        cur = dict(wl, wght=r["wght"], mean=r["mean"], cov=r["L"], is_chol=True)
+    last = rec[-1]
+    ok = last["flg"] != 0
+    means = {int(l.split()[1]): float(l.split()[2]) for l in stdout.splitlines() if l.startswith("mean ")}
+    for a in range(wl["d"]):
+        assert_close(means[a], float(np.sum(last["w"][ok] * last["X"][ok, a])), 1e-11, scale=1.0, what=f"mean_from_psim {a}")
+    lines = open(str(tmp_path / "out4.bin") + ".txt").read().splitlines()
+    assert len(lines) == int(ok.sum())
+    first = np.array(lines[0].split(), float)
+    i0 = int(np.argmax(ok))
+    want = np.array([float("% .5e" % v) for v in list(last["X"][i0]) + [last["w"][i0]]])
+    assert np.array_equal(first, want)
