@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spl", type=int, default=None)
-    ap.add_argument("--opts", default="", help="comma separated pmcgpu_set_option pairs, e.g. k1_variant=1,split_stats=0")
+    ap.add_argument("--opts", default="", help="comma separated pmcgpu_set_option pairs, e.g. split_stats=0,split_draw=0")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

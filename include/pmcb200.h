@@ -42,9 +42,12 @@ int pmcgpu_version(void);
 /* the CUDA stream all work of this context is enqueued on (a cudaStream_t), for callers that time with events */
 void *pmcgpu_stream(pmcgpu_ctx *ctx);
 
-/* tuning / test knobs: "force_generic" (1 = never use the fused small-d kernel), "spl" (samples per lane of the fused
- * kernel, 1 or 2), "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass
- * update), "guard_ratio" (pivot guard threshold of the one-pass update), "timing" (see pmcgpu_get_timing) */
+/* tuning / test knobs: "force_generic" (1 = only the literal any-shape kernels), "fused_version" (0 = newest small-d
+ * kernel that has an instantiation, 1 = first generation, 2 = second generation only), "spl" (samples per lane of the
+ * first-generation kernel, 1 or 2), "split_stats" / "split_draw" (0 = single-kernel variants of the second generation),
+ * "mma" (0 = do not use the large-d tensor path), "mma_min_d" (smallest dimension routed to it, default 17),
+ * "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass update),
+ * "guard_ratio" (pivot guard threshold of the one-pass update), "timing" (see pmcgpu_get_timing) */
 int pmcgpu_set_option(pmcgpu_ctx *ctx, const char *name, double value);
 
 /* timing of the dominant (fused) kernel, measured with CUDA events on the launching stream while option "timing" = 1:

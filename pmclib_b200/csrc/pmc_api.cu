@@ -130,8 +130,8 @@ struct pmcgpu_ctx {
   int timing = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evd = nullptr;
   double fused_ms = 0.0, stats_ms = 0.0, draw_ms = 0.0;
-  int split_draw = 1, draw_variant = 0;  // draw as its own launch: smaller code and registers for both kernels (+6 % measured)
-  int split_stats = 1, k1_variant = 1;  // 4 warps x 4 blocks per SM (128 registers): best measured launch shape
+  int split_draw = 1;   // draw as its own launch: smaller code and registers for both kernels (+6 % measured)
+  int split_stats = 1;  // statistics as their own DMMA kernel (the single-kernel MODE 2 is 15 % slower)
   DevBuf resp, partials2, dscal, zig;
   long fused_launches = 0;
   // options
@@ -485,13 +485,13 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
   bool drew_separately = false;
   if (p.valid == 2 && c->split_draw && do_draw && mode != 2) {  // draw as its own (integer-heavy) launch, then the FP64 kernel on X
     FusedArgs ad = a;
-    lrc = launch_fused2(p, ad, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), 3, c->draw_variant, &nblk, c->stream);
+    lrc = launch_fused2(p, ad, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), 3, &nblk, c->stream);
     a.do_draw = 0;
     drew_separately = true;
   }
   if (c->timing) CU(cudaEventRecord(c->evd, c->stream));
   if (!lrc)
-    lrc = (p.valid == 2) ? launch_fused2(p, a, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), mode, c->k1_variant, &nblk, c->stream)
+    lrc = (p.valid == 2) ? launch_fused2(p, a, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), mode, &nblk, c->stream)
                          : launch_fused(p, a, c->stream);
   if (lrc != 0) return fail(c, PMCGPU_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
@@ -985,8 +985,6 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "timing")) { c->timing = (int)value; c->fused_ms = 0.0; c->stats_ms = 0.0; c->draw_ms = 0.0; c->fused_launches = 0; }
   else if (!strcmp(name, "split_stats")) c->split_stats = (int)value;
   else if (!strcmp(name, "split_draw")) c->split_draw = (int)value;
-  else if (!strcmp(name, "draw_variant")) c->draw_variant = (int)value;
-  else if (!strcmp(name, "k1_variant")) c->k1_variant = (int)value;
   else if (!strcmp(name, "mma")) { c->use_mma = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_min_d")) { c->mma_min_d = (int)value; return repack_mma(c); }
   else return fail(c, PMCGPU_ERR_USAGE, "unknown option %s", name);

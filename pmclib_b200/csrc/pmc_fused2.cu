@@ -41,13 +41,8 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem);
 
 // |L^-1 (x - mu)|^2 with every parameter read from a constant bank at a compile-time offset
 template <int D, int SPL, bool TGT>
-__device__ __forceinline__ void whiten_c(int base, const double (&x)[SPL][D], double (&q)[SPL], const double *smem_mix = nullptr) {
-#ifdef PMC_F2_SMEM_PARAMS
-  const double *cp = TGT ? c_tgt : smem_mix;
-#else
+__device__ __forceinline__ void whiten_c(int base, const double (&x)[SPL][D], double (&q)[SPL]) {
   const double *cp = TGT ? c_tgt : c_mix;
-  (void)smem_mix;
-#endif
   double v[SPL][D];
 #pragma unroll
   for (int a = 0; a < D; ++a) {
@@ -140,19 +135,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
   const Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
   const int fr = lane >> 2, fc = lane & 3;  // fragment row (component / entry within a tile), k-step column (sample)
 
-  // asynchronous copy (cp.async = LDGSTS) of one tile of X rows into this warp's stage
-  auto prefetch_x = [&](long nt) {
-    if (nt < ntiles) {
-      const long nb = nt * TS;
-      const int tn = (a.N - nb) < TS ? (int)(a.N - nb) : TS;
-      if ((D & 1) == 0) { for (int c = lane; c < tn * D / 2; c += 32) cp_async16(ptile + 2 * c, a.X + (size_t)nb * D + 2 * c); }
-      else { for (int c = lane; c < tn * D; c += 32) cp_async8(ptile + c, a.X + (size_t)nb * D + c); }
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-#ifdef PMC_XPREFETCH  // measured 6 % slower than plain per-lane loads on B200 (A/B build, r01): off by default
-  if (MODE != 3 && !a.do_draw) prefetch_x((long)blockIdx.x * F2_WARPS + wid);  // prologue of the X prefetch pipeline
-#endif
   for (long tile = (long)blockIdx.x * F2_WARPS + wid; tile < ntiles; tile += (long)gridDim.x * F2_WARPS) {
     const long tbase = tile * TS;
     double x[SPL][D];
@@ -227,21 +209,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
     } else {
       // samples already in HBM: the tile was prefetched into this warp's stage with cp.async (LDGSTS) while the previous
       // tile was being computed, so the first FP64 instruction does not wait for a global load
-#ifdef PMC_XPREFETCH  // measured 6 % slower than plain per-lane loads on B200 (A/B build, r01): off by default
-      asm volatile("cp.async.wait_group 0;\n" ::);
-      __syncwarp();
-#pragma unroll
-      for (int s = 0; s < SPL; ++s) {
-        const long i = tbase + s * 32 + lane;
-        valid[s] = i < a.N;
-        kdraw[s] = 0;
-#pragma unroll
-        for (int i2 = 0; i2 < D; ++i2) x[s][i2] = valid[s] ? ptile[(s * 32 + lane) * D + i2] : 0.0;
-        if (valid[s]) kdraw[s] = (int)a.indices[i];
-      }
-      __syncwarp();
-      if (MODE != 2) prefetch_x(tile + (long)gridDim.x * F2_WARPS);  // MODE 2 re-uses the stage as its P tile: prefetch after phase 2
-#else
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
         const long i = tbase + s * 32 + lane;
@@ -261,7 +228,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
           kdraw[s] = (int)a.indices[i];
         }
       }
-#endif
     }
 
     if (MODE == 3) continue;  // draw-only kernel: the FP64 part runs as a second launch on the stored samples
@@ -325,7 +291,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         double q[SPL];
-        whiten_c<D, SPL, false>(k * ST, x, q, mixs);
+        whiten_c<D, SPL, false>(k * ST, x, q);
         const bool alive = c_mix[k * ST + f2_oSc(D)] > 0.0;
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
@@ -456,9 +422,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
         __syncwarp();
       }
     }
-#ifdef PMC_XPREFETCH  // measured 6 % slower than plain per-lane loads on B200 (A/B build, r01): off by default
-    if (MODE == 2 && !a.do_draw) prefetch_x(tile + (long)gridDim.x * F2_WARPS);
-#endif
   }
 
   // ---------------- block combine (fixed order -> deterministic) ----------------------------------------------
@@ -770,7 +733,6 @@ static int launch_k1(const FusedPlan &p, const FusedArgs &a, int *nblocks_out, c
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
   if (nb > 5) nb = 5;
-  if (MODE == 3 && nb > 2) nb = nb;  // the draw kernel writes no partials that matter
   *nblocks_out = p.grid * nb;
   kern<<<p.grid * nb, WARPS * 32, smem, s>>>(a);
   count_launch();
@@ -779,11 +741,10 @@ static int launch_k1(const FusedPlan &p, const FusedArgs &a, int *nblocks_out, c
 
 template <int D, int K, int KT, int SPL>
 static int launch_one2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode,
-                       int variant, int *nb, cudaStream_t s) {
+                       int *nb, cudaStream_t s) {
   if (h_mix && cudaMemcpyToSymbolAsync(c_mix, h_mix, sizeof(double) * K * f2_stride(D), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
   if (KT > 0 && h_tgt && cudaMemcpyToSymbolAsync(c_tgt, h_tgt, sizeof(double) * KT * f2_stride(D), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
-  // launch shapes (warps per block, min blocks per SM) chosen by A/B timing on B200; `variant` selects alternatives for experiments
-  (void)variant;
+  // launch shapes (warps per block, min blocks per SM) chosen by A/B timing on B200
   static_assert(SPL == 1, "two samples per lane measured slower (register spills); only SPL = 1 is instantiated");
   if (mode == 3) return launch_k1<D, K, KT, SPL, 3, 8, 2>(p, a, nb, s);
   if (mode == 2) return launch_k1<D, K, KT, SPL, 2, 8, 1>(p, a, nb, s);
@@ -827,10 +788,10 @@ FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want
 
 int fused2_max_blocks(const FusedPlan &p) { return p.grid * 5; }
 
-int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode, int variant,
+int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode,
                   int *nblocks_out, cudaStream_t s) {
 #define X(D_, K_, KT_, SPL_) \
-  if (p.D == D_ && p.RK == K_ && p.RE == KT_ && p.SPL == SPL_) return launch_one2<D_, K_, KT_, SPL_>(p, a, h_mix, h_tgt, mode, variant, nblocks_out, s);
+  if (p.D == D_ && p.RK == K_ && p.RE == KT_ && p.SPL == SPL_) return launch_one2<D_, K_, KT_, SPL_>(p, a, h_mix, h_tgt, mode, nblocks_out, s);
   PMC_FUSED2_TABLE(X)
 #undef X
   return -1;

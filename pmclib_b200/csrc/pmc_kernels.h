@@ -129,7 +129,7 @@ FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want
 int fused2_max_blocks(const FusedPlan &p);  // upper bound of the grid of any launch shape (size of the partials buffer)
 // mode 0: weights only, 1: weights + responsibilities (split pipeline), 2: statistics fused.  Returns blocks launched
 // through *nblocks_out.
-int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode, int variant,
+int launch_fused2(const FusedPlan &p, const FusedArgs &a, const double *h_mix, const double *h_tgt, int mode,
                   int *nblocks_out, cudaStream_t s);
 int launch_fused2_max(const FusedPlan &p, const double *partials, int nblocks, double *out2, cudaStream_t s);
 int launch_fused2_stats(const FusedPlan &p, const double *X, const double *lw, const double *resp, const short *flg,
