@@ -39,6 +39,7 @@ int pmcgpu_create(int device, pmcgpu_ctx **out);
 void pmcgpu_destroy(pmcgpu_ctx *ctx);
 const char *pmcgpu_last_error(const pmcgpu_ctx *ctx);
 int pmcgpu_version(void);
+int pmcgpu_device_count(void); /* CUDA devices visible to this process (0 without a driver) */
 /* the CUDA stream all work of this context is enqueued on (a cudaStream_t), for callers that time with events */
 void *pmcgpu_stream(pmcgpu_ctx *ctx);
 

@@ -916,6 +916,12 @@ extern "C" {
 
 int pmcgpu_version(void) { return 100; }
 
+int pmcgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 int pmcgpu_create(int device, pmcgpu_ctx **out) {
   if (!out) return PMCGPU_ERR_USAGE;
   *out = nullptr;
@@ -1703,7 +1709,7 @@ int pmcgpu_get_proposal(pmcgpu_ctx *c, double *o_wght, double *o_mean, double *o
 // page-lock / unlock a caller-owned host block so that upload/download run as DMA at PCIe speed
 int pmcgpu_pin_host(void *p, size_t bytes) {
   if (!p || !bytes) return PMCGPU_ERR_USAGE;
-  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
   if (e != cudaSuccess) { cudaGetLastError(); return PMCGPU_ERR_CUDA; }
   return 0;
 }

@@ -12,8 +12,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include "../../include/pmcb200.h"
 #include "../../include/pmclib_abi.h"
@@ -50,6 +53,45 @@ bool resident() {
   return g_resident == 1;
 }
 
+// Rendezvous of the per-GPU host threads of one iteration (single-process multi-GPU mode): the all-reduce callback of
+// every shard context meets here; the last arrival reduces in rank order (deterministic, identical on all ranks).
+struct Rendezvous {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 1, arrived = 0;
+  long gen = 0;
+  bool broken = false;
+  std::vector<double *> bufs;
+  std::vector<double> acc;
+};
+struct RvRank { Rendezvous *rv; int rank; };
+int rv_allreduce(void *user, double *buf, long len, int op) {
+  RvRank *me = (RvRank *)user;
+  Rendezvous &rv = *me->rv;
+  std::unique_lock<std::mutex> lk(rv.m);
+  if (rv.broken) return 1;
+  rv.bufs[me->rank] = buf;
+  if (++rv.arrived == rv.n) {
+    rv.acc.assign(buf, buf + len);
+    for (long i = 0; i < len; ++i) {
+      double a = rv.bufs[0][i];
+      for (int r = 1; r < rv.n; ++r) {
+        const double v = rv.bufs[r][i];
+        a = op ? (v > a ? v : a) : a + v;
+      }
+      rv.acc[i] = a;
+    }
+    for (int r = 0; r < rv.n; ++r) memcpy(rv.bufs[r], rv.acc.data(), sizeof(double) * len);
+    rv.arrived = 0;
+    ++rv.gen;
+    rv.cv.notify_all();
+    return 0;
+  }
+  const long g = rv.gen;
+  if (!rv.cv.wait_for(lk, std::chrono::seconds(600), [&] { return rv.gen != g || rv.broken; })) rv.broken = true;
+  return rv.broken ? 1 : 0;
+}
+
 struct Side {
   pmcgpu_ctx *ctx = nullptr;
   long N = 0;
@@ -57,6 +99,10 @@ struct Side {
   uint32_t iter = 0;
   bool host_stale = false;  // resident mode: HBM holds newer sample arrays than the host
   void *pinned = nullptr;   // psim->data while it is page-locked
+  // single-process multi-GPU mode (PMCB200_GPUS > 1): shard[0] == ctx, shard[g] lives on GPU g
+  std::vector<pmcgpu_ctx *> shard;
+  std::vector<RvRank> rvrank;
+  Rendezvous rv;
 };
 std::map<const pmc_simu *, Side> g_side;
 std::map<const distribution *, int> g_registered;
@@ -759,6 +805,7 @@ void pmc_simu_free(pmc_simu **melf) {
     auto it = g_side.find(s);
     if (it != g_side.end()) {
       if (it->second.pinned) pmcgpu_unpin_host(it->second.pinned);
+      for (size_t g = 1; g < it->second.shard.size(); ++g) pmcgpu_destroy(it->second.shard[g]);
       if (it->second.ctx) pmcgpu_destroy(it->second.ctx);
       g_side.erase(it);
     }
@@ -1055,6 +1102,95 @@ size_t pmc_simu_importance(pmc_simu *psim, gsl_rng *r, error **err) {
   return (size_t)nok;
 }
 
+// ---- single-process multi-GPU iteration --------------------------------------------------------------------------------------
+// An unmodified (non-MPI) pmclib driver uses every GPU of the node with PMCB200_GPUS=n: the sample is cut into n shards
+// (pmc_mpi.c:344-352 layout), one host thread per GPU runs pmcgpu_pmc_step on its shard, the small all-reduces meet in a
+// host rendezvous, every shard is copied straight into its slice of the caller's arrays.
+int gpus_wanted() {
+  static int n = -1;
+  if (n < 0) {
+    n = 1;
+    if (const char *e = getenv("PMCB200_GPUS")) n = atoi(e);
+    const int have = pmcgpu_device_count();
+    if (n > have) n = have;
+    if (n < 1) n = 1;
+  }
+  return n;
+}
+
+double pmc_step_multi(Side *s, pmc_simu *psim, mix_mvdens *m, gsl_rng *r, error **err) {
+  const int G = gpus_wanted(), K = (int)m->ncomp, d = (int)m->ndim;
+  const long N = psim->nsamples;
+  if ((int)s->shard.size() != G) {
+    s->shard.assign(1, s->ctx);
+    const int dev0 = device_ordinal(), have = pmcgpu_device_count();
+    for (int g = 1; g < G; ++g) {
+      pmcgpu_ctx *c = nullptr;
+      const int rc = pmcgpu_create((dev0 + g) % have, &c);
+      if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"libpmcb200: cannot open GPU %d", *err, nullptr, (dev0 + g) % have); s->shard.resize(1); return 0; }
+      s->shard.push_back(c);
+    }
+    s->rv.n = G;
+    s->rv.bufs.assign(G, nullptr);
+    s->rvrank.resize(G);
+    for (int g = 0; g < G; ++g) {
+      s->rvrank[g] = RvRank{&s->rv, g};
+      pmcgpu_comm_set_callback(s->shard[g], &rv_allreduce, &s->rvrank[g], g, G);
+    }
+  }
+  std::vector<long> first(G), len(G);
+  for (int g = 0; g < G; ++g) {
+    pmcgpu_shard_range(N, g, G, &first[g], &len[g]);
+    Side tmp;
+    tmp.ctx = s->shard[g];
+    const int rc = pmcgpu_resize(tmp.ctx, len[g], d);
+    if (rc) { gpu_fail(&tmp, rc, err, __func__); return 0; }
+    if (!push_proposal(&tmp, m, err) || !push_target(&tmp, psim->target, err) || !push_box(&tmp, psim->pb, psim->ndim, err)) return 0;
+    const int *fil = psim->pmc_filter ? (const int *)psim->filter_data : nullptr;
+    pmcgpu_set_filter_histogram(tmp.ctx, fil ? fil[0] : 0, fil ? fil[1] : 0, fil ? fil[2] : 0);
+  }
+  s->N = len[0];  // shard[0] is the context the phase-by-phase entry points use: side_for() sizes it back when needed
+  const uint64_t seed = seed_from(r);
+  const uint32_t iter = s->iter++;
+  std::vector<int> rcs(G, 0), retry(G, psim->retry);
+  std::vector<pmcgpu_step_result> res(G);
+  std::vector<double> w(K), mean((size_t)K * d), L((size_t)K * d * d), detL(K);
+  std::vector<int> alive(K);
+  s->rv.broken = false;
+  s->rv.arrived = 0;
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; ++g)
+    th.emplace_back([&, g]() {
+      const bool lead = g == 0;
+      int rc = pmcgpu_pmc_step(s->shard[g], seed, iter, first[g], N, 1, &retry[g], &res[g], lead ? w.data() : nullptr,
+                               lead ? mean.data() : nullptr, lead ? L.data() : nullptr, lead ? detL.data() : nullptr,
+                               lead ? alive.data() : nullptr);
+      if (rc) {  // release the ranks that may be waiting for this one
+        std::lock_guard<std::mutex> lk(s->rv.m);
+        s->rv.broken = true;
+        s->rv.cv.notify_all();
+      } else {
+        rc = pmcgpu_download(s->shard[g], psim->X + (size_t)first[g] * d, psim->indices + first[g], psim->weights + first[g],
+                             psim->log_rho + first[g], psim->flg + first[g]);
+      }
+      rcs[g] = rc;
+    });
+  for (auto &t : th) t.join();
+  for (int g = 0; g < G; ++g) pmcgpu_set_filter_histogram(s->shard[g], 0, 0, 0);
+  for (int pass = 0; pass < 2; ++pass)  // the rank that failed first, not the ranks its failure released from the rendezvous
+    for (int g = 0; g < G; ++g)
+      if (rcs[g] && (pass == 1 || rcs[g] != PMCGPU_ERR_NCCL)) { Side tmp; tmp.ctx = s->shard[g]; gpu_fail(&tmp, rcs[g], err, __func__); return 0; }
+  psim->maxW = res[0].maxW;
+  psim->maxR = res[0].maxR;
+  psim->logSum = res[0].logSum;
+  psim->isLog = 0;
+  psim->retry = retry[0];
+  if (psim->retry != 0) fprintf(stderr, "RETRY state -> %d\n", psim->retry);
+  unflatten(m, w.data(), mean.data(), L.data(), detL.data());
+  s->host_stale = false;
+  return res[0].perplexity;
+}
+
 double pmc_simu_pmc_step(pmc_simu *psim, gsl_rng *r, error **err) {
   if (!psim->pmc_update) { ERR_HERE(*err, pmc_allocate, "update function undefined", *err, nullptr); return 0; }
   const bool fast = psim->proposal && psim->target && psim->proposal->simulate == &simulate_mix_mvdens_void &&
@@ -1076,6 +1212,7 @@ double pmc_simu_pmc_step(pmc_simu *psim, gsl_rng *r, error **err) {
   Side *s = side_for(psim, err);
   if (!s) return 0;
   mix_mvdens *m = (mix_mvdens *)psim->proposal->data;
+  if (gpus_wanted() > 1 && !resident()) return pmc_step_multi(s, psim, m, r, err);
   if (!push_proposal(s, m, err) || !push_target(s, psim->target, err) || !push_box(s, psim->pb, psim->ndim, err)) return 0;
   const int K = (int)m->ncomp, d = (int)m->ndim;
   std::vector<double> w(K), mean((size_t)K * d), L((size_t)K * d * d), detL(K);

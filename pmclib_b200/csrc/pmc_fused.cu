@@ -543,11 +543,8 @@ __global__ void k_fused_combine(const double *__restrict__ partials, int nblocks
 template <int D, int RK, int RE, int NR, int SPL>
 static int launch_one(const FusedPlan &p, const FusedArgs &a, cudaStream_t s) {
   auto kern = k_fused<D, RK, RE, NR, SPL>;
-  static size_t configured = 0;
-  if (p.smem_bytes > configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return -1;
-    configured = p.smem_bytes;
-  }
+  // per device and per mixture size: set on every launch (a few hundred nanoseconds against a multi-millisecond kernel)
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return -1;
   kern<<<p.grid, p.threads, p.smem_bytes, s>>>(a);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -725,11 +725,8 @@ static int launch_k1(const FusedPlan &p, const FusedArgs &a, int *nblocks_out, c
   using C = F2Cfg<D, K, KT, SPL>;
   const size_t wd = (MODE == 2) ? C::WARP_DOUBLES : f2_ev2(C::TS * D);
   const size_t smem = ((size_t)K * C::ST + f2_ev2(K) + 2 * kZigLayers + (size_t)WARPS * wd) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> smem_set{0};
+  if (!set_max_smem_once(kern, smem, smem_set)) return -1;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
   if (nb > 5) nb = 5;
@@ -758,11 +755,8 @@ static int launch_stats2(const FusedPlan &p, const StatsArgs &a, cudaStream_t s)
   using C = F2Cfg<D, K, 0, 1>;
   size_t smem = (size_t)8 * S2Cfg<D, K>::WARP_DOUBLES * sizeof(double);
   if (smem < (size_t)C::ACC * sizeof(double)) smem = (size_t)C::ACC * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> smem_set{0};
+  if (!set_max_smem_once(kern, smem, smem_set)) return -1;
   kern<<<p.grid * 2, 256, smem, s>>>(a);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;

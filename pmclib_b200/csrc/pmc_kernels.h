@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/pmcb200.h"
 #include "pmc_dev.cuh"
 
@@ -10,6 +11,19 @@
 #endif
 
 namespace pmcb200 {
+
+// cudaFuncSetAttribute is per device: a kernel's opt-in shared-memory size must be set once on every GPU this process
+// drives (single-process multi-GPU mode of the drop-in layer), from whichever host thread gets there first.
+template <typename Kern>
+inline bool set_max_smem_once(Kern kern, size_t bytes, std::atomic<unsigned long long> &done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask.load(std::memory_order_acquire) & bit) return true;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+  done_mask.fetch_or(bit, std::memory_order_release);
+  return true;
+}
 
 constexpr int GEN_WEIGHT_THREADS = 128;
 

@@ -569,11 +569,8 @@ int launch_draw_t(const double *pack, const int4 *tiles, int ntiles, const unsig
                   uint64_t seed, uint32_t iter, long first_index, double *X, short *flg, unsigned long long *counters,
                   int sm_count, cudaStream_t s) {
   const size_t smem = (size_t)q_comp_stride(NT) * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(k_draw_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> smem_set{0};
+  if (!set_max_smem_once(k_draw_mma<NT>, smem, smem_set)) return 1;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
   k_draw_mma<NT><<<grid, 256, smem, s>>>(pack, tiles, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters);
   count_launch();
@@ -585,11 +582,8 @@ int launch_q(const double *X, long n, int d, const double *pack, int J, const in
              cudaStream_t s) {
   constexpr int TS = 64 * q_mt(NT);
   const size_t smem = (size_t)2 * q_comp_stride(NT) * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(k_q_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> smem_set{0};
+  if (!set_max_smem_once(k_q_mma<NT>, smem, smem_set)) return 1;
   const long ntile = (n + TS - 1) / TS;
   const int grid = (int)(ntile < sm_count ? ntile : sm_count);
   k_q_mma<NT><<<grid, 256, smem, s>>>(X, n, d, pack, J, kmap, Q, qs);
@@ -601,11 +595,8 @@ template <int NT>
 int launch_stats(const double *X, long n, int d, const double *G, long qs, int J, const int *kmap, int nchunk,
                  double *part, double *out, cudaStream_t s) {
   const size_t smem = ((size_t)2 * ST_SS * st_dpad(NT) + 2 * ST_CK * ST_SS) * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(k_stats_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> smem_set{0};
+  if (!set_max_smem_once(k_stats_mma<NT>, smem, smem_set)) return 1;
   long chunk_len = (n + nchunk - 1) / nchunk;
   chunk_len = ((chunk_len + ST_SS - 1) / ST_SS) * ST_SS;
   k_stats_mma<NT><<<((J + ST_CK - 1) / ST_CK) * nchunk, 32 * st_warps(NT), smem, s>>>(X, n, d, G, qs, J, kmap, nchunk, chunk_len, part);

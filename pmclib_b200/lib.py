@@ -26,7 +26,7 @@ _lib = None
 
 # every symbol include/pmcb200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "pmcgpu_create", "pmcgpu_destroy", "pmcgpu_last_error", "pmcgpu_version", "pmcgpu_stream", "pmcgpu_set_option", "pmcgpu_get_timing", "pmcgpu_get_stats_timing", "pmcgpu_get_draw_timing",
+    "pmcgpu_create", "pmcgpu_destroy", "pmcgpu_last_error", "pmcgpu_version", "pmcgpu_device_count", "pmcgpu_stream", "pmcgpu_set_option", "pmcgpu_get_timing", "pmcgpu_get_stats_timing", "pmcgpu_get_draw_timing",
     "pmcgpu_set_proposal", "pmcgpu_set_band_limit", "pmcgpu_set_target_banana", "pmcgpu_set_target_mix",
     "pmcgpu_set_target_defaults", "pmcgpu_set_target_host", "pmcgpu_set_box", "pmcgpu_resize", "pmcgpu_upload",
     "pmcgpu_download", "pmcgpu_pin_host", "pmcgpu_unpin_host", "pmcgpu_device_arrays", "pmcgpu_draw", "pmcgpu_weights", "pmcgpu_draw_weights", "pmcgpu_weights_host_post",

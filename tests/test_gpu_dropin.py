@@ -24,7 +24,7 @@ def driver(tmp_path_factory):
     return exe
 
 
-def _run(driver, tmp_path, wl, N, niter, mode, seed=4242):
+def _run(driver, tmp_path, wl, N, niter, mode, env=None, seed=4242):
     K, d = wl["K"], wl["d"]
     faces = wl["faces"]
     cfg, out = tmp_path / f"in{mode}.bin", tmp_path / f"out{mode}.bin"
@@ -35,7 +35,7 @@ def _run(driver, tmp_path, wl, N, niter, mode, seed=4242):
         f.write(np.ascontiguousarray(wl["cov"]).tobytes())
         if faces is not None:
             f.write(np.ascontiguousarray(faces).tobytes())
-    r = subprocess.run([driver, str(cfg), str(out), str(mode)], capture_output=True, text=True)
+    r = subprocess.run([driver, str(cfg), str(out), str(mode)], capture_output=True, text=True, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout + r.stderr
     raw = np.fromfile(out, np.uint8)
     rec = []
@@ -112,3 +112,34 @@ def test_c_driver_with_histogram_filter(driver, tmp_path):
     i0 = int(np.argmax(ok))
     want = np.array([float("% .5e" % v) for v in list(last["X"][i0]) + [last["w"][i0]]])
     assert np.array_equal(first, want)
+
+
+@pytest.mark.parametrize("mode", [0, 4])
+def test_c_driver_single_process_multi_gpu(driver, tmp_path, mode):
+    """PMCB200_GPUS=2: the unmodified driver's pmc_simu_pmc_step shards the sample over two GPUs inside one process
+    (host threads + rendezvous all-reduce); every iteration still matches the oracle on the samples it produced."""
+    from pmclib_b200.lib import load_library
+    if load_library().pmcgpu_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    wl = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
+    N, niter = 40001, 3
+    rec, stdout = _run(driver, tmp_path, wl, N, niter, mode, env={"PMCB200_GPUS": "2"})
+    ref, _ = _run(driver, tmp_path, wl, N, niter, mode, env={"PMCB200_GPUS": "1"})
+    cur = dict(wl)
+    filt = (20, 1, 2) if mode == 4 else None
+    for it, (r, q) in enumerate(zip(rec, ref)):
+        # Philox is counted by the global sample index: the sharded run draws the very same sample as one GPU
+        assert np.array_equal(r["idx"], q["idx"]) and np.array_equal(r["flg"], q["flg"])
+        if it == 0:
+            assert np.array_equal(r["X"], q["X"])
+        o = O.orc_iteration(r["X"], r["idx"], cur, do_update=1, in_retry=0 if it == 0 else rec[it - 1]["retry"], filt=filt)
+        assert o["rc"] == 0
+        big = max(np.max(np.abs(o["log_rho"])), 1.0)
+        assert np.array_equal(r["flg"], o["flg"])
+        assert_close(r["lr"], o["log_rho"], RTOL, what=f"it{it} log_rho")
+        assert_close(r["w"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
+        assert_close(r["perp"], o["perp"], 1e-11, what="perplexity")
+        assert_close(r["logSum"], o["logSum"], RTOL, scale=big, what="logSum")
+        assert r["retry"] == o["retry"]
+        compare_mixture(r["wght"], r["mean"], r["L"], o["o_wght"], o["o_mean"], o["o_std"], what=f"2 GPUs it{it}")
+        cur = dict(wl, wght=r["wght"], mean=r["mean"], cov=r["L"], is_chol=True)
