@@ -1210,7 +1210,7 @@ static int draw_mma(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_inde
   CU(cudaMemcpyAsync(c->dtiles.p, ht, tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   unsigned int *cursor = c->dcnt.as<unsigned int>() + K;
   CU(cudaMemcpyAsync(cursor, ht + tiles.size(), (size_t)K * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
-  launch_draw_perm(N, c->Idx.as<unsigned long long>(), cursor, c->dperm.as<unsigned int>(), c->sm_count * 4, c->stream);
+  launch_draw_perm(N, K, c->Idx.as<unsigned long long>(), cursor, c->dperm.as<unsigned int>(), c->sm_count * 8, c->stream);
   CU(cudaGetLastError());
   if (launch_draw_mma(mm.lpack.as<double>(), c->dtiles.p, ntiles, c->dperm.as<unsigned int>(), mm.dfj.as<int>(), d, seed, iter,
                       first_index, c->X.as<double>(), c->Flg.as<short>(), c->small.as<unsigned long long>() + SM_COUNTERS,

@@ -170,8 +170,8 @@ void launch_resp_q(const MixDev &m, long N, const double *w, const double *log_r
 int mma_draw_tile_samples(int d);
 void launch_draw_pick(const double *cw, int K, uint64_t seed, uint32_t iter, long first_index, long N,
                       unsigned long long *indices, unsigned int *cnt, int nblocks, cudaStream_t s);
-void launch_draw_perm(long N, const unsigned long long *indices, unsigned int *cursor, unsigned int *perm, int nblocks,
-                      cudaStream_t s);
+void launch_draw_perm(long N, int K, const unsigned long long *indices, unsigned int *cursor, unsigned int *perm,
+                      int nblocks, cudaStream_t s);
 int launch_draw_mma(const double *pack, const void *tiles, int ntiles, const unsigned int *perm, const int *dfj, int d,
                     uint64_t seed, uint32_t iter, long first_index, double *X, short *flg, unsigned long long *counters,
                     int sm_count, cudaStream_t s);

@@ -49,21 +49,26 @@ __host__ __device__ constexpr int q_tiles(int NT) {  // tiles (nt, ks) with 4 ks
 }
 __host__ __device__ constexpr int q_comp_stride(int NT) { return 8 * NT + 32 * q_tiles(NT); }
 __host__ __device__ constexpr int q_mt(int NT) { return NT <= 4 ? 4 : (NT <= 8 ? 2 : 1); }
+// components per shared-memory stage of the whitening kernel: small factors are staged several at a time so that the
+// block-wide barrier and the cp.async round trip are paid once per 640+ DMMAs per warp group
+__host__ __device__ constexpr int q_cps(int NT) { return NT <= 4 ? 4 : (NT <= 8 ? 2 : 1); }
 
 // ---- whitening ----------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(256, 1)
 k_q_mma(const double *__restrict__ X, long n, int d, const double *__restrict__ pack, int J,
         const int *__restrict__ kmap, double *__restrict__ Q, long qs) {
-  constexpr int KS = 2 * NT, MT = q_mt(NT), CS = q_comp_stride(NT), TS = 64 * MT;
-  extern __shared__ double sm[];  // [2][CS]
+  constexpr int KS = 2 * NT, MT = q_mt(NT), CS = q_comp_stride(NT), TS = 64 * MT, CPS = q_cps(NT);
+  extern __shared__ double sm[];  // [2][CPS][CS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
   const long ntile = (n + TS - 1) / TS;
   if ((long)blockIdx.x >= ntile) return;
-  auto issue = [&](int buf, int j) {
-    const double *src = pack + (size_t)j * CS;
-    double *dst = sm + (size_t)buf * CS;
-    for (int c = threadIdx.x; c < CS / 2; c += 256) cpa16(dst + 2 * c, src + 2 * c);
+  const int nstage = (J + CPS - 1) / CPS;  // stages per sample tile
+  auto issue = [&](int buf, int st) {      // components [st*CPS, min(J, st*CPS+CPS)) are contiguous in the pack
+    const int j0 = st * CPS, nj = (J - j0) < CPS ? (J - j0) : CPS;
+    const double *src = pack + (size_t)j0 * CS;
+    double *dst = sm + (size_t)buf * CPS * CS;
+    for (int c = threadIdx.x; c < nj * CS / 2; c += 256) cpa16(dst + 2 * c, src + 2 * c);
     cpa_commit();
   };
   issue(0, 0);
@@ -81,41 +86,44 @@ k_q_mma(const double *__restrict__ X, long n, int d, const double *__restrict__ 
       }
     }
     const bool last_tile = tile + gridDim.x >= ntile;
-    for (int j = 0; j < J; ++j, ++s) {
+    for (int st = 0; st < nstage; ++st, ++s) {
       cpa_wait0();
       __syncthreads();
-      if (!(last_tile && j == J - 1)) issue((s + 1) & 1, (j + 1 == J) ? 0 : j + 1);
-      const double *cb = sm + (size_t)(s & 1) * CS;
-      double C[MT][NT][2];
+      if (!(last_tile && st == nstage - 1)) issue((s + 1) & 1, (st + 1 == nstage) ? 0 : st + 1);
+      const int j0 = st * CPS, nj = (J - j0) < CPS ? (J - j0) : CPS;
+      for (int jj = 0; jj < nj; ++jj) {
+        const double *cb = sm + ((size_t)(s & 1) * CPS + jj) * CS;
+        double C[MT][NT][2];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) { C[mt][nt][0] = 0.0; C[mt][nt][1] = 0.0; }
-      const double *tp = cb + 8 * NT + lane;
+          for (int nt = 0; nt < NT; ++nt) { C[mt][nt][0] = 0.0; C[mt][nt][1] = 0.0; }
+        const double *tp = cb + 8 * NT + lane;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const double mu = cb[4 * ks + t4];
-        double a[MT];
+        for (int ks = 0; ks < KS; ++ks) {
+          const double mu = cb[4 * ks + t4];
+          double a[MT];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) a[mt] = xa[mt][ks] - mu;
+          for (int mt = 0; mt < MT; ++mt) a[mt] = xa[mt][ks] - mu;
 #pragma unroll
-        for (int nt = ks / 2; nt < NT; ++nt) {
-          const double b = *tp;
-          tp += 32;
+          for (int nt = ks / 2; nt < NT; ++nt) {
+            const double b = *tp;
+            tp += 32;
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) dmma(C[mt][nt][0], C[mt][nt][1], a[mt], b);
+            for (int mt = 0; mt < MT; ++mt) dmma(C[mt][nt][0], C[mt][nt][1], a[mt], b);
+          }
         }
-      }
-      const int k = kmap[j];
+        const int k = kmap[j0 + jj];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        double q = 0.0;
+        for (int mt = 0; mt < MT; ++mt) {
+          double q = 0.0;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) { q = fma(C[mt][nt][0], C[mt][nt][0], q); q = fma(C[mt][nt][1], C[mt][nt][1], q); }
-        q += __shfl_xor_sync(0xffffffffu, q, 1);
-        q += __shfl_xor_sync(0xffffffffu, q, 2);
-        const long row = base + mt * 8 + g;
-        if (t4 == 0 && row < n) Q[(size_t)k * qs + row] = q;
+          for (int nt = 0; nt < NT; ++nt) { q = fma(C[mt][nt][0], C[mt][nt][0], q); q = fma(C[mt][nt][1], C[mt][nt][1], q); }
+          q += __shfl_xor_sync(0xffffffffu, q, 1);
+          q += __shfl_xor_sync(0xffffffffu, q, 2);
+          const long row = base + mt * 8 + g;
+          if (t4 == 0 && row < n) Q[(size_t)k * qs + row] = q;
+        }
       }
     }
   }
@@ -451,11 +459,34 @@ __global__ void k_draw_pick(const double *__restrict__ cw, int K, uint64_t seed,
   for (int k = threadIdx.x; k < K; k += blockDim.x)
     if (sc[k]) atomicAdd(&cnt[k], sc[k]);
 }
-// perm = sample ids grouped by component (order inside a group is irrelevant: every sample is computed from its own id)
-__global__ void k_draw_perm(long N, const unsigned long long *__restrict__ indices, unsigned int *__restrict__ cursor,
-                            unsigned int *__restrict__ perm) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x)
-    perm[atomicAdd(&cursor[indices[i]], 1u)] = (unsigned int)i;
+// perm = sample ids grouped by component (order inside a group is irrelevant: every sample is computed from its own id).
+// A block ranks its samples per component with shared-memory atomics and reserves one range per component with a single
+// global atomic: K instead of PERM_CHUNK global atomics per block (1e7 atomics on 50 addresses cost 2.7 ms before).
+constexpr int PERM_PER_THREAD = 8, PERM_CHUNK = 256 * PERM_PER_THREAD;
+__global__ void __launch_bounds__(256)
+k_draw_perm(long N, int K, const unsigned long long *__restrict__ indices, unsigned int *__restrict__ cursor,
+            unsigned int *__restrict__ perm) {
+  extern __shared__ unsigned int sc[];  // [K] counts, then [K] bases
+  unsigned int *sb = sc + K;
+  for (long c0 = (long)blockIdx.x * PERM_CHUNK; c0 < N; c0 += (long)gridDim.x * PERM_CHUNK) {
+    for (int k = threadIdx.x; k < K; k += 256) sc[k] = 0;
+    __syncthreads();
+    unsigned int rank[PERM_PER_THREAD];
+    int comp[PERM_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PERM_PER_THREAD; ++u) {
+      const long i = c0 + u * 256 + threadIdx.x;
+      comp[u] = -1;
+      if (i < N) { comp[u] = (int)indices[i]; rank[u] = atomicAdd(&sc[comp[u]], 1u); }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += 256) sb[k] = sc[k] ? atomicAdd(&cursor[k], sc[k]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PERM_PER_THREAD; ++u)
+      if (comp[u] >= 0) perm[sb[comp[u]] + rank[u]] = (unsigned int)(c0 + u * 256 + threadIdx.x);
+    __syncthreads();
+  }
 }
 
 template <int NT>
@@ -581,7 +612,7 @@ template <int NT>
 int launch_q(const double *X, long n, int d, const double *pack, int J, const int *kmap, double *Q, long qs, int sm_count,
              cudaStream_t s) {
   constexpr int TS = 64 * q_mt(NT);
-  const size_t smem = (size_t)2 * q_comp_stride(NT) * sizeof(double);
+  const size_t smem = (size_t)2 * q_cps(NT) * q_comp_stride(NT) * sizeof(double);
   static std::atomic<unsigned long long> smem_set{0};
   if (!set_max_smem_once(k_q_mma<NT>, smem, smem_set)) return 1;
   const long ntile = (n + TS - 1) / TS;
@@ -731,9 +762,11 @@ void launch_draw_pick(const double *cw, int K, uint64_t seed, uint32_t iter, lon
   k_draw_pick<<<nblocks, 256, K * sizeof(unsigned int), s>>>(cw, K, seed, iter, first_index, N, indices, cnt);
   count_launch();
 }
-void launch_draw_perm(long N, const unsigned long long *indices, unsigned int *cursor, unsigned int *perm, int nblocks,
-                      cudaStream_t s) {
-  k_draw_perm<<<nblocks, 256, 0, s>>>(N, indices, cursor, perm);
+void launch_draw_perm(long N, int K, const unsigned long long *indices, unsigned int *cursor, unsigned int *perm,
+                      int nblocks, cudaStream_t s) {
+  const long chunks = (N + PERM_CHUNK - 1) / PERM_CHUNK;
+  if (chunks < nblocks) nblocks = (int)chunks;
+  k_draw_perm<<<nblocks, 256, 2 * K * sizeof(unsigned int), s>>>(N, K, indices, cursor, perm);
   count_launch();
 }
 int launch_draw_mma(const double *pack, const void *tiles, int ntiles, const unsigned int *perm, const int *dfj, int d,

@@ -114,7 +114,11 @@ def main():
         r = g.pmc_step(seed, it, first, N_total, upd, retry); retry = r.retry; it += 1
     g.set_option("timing", 1)
     _, _, l0 = g.get_timing()
+    from bench import ClockSampler  # nvidia-smi clocks / throttle reasons during the timed region
+    sampler = ClockSampler(local)
     barrier()
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
@@ -125,6 +129,7 @@ def main():
     e1.record(stream)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
     ev_ms = e0.elapsed_time(e1)
     q_ms, q_n, l1 = g.get_timing()
     s_ms, d_ms = g.get_stats_timing(), g.get_draw_timing()
@@ -169,7 +174,7 @@ def main():
             "roofline": {"bound": "fp64", "algorithmic_flop_per_sample": Ftot, "achieved": value / world * Ftot * 1e-12,
                          "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": value / world * Ftot * 1e-12 / FP64_PEAK_TFLOPS,
                          "kernels": kern},
-            "cpu_baseline": cpu, "gpu_launches": int(l1 - l0)}))
+            "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(l1 - l0)}))
     if world > 1:
         dist.destroy_process_group()
 
