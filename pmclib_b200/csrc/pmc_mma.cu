@@ -52,13 +52,15 @@ __host__ __device__ constexpr int q_mt(int NT) { return NT <= 4 ? 4 : (NT <= 8 ?
 // components per shared-memory stage of the whitening kernel: small factors are staged several at a time so that the
 // block-wide barrier and the cp.async round trip are paid once per 640+ DMMAs per warp group
 __host__ __device__ constexpr int q_cps(int NT) { return NT <= 4 ? 4 : (NT <= 8 ? 2 : 1); }
+// warps per block of the whitening kernel: as many as the register file allows (NT = 16 needs 162 registers: 12 warps)
+__host__ __device__ constexpr int q_warps(int NT) { return NT == 16 ? 12 : 8; }
 
 // ---- whitening ----------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(32 * q_warps(NT), 1)
 k_q_mma(const double *__restrict__ X, long n, int d, const double *__restrict__ pack, int J,
         const int *__restrict__ kmap, double *__restrict__ Q, long qs) {
-  constexpr int KS = 2 * NT, MT = q_mt(NT), CS = q_comp_stride(NT), TS = 64 * MT, CPS = q_cps(NT);
+  constexpr int KS = 2 * NT, MT = q_mt(NT), CS = q_comp_stride(NT), QW = q_warps(NT), TS = 8 * QW * MT, CPS = q_cps(NT);
   extern __shared__ double sm[];  // [2][CPS][CS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
   const long ntile = (n + TS - 1) / TS;
@@ -68,7 +70,7 @@ k_q_mma(const double *__restrict__ X, long n, int d, const double *__restrict__ 
     const int j0 = st * CPS, nj = (J - j0) < CPS ? (J - j0) : CPS;
     const double *src = pack + (size_t)j0 * CS;
     double *dst = sm + (size_t)buf * CPS * CS;
-    for (int c = threadIdx.x; c < nj * CS / 2; c += 256) cpa16(dst + 2 * c, src + 2 * c);
+    for (int c = threadIdx.x; c < nj * CS / 2; c += 32 * QW) cpa16(dst + 2 * c, src + 2 * c);
     cpa_commit();
   };
   issue(0, 0);
@@ -611,13 +613,13 @@ int launch_draw_t(const double *pack, const int4 *tiles, int ntiles, const unsig
 template <int NT>
 int launch_q(const double *X, long n, int d, const double *pack, int J, const int *kmap, double *Q, long qs, int sm_count,
              cudaStream_t s) {
-  constexpr int TS = 64 * q_mt(NT);
+  constexpr int TS = 8 * q_warps(NT) * q_mt(NT);
   const size_t smem = (size_t)2 * q_cps(NT) * q_comp_stride(NT) * sizeof(double);
   static std::atomic<unsigned long long> smem_set{0};
   if (!set_max_smem_once(k_q_mma<NT>, smem, smem_set)) return 1;
   const long ntile = (n + TS - 1) / TS;
   const int grid = (int)(ntile < sm_count ? ntile : sm_count);
-  k_q_mma<NT><<<grid, 256, smem, s>>>(X, n, d, pack, J, kmap, Q, qs);
+  k_q_mma<NT><<<grid, 32 * q_warps(NT), smem, s>>>(X, n, d, pack, J, kmap, Q, qs);
   count_launch();
   return cudaGetLastError() != cudaSuccess;
 }

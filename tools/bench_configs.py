@@ -19,6 +19,7 @@ FP64_PEAK_TFLOPS = 36.9  # measured, profiles/r01_fp64_peak.md
 
 CFG = {
     # name: (factory, default samples per GPU per step, update?, description)
+    "c1": (W.banana, 10_000, 1, "configs[0]: 10-D banana, 10-component Gaussian mixture proposal, 10k samples/iteration (the reference's CPU-runnable case)"),
     "c2": (W.gmm5, 1_000_000, 1, "configs[1]: 5-D 4-mode Gaussian-mixture target, 20-component Gaussian proposal, 1M samples/iteration"),
     "c4": (W.student30, 10_000_000, 0, "configs[3]: 30-D Gaussian target, fixed 50-component Student-t (nu=9) proposal, importance only, 1e9 samples streamed in steps"),
     "c5": (W.gauss128, 1_250_000, 1, "configs[4]: 128-D Gaussian target, 64-component Gaussian mixture proposal, 1e7 samples/iteration over 8 GPUs"),
@@ -41,7 +42,7 @@ def flops(wl, upd):
                 stats=(K * (d * d + 4 * d + 4)) if upd else 0)
 
 
-CPU_SAMPLE = {"c2": (1_000_000, 3), "c4": (100_000, 3), "c5": (2_000, 1)}  # (samples/iteration, iterations); c5: the reference's update runs at ~80 samples/s (denormals)
+CPU_SAMPLE = {"c1": (10_000, 11), "c2": (1_000_000, 3), "c4": (100_000, 3), "c5": (2_000, 1)}  # (samples/iteration, iterations); c5: the reference's update runs at ~80 samples/s (denormals)
 
 
 def cpu_reference(cfg, wl, upd, nworkers=1):
