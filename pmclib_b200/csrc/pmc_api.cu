@@ -143,7 +143,8 @@ struct pmcgpu_ctx {
   MmaMix mprop, mtgt;
   DevBuf Q, Qt, mpart, mstats, mpivot, dperm, dtiles, dcnt, xc;
   HostMix trial;  // scratch of the update (kept to reuse its storage)
-  std::vector<double> hW, hs1, hS2;
+  std::vector<double> hW, hG, hs1, hS2;
+  DevBuf wpart;
   long q_stride = 0;
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 17;
@@ -609,7 +610,7 @@ int run_weights_mma(pmcgpu_ctx *c, int mode, const double *post_in, const short 
 // one-pass pivoted statistics on the tensor path (Gaussian components; Q still holds ld_k for the whole store and the
 // weights are normalised).  Outputs in the layout pmcgpu_finalize_update expects.
 int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector<double> &pivot, std::vector<double> &W,
-              std::vector<double> &s1, std::vector<double> &S2) {
+              std::vector<double> &G, std::vector<double> &s1, std::vector<double> &S2) {
   const HostMix &m = c->prop;
   const int K = m.K, d = m.d, J = c->mprop.J;
   const long N = c->N;
@@ -628,26 +629,46 @@ int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector
   if (c->xc.ensure((size_t)N * d * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return 1; }  // no room for the centred copy: literal path
   CU(cudaMemsetAsync(c->mstats.p, 0, (size_t)K * len * sizeof(double), c->stream));
   if (c->timing && c->ev1) CU(cudaEventRecord(c->ev1, c->stream));
+  const bool student = m.student;
+  const int nrb = resp_q_blocks(N);
+  if (student) {
+    if (K > 256) return 1;  // block reduction scratch: 32 x K doubles of shared memory
+    CU(c->wpart.ensure((size_t)nrb * K * sizeof(double)));
+  }
   launch_resp_q(c->dprop.view, N, c->W.as<double>(), c->R.as<double>(), c->Flg.as<short>(), c->tmpo.as<unsigned long long>(),
-                c->Q.as<double>(), c->q_stride, c->stream);
+                c->Q.as<double>(), c->q_stride, student ? c->wpart.as<double>() : nullptr, c->stream);
+  CU(cudaGetLastError());
   if (launch_stats_mma(c->X.as<double>(), c->Flg.as<short>(), N, d, c->Q.as<double>(), c->q_stride, J, c->mprop.kmap.as<int>(),
                        c->mpivot.as<double>(), nchunk, c->xc.as<double>(), c->mpart.as<double>(), c->mstats.as<double>(),
                        c->sm_count, c->stream))
     return fail(c, PMCGPU_ERR_CUDA, "statistics kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (c->timing && c->ev1) CU(cudaEventRecord(c->ev2, c->stream));
   c->q_resident = false;  // Q now holds responsibilities
-  RC(stage(c, (size_t)K * len));
+  RC(stage(c, (size_t)K * len + (student ? (size_t)nrb * K : 0)));
   CU(cudaMemcpyAsync(c->hstage, c->mstats.p, (size_t)K * len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (student)
+    CU(cudaMemcpyAsync(c->hstage + (size_t)K * len, c->wpart.p, (size_t)nrb * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  std::vector<double> wsum;
+  if (student) {  // weight_d = sum_i w8 (pmc.c:1392), block partials added in block order
+    wsum.assign(K, 0.0);
+    const double *wp = c->hstage + (size_t)K * len;
+    for (int b = 0; b < nrb; ++b)
+      for (int k = 0; k < K; ++k) wsum[k] += wp[(size_t)b * K + k];
+    int rcw = allreduce_host(c, wsum.data(), K, 0);
+    if (rcw) return rcw;
+  }
   if (c->timing && c->ev1) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats_ms += ms; }
   int rc = allreduce_host(c, c->hstage, (long)((size_t)K * len), 0);  // in place in the pinned staging buffer
   if (rc) return rc;
   W.resize(K);
+  G.resize(K);
   s1.resize((size_t)K * d);
   S2.resize((size_t)K * d * d);
   for (int k = 0; k < K; ++k) {
     const double *sk = c->hstage + (size_t)k * len;
-    W[k] = sk[0];
+    G[k] = sk[0];                       // weight_gamma_d
+    W[k] = student ? wsum[k] : sk[0];   // weight_d
     memcpy(s1.data() + (size_t)k * d, sk + 1, d * sizeof(double));
     memcpy(S2.data() + (size_t)k * d * d, sk + 1 + d, (size_t)d * d * sizeof(double));
   }
@@ -1590,9 +1611,9 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   // ---- update
   if (do_update) {
     // a NaN maximum (the i==0 quirk) poisons the reference's responsibilities: only the literal path reproduces that
-    const bool mma_stats = !p.valid && !c->force_precise && !m0.student && c->q_resident && mma_usable(c, 0);
+    const bool mma_stats = !p.valid && !c->force_precise && c->q_resident && mma_usable(c, 0);
     bool precise = !(fused_stats || mma_stats) || std::isnan(maxR) || std::isnan(maxW);
-    std::vector<double> &W = c->hW, &s1 = c->hs1, &S2 = c->hS2;
+    std::vector<double> &W = c->hW, &G = c->hG, &s1 = c->hs1, &S2 = c->hS2;
     std::vector<double> pivot(d);
     std::vector<size_t> count(K);
     if (!precise) {
@@ -1634,7 +1655,7 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
       } else {
         rc = count_indices_impl(c, count, true);
         if (rc) return rc;
-        rc = stats_mma(c, count, pivot, W, s1, S2);
+        rc = stats_mma(c, count, pivot, W, G, s1, S2);
         if (rc == 1) precise = true;
         else if (rc) return rc;
       }
@@ -1645,7 +1666,7 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
       trial = c->prop;
       int retry_trial = retry_local;
       std::vector<int> alive(K);
-      rc = pmcgpu_finalize_update(K, d, W.data(), W.data(), s1.data(), S2.data(), pivot.data(), 0, count.data(), N_total,
+      rc = pmcgpu_finalize_update(K, d, W.data(), fused_stats ? W.data() : G.data(), s1.data(), S2.data(), pivot.data(), 0, count.data(), N_total,
                                   trial.band.empty() ? nullptr : trial.band.data(), &retry_trial, trial.wght.data(),
                                   trial.mean.data(), trial.L.data(), trial.detL.data(), alive.data());
       // pivot guard: the one-pass covariance loses ~eps*(1 + r) relative accuracy, r = (mu'-pivot)^2 / Sigma'_aa

@@ -163,8 +163,10 @@ void launch_weights_q(const MixDev &m, const TargetDev &tg, int mode, const doub
                       long qs, double *lw, double *log_rho, short *flg, double *blk_maxw, double *blk_maxr,
                       unsigned long long *counters, double *first_vals, cudaStream_t s);
 void launch_lse_q(const MixDev &m, long n, double *Q, long qs, double *out, cudaStream_t s);
+// wpart (Student-t mixtures only, else nullptr): [resp_q_blocks(N)][K] block sums of the un-gamma-weighted responsibilities
+int resp_q_blocks(long N);
 void launch_resp_q(const MixDev &m, long N, const double *w, const double *log_rho, const short *flg,
-                   const unsigned long long *count, double *Q, long qs, cudaStream_t s);
+                   const unsigned long long *count, double *Q, long qs, double *wpart, cudaStream_t s);
 // grouped draw: component pick + histogram, permutation, then x = mu + L g tile by tile (tiles: int4 {packed comp, first
 // position in perm, samples, 0})
 int mma_draw_tile_samples(int d);

@@ -231,22 +231,49 @@ __global__ void k_lse_q(MixDev m, long n, double *__restrict__ Q, long qs, doubl
 }
 
 // responsibilities in place of ld: g[k][i] = w_i alpha_k exp(ld_k(x_i) - log_rho_i) for ok samples and components with
-// count > MINCOUNT (pmc.c:1382-1390; the reference's common factor exp(maxR - 500) is dropped, it cancels)
-__global__ void k_resp_q(MixDev m, long N, const double *__restrict__ w, const double *__restrict__ log_rho,
-                         const short *__restrict__ flg, const unsigned long long *__restrict__ count,
-                         double *__restrict__ Q, long qs) {
+// count > MINCOUNT (pmc.c:1382-1390; the reference's common factor exp(maxR - 500) is dropped, it cancels).
+// Student-t components (pmc.c:1391-1397): the stored value is gamma g with gamma = (nu + d) / (nu + q_k(x_i)); q is
+// recovered from the log-density (expm1 keeps it accurate for small q) and sum_i g, which the reference divides the
+// covariance by (weight_d, pmc.c:1459-1460), is reduced per block in a fixed order into wpart[block][K].
+constexpr int RESP_THREADS = 1024;
+__global__ void __launch_bounds__(RESP_THREADS)
+k_resp_q(MixDev m, long N, const double *__restrict__ w, const double *__restrict__ log_rho,
+         const short *__restrict__ flg, const unsigned long long *__restrict__ count, double *__restrict__ Q, long qs,
+         double *__restrict__ wpart /* nullptr for Gaussian mixtures */) {
+  extern __shared__ double sw[];  // [32 warps][K] when wpart != nullptr
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const bool ok = flg[i] != 0;
-  const double wi = w[i], lr = log_rho[i];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool live = i < N;
+  const bool ok = live && flg[i] != 0;
+  const double wi = live ? w[i] : 0.0, lr = live ? log_rho[i] : 0.0;
   for (int k = 0; k < m.K; ++k) {
-    if (!(m.alpha[k] > 0.0)) continue;
-    double g = 0.0;
-    if (ok && count[k] > kMinCount) {
-      g = wi * (m.alpha[k] * exp(Q[(size_t)k * qs + i] - lr));  // the column holds ld_k since k_weights_q
+    double g = 0.0, gg = 0.0;
+    const bool alive = m.alpha[k] > 0.0;
+    if (alive && ok && count[k] > kMinCount) {
+      const double ld = Q[(size_t)k * qs + i];  // the column holds ld_k since k_weights_q
+      g = wi * (m.alpha[k] * exp(ld - lr));
       if (!(g == g) || isinf(g)) g = 0.0;
+      gg = g;
+      if (m.df[k] != -1) {
+        const double n = (double)m.df[k];
+        const double q = n * expm1((m.gam[k] - m.norm[k] - m.logdet[k] - ld) / (0.5 * (n + m.d)));
+        gg = ((n + m.d) / (n + q)) * g;
+        if (!(gg == gg) || isinf(gg)) gg = 0.0;
+      }
     }
-    Q[(size_t)k * qs + i] = g;
+    if (alive && live) Q[(size_t)k * qs + i] = gg;
+    if (wpart) {
+      const double s = warp_sum(g);
+      if (lane == 0) sw[wid * m.K + k] = s;
+    }
+  }
+  if (wpart) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < m.K; k += blockDim.x) {
+      double s = 0.0;
+      for (int v = 0; v < RESP_THREADS / 32; ++v) s += sw[v * m.K + k];
+      wpart[(size_t)blockIdx.x * m.K + k] = s;
+    }
   }
 }
 
@@ -719,10 +746,12 @@ void launch_lse_q(const MixDev &m, long n, double *Q, long qs, double *out, cuda
   count_launch();
 }
 
+int resp_q_blocks(long N) { return (int)((N + RESP_THREADS - 1) / RESP_THREADS); }
 void launch_resp_q(const MixDev &m, long N, const double *w, const double *log_rho, const short *flg,
-                   const unsigned long long *count, double *Q, long qs, cudaStream_t s) {
+                   const unsigned long long *count, double *Q, long qs, double *wpart, cudaStream_t s) {
   if (N <= 0) return;
-  k_resp_q<<<(int)((N + 127) / 128), 128, 0, s>>>(m, N, w, log_rho, flg, count, Q, qs);
+  const size_t smem = wpart ? (size_t)(RESP_THREADS / 32) * m.K * sizeof(double) : 0;
+  k_resp_q<<<resp_q_blocks(N), RESP_THREADS, smem, s>>>(m, N, w, log_rho, flg, count, Q, qs, wpart);
   count_launch();
 }
 

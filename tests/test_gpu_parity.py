@@ -180,3 +180,26 @@ def test_log_pdf_entry_points(gpu, oracle_runs):
         assert_close(gpu.proposal_log_pdf(X[:3000]), o["log_rho"][:3000], RTOL, what="proposal_log_pdf")
         post = gpu.target_log_pdf(X[:3000])
         assert_close(post - o["log_rho"][:3000], o["logw"][:3000], RTOL, scale=np.max(np.abs(o["log_rho"])), what="target")
+
+
+@pytest.mark.parametrize("d,K,df,N", [(5, 4, 5, 20000), (10, 6, 9, 30000), (24, 5, 7, 30000)])
+def test_student_t_update(gpu, d, K, df, N):
+    """Rao-Blackwellised update of a Student-t proposal (gamma-weighted statistics, pmc.c:1386-1398, 1459-1460: the
+    covariance is divided by weight_d, not weight_gamma_d) against the oracle's full iteration."""
+    wl = W.gauss128(d=d, K=K, seed=40 + d)
+    wl["df"] = np.full(K, df, np.int32)
+    X, idx = O.orc_simulate(N, wl, seed=19)
+    o = O.orc_iteration(X, idx, wl, do_update=1)
+    assert o["rc"] == 0
+    for mma in (0, 1):
+        gpu.set_option("force_generic", 0)
+        gpu.set_option("force_precise", 0)
+        gpu.set_option("mma", mma)
+        gpu.set_workload(wl)
+        gpu.resize(N, d)
+        gpu.upload(X=X, indices=idx, flg=np.ones(N, np.int16))
+        r = gpu.step_given(0, N, 1.0, 1, 0)
+        assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
+        assert r.retry == o["retry"]
+        errs = compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=f"student d={d} mma={mma}")
+        print(f"student-t d={d} K={K} df={df} mma={mma} precise={r.used_precise_path}", errs)
