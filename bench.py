@@ -264,12 +264,15 @@ def main():
         from pmclib_b200.api import _p
         prop = g.get_proposal()
 
+        # the caller's pmc_simu arrays are attached as the host sink: X and indices cross PCIe while the FP64 kernels
+        # run, log_rho after the weight kernel, weights and flags after the normalisation (second stream)
+        g._ck(g.lib.pmcgpu_set_host_sink(g.h, _p(host["X"]), _p(host["indices"]), _p(host["weights"]), _p(host["log_rho"]), _p(host["flg"])))
+
         def e2e_step(it_, retry_):
-            # host -> device: the proposal the caller holds (reference layout), then the iteration, then the whole
-            # pmc_simu payload back to host memory, as pmc_simu_pmc_step's contract promises
+            # host -> device: the proposal the caller holds (reference layout), then the iteration, which delivers the
+            # whole pmc_simu payload into host memory, as pmc_simu_pmc_step's contract promises
             g.set_proposal(prop["wght"], prop["mean"], prop["L"], prop["detL"], None)
             rr = g.pmc_step(seed, it_, first, N_total, 1, retry_)
-            g._ck(g.lib.pmcgpu_download(g.h, _p(host["X"]), _p(host["indices"]), _p(host["weights"]), _p(host["log_rho"]), _p(host["flg"])))
             prop.update(wght=rr.wght, mean=rr.mean, L=rr.L, detL=rr.detL)
             return rr
         rr = e2e_step(it, retry); it += 1
@@ -289,7 +292,8 @@ def main():
         d2h = n_local * (8 * d + 8 + 8 + 8 + 2)
         e2e = {"value": N_total * nst / (float(t[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": nst,
-               "path": "pmcgpu_set_proposal (host mixture) -> pmcgpu_pmc_step -> pmcgpu_download of X, indices, weights, log_rho, flg into pinned host buffers"}
+               "path": "pmcgpu_set_proposal (host mixture) -> pmcgpu_pmc_step with the host sink attached: X, indices, weights, log_rho, flg land in pinned host buffers (D2H on a second stream, overlapped with the kernels)"}
+        g._ck(g.lib.pmcgpu_set_host_sink(g.h, None, None, None, None, None))
 
     if rank != 0:
         if world > 1:

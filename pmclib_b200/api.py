@@ -179,6 +179,12 @@ class PmcGpu:
         return out
 
     # ---- phases -------------------------------------------------------------------------------------
+    def set_host_sink(self, X=None, indices=None, weights=None, log_rho=None, flg=None):
+        """Host arrays pmc_step fills while the iteration runs (D2H overlapped with the kernels); all None detaches.
+        The caller keeps the arrays alive (and ideally page-locked) while the sink is attached."""
+        self._sink = (X, indices, weights, log_rho, flg)
+        self._ck(self.lib.pmcgpu_set_host_sink(self.h, _p(X), _p(indices), _p(weights), _p(log_rho), _p(flg)))
+
     def draw(self, seed, it=0, first_index=0):
         nrej = C.c_long()
         self._ck(self.lib.pmcgpu_draw(self.h, seed, it, first_index, C.byref(nrej)))

@@ -149,6 +149,11 @@ struct pmcgpu_ctx {
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 17;
   int filt_nbins = 0, filt_cl = 0, filt_cr = 0;  // filter_histogram inside the iteration (0 = off)
+  // host sink: arrays of the caller that pmcgpu_pmc_step fills while the iteration is still running
+  struct Sink { double *X = nullptr; size_t *idx = nullptr; double *w = nullptr, *lr = nullptr; short *flg = nullptr; bool on = false; } sink;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
+  bool sink_active = false;  // inside a drawing iteration with a sink attached
   // comm
   int rank = 0, nranks = 1;
   void *nccl_comm = nullptr;
@@ -360,6 +365,26 @@ int allreduce_host(pmcgpu_ctx *c, double *buf, long n, int op /*0 sum, 1 max*/) 
   return 0;
 }
 
+// ---- host sink: device->host copies on a second stream, overlapped with the kernels that follow ------------------------
+enum { SINK_DRAWN = 1, SINK_RHO = 2, SINK_FINAL = 4 };
+int sink_copy(pmcgpu_ctx *c, int what) {
+  if (!c->sink_active) return 0;
+  if (!c->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+  }
+  CU(cudaEventRecord(c->ev_copy, c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+  const size_t N = c->N;
+  const pmcgpu_ctx::Sink &k = c->sink;
+  if ((what & SINK_DRAWN) && k.X) CU(cudaMemcpyAsync(k.X, c->X.p, N * c->d * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+  if ((what & SINK_DRAWN) && k.idx) CU(cudaMemcpyAsync(k.idx, c->Idx.p, N * sizeof(size_t), cudaMemcpyDeviceToHost, c->copy_stream));
+  if ((what & SINK_RHO) && k.lr) CU(cudaMemcpyAsync(k.lr, c->R.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+  if ((what & SINK_FINAL) && k.w) CU(cudaMemcpyAsync(k.w, c->W.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+  if ((what & SINK_FINAL) && k.flg) CU(cudaMemcpyAsync(k.flg, c->Flg.p, N * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
+  return 0;
+}
+
 // the reference's running maximum with its unconditional i==0 assignment (pmc.c:535,552,579)
 double fold_max(double m_all, bool has_first, bool reached0, double v0) {
   if (has_first && reached0) return std::isnan(v0) ? v0 : (m_all > v0 ? m_all : v0);
@@ -489,12 +514,14 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
     lrc = launch_fused2(p, ad, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), 3, &nblk, c->stream);
     a.do_draw = 0;
     drew_separately = true;
+    if (!lrc) RC(sink_copy(c, SINK_DRAWN));  // X and indices are final: they travel while the FP64 kernels run
   }
   if (c->timing) CU(cudaEventRecord(c->evd, c->stream));
   if (!lrc)
     lrc = (p.valid == 2) ? launch_fused2(p, a, c->prop_pack_host.data(), c->tgt_pack_host.empty() ? nullptr : c->tgt_pack_host.data(), mode, &nblk, c->stream)
                          : launch_fused(p, a, c->stream);
   if (lrc != 0) return fail(c, PMCGPU_ERR_CUDA, "fused kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  RC(sink_copy(c, (do_draw && !drew_separately ? SINK_DRAWN : 0) | SINK_RHO));
   if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
   int crc = 0;
   if (mode == 1) {
@@ -978,6 +1005,7 @@ int pmcgpu_create(int device, pmcgpu_ctx **out) {
 }
 
 void pmcgpu_destroy(pmcgpu_ctx *c) {
+  if (c && c->copy_stream) { cudaSetDevice(c->device); cudaStreamDestroy(c->copy_stream); if (c->ev_copy) cudaEventDestroy(c->ev_copy); }
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
@@ -1520,7 +1548,7 @@ int pmcgpu_isinbox(pmcgpu_ctx *c, long n, const double *x, int *inside) {
 }
 
 // ---- the iteration ------------------------------------------------------------------------------------------------
-static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, long first_index, long N_total,
+static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, long first_index, long N_total,
                      double t_temper, int do_update, int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean,
                      double *o_L, double *o_detL, int *o_alive) {
   int rc = check_ready(c, true);
@@ -1554,10 +1582,12 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
       rc = pmcgpu_draw(c, seed, iter, first_index, &nrej);
       if (rc) return rc;
       o.counters[CNT_REJECT] = (unsigned long long)nrej;
+      RC(sink_copy(c, SINK_DRAWN));
     }
     const unsigned long long keep_rej = o.counters[CNT_REJECT];
     rc = run_weights_generic(c, 0, nullptr, nullptr, t_temper, first_index, o);
     if (rc) return rc;
+    RC(sink_copy(c, SINK_RHO));
     o.counters[CNT_REJECT] = keep_rej;
   }
   tick("draw+weights");
@@ -1607,6 +1637,7 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   r.ess = 1 / Q;
   r.perplexity = std::exp(-H) / (double)(N_total - nexit);
   r.ln_evidence = r.logSum - std::log((double)(N_total - nexit));
+  RC(sink_copy(c, SINK_FINAL));  // weights and flags are final; they travel while the update runs
   tick("normalise+perplexity");
   // ---- update
   if (do_update) {
@@ -1708,6 +1739,34 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   if (res) *res = r;
   export_proposal(c, o_wght, o_mean, o_L, o_detL, o_alive);
   tick("export");
+  return 0;
+}
+
+// the iteration with the host sink armed: whatever happens, no copy into the caller's arrays is in flight on return
+static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, long first_index, long N_total,
+                     double t_temper, int do_update, int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean,
+                     double *o_L, double *o_detL, int *o_alive) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  c->sink_active = c->sink.on && do_draw;
+  const int rc = step_core(c, do_draw, seed, iter, first_index, N_total, t_temper, do_update, retry, res, o_wght, o_mean,
+                           o_L, o_detL, o_alive);
+  if (c->sink_active) {
+    c->sink_active = false;
+    cudaSetDevice(c->device);
+    if (c->copy_stream && cudaStreamSynchronize(c->copy_stream) != cudaSuccess && rc == 0)
+      return fail(c, PMCGPU_ERR_CUDA, "copy to the host sink failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  return rc;
+}
+
+int pmcgpu_set_host_sink(pmcgpu_ctx *c, double *X, size_t *indices, double *weights, double *log_rho, short *flg) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  c->sink.X = X;
+  c->sink.idx = indices;
+  c->sink.w = weights;
+  c->sink.lr = log_rho;
+  c->sink.flg = flg;
+  c->sink.on = X || indices || weights || log_rho || flg;
   return 0;
 }
 

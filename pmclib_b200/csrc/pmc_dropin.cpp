@@ -1162,16 +1162,16 @@ double pmc_step_multi(Side *s, pmc_simu *psim, mix_mvdens *m, gsl_rng *r, error 
   for (int g = 0; g < G; ++g)
     th.emplace_back([&, g]() {
       const bool lead = g == 0;
-      int rc = pmcgpu_pmc_step(s->shard[g], seed, iter, first[g], N, 1, &retry[g], &res[g], lead ? w.data() : nullptr,
-                               lead ? mean.data() : nullptr, lead ? L.data() : nullptr, lead ? detL.data() : nullptr,
-                               lead ? alive.data() : nullptr);
+      pmcgpu_set_host_sink(s->shard[g], psim->X + (size_t)first[g] * d, psim->indices + first[g], psim->weights + first[g],
+                           psim->log_rho + first[g], psim->flg + first[g]);
+      const int rc = pmcgpu_pmc_step(s->shard[g], seed, iter, first[g], N, 1, &retry[g], &res[g], lead ? w.data() : nullptr,
+                                     lead ? mean.data() : nullptr, lead ? L.data() : nullptr, lead ? detL.data() : nullptr,
+                                     lead ? alive.data() : nullptr);
+      pmcgpu_set_host_sink(s->shard[g], nullptr, nullptr, nullptr, nullptr, nullptr);
       if (rc) {  // release the ranks that may be waiting for this one
         std::lock_guard<std::mutex> lk(s->rv.m);
         s->rv.broken = true;
         s->rv.cv.notify_all();
-      } else {
-        rc = pmcgpu_download(s->shard[g], psim->X + (size_t)first[g] * d, psim->indices + first[g], psim->weights + first[g],
-                             psim->log_rho + first[g], psim->flg + first[g]);
       }
       rcs[g] = rc;
     });
@@ -1221,8 +1221,12 @@ double pmc_simu_pmc_step(pmc_simu *psim, gsl_rng *r, error **err) {
   pmcgpu_step_result res;
   const int *fil = psim->pmc_filter ? (const int *)psim->filter_data : nullptr;  // the shipped filter runs on the device
   pmcgpu_set_filter_histogram(s->ctx, fil ? fil[0] : 0, fil ? fil[1] : 0, fil ? fil[2] : 0);
+  // host arrays are filled while the iteration runs (second stream), unless the sample is to stay resident in HBM
+  const bool sink = !resident();
+  if (sink) pmcgpu_set_host_sink(s->ctx, psim->X, psim->indices, psim->weights, psim->log_rho, psim->flg);
   const int rc = pmcgpu_pmc_step(s->ctx, seed_from(r), s->iter++, 0, psim->nsamples, 1, &retry, &res, w.data(), mean.data(),
                                  L.data(), detL.data(), alive.data());
+  pmcgpu_set_host_sink(s->ctx, nullptr, nullptr, nullptr, nullptr, nullptr);
   pmcgpu_set_filter_histogram(s->ctx, 0, 0, 0);
   if (rc) { gpu_fail(s, rc, err, __func__); return 0; }
   psim->maxW = res.maxW;
@@ -1233,8 +1237,7 @@ double pmc_simu_pmc_step(pmc_simu *psim, gsl_rng *r, error **err) {
   if (retry != 0) fprintf(stderr, "RETRY state -> %d\n", retry);
   // mix_mvdens_ran would have normalised the weights before the draw; the update then replaces everything
   unflatten(m, w.data(), mean.data(), L.data(), detL.data());
-  s->host_stale = resident();
-  if (!s->host_stale && !pull_samples(s, psim, true, true, true, true, true, err)) return 0;
+  s->host_stale = !sink;
   return res.perplexity;
 }
 

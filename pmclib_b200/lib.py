@@ -29,7 +29,7 @@ EXPORTS = [
     "pmcgpu_create", "pmcgpu_destroy", "pmcgpu_last_error", "pmcgpu_version", "pmcgpu_device_count", "pmcgpu_stream", "pmcgpu_set_option", "pmcgpu_get_timing", "pmcgpu_get_stats_timing", "pmcgpu_get_draw_timing",
     "pmcgpu_set_proposal", "pmcgpu_set_band_limit", "pmcgpu_set_target_banana", "pmcgpu_set_target_mix",
     "pmcgpu_set_target_defaults", "pmcgpu_set_target_host", "pmcgpu_set_box", "pmcgpu_resize", "pmcgpu_upload",
-    "pmcgpu_download", "pmcgpu_pin_host", "pmcgpu_unpin_host", "pmcgpu_device_arrays", "pmcgpu_draw", "pmcgpu_weights", "pmcgpu_draw_weights", "pmcgpu_weights_host_post",
+    "pmcgpu_download", "pmcgpu_set_host_sink", "pmcgpu_pin_host", "pmcgpu_unpin_host", "pmcgpu_device_arrays", "pmcgpu_draw", "pmcgpu_weights", "pmcgpu_draw_weights", "pmcgpu_weights_host_post",
     "pmcgpu_proposal_log_pdf", "pmcgpu_target_log_pdf", "pmcgpu_normalize", "pmcgpu_perplexity_ess",
     "pmcgpu_filter_histogram", "pmcgpu_set_filter_histogram", "pmcgpu_weighted_mean",
     "pmcgpu_count_indices", "pmcgpu_update_rb", "pmcgpu_update_hard", "pmcgpu_ranindx", "pmcgpu_isinbox",
@@ -75,6 +75,7 @@ def load_library(build_if_missing: bool = False):
     L.pmcgpu_weighted_mean.argtypes = [vp, i32, C.POINTER(dbl)]
     L.pmcgpu_upload.argtypes = [vp, vp, vp, vp, vp, vp]
     L.pmcgpu_download.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.pmcgpu_set_host_sink.argtypes = [vp, vp, vp, vp, vp, vp]
     L.pmcgpu_pin_host.argtypes = [vp, C.c_size_t]
     L.pmcgpu_unpin_host.argtypes = [vp]
     L.pmcgpu_device_arrays.argtypes = [vp, C.POINTER(vp)]

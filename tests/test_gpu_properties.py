@@ -130,3 +130,30 @@ def test_nan_and_flag_semantics_on_gpu(gpu):
     with pytest.raises(Exception) as e:
         gpu.step_given(0, 64, 1.0, 0, 0)
     assert "-6017" in str(e.value)
+
+
+@pytest.mark.parametrize("wlname", ["banana", "gauss40"])
+def test_host_sink_equals_download(gpu, wlname):
+    """pmcgpu_set_host_sink: the arrays streamed to the host during the iteration (second stream, overlapped with the
+    kernels) are bit-identical to what pmcgpu_download returns afterwards, on the fused and on the tensor path."""
+    wl = W.banana() if wlname == "banana" else W.gauss128(d=40, K=6, seed=31)
+    N, d = 300_007, wl["d"]
+    gpu.set_option("force_generic", 0)
+    gpu.set_option("mma", 1)
+    gpu.set_workload(wl)
+    gpu.resize(N, d)
+    host = dict(X=np.full((N, d), np.nan), indices=np.zeros(N, np.uint64), weights=np.full(N, np.nan),
+                log_rho=np.full(N, np.nan), flg=np.full(N, -7, np.int16))
+    gpu.set_host_sink(**host)
+    try:
+        r = gpu.pmc_step(11, 0)
+    finally:
+        gpu.set_host_sink()
+    got = gpu.download()
+    for k in host:
+        assert np.array_equal(host[k], got[k]), k
+    assert abs(np.sum(host["weights"][host["flg"] == 1]) - 1.0) < 1e-10
+    # detached: the next iteration leaves the host arrays alone
+    before = host["X"].copy()
+    gpu.pmc_step(11, 1)
+    assert np.array_equal(before, host["X"])
