@@ -148,6 +148,7 @@ struct pmcgpu_ctx {
   long q_stride = 0;
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 17;
+  long mma_max_chunk = 0;  // test knob: cap of the samples whitened per pass (0 = as many as memory allows)
   int filt_nbins = 0, filt_cl = 0, filt_cr = 0;  // filter_histogram inside the iteration (0 = off)
   // host sink: arrays of the caller that pmcgpu_pmc_step fills while the iteration is still running
   struct Sink { double *X = nullptr; size_t *idx = nullptr; double *w = nullptr, *lr = nullptr; short *flg = nullptr; bool on = false; } sink;
@@ -585,6 +586,7 @@ int run_weights_mma(pmcgpu_ctx *c, int mode, const double *post_in, const short 
   const size_t budget = std::min<size_t>((free_b + have) / 2, (size_t)64 << 30);
   long chunk = (long)(budget / (sizeof(double) * (size_t)(K + Kt)));
   chunk = std::max<long>(1024, (chunk / 1024) * 1024);
+  if (c->mma_max_chunk > 0 && chunk > c->mma_max_chunk) chunk = c->mma_max_chunk;
   if (chunk > N) chunk = N;
   const long qs = chunk;
   CU(c->Q.ensure((size_t)K * qs * sizeof(double)));
@@ -1042,6 +1044,7 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "split_draw")) c->split_draw = (int)value;
   else if (!strcmp(name, "mma")) { c->use_mma = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_min_d")) { c->mma_min_d = (int)value; return repack_mma(c); }
+  else if (!strcmp(name, "mma_max_chunk")) c->mma_max_chunk = (long)value;
   else return fail(c, PMCGPU_ERR_USAGE, "unknown option %s", name);
   return 0;
 }

@@ -193,3 +193,22 @@ def test_mma_draw_equals_literal_draw(gpu, name, N):
     # every component that has weight is used, none without
     used_k = np.unique(b["indices"])
     assert set(used_k.tolist()) <= set(np.nonzero(wl["wght"] > 0)[0].tolist())
+
+
+def test_mma_chunked_whitening_when_q_does_not_fit(gpu, oracle_runs):
+    """When K x N log-densities do not fit in memory the samples are whitened in passes (forced here with the test knob
+    mma_max_chunk): same weights; the update then runs through the literal two-pass kernels."""
+    name = "d100_K3"
+    wl, X, idx, o = oracle_runs(name)
+    _setup(gpu, wl, X, idx)
+    gpu.set_option("mma_max_chunk", 2048)
+    try:
+        r = gpu.step_given(0, len(X), 1.0, 1, 0)
+    finally:
+        gpu.set_option("mma_max_chunk", 0)
+    got = gpu.download(X=False, indices=False)
+    assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho")
+    assert_close(got["weights"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
+    assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
+    assert r.used_precise_path == 1
+    compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
