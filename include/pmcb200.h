@@ -118,7 +118,7 @@ int pmcgpu_target_log_pdf(pmcgpu_ctx *ctx, long n, const double *x, double *out)
 int pmcgpu_normalize(pmcgpu_ctx *ctx, double maxW, double *logSum, long *count);
 /* perplexity_and_ess (pmc.c:1041-1077, MC_UNORM) and the flagged-out count evidence() needs (pmc.c:1088-1105) */
 int pmcgpu_perplexity_ess(pmcgpu_ctx *ctx, double *perp, double *ess, long *n_flagged_out);
-/* Host sink for pmcgpu_pmc_step: the caller's pmc_simu arrays (any may be NULL; all NULL detaches).  While attached, the
+/* Host sink for pmcgpu_pmc_step and pmcgpu_draw_weights: the caller's pmc_simu arrays (any may be NULL; all NULL detaches).  While attached, the
  * iteration copies X and indices to the host as soon as the draw has finished, log_rho after the weight kernel and the
  * normalised weights and flags after the normalisation, on a second stream, overlapped with the kernels that follow;
  * pmcgpu_pmc_step returns when the arrays are complete.  Page-locked host memory (pmcgpu_pin_host) is needed for the

@@ -1355,8 +1355,8 @@ int pmcgpu_weights_host_post(pmcgpu_ctx *c, const double *post, const short *ok,
   return weights_common(c, 1, post, ok, t_temper, first_index, nok, maxW, maxR);
 }
 
-int pmcgpu_draw_weights(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, double t_temper, long *nok,
-                        double *maxW, double *maxR, long *n_reject) {
+static int draw_weights_core(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, double t_temper, long *nok,
+                             double *maxW, double *maxR, long *n_reject) {
   int rc = check_ready(c, true);
   if (rc) return rc;
   cudaSetDevice(c->device);
@@ -1373,11 +1373,14 @@ int pmcgpu_draw_weights(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_
     long nrej = 0;
     rc = pmcgpu_draw(c, seed, iter, first_index, &nrej);
     if (rc) return rc;
+    RC(sink_copy(c, SINK_DRAWN));
     rc = run_weights_generic(c, 0, nullptr, nullptr, t_temper, first_index, o);
     if (rc) return rc;
+    RC(sink_copy(c, SINK_RHO));
     o.counters[CNT_REJECT] = (unsigned long long)nrej;
     o.counters[CNT_DRAWFAIL] = 0;
   }
+  RC(sink_copy(c, SINK_FINAL));  // log-weights and flags (pmc_simu_importance leaves the sample un-normalised)
   if (n_reject) *n_reject = (long)o.counters[CNT_REJECT];
   if (o.counters[CNT_DRAWFAIL] || (long)o.counters[CNT_REJECT] > 5 * c->N)
     return fail(c, kErrTooManySteps, "Too many points (%llu) outside of box", o.counters[CNT_REJECT]);
@@ -1387,6 +1390,20 @@ int pmcgpu_draw_weights(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_
   if (maxW) *maxW = fold_max(mw, o.has_first, o.first[3] != 0.0, o.first[2]);
   if (maxR) *maxR = fold_max(o.R_all, o.has_first, o.first[1] != 0.0, o.first[0]);
   return 0;
+}
+
+int pmcgpu_draw_weights(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, double t_temper, long *nok,
+                        double *maxW, double *maxR, long *n_reject) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  c->sink_active = c->sink.on;  // with a host sink attached the arrays travel while the weight kernels run
+  const int rc = draw_weights_core(c, seed, iter, first_index, t_temper, nok, maxW, maxR, n_reject);
+  if (c->sink_active) {
+    c->sink_active = false;
+    cudaSetDevice(c->device);
+    if (c->copy_stream && cudaStreamSynchronize(c->copy_stream) != cudaSuccess && rc == 0)
+      return fail(c, PMCGPU_ERR_CUDA, "copy to the host sink failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  return rc;
 }
 
 int pmcgpu_proposal_log_pdf(pmcgpu_ctx *c, long n, const double *x, double *out) {

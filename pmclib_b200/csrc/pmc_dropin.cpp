@@ -1092,13 +1092,15 @@ size_t pmc_simu_importance(pmc_simu *psim, gsl_rng *r, error **err) {
   if (!push_proposal(s, m, err) || !push_target(s, psim->target, err) || !push_box(s, psim->pb, psim->ndim, err)) return 0;
   long nok = 0, nrej = 0;
   double maxW = 0, maxR = 0;
+  const bool sink = !resident();
+  if (sink) pmcgpu_set_host_sink(s->ctx, psim->X, psim->indices, psim->weights, psim->log_rho, psim->flg);
   const int rc = pmcgpu_draw_weights(s->ctx, seed_from(r), s->iter++, 0, 1.0, &nok, &maxW, &maxR, &nrej);
+  pmcgpu_set_host_sink(s->ctx, nullptr, nullptr, nullptr, nullptr, nullptr);
   if (rc) { gpu_fail(s, rc, err, __func__); return 0; }
   psim->maxW = maxW;
   psim->maxR = maxR;
   psim->isLog = 1;
-  s->host_stale = resident();
-  if (!s->host_stale && !pull_samples(s, psim, true, true, true, true, true, err)) return 0;
+  s->host_stale = !sink;
   return (size_t)nok;
 }
 

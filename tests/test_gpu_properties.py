@@ -153,6 +153,19 @@ def test_host_sink_equals_download(gpu, wlname):
     for k in host:
         assert np.array_equal(host[k], got[k]), k
     assert abs(np.sum(host["weights"][host["flg"] == 1]) - 1.0) < 1e-10
+    # importance only (pmc_simu_importance): log-weights and flags, un-normalised
+    gpu.set_workload(wl)
+    gpu.set_host_sink(**host)
+    try:
+        from pmclib_b200.api import C as _C
+        nok, mw, mr, nrej = _C.c_long(), _C.c_double(), _C.c_double(), _C.c_long()
+        gpu._ck(gpu.lib.pmcgpu_draw_weights(gpu.h, 12, 5, 0, 1.0, _C.byref(nok), _C.byref(mw), _C.byref(mr), _C.byref(nrej)))
+    finally:
+        gpu.set_host_sink()
+    got = gpu.download()
+    for k in host:
+        assert np.array_equal(host[k], got[k]), k
+    assert mw.value == np.max(host["weights"][host["flg"] == 1])
     # detached: the next iteration leaves the host arrays alone
     before = host["X"].copy()
     gpu.pmc_step(11, 1)
