@@ -46,7 +46,7 @@ void *pmcgpu_stream(pmcgpu_ctx *ctx);
 /* tuning / test knobs: "force_generic" (1 = only the literal any-shape kernels), "fused_version" (0 = newest small-d
  * kernel that has an instantiation, 1 = first generation, 2 = second generation only), "spl" (samples per lane of the
  * first-generation kernel, 1 or 2), "split_stats" / "split_draw" (0 = single-kernel variants of the second generation),
- * "mma" (0 = do not use the large-d tensor path), "mma_min_d" (smallest dimension routed to it, default 17),
+ * "mma" (0 = do not use the large-d tensor path), "mma_min_d" (smallest dimension routed to it when no fused small-d kernel is instantiated for the shape, default 2),
  * "mma_max_chunk" (test knob: samples whitened per pass; 0 = as many as memory allows),
  * "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass update),
  * "guard_ratio" (pivot guard threshold of the one-pass update), "timing" (see pmcgpu_get_timing) */

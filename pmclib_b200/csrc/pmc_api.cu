@@ -139,7 +139,7 @@ struct pmcgpu_ctx {
   int force_generic = 0, spl = 1, max_attempts = 10000, force_precise = 0;
   double guard_ratio = 200.0;
   // large-d tensor path (pmc_mma.cu)
-  struct MmaMix { DevBuf pack, lpack, kmap, dfj; int J = 0; bool valid = false; std::vector<int> alive; };
+  struct MmaMix { DevBuf pack, lpack, kmap, dfj; int J = 0; bool valid = false, dirty = false; std::vector<int> alive; };
   MmaMix mprop, mtgt;
   DevBuf Q, Qt, mpart, mstats, mpivot, dperm, dtiles, dcnt, xc;
   HostMix trial;  // scratch of the update (kept to reuse its storage)
@@ -147,7 +147,7 @@ struct pmcgpu_ctx {
   DevBuf wpart;
   long q_stride = 0;
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
-  int use_mma = 1, mma_min_d = 17;
+  int use_mma = 1, mma_min_d = 2;  // any shape without a fused small-d instantiation goes to the tensor path (30x the literal kernels at d = 7..16)
   long mma_max_chunk = 0;  // test knob: cap of the samples whitened per pass (0 = as many as memory allows)
   int filt_nbins = 0, filt_cl = 0, filt_cr = 0;  // filter_histogram inside the iteration (0 = off)
   // host sink: arrays of the caller that pmcgpu_pmc_step fills while the iteration is still running
@@ -310,8 +310,9 @@ int install_proposal(pmcgpu_ctx *c) {
   derive_mix(c->prop);
   int rc = upload_mix(c, c->prop, c->dprop);
   if (rc) return rc;
-  rc = pack_mma(c, c->prop, c->mprop);
-  if (rc) return rc;
+  c->mprop.valid = false;  // packed for the tensor path on first use (ensure_mma): shapes with a fused kernel never need it
+  c->mprop.dirty = true;
+  c->q_resident = false;
   return pack_small(c, c->prop, c->dprop_pack, c->prop_pack_doubles, c->prop_pack_host);
 }
 
@@ -564,6 +565,16 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
 
 constexpr long GEN_CHUNK = 1L << 18;
 
+// tensor-path packs are built lazily, the first time a call cannot be served by a fused small-d kernel
+int ensure_mma(pmcgpu_ctx *c) {
+  if (c->mprop.dirty) { c->mprop.dirty = false; RC(pack_mma(c, c->prop, c->mprop)); }
+  if (c->mtgt.dirty) {
+    c->mtgt.dirty = false;
+    if (c->tmix.K && (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX)) RC(pack_mma(c, c->tmix, c->mtgt));
+  }
+  return 0;
+}
+
 // can the large-d tensor path evaluate this configuration?  (mode 1 = target values supplied by the host)
 bool mma_usable(const pmcgpu_ctx *c, int mode) {
   if (!c->use_mma || c->force_generic || !c->mprop.valid || c->nfull != 0) return false;
@@ -706,6 +717,7 @@ int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector
 
 int run_weights_generic(pmcgpu_ctx *c, int mode, const double *post_in, const short *ok_in, double t_temper,
                         long first_index, WeightOut &o) {
+  RC(ensure_mma(c));
   if (mma_usable(c, mode)) return run_weights_mma(c, mode, post_in, ok_in, t_temper, first_index, o);
   c->q_resident = false;
   const long N = c->N;
@@ -1026,14 +1038,16 @@ const char *pmcgpu_last_error(const pmcgpu_ctx *c) { return c ? c->err.c_str() :
 void *pmcgpu_stream(pmcgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 static int repack_mma(pmcgpu_ctx *c) {
-  if (c->prop.K) RC(pack_mma(c, c->prop, c->mprop));
-  if (c->tmix.K && (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX)) RC(pack_mma(c, c->tmix, c->mtgt));
+  c->mprop.valid = c->mtgt.valid = false;
+  c->mprop.dirty = c->prop.K != 0;
+  c->mtgt.dirty = c->tmix.K != 0;
+  c->q_resident = false;
   return 0;
 }
 
 int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   if (!c || !name) return PMCGPU_ERR_USAGE;
-  if (!strcmp(name, "force_generic")) c->force_generic = (int)value;
+  if (!strcmp(name, "force_generic")) { c->force_generic = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "spl")) c->spl = (int)value;
   else if (!strcmp(name, "fused_version")) c->fused_version = (int)value;
   else if (!strcmp(name, "max_attempts")) c->max_attempts = (int)value;
@@ -1109,8 +1123,8 @@ int pmcgpu_set_target_mix(pmcgpu_ctx *c, int kind, int K, int d, const double *w
   c->td = d;
   rc = upload_mix(c, c->tmix, c->dtmix);
   if (rc) return rc;
-  rc = pack_mma(c, c->tmix, c->mtgt);
-  if (rc) return rc;
+  c->mtgt.valid = false;
+  c->mtgt.dirty = true;
   return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles, c->tgt_pack_host);
 }
 
@@ -1218,6 +1232,8 @@ int pmcgpu_device_arrays(pmcgpu_ctx *c, void **out) {
 
 // Grouped draw on the tensor path (no box): returns 1 if the configuration is not covered (caller uses the generic kernel)
 static int draw_mma(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index) {
+  if (c->nfaces > 0) return 1;
+  RC(ensure_mma(c));
   const pmcgpu_ctx::MmaMix &mm = c->mprop;
   if (!c->use_mma || c->force_generic || !mm.valid || c->nfaces > 0 || c->N >= (1L << 31)) return 1;
   const int K = c->prop.K, d = c->prop.d, J = mm.J;
