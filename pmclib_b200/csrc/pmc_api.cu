@@ -116,8 +116,10 @@ struct pmcgpu_ctx {
   int nfaces = 0, box_d = 0;
   std::vector<double> faces;
   DevBuf dfaces;
-  bool box_slab = false;
-  double lo_thr[FUSED_MAXD], hi_thr[FUSED_MAXD];
+  bool box_slab = false;      // slab box that the fused small-d kernels can test (d <= FUSED_MAXD)
+  bool box_slab_any = false;  // slab box of any dimension (tensor-path draw)
+  double lo_thr[PMCB200_MAXD], hi_thr[PMCB200_MAXD];
+  DevBuf dthr, dredo;
   // store
   long N = 0;
   int d = 0;
@@ -1159,7 +1161,8 @@ int pmcgpu_set_box(pmcgpu_ctx *c, int d, int nfaces, const double *faces) {
   cudaSetDevice(c->device);
   c->nfaces = 0;
   c->box_slab = false;
-  for (int j = 0; j < FUSED_MAXD; ++j) { c->lo_thr[j] = INFINITY; c->hi_thr[j] = INFINITY; }
+  c->box_slab_any = false;
+  for (int j = 0; j < PMCB200_MAXD; ++j) { c->lo_thr[j] = INFINITY; c->hi_thr[j] = INFINITY; }
   if (nfaces <= 0 || !faces) return 0;
   if (d < 1 || d > PMCB200_MAXD) return fail(c, PMCGPU_ERR_USAGE, "box dimension %d", d);
   c->faces.assign(faces, faces + (size_t)nfaces * (d + 1));
@@ -1169,7 +1172,7 @@ int pmcgpu_set_box(pmcgpu_ctx *c, int d, int nfaces, const double *faces) {
   c->nfaces = nfaces;
   // canonical slab form: every face is -e_j or +e_j (then thr - c.x reduces to one exact-coefficient operation and the
   // tightest threshold per axis decides, rounding being monotone) -> the fused kernel can test it bit-exactly
-  bool slab = d <= FUSED_MAXD;
+  bool slab = true;
   for (int f = 0; f < nfaces && slab; ++f) {
     const double *cf = faces + (size_t)f * (d + 1);
     int axis = -1;
@@ -1181,7 +1184,14 @@ int pmcgpu_set_box(pmcgpu_ctx *c, int d, int nfaces, const double *faces) {
     if (cf[axis] < 0) { if (cf[d] < c->lo_thr[axis]) c->lo_thr[axis] = cf[d]; }
     else { if (cf[d] < c->hi_thr[axis]) c->hi_thr[axis] = cf[d]; }
   }
-  c->box_slab = slab;
+  c->box_slab = slab && d <= FUSED_MAXD;
+  c->box_slab_any = slab;
+  if (slab) {  // thresholds of the -e_j faces, then of the +e_j faces, for the tensor-path draw
+    std::vector<double> thr(2 * (size_t)d);
+    for (int j = 0; j < d; ++j) { thr[j] = c->lo_thr[j]; thr[d + j] = c->hi_thr[j]; }
+    CU(c->dthr.ensure(thr.size() * sizeof(double)));
+    CU(cudaMemcpy(c->dthr.p, thr.data(), thr.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -1232,13 +1242,15 @@ int pmcgpu_device_arrays(pmcgpu_ctx *c, void **out) {
 
 // Grouped draw on the tensor path (no box): returns 1 if the configuration is not covered (caller uses the generic kernel)
 static int draw_mma(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index) {
-  if (c->nfaces > 0) return 1;
+  if (c->nfaces > 0 && (!c->box_slab_any || c->box_d != c->d)) return 1;
   RC(ensure_mma(c));
   const pmcgpu_ctx::MmaMix &mm = c->mprop;
-  if (!c->use_mma || c->force_generic || !mm.valid || c->nfaces > 0 || c->N >= (1L << 31)) return 1;
+  if (!c->use_mma || c->force_generic || !mm.valid || c->N >= (1L << 31)) return 1;
   const int K = c->prop.K, d = c->prop.d, J = mm.J;
   const long N = c->N;
-  CU(c->dcnt.ensure((size_t)2 * K * sizeof(unsigned int)));
+  CU(c->dcnt.ensure((size_t)(2 * K + 1) * sizeof(unsigned int)));
+  const bool boxed = c->nfaces > 0;
+  if (boxed) CU(c->dredo.ensure((size_t)N * sizeof(unsigned int)));
   CU(c->dperm.ensure((size_t)N * sizeof(unsigned int)));
   CU(cudaMemsetAsync(c->dcnt.p, 0, (size_t)K * sizeof(unsigned int), c->stream));
   if (c->timing) {
@@ -1280,10 +1292,27 @@ static int draw_mma(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_inde
   CU(cudaMemcpyAsync(cursor, ht + tiles.size(), (size_t)K * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
   launch_draw_perm(N, K, c->Idx.as<unsigned long long>(), cursor, c->dperm.as<unsigned int>(), c->sm_count * 8, c->stream);
   CU(cudaGetLastError());
+  unsigned int *nredo = c->dcnt.as<unsigned int>() + 2 * K;
+  if (boxed) CU(cudaMemsetAsync(nredo, 0, sizeof(unsigned int), c->stream));
   if (launch_draw_mma(mm.lpack.as<double>(), c->dtiles.p, ntiles, c->dperm.as<unsigned int>(), mm.dfj.as<int>(), d, seed, iter,
                       first_index, c->X.as<double>(), c->Flg.as<short>(), c->small.as<unsigned long long>() + SM_COUNTERS,
-                      c->sm_count, c->stream))
+                      boxed ? c->dthr.as<double>() : nullptr, boxed ? c->dredo.as<unsigned int>() : nullptr, nredo, c->sm_count,
+                      c->stream))
     return fail(c, PMCGPU_ERR_CUDA, "draw kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (boxed) {  // the samples whose first attempt left the box: literal kernel, same Philox stream from attempt 1 on
+    RC(stage(c, 1));
+    unsigned int *hn = reinterpret_cast<unsigned int *>(c->hstage);
+    CU(cudaMemcpyAsync(hn, nredo, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const long nr = (long)hn[0];
+    if (nr > 0) {
+      BoxDev bx{c->nfaces, c->box_d, c->dfaces.as<double>()};
+      launch_draw_generic(c->dprop.view, bx, seed, iter, first_index, nr, c->max_attempts, c->X.as<double>(),
+                          c->Idx.as<unsigned long long>(), c->Flg.as<short>(), c->small.as<unsigned long long>() + SM_COUNTERS,
+                          c->stream, c->dredo.as<unsigned int>(), 1);
+      CU(cudaGetLastError());
+    }
+  }
   if (c->timing) {
     CU(cudaEventRecord(c->evd, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1307,8 +1336,9 @@ int pmcgpu_draw(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, l
     unsigned long long cnt[CNT_NUM];
     rc = read_small(c, cnt, nullptr, nullptr);
     if (rc) return rc;
-    if (n_reject) *n_reject = 0;
-    if (cnt[CNT_DRAWFAIL]) return fail(c, kErrTooManySteps, "Too many points (%llu) outside of box", cnt[CNT_DRAWFAIL]);
+    if (n_reject) *n_reject = (long)cnt[CNT_REJECT];
+    if (cnt[CNT_DRAWFAIL] || (long)cnt[CNT_REJECT] > 5 * c->N)
+      return fail(c, kErrTooManySteps, "Too many points (%llu) outside of box", cnt[CNT_REJECT]);
     return 0;
   }
   if (rc != 1) return rc;

@@ -65,11 +65,15 @@ __device__ double target_log_pdf_generic(const TargetDev &t, const double *xfree
 }
 
 // ---- draw (pmc.c:266-298, mvdens.c:730-782, 279-317) ---------------------------------------------------------
+// list != nullptr: only the samples list[0..N) are (re)drawn, starting at attempt number attempt0 (the tensor-path draw
+// hands over the samples whose first attempt fell outside the box)
 __global__ void k_draw_generic(MixDev m, BoxDev bx, uint64_t seed, uint32_t iter, long first_index, long N,
                                int max_attempts, double *__restrict__ X, unsigned long long *__restrict__ indices,
-                               short *__restrict__ flg, unsigned long long *counters) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= N) return;
+                               short *__restrict__ flg, unsigned long long *counters,
+                               const unsigned int *__restrict__ list, int attempt0) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  const long i = list ? (long)list[t] : t;
   const int d = m.d;
   double x[MAXD];
   const uint64_t gi = (uint64_t)(first_index + i);
@@ -77,7 +81,7 @@ __global__ void k_draw_generic(MixDev m, BoxDev bx, uint64_t seed, uint32_t iter
   unsigned long long rejects = 0;
   int k = 0;
   bool ok = false;
-  for (int attempt = 0; attempt < max_attempts; ++attempt) {
+  for (int attempt = attempt0; attempt < max_attempts; ++attempt) {
     st.attempt = attempt;
     st.call = 0;
     const uint4 r0 = st.next();
@@ -491,8 +495,8 @@ void count_launch(int n) { g_launches += n; }
 
 void launch_draw_generic(const MixDev &m, const BoxDev &bx, uint64_t seed, uint32_t iter, long first_index, long N,
                          int max_attempts, double *X, unsigned long long *indices, short *flg,
-                         unsigned long long *counters, cudaStream_t s) {
-  if (N > 0) { k_draw_generic<<<nblk(N, 128), 128, 0, s>>>(m, bx, seed, iter, first_index, N, max_attempts, X, indices, flg, counters); count_launch(); }
+                         unsigned long long *counters, cudaStream_t s, const unsigned int *list, int attempt0) {
+  if (N > 0) { k_draw_generic<<<nblk(N, 128), 128, 0, s>>>(m, bx, seed, iter, first_index, N, max_attempts, X, indices, flg, counters, list, attempt0); count_launch(); }
 }
 void launch_weights_generic(const MixDev &m, const TargetDev &tg, int mode, const double *post_in, const short *ok_in,
                             double t_temper, long first_index, long N, const double *X, double *lw, double *log_rho,

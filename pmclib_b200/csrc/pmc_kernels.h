@@ -45,7 +45,7 @@ void count_launch(int n = 1);
 // ---- generic kernels (pmc_generic.cu) ------------------------------------------------------------------------
 void launch_draw_generic(const MixDev &m, const BoxDev &bx, uint64_t seed, uint32_t iter, long first_index, long N,
                          int max_attempts, double *X, unsigned long long *indices, short *flg,
-                         unsigned long long *counters, cudaStream_t s);
+                         unsigned long long *counters, cudaStream_t s, const unsigned int *list = nullptr, int attempt0 = 0);
 void launch_weights_generic(const MixDev &m, const TargetDev &tg, int mode, const double *post_in, const short *ok_in,
                             double t_temper, long first_index, long N, const double *X, double *lw, double *log_rho,
                             short *flg, double *ldscratch, int ldstride, double *blk_maxw, double *blk_maxr,
@@ -174,9 +174,11 @@ void launch_draw_pick(const double *cw, int K, uint64_t seed, uint32_t iter, lon
                       unsigned long long *indices, unsigned int *cnt, int nblocks, cudaStream_t s);
 void launch_draw_perm(long N, int K, const unsigned long long *indices, unsigned int *cursor, unsigned int *perm,
                       int nblocks, cudaStream_t s);
+// thr: nullptr, or the slab box as [d] thresholds of the -e_j faces followed by [d] of the +e_j faces; samples whose
+// first attempt falls outside are appended to redo[] (count in *nredo) with flg = 0
 int launch_draw_mma(const double *pack, const void *tiles, int ntiles, const unsigned int *perm, const int *dfj, int d,
                     uint64_t seed, uint32_t iter, long first_index, double *X, short *flg, unsigned long long *counters,
-                    int sm_count, cudaStream_t s);
+                    const double *thr, unsigned int *redo, unsigned int *nredo, int sm_count, cudaStream_t s);
 int mma_stats_chunks(long n, int J, int sm_count);
 size_t mma_stats_partial_doubles(int d, int J, int nchunk);
 // out[k] = { W_k, s1_k[d], S2_k[d*d] } for the J packed components (rows of other components untouched).  Xc is a

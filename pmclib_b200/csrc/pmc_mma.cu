@@ -522,7 +522,8 @@ template <int NT>
 __global__ void __launch_bounds__(256, 1)
 k_draw_mma(const double *__restrict__ pack, const int4 *__restrict__ tiles, int ntiles, const unsigned int *__restrict__ perm,
            const int *__restrict__ dfj, int d, uint64_t seed, uint32_t iter, long first_index, double *__restrict__ X,
-           short *__restrict__ flg, unsigned long long *counters) {
+           short *__restrict__ flg, unsigned long long *counters, const double *__restrict__ thr,
+           unsigned int *__restrict__ redo, unsigned int *__restrict__ nredo) {
   constexpr int KS = 2 * NT, MT = q_mt(NT), CS = q_comp_stride(NT);
   extern __shared__ double sm[];  // [CS]: mean and factor tiles of the current component
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
@@ -596,29 +597,32 @@ k_draw_mma(const double *__restrict__ pack, const int4 *__restrict__ tiles, int 
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const double corr = (df != -1) ? __shfl_sync(0xffffffffu, corr_mine, (lane & ~3) + (mt & 3)) : 1.0;
-      bool fin = true;
+      bool fin = true, inb = true;
       if (sid[mt] >= 0) {
         double *xr = X + (size_t)sid[mt] * d;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          const int a = 8 * nt + 2 * t4;
-          if (a < d) {
-            const double v = C[mt][nt][0] * corr + sm[a];
-            fin = fin && isfinite(v);
-            xr[a] = v;
-          }
-          if (a + 1 < d) {
-            const double v = C[mt][nt][1] * corr + sm[a + 1];
-            fin = fin && isfinite(v);
-            xr[a + 1] = v;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int a = 8 * nt + 2 * t4 + e;
+            if (a < d) {
+              const double v = C[mt][nt][e] * corr + sm[a];
+              fin = fin && isfinite(v);
+              if (thr) inb = inb && !(v < -thr[a]) && !(v > thr[d + a]);  // slab faces -e_a and +e_a (parabox.c:112-136)
+              xr[a] = v;
+            }
           }
         }
       }
-      const unsigned bad = __ballot_sync(0xffffffffu, !fin);
+      const unsigned bad = __ballot_sync(0xffffffffu, !fin), out = __ballot_sync(0xffffffffu, !inb);
       if (t4 == 0 && sid[mt] >= 0) {
-        const bool ok = ((bad >> (lane & ~3)) & 0xfu) == 0;
-        flg[sid[mt]] = ok ? 1 : 0;
-        if (!ok) atomicAdd(&counters[CNT_DRAWFAIL], 1ull);
+        const bool ok = ((bad >> (lane & ~3)) & 0xfu) == 0, inside = ((out >> (lane & ~3)) & 0xfu) == 0;
+        flg[sid[mt]] = (ok && inside) ? 1 : 0;
+        if (thr && !(ok && inside)) {  // redrawn by the literal kernel from attempt 1 on
+          redo[atomicAdd(nredo, 1u)] = (unsigned int)sid[mt];
+          atomicAdd(&counters[CNT_REJECT], 1ull);
+        }
+        else if (!ok) atomicAdd(&counters[CNT_DRAWFAIL], 1ull);
       }
     }
   }
@@ -627,12 +631,12 @@ k_draw_mma(const double *__restrict__ pack, const int4 *__restrict__ tiles, int 
 template <int NT>
 int launch_draw_t(const double *pack, const int4 *tiles, int ntiles, const unsigned int *perm, const int *dfj, int d,
                   uint64_t seed, uint32_t iter, long first_index, double *X, short *flg, unsigned long long *counters,
-                  int sm_count, cudaStream_t s) {
+                  const double *thr, unsigned int *redo, unsigned int *nredo, int sm_count, cudaStream_t s) {
   const size_t smem = (size_t)q_comp_stride(NT) * sizeof(double);
   static std::atomic<unsigned long long> smem_set{0};
   if (!set_max_smem_once(k_draw_mma<NT>, smem, smem_set)) return 1;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  k_draw_mma<NT><<<grid, 256, smem, s>>>(pack, tiles, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters);
+  k_draw_mma<NT><<<grid, 256, smem, s>>>(pack, tiles, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, thr, redo, nredo);
   count_launch();
   return cudaGetLastError() != cudaSuccess;
 }
@@ -802,14 +806,14 @@ void launch_draw_perm(long N, int K, const unsigned long long *indices, unsigned
 }
 int launch_draw_mma(const double *pack, const void *tiles, int ntiles, const unsigned int *perm, const int *dfj, int d,
                     uint64_t seed, uint32_t iter, long first_index, double *X, short *flg, unsigned long long *counters,
-                    int sm_count, cudaStream_t s) {
+                    const double *thr, unsigned int *redo, unsigned int *nredo, int sm_count, cudaStream_t s) {
   if (ntiles <= 0) return 0;
   const int4 *t4 = reinterpret_cast<const int4 *>(tiles);
   switch (mma_nt(d)) {
-    case 2: return launch_draw_t<2>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, sm_count, s);
-    case 4: return launch_draw_t<4>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, sm_count, s);
-    case 8: return launch_draw_t<8>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, sm_count, s);
-    case 16: return launch_draw_t<16>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, sm_count, s);
+    case 2: return launch_draw_t<2>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, thr, redo, nredo, sm_count, s);
+    case 4: return launch_draw_t<4>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, thr, redo, nredo, sm_count, s);
+    case 8: return launch_draw_t<8>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, thr, redo, nredo, sm_count, s);
+    case 16: return launch_draw_t<16>(pack, t4, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, thr, redo, nredo, sm_count, s);
   }
   return 1;
 }

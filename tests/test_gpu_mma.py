@@ -166,14 +166,17 @@ def test_mma_full_step_draw(gpu):
     assert abs(np.sum(got["weights"]) - 1.0) < 1e-10
 
 
-@pytest.mark.parametrize("name,N", [("d128_K64_c5", 20011), ("d30_K50_student_c4", 30000), ("d33_K4_banana", 9000),
-                                    ("d17_K5_banana", 777)])
-def test_mma_draw_equals_literal_draw(gpu, name, N):
+@pytest.mark.parametrize("name,N,box", [("d128_K64_c5", 20011, None), ("d30_K50_student_c4", 30000, None),
+                                        ("d33_K4_banana", 9000, None), ("d17_K5_banana", 777, None),
+                                        ("d17_K5_banana", 20000, 2.2), ("d30_K50_student_c4", 20000, 4.0),
+                                        ("d64_K5_mix", 6000, 3.3)])
+def test_mma_draw_equals_literal_draw(gpu, name, N, box):
     """The grouped tensor-path draw uses the Philox counters of the literal kernel: same components bit-exactly, same
     points up to the rounding of the summation order (the literal kernel follows cblas dtrmv, mvdens.c:302)."""
     wl = CASES[name][0]()
-    wl = dict(wl, faces=None)
+    wl = dict(wl, faces=None if box is None else W.box_faces(wl["d"], -box, box))
     out = {}
+    rej = {}
     for mma in (0, 1):
         gpu.set_option("force_generic", 0)
         gpu.set_option("mma", mma)
@@ -183,13 +186,18 @@ def test_mma_draw_equals_literal_draw(gpu, name, N):
         nrej = gpu.draw(77, 3, first_index=1000)
         used = gpu.get_draw_timing() > 0.0
         gpu.set_option("timing", 0)
-        assert nrej == 0 and used == bool(mma)
+        assert used == bool(mma)
+        rej[mma] = nrej
         out[mma] = gpu.download(weights=False, log_rho=False)
+    # a slab box: first attempts on the tensor path, the rejected samples redrawn by the literal kernel from attempt 1
+    assert rej[0] == rej[1] and (rej[0] > 0) == (box is not None)
     a, b = out[0], out[1]
     assert np.array_equal(a["indices"], b["indices"])
     assert np.array_equal(b["flg"], np.ones(N, np.int16))
     scale = np.max(np.abs(a["X"]))
     assert np.max(np.abs(a["X"] - b["X"])) <= 1e-13 * scale
+    if box is not None:
+        assert np.all(np.abs(b["X"]) <= box)
     # every component that has weight is used, none without
     used_k = np.unique(b["indices"])
     assert set(used_k.tolist()) <= set(np.nonzero(wl["wght"] > 0)[0].tolist())
