@@ -48,7 +48,7 @@ void *pmcgpu_stream(pmcgpu_ctx *ctx);
  * first-generation kernel, 1 or 2), "split_stats" / "split_draw" (0 = single-kernel variants of the second generation),
  * "mma" (0 = do not use the large-d tensor path), "mma_min_d" (smallest dimension routed to it when no fused small-d kernel is instantiated for the shape, default 2),
  * "mma_max_chunk" (test knob: samples whitened per pass; 0 = as many as memory allows),
- * "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass update),
+ * "t_temper" (t_iter_tempered used by pmcgpu_pmc_step, pmc.c:570; default 1), "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass update),
  * "guard_ratio" (pivot guard threshold of the one-pass update), "timing" (see pmcgpu_get_timing) */
 int pmcgpu_set_option(pmcgpu_ctx *ctx, const char *name, double value);
 

@@ -150,6 +150,7 @@ struct pmcgpu_ctx {
   long q_stride = 0;
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 2;  // any shape without a fused small-d instantiation goes to the tensor path (30x the literal kernels at d = 7..16)
+  double t_temper = 1.0;  // t_iter_tempered of pmcgpu_pmc_step (pmc.c:570: weight = t * post - rloc)
   long mma_max_chunk = 0;  // test knob: cap of the samples whitened per pass (0 = as many as memory allows)
   int filt_nbins = 0, filt_cl = 0, filt_cr = 0;  // filter_histogram inside the iteration (0 = off)
   // host sink: arrays of the caller that pmcgpu_pmc_step fills while the iteration is still running
@@ -1061,6 +1062,7 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "mma")) { c->use_mma = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_min_d")) { c->mma_min_d = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_max_chunk")) c->mma_max_chunk = (long)value;
+  else if (!strcmp(name, "t_temper")) { if (!(value >= 0)) return fail(c, -6019, "t_iter_tempered=%g should be > 0", value); c->t_temper = value; }
   else return fail(c, PMCGPU_ERR_USAGE, "unknown option %s", name);
   return 0;
 }
@@ -1839,7 +1841,7 @@ int pmcgpu_set_host_sink(pmcgpu_ctx *c, double *X, size_t *indices, double *weig
 int pmcgpu_pmc_step(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, long N_total, int do_update,
                     int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean, double *o_L, double *o_detL,
                     int *o_alive) {
-  return step_impl(c, 1, seed, iter, first_index, N_total, 1.0, do_update, retry, res, o_wght, o_mean, o_L, o_detL, o_alive);
+  return step_impl(c, 1, seed, iter, first_index, N_total, c->t_temper, do_update, retry, res, o_wght, o_mean, o_L, o_detL, o_alive);
 }
 int pmcgpu_step_given(pmcgpu_ctx *c, long first_index, long N_total, double t_temper, int do_update, int *retry,
                       pmcgpu_step_result *res, double *o_wght, double *o_mean, double *o_L, double *o_detL, int *o_alive) {

@@ -203,3 +203,31 @@ def test_student_t_update(gpu, d, K, df, N):
         assert r.retry == o["retry"]
         errs = compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=f"student d={d} mma={mma}")
         print(f"student-t d={d} K={K} df={df} mma={mma} precise={r.used_precise_path}", errs)
+
+
+@pytest.mark.parametrize("name,generic", [("c1_banana_d10_K10", 0), ("c2_gmm_d5_K20", 0), ("d7_K3_generic_only", 0),
+                                          ("d7_K3_generic_only", 1), ("c5_gauss_d128_K64", 0)])
+def test_tempered_weights(gpu, oracle_runs, name, generic):
+    """t_iter_tempered (pmc.c:570): log-weight = t * log-posterior - log-proposal, on every kernel family; the option
+    "t_temper" gives pmcgpu_pmc_step the same temperature."""
+    wl, X, idx, _ = oracle_runs(name)
+    t = 0.37
+    o = O.orc_iteration(X, idx, wl, t=t, do_update=1)
+    _setup(gpu, wl, X, idx, generic)
+    r = gpu.step_given(0, len(X), t, 1, 0)
+    big = max(np.max(np.abs(o["log_rho"])), 1.0)
+    assert_close(r.maxW, o["maxW"], RTOL, scale=big, what="maxW")
+    assert_close(r.logSum, o["logSum"], RTOL, scale=big, what="logSum")
+    assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
+    compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
+    # the drawing iteration with the option: same temperature reaches the weight kernels
+    gpu.set_workload(wl)
+    gpu.set_option("t_temper", t)
+    try:
+        a = gpu.pmc_step(3, 0, do_update=0)
+    finally:
+        gpu.set_option("t_temper", 1.0)
+    got = gpu.download()
+    o2 = O.orc_iteration(got["X"], got["indices"], wl, t=t, do_update=0)
+    assert_close(a.logSum, o2["logSum"], RTOL, scale=max(np.max(np.abs(o2["log_rho"])), 1.0), what="logSum (drawn)")
+    assert_close(a.perplexity, o2["perp"], 1e-11, what="perplexity (drawn)")
