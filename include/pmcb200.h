@@ -134,6 +134,13 @@ int pmcgpu_filter_histogram(pmcgpu_ctx *ctx, int nbins, int clipleft, int clipri
 int pmcgpu_set_filter_histogram(pmcgpu_ctx *ctx, int nbins, int clipleft, int clipright);
 /* mean_from_psim (pmc.c:1108-1120): sum over flg != 0 of weights[i] * X[i][a] */
 int pmcgpu_weighted_mean(pmcgpu_ctx *ctx, int a, double *mean);
+/* Resampling of the resident weighted sample.  sample_from_pmc_simu (pmc.c:1585-1601): isample[N], each entry an index
+ * drawn with probability proportional to weights[i] (all entries, whatever their flag, as the reference).
+ * resample_residual (pmc.c:1605-1626): multiplicity[N] = multinomial(N trials) over the residual weights
+ * N w_i - int(N w_i).  Philox is keyed by (seed, stream) and counted by the draw number: distributionally equivalent to
+ * the reference's gsl_ran_discrete / gsl_ran_multinomial, not stream-identical. */
+int pmcgpu_sample_indices(pmcgpu_ctx *ctx, uint64_t seed, uint32_t stream, size_t *isample);
+int pmcgpu_resample_residual(pmcgpu_ctx *ctx, uint64_t seed, uint32_t stream, unsigned int *multiplicity);
 /* prepare_update's histogram (pmc.c:1559-1564): count[K] of indices over flg==1 */
 int pmcgpu_count_indices(pmcgpu_ctx *ctx, size_t *count);
 /* update_prop_rb (pmc.c:1323-1469) + prepare_update + cleanup_after_update on the resident, normalised sample:

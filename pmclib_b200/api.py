@@ -241,6 +241,18 @@ class PmcGpu:
         self._ck(self.lib.pmcgpu_weighted_mean(self.h, a, C.byref(m)))
         return m.value
 
+    def sample_indices(self, seed, stream=0):
+        """sample_from_pmc_simu (pmc.c:1585-1601): N indices drawn with probability proportional to the weights."""
+        out = np.empty(self.N, np.uint64)
+        self._ck(self.lib.pmcgpu_sample_indices(self.h, seed, stream, _p(out)))
+        return out
+
+    def resample_residual(self, seed, stream=0):
+        """resample_residual (pmc.c:1605-1626): multinomial multiplicities of the residual weights."""
+        out = np.empty(self.N, np.uint32)
+        self._ck(self.lib.pmcgpu_resample_residual(self.h, seed, stream, _p(out)))
+        return out
+
     def count_indices(self):
         c = np.zeros(self.K, np.uint64)
         self._ck(self.lib.pmcgpu_count_indices(self.h, _p(c)))

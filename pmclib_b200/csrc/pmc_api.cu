@@ -146,7 +146,7 @@ struct pmcgpu_ctx {
   DevBuf Q, Qt, mpart, mstats, mpivot, dperm, dtiles, dcnt, xc;
   HostMix trial;  // scratch of the update (kept to reuse its storage)
   std::vector<double> hW, hG, hs1, hS2;
-  DevBuf wpart;
+  DevBuf wpart, cdf, cdfsum, rsout;
   long q_stride = 0;
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 2;  // any shape without a fused small-d instantiation goes to the tensor path (30x the literal kernels at d = 7..16)
@@ -1547,6 +1547,38 @@ int pmcgpu_weighted_mean(pmcgpu_ctx *c, int a, double *mean) {
   if (rc) return rc;
   *mean = s;
   return 0;
+}
+
+// ---- resampling of the weighted sample (pmc.c:1585-1626) ----------------------------------------------------------------
+static int resample_common(pmcgpu_ctx *c, uint64_t seed, uint32_t stream, int mode, void *out_host) {
+  if (!c || c->N <= 0 || !out_host) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  const long N = c->N;
+  CU(c->cdf.ensure((size_t)N * sizeof(double)));
+  CU(c->cdfsum.ensure((size_t)scan_blocks(N) * sizeof(double)));
+  const size_t obytes = (size_t)N * (mode == 0 ? sizeof(unsigned long long) : sizeof(unsigned int));
+  CU(c->rsout.ensure(obytes));
+  if (mode == 1) CU(cudaMemsetAsync(c->rsout.p, 0, obytes, c->stream));
+  launch_weight_cdf(N, c->W.as<double>(), mode, c->cdf.as<double>(), c->cdfsum.as<double>(), c->stream);
+  CU(cudaGetLastError());
+  RC(stage(c, 1));
+  CU(cudaMemcpyAsync(c->hstage, c->cdf.as<double>() + (N - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (!(c->hstage[0] > 0.0)) {
+    if (mode == 1) { memset(out_host, 0, obytes); return 0; }  // no residual mass: every multiplicity is zero
+    return fail(c, kErrNegWeight, "Sum of weights <= 0 (got %g): nothing to sample from", c->hstage[0]);
+  }
+  launch_resample(N, N, c->cdf.as<double>(), seed, stream, mode, c->rsout.as<unsigned long long>(), c->rsout.as<unsigned int>(), c->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_host, c->rsout.p, obytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int pmcgpu_sample_indices(pmcgpu_ctx *c, uint64_t seed, uint32_t stream, size_t *isample) {
+  return resample_common(c, seed, stream, 0, isample);
+}
+int pmcgpu_resample_residual(pmcgpu_ctx *c, uint64_t seed, uint32_t stream, unsigned int *multiplicity) {
+  return resample_common(c, seed, stream, 1, multiplicity);
 }
 
 int pmcgpu_count_indices(pmcgpu_ctx *c, size_t *count) {

@@ -1301,6 +1301,30 @@ void out_pmc_simu(const char *name, const pmc_simu *psim, error **err) {
   fclose(out);
 }
 
+// resampling after the last iteration (pmc.c:1585-1626): results are malloc'ed, owned by the caller as in the reference
+size_t *sample_from_pmc_simu(const pmc_simu *cpsim, const gsl_rng *rng, error **err) {
+  pmc_simu *psim = const_cast<pmc_simu *>(cpsim);
+  Side *s = side_for(psim, err);
+  if (!s) return nullptr;
+  if (!push_samples(s, psim, false, false, true, false, false, err)) return nullptr;
+  size_t *isample = (size_t *)xmalloc(sizeof(size_t) * psim->nsamples, err);
+  if (!isample) return nullptr;
+  const int rc = pmcgpu_sample_indices(s->ctx, seed_from(const_cast<gsl_rng *>(rng)), s->iter++, isample);
+  if (rc) { gpu_fail(s, rc, err, __func__); free(isample); return nullptr; }
+  return isample;
+}
+unsigned int *resample_residual(const pmc_simu *cpsim, const gsl_rng *rng, error **err) {
+  pmc_simu *psim = const_cast<pmc_simu *>(cpsim);
+  Side *s = side_for(psim, err);
+  if (!s) return nullptr;
+  if (!push_samples(s, psim, false, false, true, false, false, err)) return nullptr;
+  unsigned int *n = (unsigned int *)xmalloc(sizeof(unsigned int) * psim->nsamples, err);
+  if (!n) return nullptr;
+  const int rc = pmcgpu_resample_residual(s->ctx, seed_from(const_cast<gsl_rng *>(rng)), s->iter++, n);
+  if (rc) { gpu_fail(s, rc, err, __func__); free(n); return nullptr; }
+  return n;
+}
+
 // ---- additions ------------------------------------------------------------------------------------------------------------------
 int pmcb200_register_target(distribution *dist, int kind) {
   if (!dist || kind < PMCGPU_TGT_BANANA || kind > PMCGPU_TGT_MIX) return PMCGPU_ERR_USAGE;

@@ -79,6 +79,12 @@ void launch_flag_outside(long N, const double *w, short *flg, double bl, double 
 void launch_weighted_coord(long N, int d, int a, const double *X, const double *w, const short *flg, double *partial,
                            int nblocks, cudaStream_t s);
 
+// ---- resampling (pmc_post.cu) ------------------------------------------------------------------------------------
+long scan_blocks(long N);
+void launch_weight_cdf(long N, const double *w, int mode, double *cdf, double *blocksum, cudaStream_t s);
+void launch_resample(long N, long ndraw, const double *cdf, uint64_t seed, uint32_t stream, int mode,
+                     unsigned long long *isample, unsigned int *counts, cudaStream_t s);
+
 // ---- fused small-d iteration kernel (pmc_fused.cu) -----------------------------------------------------------
 constexpr int FUSED_MAXD = 16;
 
