@@ -38,6 +38,38 @@ struct TargetDev {
   const double *def_val;
 };
 
+#ifdef __CUDACC__
+// Common end of the one-thread-per-sample weight kernels (k_weights_generic, k_weights_q): block maxima of the log-weight
+// and of log_rho with the reference's "v > m" semantics (a NaN never wins, pmc.c:552-554,579) and the count of ok samples.
+__device__ __forceinline__ void weight_block_epilogue(double my_w, double my_r, bool okflag, double *blk_maxw,
+                                                      double *blk_maxr, unsigned long long *counters) {
+  if (my_w != my_w) my_w = -INFINITY;
+  if (my_r != my_r) my_r = -INFINITY;
+  my_w = warp_max_nan_ignoring(my_w);
+  my_r = warp_max_nan_ignoring(my_r);
+  __shared__ double sw[32], sr[32];
+  __shared__ unsigned int scnt;
+  if (threadIdx.x == 0) scnt = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sw[wid] = my_w; sr[wid] = my_r; }
+  const unsigned int nok = __popc(__ballot_sync(0xffffffffu, okflag));
+  if (lane == 0 && nok) atomicAdd(&scnt, nok);
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double a = lane < nw ? sw[lane] : -INFINITY, b = lane < nw ? sr[lane] : -INFINITY;
+    a = warp_max_nan_ignoring(a);
+    b = warp_max_nan_ignoring(b);
+    if (lane == 0) {
+      blk_maxw[blockIdx.x] = a;
+      blk_maxr[blockIdx.x] = b;
+      if (scnt) atomicAdd(&counters[CNT_NOK], (unsigned long long)scnt);
+    }
+  }
+}
+#endif
+
 // number of kernels launched by this library in this process (bench.py reports it as gpu_launches)
 long launch_count();
 void count_launch(int n = 1);

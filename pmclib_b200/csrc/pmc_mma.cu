@@ -198,30 +198,7 @@ __global__ void k_weights_q(MixDev m, TargetDev tg, int mode, const double *__re
       first_vals[3] = reached_w ? 1.0 : 0.0;
     }
   }
-  if (my_w != my_w) my_w = -INFINITY;
-  if (my_r != my_r) my_r = -INFINITY;
-  my_w = warp_max_nan_ignoring(my_w);
-  my_r = warp_max_nan_ignoring(my_r);
-  __shared__ double sw[32], sr[32];
-  __shared__ unsigned int scnt;
-  if (threadIdx.x == 0) scnt = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) { sw[wid] = my_w; sr[wid] = my_r; }
-  const unsigned int nok = __popc(__ballot_sync(0xffffffffu, okflag));
-  if (lane == 0 && nok) atomicAdd(&scnt, nok);
-  __syncthreads();
-  if (wid == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    double a = lane < nw ? sw[lane] : -INFINITY, b = lane < nw ? sr[lane] : -INFINITY;
-    a = warp_max_nan_ignoring(a);
-    b = warp_max_nan_ignoring(b);
-    if (lane == 0) {
-      blk_maxw[blockIdx.x] = a;
-      blk_maxr[blockIdx.x] = b;
-      if (scnt) atomicAdd(&counters[CNT_NOK], (unsigned long long)scnt);
-    }
-  }
+  weight_block_epilogue(my_w, my_r, okflag, blk_maxw, blk_maxr, counters);
 }
 
 // mixture log-density only (pmcgpu_proposal_log_pdf on the large-d path)
