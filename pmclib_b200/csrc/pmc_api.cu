@@ -370,6 +370,16 @@ int allreduce_host(pmcgpu_ctx *c, double *buf, long n, int op /*0 sum, 1 max*/) 
   return 0;
 }
 
+// sum over ranks of a device buffer, in place on the context's stream (NCCL ranks only; returns 1 when the ranks are
+// connected through a host callback instead, then the caller reduces on the host)
+int allreduce_device_sum(pmcgpu_ctx *c, double *dbuf, size_t n) {
+  if (c->nranks <= 1) return 0;
+  if (c->cb || !c->nccl_comm) return 1;
+  const int r = g_nccl.AllReduce(dbuf, dbuf, n, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream);
+  if (r != 0) return fail(c, PMCGPU_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  return 0;
+}
+
 // ---- host sink: device->host copies on a second stream, overlapped with the kernels that follow ------------------------
 enum { SINK_DRAWN = 1, SINK_RHO = 2, SINK_FINAL = 4 };
 int sink_copy(pmcgpu_ctx *c, int what) {
@@ -686,6 +696,9 @@ int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector
                        c->sm_count, c->stream))
     return fail(c, PMCGPU_ERR_CUDA, "statistics kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (c->timing && c->ev1) CU(cudaEventRecord(c->ev2, c->stream));
+  // K (1 + d + d^2) statistics (8.5 MB at d = 128, K = 64): reduced over NVLink before they cross PCIe once
+  const int dev_reduced = allreduce_device_sum(c, c->mstats.as<double>(), (size_t)K * len);
+  if (dev_reduced < 0) return dev_reduced;
   c->q_resident = false;  // Q now holds responsibilities
   RC(stage(c, (size_t)K * len + (student ? (size_t)nrb * K : 0)));
   CU(cudaMemcpyAsync(c->hstage, c->mstats.p, (size_t)K * len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -702,7 +715,7 @@ int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector
     if (rcw) return rcw;
   }
   if (c->timing && c->ev1) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats_ms += ms; }
-  int rc = allreduce_host(c, c->hstage, (long)((size_t)K * len), 0);  // in place in the pinned staging buffer
+  int rc = dev_reduced == 1 ? allreduce_host(c, c->hstage, (long)((size_t)K * len), 0) : 0;  // host-callback ranks: in place in the pinned staging buffer
   if (rc) return rc;
   W.resize(K);
   G.resize(K);
