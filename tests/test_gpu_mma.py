@@ -220,3 +220,34 @@ def test_mma_chunked_whitening_when_q_does_not_fit(gpu, oracle_runs):
     assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
     assert r.used_precise_path == 1
     compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
+
+
+@pytest.mark.parametrize("N", [1, 5, 70, 257])
+def test_mma_tiny_samples(gpu, N):
+    """Sample counts far below one tile (8..256 samples per block tile): weights agree with the oracle; the update of a
+    starved mixture reports the reference's error (every component below MINCOUNT -> pmc_negWeight, pmc.c:1529)."""
+    wl = W.banana(d=7, K=3, seed=9, mean_sigma=2.0, var=6.0, box=30.0)
+    X, idx = O.orc_simulate(max(N, 8), wl, seed=5)
+    X, idx = X[:N].copy(), idx[:N].copy()
+    o = O.orc_iteration(X, idx, wl, do_update=1)
+    _setup(gpu, wl, X, idx)
+    nok, maxW, maxR = gpu.weights(1.0)
+    got = gpu.download(X=False, indices=False)
+    assert nok == o["nok"]
+    assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho")
+    assert_close(maxW, o["maxW"], RTOL, scale=max(np.max(np.abs(o["log_rho"])), 1.0), what="maxW")
+    _setup(gpu, wl, X, idx)
+    if o["rc"] != 0:
+        with pytest.raises(Exception) as e:
+            gpu.step_given(0, N, 1.0, 1, 0)
+        assert str(o["rc"]) in str(e.value)
+    else:
+        r = gpu.step_given(0, N, 1.0, 1, 0)
+        compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=f"N={N}")
+    # and a drawing iteration of that size runs through the grouped draw
+    gpu.set_workload(wl)
+    gpu.resize(N, wl["d"])
+    try:
+        gpu.pmc_step(3, 0, do_update=0)
+    except Exception as e:   # all-flagged / no-sample errors of the reference are legitimate at N = 1
+        assert "-60" in str(e)
