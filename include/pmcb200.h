@@ -141,6 +141,10 @@ int pmcgpu_weighted_mean(pmcgpu_ctx *ctx, int a, double *mean);
  * the reference's gsl_ran_discrete / gsl_ran_multinomial, not stream-identical. */
 int pmcgpu_sample_indices(pmcgpu_ctx *ctx, uint64_t seed, uint32_t stream, size_t *isample);
 int pmcgpu_resample_residual(pmcgpu_ctx *ctx, uint64_t seed, uint32_t stream, unsigned int *multiplicity);
+/* clip_weights (pmc.c:1134-1188) on the resident normalised weights: the samples carrying the n largest weights are
+ * zeroed and flagged out, the remaining ok weights re-normalised to one.  Reproduces the reference's initialisation of
+ * its candidate array (copies of weights[0], samples j < n never offered).  Error -6015 (pmc_infnan) if nothing is left. */
+int pmcgpu_clip_weights(pmcgpu_ctx *ctx, int n, double *threshold, long *n_clipped, double *sum_after);
 /* prepare_update's histogram (pmc.c:1559-1564): count[K] of indices over flg==1 */
 int pmcgpu_count_indices(pmcgpu_ctx *ctx, size_t *count);
 /* update_prop_rb (pmc.c:1323-1469) + prepare_update + cleanup_after_update on the resident, normalised sample:

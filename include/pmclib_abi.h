@@ -247,6 +247,7 @@ void out_pmc_simu(const char *name, const pmc_simu *psim, error **err);         
 int *filter_histogram_init(int nbins, int clipleft, int clipright, error **err);       /* pmc.c:699-707 */
 void filter_histogram(pmc_simu *psim, void *filter_data, error **err);                  /* pmc.c:709-770 */
 double mean_from_psim(double *X, double *w, short *flg, int nsamples, int ndim, int a); /* pmc.c:1108-1120 */
+void clip_weights(pmc_simu *psim, int n, FILE *OUT, error **err);                        /* pmc.c:1134-1188 */
 size_t *sample_from_pmc_simu(const pmc_simu *psim, const gsl_rng *rng, error **err);     /* pmc.c:1585-1601 */
 unsigned int *resample_residual(const pmc_simu *psim, const gsl_rng *rng, error **err);  /* pmc.c:1605-1626 */
 #endif

@@ -556,3 +556,39 @@ double orc_mean_from_psim(const double *X, const double *w, const short *flg, lo
   }
   return m;
 }
+
+/* clip_weights (pmc.c:1134-1188), literally, including the initialisation loop that tests flg[i] but copies weights[j]
+ * with j stuck at 0 (pmc.c:1144-1151).  Returns 0, or -6015 (pmc_infnan) when no weight is left; *thr = the threshold. */
+static int orc_dcmp(const void *a, const void *b) {
+  const double x = *(const double *)a, y = *(const double *)b;
+  return (x < y) ? -1 : (x > y) ? 1 : 0;
+}
+int orc_clip_weights(long N, double *weights, short *flg, int n, double *thr) {
+  if (n == 0) return 0;
+  double *mw = (double *)calloc(n, sizeof(double));
+  long i = 0, j = 0;
+  while (i < n && j < N) {
+    if (flg[i] == 0) { j++; continue; }
+    mw[i] = weights[j];
+    i++;
+  }
+  qsort(mw, n, sizeof(double), orc_dcmp);
+  for (j = n; j < N; j++) {
+    if (flg[j] == 0) continue;
+    if (mw[0] < weights[j]) { mw[0] = weights[j]; qsort(mw, n, sizeof(double), orc_dcmp); }
+  }
+  double sum = 0.0;
+  for (j = 0; j < N; j++) {
+    if (flg[j] == 0) continue;
+    if (weights[j] >= mw[0]) { weights[j] = 0.0; flg[j] = 0; }
+    else sum += weights[j];
+  }
+  if (thr) *thr = mw[0];
+  free(mw);
+  if (sum <= 0) return -6015;
+  for (j = 0; j < N; j++) {
+    if (flg[j] == 0) continue;
+    weights[j] /= sum;
+  }
+  return 0;
+}

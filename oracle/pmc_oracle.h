@@ -103,6 +103,7 @@ long orc_simulate(long N, orc_mix *m, int nfaces, const double *faces, unsigned 
                   double *X, size_t *indices, short *flg, double *cw_scratch);
 
 /* filter_histogram (pmc.c:709-770), mean_from_psim (pmc.c:1108-1120) */
+int orc_clip_weights(long N, double *weights, short *flg, int n, double *thr); /* pmc.c:1134-1188 */
 long orc_filter_histogram(long N, const double *weights, short *flg, int nbins, int cl, int cr);
 double orc_mean_from_psim(const double *X, const double *w, const short *flg, long N, int d, int a);
 

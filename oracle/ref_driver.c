@@ -391,3 +391,14 @@ long ref_filter_histogram(long N, double *weights, short *flg, int nbins, int cl
   return rc ? rc : before - after;
 }
 double ref_mean_from_psim(double *X, double *w, short *flg, int N, int d, int a) { return mean_from_psim(X, w, flg, N, d, a); }
+
+int ref_clip_weights(long N, double *weights, short *flg, int n) {
+  error *e = initError(), **err = &e;
+  pmc_simu ps;
+  memset(&ps, 0, sizeof ps);
+  ps.nsamples = N; ps.weights = weights; ps.flg = flg;
+  clip_weights(&ps, n, NULL, err);
+  int rc = take_err(err);
+  endError(err);
+  return rc;
+}

@@ -241,6 +241,12 @@ class PmcGpu:
         self._ck(self.lib.pmcgpu_weighted_mean(self.h, a, C.byref(m)))
         return m.value
 
+    def clip_weights(self, n):
+        """clip_weights (pmc.c:1134-1188): returns (threshold, number clipped, sum of the remaining weights before rescaling)."""
+        T, nc, S = C.c_double(), C.c_long(), C.c_double()
+        self._ck(self.lib.pmcgpu_clip_weights(self.h, n, C.byref(T), C.byref(nc), C.byref(S)))
+        return T.value, nc.value, S.value
+
     def sample_indices(self, seed, stream=0):
         """sample_from_pmc_simu (pmc.c:1585-1601): N indices drawn with probability proportional to the weights."""
         out = np.empty(self.N, np.uint64)

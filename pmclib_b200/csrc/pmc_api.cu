@@ -1594,6 +1594,71 @@ int pmcgpu_resample_residual(pmcgpu_ctx *c, uint64_t seed, uint32_t stream, unsi
   return resample_common(c, seed, stream, 1, multiplicity);
 }
 
+// ---- clip_weights (pmc.c:1134-1188) ------------------------------------------------------------------------------------
+// The reference keeps the n largest candidates in a small sorted array; its initialisation loop (pmc.c:1144-1151) fills
+// that array with m copies of weights[0] (m = number of leading samples i < n with flg[i] != 0) and zeros, and samples
+// j < n are never offered.  The threshold is therefore the n-th largest of  {w0 x m} U {0 x (n-m)} U {w_j : j >= n, ok},
+// found here by a bitwise search over the order-preserving integer keys (64 counting passes).
+static unsigned long long host_dkey(double v) {
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+int pmcgpu_clip_weights(pmcgpu_ctx *c, int n, double *threshold, long *n_clipped, double *sum_after) {
+  if (!c || c->N <= 0 || n < 0) return PMCGPU_ERR_USAGE;
+  if (n == 0) { if (n_clipped) *n_clipped = 0; return 0; }
+  if (n > c->N) return fail(c, PMCGPU_ERR_USAGE, "clip_weights: n=%d exceeds the sample size %ld", n, c->N);
+  cudaSetDevice(c->device);
+  const long N = c->N;
+  const int nb = c->sm_count * 8;
+  RC(stage(c, (size_t)n / 4 + 8 + nb));
+  short *hf = reinterpret_cast<short *>(c->hstage + 2);
+  CU(cudaMemcpyAsync(c->hstage, c->W.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(hf, c->Flg.p, (size_t)n * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const double w0 = c->hstage[0];
+  int m = 0;
+  while (m < n && hf[m] != 0) ++m;
+  // extras of the reference's initial array, as keys
+  const unsigned long long k_w0 = host_dkey(w0), k_zero = host_dkey(0.0);
+  auto extras_ge = [&](unsigned long long key) { return (unsigned long long)((k_w0 >= key ? m : 0) + (k_zero >= key ? n - m : 0)); };
+  int rc = zero_small(c);
+  if (rc) return rc;
+  unsigned long long *cnt = c->small.as<unsigned long long>() + SM_COUNTERS;
+  unsigned long long key = 0;
+  for (int b = 63; b >= 0; --b) {
+    const unsigned long long trial = key | (1ull << b);
+    CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+    launch_count_key_ge(N, n, c->W.as<double>(), c->Flg.as<short>(), trial, cnt, nb, c->stream);
+    CU(cudaGetLastError());
+    unsigned long long hc = 0;
+    CU(cudaMemcpyAsync(&hc, cnt, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (hc + extras_ge(trial) >= (unsigned long long)n) key = trial;
+  }
+  unsigned long long bits = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+  double T;
+  memcpy(&T, &bits, 8);
+  CU(c->blkmax.ensure((size_t)2 * nb * sizeof(double)));
+  CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+  launch_clip_apply(N, T, c->W.as<double>(), c->Flg.as<short>(), c->blkmax.as<double>(), cnt, nb, c->stream);
+  CU(cudaGetLastError());
+  unsigned long long hclip = 0;
+  CU(cudaMemcpyAsync(c->hstage, c->blkmax.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&hclip, cnt, sizeof hclip, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double S = 0.0;
+  for (int b = 0; b < nb; ++b) S += c->hstage[b];
+  if (threshold) *threshold = T;
+  if (n_clipped) *n_clipped = (long)hclip;
+  if (sum_after) *sum_after = S;
+  if (S <= 0) return fail(c, -6015, "Sum of weights (%g) has to be larger than zero", S);  // pmc_infnan, pmc.c:1180
+  launch_scale_ok(N, S, c->W.as<double>(), c->Flg.as<short>(), nb, c->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int pmcgpu_count_indices(pmcgpu_ctx *c, size_t *count) {
   if (!c || !count || c->prop.K == 0) return PMCGPU_ERR_USAGE;
   cudaSetDevice(c->device);

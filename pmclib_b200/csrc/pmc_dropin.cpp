@@ -1301,6 +1301,19 @@ void out_pmc_simu(const char *name, const pmc_simu *psim, error **err) {
   fclose(out);
 }
 
+void clip_weights(pmc_simu *psim, int n, FILE *OUT, error **err) {
+  if (n == 0) return;
+  Side *s = side_for(psim, err);
+  if (!s) return;
+  if (!push_samples(s, psim, false, false, true, false, true, err)) return;
+  double T = 0, S = 0;
+  long nc = 0;
+  const int rc = pmcgpu_clip_weights(s->ctx, n, &T, &nc, &S);
+  if (OUT) fprintf(OUT, "clip_weights: setting %d weights larger than %g to zero (%ld samples)\n", n, T, nc);
+  if (rc) { gpu_fail(s, rc, err, __func__); return; }
+  if (!s->host_stale) pull_samples(s, psim, false, false, true, false, true, err);
+}
+
 // resampling after the last iteration (pmc.c:1585-1626): results are malloc'ed, owned by the caller as in the reference
 size_t *sample_from_pmc_simu(const pmc_simu *cpsim, const gsl_rng *rng, error **err) {
   pmc_simu *psim = const_cast<pmc_simu *>(cpsim);

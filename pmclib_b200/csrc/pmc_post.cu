@@ -76,7 +76,67 @@ __global__ void k_resample(long N, long ndraw, const double *__restrict__ cdf, u
   else atomicAdd(&counts[lo], 1u);
 }
 
+// ---- clip_weights (pmc.c:1134-1188) ----------------------------------------------------------------------------------
+// order-preserving 64-bit key of a double (total order of IEEE-754 values, NaNs excluded by the callers)
+__device__ __forceinline__ unsigned long long dkey(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+// number of ok samples j >= first whose weight key is >= key (one step of the bitwise search for the n-th largest)
+__global__ void k_count_key_ge(long N, long first, const double *__restrict__ w, const short *__restrict__ flg,
+                               unsigned long long key, unsigned long long *cnt) {
+  unsigned int n = 0;
+  for (long j = first + blockIdx.x * (long)blockDim.x + threadIdx.x; j < N; j += (long)gridDim.x * blockDim.x) {
+    const double v = w[j];
+    if (flg[j] != 0 && v == v && dkey(v) >= key) ++n;
+  }
+  const unsigned int c = (unsigned int)warp_sum_ll(n);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(cnt, (unsigned long long)c);
+}
+// ok samples with weight >= T are zeroed and flagged out, the others are summed (block partials, fixed order)
+__global__ void k_clip_apply(long N, double T, double *__restrict__ w, short *__restrict__ flg, double *__restrict__ partial,
+                             unsigned long long *cnt) {
+  double acc = 0.0;
+  unsigned int n = 0;
+  for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < N; j += (long)gridDim.x * blockDim.x) {
+    if (flg[j] == 0) continue;
+    const double v = w[j];
+    if (v >= T) { w[j] = 0.0; flg[j] = 0; ++n; }
+    else acc += v;
+  }
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const double sw = warp_sum(acc);
+  if (lane == 0) sh[wid] = sw;
+  __syncthreads();
+  if (wid == 0) {
+    const double t = warp_sum(lane < nw ? sh[lane] : 0.0);
+    if (lane == 0) partial[blockIdx.x] = t;
+  }
+  const unsigned int c = (unsigned int)warp_sum_ll(n);
+  if (lane == 0 && c) atomicAdd(cnt, (unsigned long long)c);
+}
+__global__ void k_scale_ok(long N, double S, double *__restrict__ w, const short *__restrict__ flg) {
+  for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < N; j += (long)gridDim.x * blockDim.x)
+    if (flg[j] != 0) w[j] /= S;
+}
+
 }  // namespace
+
+void launch_count_key_ge(long N, long first, const double *w, const short *flg, unsigned long long key,
+                         unsigned long long *cnt, int nblocks, cudaStream_t s) {
+  k_count_key_ge<<<nblocks, 256, 0, s>>>(N, first, w, flg, key, cnt);
+  count_launch();
+}
+void launch_clip_apply(long N, double T, double *w, short *flg, double *partial, unsigned long long *cnt, int nblocks,
+                       cudaStream_t s) {
+  k_clip_apply<<<nblocks, 256, 0, s>>>(N, T, w, flg, partial, cnt);
+  count_launch();
+}
+void launch_scale_ok(long N, double S, double *w, const short *flg, int nblocks, cudaStream_t s) {
+  k_scale_ok<<<nblocks, 256, 0, s>>>(N, S, w, flg);
+  count_launch();
+}
 
 long scan_blocks(long N) { return (N + SCAN_CHUNK - 1) / SCAN_CHUNK; }
 

@@ -31,7 +31,7 @@ EXPORTS = [
     "pmcgpu_set_target_defaults", "pmcgpu_set_target_host", "pmcgpu_set_box", "pmcgpu_resize", "pmcgpu_upload",
     "pmcgpu_download", "pmcgpu_set_host_sink", "pmcgpu_pin_host", "pmcgpu_unpin_host", "pmcgpu_device_arrays", "pmcgpu_draw", "pmcgpu_weights", "pmcgpu_draw_weights", "pmcgpu_weights_host_post",
     "pmcgpu_proposal_log_pdf", "pmcgpu_target_log_pdf", "pmcgpu_normalize", "pmcgpu_perplexity_ess",
-    "pmcgpu_filter_histogram", "pmcgpu_set_filter_histogram", "pmcgpu_weighted_mean", "pmcgpu_sample_indices", "pmcgpu_resample_residual",
+    "pmcgpu_filter_histogram", "pmcgpu_set_filter_histogram", "pmcgpu_weighted_mean", "pmcgpu_sample_indices", "pmcgpu_resample_residual", "pmcgpu_clip_weights",
     "pmcgpu_count_indices", "pmcgpu_update_rb", "pmcgpu_update_hard", "pmcgpu_ranindx", "pmcgpu_isinbox",
     "pmcgpu_pmc_step", "pmcgpu_step_given", "pmcgpu_get_proposal", "pmcgpu_shard_range", "pmcgpu_nccl_unique_id",
     "pmcgpu_comm_init", "pmcgpu_comm_set_callback", "pmcgpu_stats_len", "pmcgpu_finalize_update", "pmcgpu_cholesky",
@@ -73,6 +73,7 @@ def load_library(build_if_missing: bool = False):
     L.pmcgpu_filter_histogram.argtypes = [vp, i32, i32, i32, lng, C.POINTER(lng)]
     L.pmcgpu_set_filter_histogram.argtypes = [vp, i32, i32, i32]
     L.pmcgpu_weighted_mean.argtypes = [vp, i32, C.POINTER(dbl)]
+    L.pmcgpu_clip_weights.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(lng), C.POINTER(dbl)]
     L.pmcgpu_sample_indices.argtypes = [vp, C.c_uint64, C.c_uint32, vp]
     L.pmcgpu_resample_residual.argtypes = [vp, C.c_uint64, C.c_uint32, vp]
     L.pmcgpu_upload.argtypes = [vp, vp, vp, vp, vp, vp]

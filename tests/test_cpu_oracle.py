@@ -154,3 +154,39 @@ def test_mean_from_psim_restatement_equals_reference():
     R.ref_mean_from_psim.restype = C.c_double
     for a in range(d):
         assert R.ref_mean_from_psim(O.P(X), O.P(w), O.P(flg), N, d, a) == L.orc_mean_from_psim(O.P(X), O.P(w), O.P(flg), C.c_long(N), d, a)
+
+
+def _clip_case(case, N=3000, seed=23):
+    rng = np.random.default_rng(seed)
+    w = rng.gamma(0.6, 1.0, N)
+    w /= w.sum()
+    flg = (rng.uniform(size=N) > 0.1).astype(np.int16)
+    flg[:40] = 1
+    if case == "first_flagged":
+        flg[0] = 0          # the candidate array starts as zeros only
+    if case == "early_gap":
+        flg[3] = 0          # three copies of weights[0], then zeros
+    if case == "w0_largest":
+        w[0] = 0.5
+    if case == "ties":
+        w[100:140] = w[100]
+    return w, flg
+
+
+@pytest.mark.parametrize("case", ["plain", "first_flagged", "early_gap", "w0_largest", "ties"])
+@pytest.mark.parametrize("n", [1, 5, 37])
+def test_clip_weights_restatement_equals_reference(case, n):
+    """clip_weights (pmc.c:1134-1188) with the quirks of its initialisation loop: flags and weights bit-exact."""
+    import ctypes as C
+    R = O.ref()
+    if R is None:
+        pytest.skip("compiled reference not available")
+    L = O.orc()
+    w, flg = _clip_case(case)
+    w1, f1, w2, f2 = w.copy(), flg.copy(), w.copy(), flg.copy()
+    rc1 = R.ref_clip_weights(C.c_long(len(w)), O.P(w1), O.P(f1), n)
+    thr = C.c_double()
+    rc2 = L.orc_clip_weights(C.c_long(len(w)), O.P(w2), O.P(f2), n, C.byref(thr))
+    assert rc1 == rc2 == 0
+    assert np.array_equal(f1, f2) and np.array_equal(w1, w2)
+    assert (flg != 0).sum() - (f2 != 0).sum() >= 1

@@ -86,3 +86,37 @@ def test_iteration_with_filter(gpu, name):
     assert_close(r.ess, o["ess"], 1e-11, what="ESS")
     assert r.retry == o["retry"]
     compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
+
+
+@pytest.mark.parametrize("case", ["plain", "first_flagged", "early_gap", "w0_largest", "ties"])
+@pytest.mark.parametrize("n", [1, 5, 37])
+def test_clip_weights(gpu, case, n):
+    """clip_weights (pmc.c:1134-1188): threshold and flags bit-exact, re-normalised weights to 1e-12 (the device sums in a
+    different order)."""
+    from test_cpu_oracle import _clip_case
+    w, flg = _clip_case(case, N=50_000, seed=31)
+    N = len(w)
+    wo, fo = w.copy(), flg.copy()
+    thr = C.c_double()
+    rc = O.orc().orc_clip_weights(C.c_long(N), O.P(wo), O.P(fo), n, C.byref(thr))
+    assert rc == 0
+    gpu.set_workload(W.shipped_example())
+    gpu.resize(N, 2)
+    gpu.upload(X=np.zeros((N, 2)), weights=w, flg=flg)
+    T, nclip, S = gpu.clip_weights(n)
+    got = gpu.download(X=False, indices=False, log_rho=False)
+    assert T == thr.value
+    assert np.array_equal(got["flg"], fo)
+    assert nclip == int((flg != 0).sum() - (fo != 0).sum())
+    assert_close(got["weights"], wo, RTOL, scale=np.max(wo), what="clipped weights")
+
+
+def test_clip_weights_nothing_left(gpu):
+    N = 100
+    w = np.full(N, 1.0 / N)
+    gpu.set_workload(W.shipped_example())
+    gpu.resize(N, 2)
+    gpu.upload(X=np.zeros((N, 2)), weights=w, flg=np.ones(N, np.int16))
+    with pytest.raises(Exception) as e:
+        gpu.clip_weights(3)     # all weights equal the threshold: everything is clipped -> pmc_infnan
+    assert "-6015" in str(e.value)
