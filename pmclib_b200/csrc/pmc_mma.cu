@@ -1,5 +1,6 @@
-// pmc_mma.cu — the large-d path (16 < d <= 128): whitening and Rao-Blackwell statistics as dense FP64 contractions on
-// the tensor path (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4).
+// pmc_mma.cu — the tensor path: whitening, Rao-Blackwell statistics and the grouped draw as dense FP64 contractions
+// (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4) for every shape d <= 128 that has no fused small-d instantiation — above all the
+// large dimensions (configs[3] d = 30, configs[4] d = 128).
 //
 // Why a separate path: with one sample per lane (pmc_fused2.cu) a d x d triangular factor no longer fits the constant
 // bank / registers, and the generic kernels (one thread per sample, factor streamed from L2) run at ~4 % of the FP64
@@ -20,6 +21,9 @@
 // The inverse factors are formed on the host in extended precision (mma_pack_mixture); a product with Linv differs from
 // the reference's forward substitution (mvdens.c:341) by O(eps cond(L)) — inside the 1e-12 parity tolerance for the
 // well-conditioned factors a PMC proposal has (tests/test_gpu_mma.py measures it against the oracle).
+//
+//   k_draw_pick/perm/mma  x = mu_k + L_k g with the samples grouped by component (same Philox counters as the literal
+//                    kernel); inside a slab box the rejected first attempts are handed to the literal kernel.
 #include <algorithm>
 #include <cmath>
 #include <vector>
