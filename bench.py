@@ -315,7 +315,7 @@ def main():
         bytes_k1 = BYTES_PER_SAMPLE + (8.0 * wl["K"] if split else 0.0)
         if split and msd > 0:
             bytes_k1 = 8.0 * wl["d"] + 8 + 18 + 8.0 * wl["K"]   # reads X and indices, writes weights, log_rho, flg, responsibilities
-        roof = {"bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
+        roof = {"bound": "tensor", "bound_detail": "FP64 pipe: DFMA and the FP64 tensor instruction DMMA share it on B200 (36.9 / 37.15 TFLOP/s measured, not additive)", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
                 "traffic": None, "kernel": ("k_fused2<MODE 1> (mixture log-density + target + log-weights)" if msd > 0 else "k_fused2 (draw + mixture log-density + target + log-weights)") if split else "k_fused2 (single pass)",
                 "kernel_ms": ms, "kernel_share_of_step": fused_ms / ev_ms, "algorithmic_flop_per_sample": flop,
                 "peak_source": "measured DFMA peak, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)",
