@@ -1,3 +1,5 @@
+"""configs[3] shape: wall-clock of draw and weights separately over 45 iterations (shows the steady state and the power-cap
+episodes of the 100 %-duty DMMA whitening)."""
 import os, sys, time
 sys.path.insert(0, "/root/repo")
 from pmclib_b200 import PmcGpu, workloads as W

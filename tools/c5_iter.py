@@ -1,3 +1,5 @@
+"""A few full iterations at the configs[4] shape (N5 samples, ITERS iterations): the command profiled by ncu for
+profiles/r01_mma_ncu.txt; PMCB200_TRACE=1 prints the wall-clock of the phases."""
 import os, sys
 sys.path.insert(0, "/root/repo")
 from pmclib_b200 import PmcGpu, workloads as W
