@@ -1,7 +1,7 @@
 """configs[3] shape: wall-clock of draw and weights separately over 45 iterations (shows the steady state and the power-cap
 episodes of the 100 %-duty DMMA whitening)."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pmclib_b200 import PmcGpu, workloads as W
 g = PmcGpu(0); wl = W.student30(); g.set_workload(wl); g.resize(10_000_000, wl["d"])
 td=[]; tw=[]
