@@ -662,8 +662,12 @@ int run_weights_mma(pmcgpu_ctx *c, int mode, const double *post_in, const short 
 
 // one-pass pivoted statistics on the tensor path (Gaussian components; Q still holds ld_k for the whole store and the
 // weights are normalised).  Outputs in the layout pmcgpu_finalize_update expects.
+struct StatView {  // per-component sufficient statistics with explicit strides (doubles)
+  const double *W = nullptr, *G = nullptr, *s1 = nullptr, *S2 = nullptr;
+  size_t sW = 1, sG = 1, ss1 = 0, sS2 = 0;
+};
 int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector<double> &pivot, std::vector<double> &W,
-              std::vector<double> &G, std::vector<double> &s1, std::vector<double> &S2) {
+              StatView &view) {
   const HostMix &m = c->prop;
   const int K = m.K, d = m.d, J = c->mprop.J;
   const long N = c->N;
@@ -717,17 +721,17 @@ int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector
   if (c->timing && c->ev1) { float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats_ms += ms; }
   int rc = dev_reduced == 1 ? allreduce_host(c, c->hstage, (long)((size_t)K * len), 0) : 0;  // host-callback ranks: in place in the pinned staging buffer
   if (rc) return rc;
-  W.resize(K);
-  G.resize(K);
-  s1.resize((size_t)K * d);
-  S2.resize((size_t)K * d * d);
-  for (int k = 0; k < K; ++k) {
-    const double *sk = c->hstage + (size_t)k * len;
-    G[k] = sk[0];                       // weight_gamma_d
-    W[k] = student ? wsum[k] : sk[0];   // weight_d
-    memcpy(s1.data() + (size_t)k * d, sk + 1, d * sizeof(double));
-    memcpy(S2.data() + (size_t)k * d * d, sk + 1 + d, (size_t)d * d * sizeof(double));
-  }
+  // the reduced buffer { W_gamma, s1[d], S2[d*d] } x K stays in the pinned staging area and is read in place by the
+  // finalisation (strides = len); only the Student-t weight sums live elsewhere
+  if (student) W = wsum;
+  view.G = c->hstage;
+  view.sG = len;
+  view.W = student ? W.data() : c->hstage;
+  view.sW = student ? 1 : len;
+  view.s1 = c->hstage + 1;
+  view.ss1 = len;
+  view.S2 = c->hstage + 1 + d;
+  view.sS2 = len;
   return 0;
 }
 
@@ -1822,7 +1826,8 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
     // a NaN maximum (the i==0 quirk) poisons the reference's responsibilities: only the literal path reproduces that
     const bool mma_stats = !p.valid && !c->force_precise && c->q_resident && mma_usable(c, 0);
     bool precise = !(fused_stats || mma_stats) || std::isnan(maxR) || std::isnan(maxW);
-    std::vector<double> &W = c->hW, &G = c->hG, &s1 = c->hs1, &S2 = c->hS2;
+    std::vector<double> &W = c->hW, &s1 = c->hs1, &S2 = c->hS2;
+    StatView sv;
     std::vector<double> pivot(d);
     std::vector<size_t> count(K);
     if (!precise) {
@@ -1861,35 +1866,55 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
           for (int a = 0; a < d; ++a)
             for (int b = a; b < d; ++b) { S2[(size_t)k * d * d + (size_t)a * d + b] = sk[e]; S2[(size_t)k * d * d + (size_t)b * d + a] = sk[e]; ++e; }
         }
+        sv.W = sv.G = W.data();
+        sv.s1 = s1.data();
+        sv.ss1 = (size_t)d;
+        sv.S2 = S2.data();
+        sv.sS2 = (size_t)d * d;
       } else {
         rc = count_indices_impl(c, count, true);
         if (rc) return rc;
-        rc = stats_mma(c, count, pivot, W, G, s1, S2);
+        rc = stats_mma(c, count, pivot, W, sv);
         if (rc == 1) precise = true;
         else if (rc) return rc;
       }
       tick("statistics");
     }
     if (!precise) {
+      // the trial proposal is written next to the current one (whose factors double as the snapshot that
+      // cleanup_after_update restores on a first failed factorisation): no 8 MB copies at d = 128, K = 64
       HostMix &trial = c->trial;
-      trial = c->prop;
+      trial.K = K;
+      trial.d = d;
+      trial.df = c->prop.df;
+      trial.band = c->prop.band;
+      trial.student = c->prop.student;
+      trial.detL = c->prop.detL;
+      trial.wght.resize(K);
+      trial.mean.resize((size_t)K * d);
+      trial.L.resize((size_t)K * d * d);
       int retry_trial = retry_local;
       std::vector<int> alive(K);
-      rc = pmcgpu_finalize_update(K, d, W.data(), fused_stats ? W.data() : G.data(), s1.data(), S2.data(), pivot.data(), 0, count.data(), N_total,
-                                  trial.band.empty() ? nullptr : trial.band.data(), &retry_trial, trial.wght.data(),
-                                  trial.mean.data(), trial.L.data(), trial.detL.data(), alive.data());
+      rc = finalize_update_strided(K, d, sv.W, sv.sW, sv.G, sv.sG, sv.s1, sv.ss1, sv.S2, sv.sS2, pivot.data(), 0, count.data(),
+                                   N_total, trial.band.empty() ? nullptr : trial.band.data(), &retry_trial, c->prop.L.data(),
+                                   trial.wght.data(), trial.mean.data(), trial.L.data(), trial.detL.data(), alive.data());
       // pivot guard: the one-pass covariance loses ~eps*(1 + r) relative accuracy, r = (mu'-pivot)^2 / Sigma'_aa
+      std::vector<double> worst_k(K, 0.0);
+      if (rc == 0)
+        parallel_components(K, (double)d * d * 4.0, [&](int k) {
+          if (!(trial.wght[k] > 0.0)) return;
+          double worst = 0.0;
+          for (int a = 0; a < d; ++a) {
+            double var = 0.0;  // Sigma'_aa = sum_j L_aj^2
+            for (int j = 0; j <= a; ++j) { const double l = trial.L[(size_t)k * d * d + (size_t)a * d + j]; var += l * l; }
+            const double dm = trial.mean[(size_t)k * d + a] - pivot[a];
+            const double ratio = dm * dm / var;
+            if (!(ratio <= worst)) worst = ratio;
+          }
+          worst_k[k] = worst;
+        });
       double worst = 0.0;
-      for (int k = 0; k < K && rc == 0; ++k) {
-        if (!(trial.wght[k] > 0.0)) continue;
-        for (int a = 0; a < d; ++a) {
-          double var = 0.0;  // Sigma'_aa = sum_j L_aj^2
-          for (int j = 0; j <= a; ++j) { const double l = trial.L[(size_t)k * d * d + (size_t)a * d + j]; var += l * l; }
-          const double dm = trial.mean[(size_t)k * d + a] - pivot[a];
-          const double ratio = dm * dm / var;
-          if (!(ratio <= worst)) worst = ratio;
-        }
-      }
+      for (int k = 0; k < K; ++k) if (!(worst_k[k] <= worst)) worst = worst_k[k];
       tick("finalise+guard");
       if (rc != 0 || retry_trial != 0 || !(worst <= c->guard_ratio)) {
         precise = true;  // anything unusual (failed factorisation, ill-conditioned pivot) goes through the literal path

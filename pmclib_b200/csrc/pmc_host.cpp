@@ -136,19 +136,14 @@ int host_cleanup_after_update(int K, int d, const size_t *count, double minwgt, 
 
 }  // namespace pmcb200
 
-extern "C" {
+namespace pmcb200 {
 
-int pmcgpu_cholesky(int d, double *a, double *detL) { return pmcb200::host_cholesky(d, a, detL); }
-
-long pmcgpu_stats_len(int K, int d) { return (long)K * (2 + d + (long)d * d) + 8; }
-
-// New proposal from pivoted one-pass statistics (SURVEY.md appendix B):
-//   mu'_k = c + s1_k / G_k ;  Sigma'_k = (S2_k - s1_k s1_k^T / G_k) / W_k ;  alpha'_k = W_k (normalised in cleanup)
-// Components with count <= MINCOUNT get weight 0, mean 0, zero matrix exactly as pmc.c:1410-1425.
-int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const double *s1, const double *S2,
-                           const double *pivot, int pivot_per_component, const size_t *count, long N_total,
-                           const size_t *band_limit, int *retry, double *wght, double *mean, double *L, double *detL,
-                           int *alive) {
+// The work of pmcgpu_finalize_update with explicit component strides of the statistics (so that the reduced buffer
+// { W, s1[d], S2[d*d] } x K of the tensor path is read in place) and the old factors as a separate read-only array.
+int finalize_update_strided(int K, int d, const double *W, size_t sW, const double *G, size_t sG, const double *s1,
+                            size_t ss1, const double *S2, size_t sS2, const double *pivot, int pivot_per_component,
+                            const size_t *count, long N_total, const size_t *band_limit, int *retry, const double *oldL,
+                            double *wght, double *mean, double *L, double *detL, int *alive) {
   const size_t dd = (size_t)d * d;
   static const bool trace = getenv("PMCB200_TRACE") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
@@ -158,27 +153,22 @@ int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const
     fprintf(stderr, "[pmcb200]   finalize: %-16s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
     t_prev = now;
   };
-  // old factors, restored by cleanup_after_update on a first failed factorisation; the buffer persists across calls
-  // (a fresh 8 MB vector per iteration costs more in page faults than the copy itself)
-  static thread_local std::vector<double> snapshot;
-  snapshot.resize(K * dd);
-  double *const snap = snapshot.data();  // (the worker threads must not name the thread_local object itself)
-  pmcb200::parallel_components(K, (double)d * d * 16.0, [&, snap](int k) {
-    std::memcpy(snap + k * dd, L + k * dd, sizeof(double) * dd);
+  parallel_components(K, (double)d * d * 16.0, [&](int k) {
     double *cov = L + k * dd;
     double *mu = mean + (size_t)k * d;
     if (count[k] > (size_t)kMinCount) {
       const double *c = pivot + (pivot_per_component ? (size_t)k * d : 0);
-      const double *s = s1 + (size_t)k * d;
-      const double *S = S2 + k * dd;
+      const double *s = s1 + (size_t)k * ss1;
+      const double *S = S2 + (size_t)k * sS2;
+      const double Wk = W[(size_t)k * sW], Gk = G[(size_t)k * sG];
       const size_t bl = band_limit ? band_limit[k] : (size_t)d;
-      wght[k] = W[k];
+      wght[k] = Wk;
       // scale-free form: the statistics may carry any common factor (the reference's exp(maxR-500) is ~1e-217), so
       // never multiply two of them: shift = s1/G is O(1), S2/W is O(1), G/W is O(1)
       std::vector<double> shift(d);
-      for (int a = 0; a < d; ++a) { shift[a] = s[a] / G[k]; mu[a] = c[a] + shift[a]; }
-      const double invW = 1.0 / W[k];
-      const double gw = G[k] * invW;
+      for (int a = 0; a < d; ++a) { shift[a] = s[a] / Gk; mu[a] = c[a] + shift[a]; }
+      const double invW = 1.0 / Wk;
+      const double gw = Gk * invW;
       for (int a = 0; a < d; ++a)
         for (int b = a; b < d; ++b) {
           double v = 0.0;
@@ -193,12 +183,37 @@ int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const
     }
   });
   tick("covariances");
-  const int rc = pmcb200::host_cleanup_after_update(K, d, count, 1.0 / (double)N_total, retry, snap, wght,
-                                                    mean, L, detL);
+  const int rc = host_cleanup_after_update(K, d, count, 1.0 / (double)N_total, retry, oldL, wght, mean, L, detL);
   tick("cleanup+cholesky");
   if (alive)
     for (int k = 0; k < K; ++k) alive[k] = wght[k] > 0.0 ? 1 : 0;
   return rc;
+}
+
+}  // namespace pmcb200
+
+extern "C" {
+
+int pmcgpu_cholesky(int d, double *a, double *detL) { return pmcb200::host_cholesky(d, a, detL); }
+
+long pmcgpu_stats_len(int K, int d) { return (long)K * (2 + d + (long)d * d) + 8; }
+
+// New proposal from pivoted one-pass statistics (SURVEY.md appendix B):
+//   mu'_k = c + s1_k / G_k ;  Sigma'_k = (S2_k - s1_k s1_k^T / G_k) / W_k ;  alpha'_k = W_k (normalised in cleanup)
+// Components with count <= MINCOUNT get weight 0, mean 0, zero matrix exactly as pmc.c:1410-1425.
+int pmcgpu_finalize_update(int K, int d, const double *W, const double *G, const double *s1, const double *S2,
+                           const double *pivot, int pivot_per_component, const size_t *count, long N_total,
+                           const size_t *band_limit, int *retry, double *wght, double *mean, double *L, double *detL,
+                           int *alive) {
+  const size_t dd = (size_t)d * d;
+  // old factors, restored by cleanup_after_update on a first failed factorisation; the buffer persists across calls
+  // (a fresh 8 MB vector per iteration costs more in page faults than the copy itself)
+  static thread_local std::vector<double> snapshot;
+  snapshot.resize(K * dd);
+  double *const snap = snapshot.data();  // (the worker threads must not name the thread_local object itself)
+  pmcb200::parallel_components(K, (double)d * d * 16.0, [=](int k) { std::memcpy(snap + k * dd, L + k * dd, sizeof(double) * dd); });
+  return pmcb200::finalize_update_strided(K, d, W, 1, G, 1, s1, (size_t)d, S2, dd, pivot, pivot_per_component, count, N_total,
+                                          band_limit, retry, snap, wght, mean, L, detL, alive);
 }
 
 }  // extern "C"

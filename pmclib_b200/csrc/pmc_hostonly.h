@@ -27,6 +27,10 @@ void parallel_components(int K, double work_per_component, F fn) {
 }
 
 int host_cholesky(int d, double *a, double *detL);
+int finalize_update_strided(int K, int d, const double *W, size_t sW, const double *G, size_t sG, const double *s1,
+                            size_t ss1, const double *S2, size_t sS2, const double *pivot, int pivot_per_component,
+                            const size_t *count, long N_total, const size_t *band_limit, int *retry, const double *oldL,
+                            double *wght, double *mean, double *L, double *detL, int *alive);
 int host_cleanup_after_update(int K, int d, const size_t *count, double minwgt, int *retry, const double *snapshot,
                               double *wght, double *mean, double *L, double *detL);
 }  // namespace pmcb200
