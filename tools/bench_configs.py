@@ -75,8 +75,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c5", choices=list(CFG))
     ap.add_argument("--samples", type=int, default=0, help="samples per GPU per step")
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--opts", default="")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
