@@ -13,7 +13,8 @@
  *     df[K] (-1 = Gaussian, else Student-t degrees of freedom).
  *   - the sample store mirrors pmc_simu (pmc.h:76-108): X[N*d] row-major, weights[N], log_rho[N],
  *     indices[N] (size_t), flg[N] (short); it lives in HBM and is copied to/from host buffers only by
- *     pmcgpu_upload / pmcgpu_download.
+ *     pmcgpu_upload / pmcgpu_download, or streamed to an attached host sink while an iteration runs
+ *     (pmcgpu_set_host_sink).
  *   - one context = one GPU = one caller thread (the reference is not re-entrant either).
  */
 #ifndef PMCB200_H
