@@ -247,6 +247,10 @@ void out_pmc_simu(const char *name, const pmc_simu *psim, error **err);         
 int *filter_histogram_init(int nbins, int clipleft, int clipright, error **err);       /* pmc.c:699-707 */
 void filter_histogram(pmc_simu *psim, void *filter_data, error **err);                  /* pmc.c:709-770 */
 double mean_from_psim(double *X, double *w, short *flg, int nsamples, int ndim, int a); /* pmc.c:1108-1120 */
+void prepare_update(mix_mvdens *m, size_t *count, pmc_simu *psim, double **pbuf, error **err);                    /* pmc.c:1535-1579 */
+void cleanup_after_update(mix_mvdens *m, size_t *count, double minwgt, pmc_simu *psim, double *buf, error **err); /* pmc.c:1471-1533 */
+int double_cmp(const void *av, const void *bv);                                          /* pmc.c:1122-1131 */
+void pmc_simu_print(FILE *where, pmc_simu *psim, double nrm);                            /* pmc.c:327-331 */
 void clip_weights(pmc_simu *psim, int n, FILE *OUT, error **err);                        /* pmc.c:1134-1188 */
 size_t *sample_from_pmc_simu(const pmc_simu *psim, const gsl_rng *rng, error **err);     /* pmc.c:1585-1601 */
 unsigned int *resample_residual(const pmc_simu *psim, const gsl_rng *rng, error **err);  /* pmc.c:1605-1626 */

@@ -20,6 +20,7 @@
 #include <vector>
 #include "../../include/pmcb200.h"
 #include "../../include/pmclib_abi.h"
+#include "pmc_hostonly.h"
 
 namespace {
 
@@ -1071,6 +1072,77 @@ void update_prop_rb_void(void *m, pmc_simu *psim, error **err) {
   FWD(*err, );
 }
 void update_prop(mix_mvdens *m, pmc_simu *psim, error **err) { update_common(m, psim, 1, err); }
+
+// ---- the two halves of the update as separate entry points (pmc.c:1471-1579), for callers that write their own update ----------
+void prepare_update(mix_mvdens *m, size_t *count, pmc_simu *psim, double **pbuf, error **err) {
+  double *buf = nullptr;
+  if (psim->isLog == 1) {
+    normalize_importance_weight(psim, err);
+    FWD(*err, );
+  }
+  m->init_cwght = 0.0;
+  {  // count[index] += 1 over flg == 1: histogram on the device, added to the caller's array as the reference does
+    Side *s = side_for(psim, err);
+    if (!s) return;
+    if (!push_proposal(s, m, err)) return;   // sizes the histogram (and factorises, as line 1566 would below)
+    if (!push_samples(s, psim, false, true, false, false, true, err)) return;
+    std::vector<size_t> c(m->ncomp);
+    const int rc = pmcgpu_count_indices(s->ctx, c.data());
+    if (rc) { gpu_fail(s, rc, err, __func__); return; }
+    for (size_t k = 0; k < m->ncomp; ++k) count[k] += c[k];
+  }
+  mix_mvdens_cholesky_decomp(m, err);
+  FWD(*err, );
+  if (psim->retry == 0) {
+    const size_t dd = m->ndim * m->ndim;
+    buf = (double *)xmalloc(sizeof(double) * m->ncomp * dd, err);
+    if (!buf) return;
+    for (size_t i = 0; i < m->ncomp; ++i) memcpy(buf + i * dd, m->comp[i]->std, sizeof(double) * dd);
+  }
+  *pbuf = buf;
+}
+void cleanup_after_update(mix_mvdens *m, size_t *count, double minwgt, pmc_simu *psim, double *buf, error **err) {
+  const int K = (int)m->ncomp, d = (int)m->ndim;
+  const size_t dd = (size_t)d * d;
+  std::vector<double> w(m->wght, m->wght + K), mean((size_t)K * d), L(K * dd), detL(K);
+  for (int k = 0; k < K; ++k) {
+    memcpy(&mean[(size_t)k * d], m->comp[k]->mean, d * sizeof(double));
+    memcpy(&L[k * dd], m->comp[k]->std, dd * sizeof(double));
+    detL[k] = m->comp[k]->detL;
+  }
+  std::vector<double> zero;
+  const double *snap = buf;
+  if (!snap) { zero.assign(K * dd, 0.0); snap = zero.data(); }  // only read when retry == 0, where the reference has a buffer
+  int retry = psim->retry;
+  const int rc = pmcb200::host_cleanup_after_update(K, d, count, minwgt, &retry, snap, w.data(), mean.data(), L.data(), detL.data());
+  psim->retry = retry;
+  if (retry != 0) fprintf(stderr, "RETRY state -> %d\n", retry);
+  for (int k = 0; k < K; ++k) {
+    mvdens *c = m->comp[k];
+    m->wght[k] = w[k];
+    memcpy(c->mean, &mean[(size_t)k * d], d * sizeof(double));
+    memcpy(c->std, &L[k * dd], dd * sizeof(double));
+    if (w[k] > 0) { c->detL = detL[k]; c->chol = 1; }
+  }
+  if (rc) ERR_HERE(*err, rc, "Sum of weight is <= 0 after the update", *err, nullptr);
+}
+int double_cmp(const void *av, const void *bv) {
+  const double a = *(const double *)av, b = *(const double *)bv;
+  return (a < b) ? -1 : (a > b) ? 1 : 0;
+}
+// print_step (tools.c:301-313) for every sample
+void pmc_simu_print(FILE *where, pmc_simu *psim, double nrm) {
+  error *e = initError(), **err = &e;
+  const int rc = pmcb200_sync_host(psim, err);
+  endError(err);
+  if (rc != 0) return;
+  FILE *rf = where ? where : stdout;
+  for (long i = 0; i < psim->nsamples; ++i) {
+    fprintf(rf, "%1d %10g", (int)psim->flg[i], nrm * psim->weights[i]);
+    for (int j = 0; j < psim->ndim; ++j) fprintf(rf, " %10g", psim->X[(size_t)i * psim->ndim + j]);
+    fprintf(rf, "\n");
+  }
+}
 
 // ---- the iteration (pmc.c:175-219) -------------------------------------------------------------------------------------------
 size_t pmc_simu_importance(pmc_simu *psim, gsl_rng *r, error **err) {

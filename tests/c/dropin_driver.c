@@ -109,7 +109,7 @@ int main(int argc, char **argv) {
   if (!out) return 5;
   for (int it = 0; it < niter; ++it) {
     double perp, ess = 0, lne = 0;
-    if (mode == 1) {
+    if (mode == 1 || mode == 5) {
       psim->proposal->simulate(psim, psim->proposal->data, &rng, psim->pb, err); CHECK(err, "simulate");
       generic_get_importance_weight_and_deduced_verb(psim, psim->proposal, &distribution_lkl, &distribution_lkl,
                                                      &distribution_retrieve, psim->target, 1.0, 1, err); CHECK(err, "weights");
@@ -117,7 +117,18 @@ int main(int argc, char **argv) {
       /* nothing: the step does it all */
     }
     /* snapshot of what the update will see, for the oracle: written after the step below (X, indices survive it) */
-    if (mode == 1) {
+    if (mode == 5) { /* prepare_update as a separate entry point (pmc.c:1535-1579): normalises, counts, factorises, snapshots */
+      size_t *count = calloc(K, sizeof(size_t));
+      double *buf = NULL;
+      prepare_update(m, count, psim, &buf, err); CHECK(err, "prepare_update");
+      size_t tot = 0, nokf = 0;
+      for (int k = 0; k < K; ++k) tot += count[k];
+      for (long i = 0; i < N; ++i) nokf += psim->flg[i] == 1;
+      printf("prepare_update count %zu ok %zu isLog %d snapshot %d\n", tot, nokf, psim->isLog, buf != NULL);
+      if (buf && memcmp(buf, m->comp[0]->std, sizeof(double) * d * d) != 0) { fprintf(stderr, "snapshot differs\n"); return 12; }
+      free(count); free(buf);
+    }
+    if (mode == 1 || mode == 5) {
       normalize_importance_weight(psim, err); CHECK(err, "normalize");
       psim->pmc_update(psim->proposal->data, psim, err); CHECK(err, "update");
       perp = perplexity_and_ess(psim, MC_UNORM, &ess, err); CHECK(err, "perplexity");

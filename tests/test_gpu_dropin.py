@@ -56,7 +56,7 @@ def _run(driver, tmp_path, wl, N, niter, mode, env=None, seed=4242):
     return rec, r.stdout
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 5])
 def test_c_driver_iterations_match_oracle(driver, tmp_path, mode):
     wl = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
     N, niter = 40000, 3
@@ -81,6 +81,11 @@ def test_c_driver_iterations_match_oracle(driver, tmp_path, mode):
         print(f"mode {mode} iteration {it}: perp {r['perp']:.4f} update errors {errs}")
         # the next iteration starts from the proposal the library produced (factors)
         cur = dict(wl, wght=r["wght"], mean=r["mean"], cov=r["L"], is_chol=True)
+    if mode == 5:  # prepare_update as its own entry point: histogram of the ok samples, normalised state, snapshot taken
+        lines = [l.split() for l in stdout.splitlines() if l.startswith("prepare_update")]
+        assert len(lines) == niter
+        for l in lines:
+            assert l[2] == l[4] and l[6] == "0" and l[8] == "1"
     if mode == 2:
         assert f"user callback calls {N * niter}" in stdout  # the opaque target really ran on the host, once per sample
 
