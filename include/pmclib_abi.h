@@ -247,6 +247,9 @@ void out_pmc_simu(const char *name, const pmc_simu *psim, error **err);         
 int *filter_histogram_init(int nbins, int clipleft, int clipright, error **err);       /* pmc.c:699-707 */
 void filter_histogram(pmc_simu *psim, void *filter_data, error **err);                  /* pmc.c:709-770 */
 double mean_from_psim(double *X, double *w, short *flg, int nsamples, int ndim, int a); /* pmc.c:1108-1120 */
+FILE *fopen_err(const char *fname, const char *mode, error **err);  /* io.c:103-109 */
+void *malloc_err(size_t sz, error **err);                          /* io.c:111-120 */
+void *calloc_err(size_t nl, size_t sz1, error **err);              /* io.c:122-131 */
 void prepare_update(mix_mvdens *m, size_t *count, pmc_simu *psim, double **pbuf, error **err);                    /* pmc.c:1535-1579 */
 void cleanup_after_update(mix_mvdens *m, size_t *count, double minwgt, pmc_simu *psim, double *buf, error **err); /* pmc.c:1471-1533 */
 int double_cmp(const void *av, const void *bv);                                          /* pmc.c:1122-1131 */

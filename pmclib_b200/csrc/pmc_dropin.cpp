@@ -1410,6 +1410,25 @@ unsigned int *resample_residual(const pmc_simu *cpsim, const gsl_rng *rng, error
   return n;
 }
 
+// ---- liberrorio helpers that target likelihoods written against pmclib commonly call (io.c:103-131) -----------------------
+FILE *fopen_err(const char *fname, const char *mode, error **err) {
+  FILE *fp = fopen(fname, mode);
+  if (!fp) *err = newErrorVA(-101 /* err_io */, __func__, (char *)"", (char *)"Cannot open file '%s' (mode \"%s\")", *err, nullptr, fname, mode);
+  return fp;
+}
+void *malloc_err(size_t sz, error **err) {
+  if (sz <= 0) { *err = newErrorVA(err_allocate, __func__, (char *)"", (char *)"Size %ld has to be positive", *err, nullptr, (long)sz); return nullptr; }
+  void *res = malloc(sz);
+  if (!res) *err = newErrorVA(err_allocate, __func__, (char *)"", (char *)"Cannot allocate %ld bytes", *err, nullptr, (long)sz);
+  return res;
+}
+void *calloc_err(size_t nl, size_t sz1, error **err) {
+  if (nl <= 0) { *err = newErrorVA(err_allocate, __func__, (char *)"", (char *)"Size %ld has to be positive", *err, nullptr, (long)nl); return nullptr; }
+  void *res = calloc(nl, sz1);
+  if (!res) *err = newErrorVA(err_allocate, __func__, (char *)"", (char *)"Cannot allocate %ld objects of %ld bytes", *err, nullptr, (long)nl, (long)sz1);
+  return res;
+}
+
 // ---- additions ------------------------------------------------------------------------------------------------------------------
 int pmcb200_register_target(distribution *dist, int kind) {
   if (!dist || kind < PMCGPU_TGT_BANANA || kind > PMCGPU_TGT_MIX) return PMCGPU_ERR_USAGE;

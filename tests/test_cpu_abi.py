@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported():
               "normalize_importance_weight", "perplexity", "perplexity_and_ess", "evidence", "update_prop", "update_prop_rb",
               "update_prop_rb_void", "mix_mvdens_distribution", "pmc_simu_dump", "out_pmc_simu", "filter_histogram_init",
               "filter_histogram", "mean_from_psim", "sample_from_pmc_simu", "resample_residual", "clip_weights", "prepare_update", "cleanup_after_update",
-              "double_cmp", "pmc_simu_print", "mix_mvdens_alloc", "mix_mvdens_free",
+              "double_cmp", "pmc_simu_print", "fopen_err", "malloc_err", "calloc_err", "mix_mvdens_alloc", "mix_mvdens_free",
               "mix_mvdens_free_void", "mix_mvdens_cholesky_decomp", "mix_mvdens_log_pdf", "mix_mvdens_log_pdf_void",
               "mix_mvdens_dump", "mix_mvdens_dwnp", "mix_mvdens_print", "mvdens_alloc", "mvdens_init", "mvdens_free",
               "mvdens_cholesky_decomp", "mvdens_log_pdf", "mvdens_log_pdf_void", "scalar_product", "determinant", "ranindx",
