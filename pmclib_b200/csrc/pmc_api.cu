@@ -164,6 +164,15 @@ struct pmcgpu_ctx {
   pmcgpu_allreduce_fn cb = nullptr;
   void *cb_user = nullptr;
   DevBuf dcoll;
+  // third-generation small-d iteration (pmc_iter3.cu)
+  int gen3 = 1;                 // option "gen3": 0 = second-generation kernels only
+  int w3_variant = 0;           // option "w3_variant": launch shape of the third-generation weights kernel
+  double gen3_max_ratio = 100;  // largest |mu' / L_jj| the pre-scaled solve is trusted with (option "gen3_max_ratio")
+  bool i3_dirty = true;         // packs must be rebuilt (proposal or target changed)
+  double i3_ratio = 0.0;
+  double i3_shift[FUSED_MAXD] = {0};
+  std::vector<double> i3_hw, i3_ht, i3_hd, i3_hcw;
+  DevBuf i3_gpack, i3_wpart, i3_scal, i3_coll, i3_spart, i3_out;
 };
 
 namespace {
@@ -316,6 +325,7 @@ int install_proposal(pmcgpu_ctx *c) {
   c->mprop.valid = false;  // packed for the tensor path on first use (ensure_mma): shapes with a fused kernel never need it
   c->mprop.dirty = true;
   c->q_resident = false;
+  c->i3_dirty = true;
   return pack_small(c, c->prop, c->dprop_pack, c->prop_pack_doubles, c->prop_pack_host);
 }
 
@@ -334,7 +344,7 @@ TargetDev target_view(const pmcgpu_ctx *c) {
 
 FusedPlan plan_for(const pmcgpu_ctx *c) {
   FusedPlan none{};
-  if (c->force_generic || c->prop.K == 0 || c->prop.student || c->prop.d > FUSED_MAXD || c->nfull != 0) return none;
+  if (c->force_generic || c->fused_version == 3 || c->prop.K == 0 || c->prop.student || c->prop.d > FUSED_MAXD || c->nfull != 0) return none;
   if (c->prop_pack_doubles == 0) return none;
   int Kt = 0;
   if (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX) {
@@ -573,6 +583,203 @@ int run_fused(pmcgpu_ctx *c, const FusedPlan &p, int do_draw, int do_stats, uint
   memcpy(o.count_k, u + SM_COUNTK, 64 * 8);
   memcpy(o.first, c->hstage + p.nstat + 4 + SM_FIRST, 4 * 8);
   o.has_first = (first_index == 0);
+  return 0;
+}
+
+
+// ---- third-generation small-d iteration (pmc_iter3.cu) -------------------------------------------------------------
+void mixture_pivot(const HostMix &m, double *pivot) {  // mixture mean over the live components
+  double sw = 0.0;
+  for (int k = 0; k < m.K; ++k) if (m.wght[k] > 0) sw += m.wght[k];
+  for (int j = 0; j < m.d; ++j) {
+    double s = 0.0;
+    for (int k = 0; k < m.K; ++k) if (m.wght[k] > 0) s += m.wght[k] * m.mean[(size_t)k * m.d + j];
+    pivot[j] = s / sw;
+  }
+}
+
+// packs of the current proposal / target for the third-generation kernels; the instantiation may have more components
+// than the mixture (K rounded up): the extra ones are packed as dead components
+int pack_iter3(pmcgpu_ctx *c, const Iter3Plan &p) {
+  if (!c->i3_dirty) return 0;
+  const HostMix &m = c->prop;
+  const int D = m.d, ws = iter3_wstride(D), ds = iter3_dstride(D);
+  for (int j = 0; j < FUSED_MAXD; ++j) c->i3_shift[j] = 0.0;
+  mixture_pivot(m, c->i3_shift);
+  std::vector<double> wg(p.K, 0.0), mu((size_t)p.K * D, 0.0), L((size_t)p.K * D * D, 0.0), ld(p.K, 0.0);
+  memcpy(wg.data(), m.wght.data(), m.K * sizeof(double));
+  memcpy(mu.data(), m.mean.data(), (size_t)m.K * D * sizeof(double));
+  memcpy(L.data(), m.L.data(), (size_t)m.K * D * D * sizeof(double));
+  memcpy(ld.data(), m.logdet.data(), m.K * sizeof(double));
+  c->i3_hw.assign((size_t)p.K * ws, 0.0);
+  c->i3_hd.assign((size_t)p.K * ds, 0.0);
+  iter3_pack_w(p.K, D, wg.data(), mu.data(), L.data(), ld.data(), c->i3_shift, c->i3_hw.data());
+  iter3_pack_d(p.K, D, mu.data(), L.data(), c->i3_hd.data());
+  c->i3_ratio = iter3_shift_ratio(m.K, D, m.wght.data(), m.mean.data(), m.L.data(), c->i3_shift);
+  // ranindx (mvdens.c:776): the index is the number of the first K-1 cumulative weights below z
+  c->i3_hcw.assign(64, INFINITY);
+  for (int k = 0; k + 1 < m.K; ++k) c->i3_hcw[k] = m.cw[k];
+  c->i3_ht.clear();
+  if (p.KT > 0 && (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX)) {
+    const HostMix &t = c->tmix;
+    std::vector<double> twg(p.KT, 0.0), tmu((size_t)p.KT * D, 0.0), tL((size_t)p.KT * D * D, 0.0), tld(p.KT, 0.0);
+    memcpy(twg.data(), t.wght.data(), t.K * sizeof(double));
+    memcpy(tmu.data(), t.mean.data(), (size_t)t.K * D * sizeof(double));
+    memcpy(tL.data(), t.L.data(), (size_t)t.K * D * D * sizeof(double));
+    memcpy(tld.data(), t.logdet.data(), t.K * sizeof(double));
+    c->i3_ht.assign((size_t)p.KT * ws, 0.0);
+    iter3_pack_w(p.KT, D, twg.data(), tmu.data(), tL.data(), tld.data(), c->i3_shift, c->i3_ht.data());
+    const double tr = iter3_shift_ratio(t.K, D, t.wght.data(), t.mean.data(), t.L.data(), c->i3_shift);
+    if (!(tr <= c->i3_ratio)) c->i3_ratio = tr;
+  }
+  CU(c->i3_gpack.ensure(c->i3_hd.size() * sizeof(double)));
+  CU(cudaMemcpyAsync(c->i3_gpack.p, c->i3_hd.data(), c->i3_hd.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->i3_dirty = false;
+  return 0;
+}
+
+Iter3Plan plan3_for(pmcgpu_ctx *c) {
+  Iter3Plan none{};
+  if (!c->gen3 || c->fused_version == 1 || c->fused_version == 2 || c->force_generic || c->prop.K == 0 || c->prop.student || c->prop.d > FUSED_MAXD || c->nfull != 0)
+    return none;
+  int Kt = 0;
+  if (c->tkind == PMCGPU_TGT_MVDENS || c->tkind == PMCGPU_TGT_MIX) {
+    if (c->tmix.student || c->tmix.d != c->prop.d || c->tmix.K < 1) return none;
+    Kt = c->tmix.K;
+  } else if (c->tkind == PMCGPU_TGT_BANANA) {
+    if (c->td != c->prop.d || c->td < 2) return none;
+  } else if (c->tkind != PMCGPU_TGT_HOST) {
+    return none;
+  }
+  if (c->nfaces > 0 && !c->box_slab) return none;
+  Iter3Plan p = iter3_plan(c->prop.d, c->prop.K, Kt, c->tkind, c->sm_count);
+  if (!p.valid) return none;
+  if (pack_iter3(c, p) != 0) return none;
+  if (!(c->i3_ratio <= c->gen3_max_ratio)) return none;  // far-off narrow components: the second generation subtracts the means exactly
+  return p;
+}
+
+struct Iter3Out {
+  double scal[I3_SCAL_LEN] = {0};
+  std::vector<double> out;  // stats[K3*E] (with_stats) | H, Q, ok, flagged-out | count_k[K3]
+  bool clean = false;
+};
+
+// reduction over ranks of n doubles of a device buffer, op 0 = sum, 1 = max: NCCL in place on the stream, or the host
+// callback through the staging buffer
+int allreduce_dev(pmcgpu_ctx *c, double *dbuf, long n, int op) {
+  if (c->nranks <= 1) return 0;
+  if (!c->cb) {
+    if (!c->nccl_comm) return fail(c, PMCGPU_ERR_NCCL, "nranks=%d but no communicator attached", c->nranks);
+    const int r = g_nccl.AllReduce(dbuf, dbuf, (size_t)n, kNcclFloat64, op == 0 ? kNcclSum : kNcclMax, c->nccl_comm, c->stream);
+    if (r != 0) return fail(c, PMCGPU_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    return 0;
+  }
+  RC(stage(c, (size_t)n));
+  CU(cudaMemcpyAsync(c->hstage, dbuf, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->cb(c->cb_user, c->hstage, n, op) != 0) return fail(c, PMCGPU_ERR_NCCL, "allreduce callback failed");
+  CU(cudaMemcpyAsync(dbuf, c->hstage, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// draw (optional) -> weights -> maxima/normaliser -> statistics + normalisation -> one device-to-host copy.
+// stage_limit: 1 = stop after the weights and their reductions (log-weights stay un-normalised), 2 = full.
+int run_iter3(pmcgpu_ctx *c, const Iter3Plan &p, int do_draw, int stage_limit, int with_stats, uint64_t seed, uint32_t iter,
+              long first_index, long N_total, double t_temper, const double *post_in, const short *ok_in, Iter3Out &o) {
+  const HostMix &m = c->prop;
+  const int D = m.d;
+  const long N = c->N;
+  RC(zero_small(c));
+  unsigned long long *sm = c->small.as<unsigned long long>();
+  CU(c->i3_wpart.ensure((size_t)p.weights_blocks * 4 * sizeof(double)));
+  CU(c->i3_scal.ensure(I3_SCAL_LEN * sizeof(double)));
+  CU(c->i3_coll.ensure(I3_COLL_LEN * sizeof(double)));
+  const int nout = (with_stats ? p.K * p.E : 0) + 4 + p.K;
+  CU(c->i3_out.ensure((size_t)(p.K * p.E + 4 + p.K) * sizeof(double)));
+  if (stage_limit >= 2) {
+    CU(c->i3_spart.ensure((size_t)p.stats_blocks * p.partial_len * sizeof(double)));
+    if (with_stats) CU(c->resp.ensure((size_t)p.K * N * sizeof(double)));
+  }
+  if (iter3_upload(p, c->i3_hw.data(), (int)c->i3_hw.size(), c->i3_ht.empty() ? nullptr : c->i3_ht.data(), (int)c->i3_ht.size(),
+                   c->i3_hd.data(), (int)c->i3_hd.size(), c->i3_hcw.data(), 64, c->stream))
+    return fail(c, PMCGPU_ERR_CUDA, "constant upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (c->timing) {
+    if (!c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->ev2)); CU(cudaEventCreate(&c->evd)); }
+    CU(cudaEventRecord(c->ev0, c->stream));
+  }
+  if (do_draw) {
+    Iter3Draw d{};
+    d.N = N; d.first_index = first_index; d.seed = seed; d.iter = iter; d.max_attempts = c->max_attempts;
+    d.has_box = c->nfaces > 0;
+    for (int j = 0; j < FUSED_MAXD; ++j) { d.lo_thr[j] = c->lo_thr[j]; d.hi_thr[j] = c->hi_thr[j]; }
+    d.X = c->X.as<double>(); d.indices = c->Idx.as<unsigned long long>(); d.flg = c->Flg.as<short>();
+    d.zig = c->zig.as<double2>(); d.gpack = c->i3_gpack.as<double>(); d.counters = sm + SM_COUNTERS;
+    if (launch_draw3(p, d, c->stream)) return fail(c, PMCGPU_ERR_CUDA, "draw kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    RC(sink_copy(c, SINK_DRAWN));
+  }
+  if (c->timing) CU(cudaEventRecord(c->evd, c->stream));
+  int wblocks = 0;
+  {
+    Iter3Weights w{};
+    w.X = c->X.as<double>(); w.N = N; w.first_index = first_index; w.tgt_kind = c->tkind; w.b = c->tb; w.sig1 = c->tsig1;
+    w.t_temper = t_temper; w.post_in = post_in; w.ok_in = ok_in;
+    for (int j = 0; j < FUSED_MAXD; ++j) w.shift[j] = c->i3_shift[j];
+    w.lw = c->W.as<double>(); w.log_rho = c->R.as<double>(); w.flg = c->Flg.as<short>();
+    w.resp = (stage_limit >= 2 && with_stats) ? c->resp.as<double>() : nullptr;
+    w.partials = c->i3_wpart.as<double>(); w.counters = sm + SM_COUNTERS; w.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
+    w.mix = c->dprop.view; w.tmix = c->dtmix.view; w.variant = c->w3_variant;
+    if (launch_weights3(p, w, &wblocks, c->stream)) return fail(c, PMCGPU_ERR_CUDA, "weights kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
+  RC(sink_copy(c, SINK_RHO));
+  const double *fv = reinterpret_cast<const double *>(sm + SM_FIRST);
+  double *coll = c->i3_coll.as<double>(), *scal = c->i3_scal.as<double>();
+  const int has_first = first_index == 0;
+  if (c->nranks <= 1) {
+    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 7, (double)N_total, c->stream))
+      return fail(c, PMCGPU_ERR_CUDA, "reduction launch failed");
+  } else {
+    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 1, (double)N_total, c->stream))
+      return fail(c, PMCGPU_ERR_CUDA, "reduction launch failed");
+    RC(allreduce_dev(c, coll, 8, 1));
+    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 2, (double)N_total, c->stream))
+      return fail(c, PMCGPU_ERR_CUDA, "reduction launch failed");
+    RC(allreduce_dev(c, coll + 8, 8, 0));
+    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 4, (double)N_total, c->stream))
+      return fail(c, PMCGPU_ERR_CUDA, "reduction launch failed");
+  }
+  if (stage_limit >= 2) {
+    Iter3Stats st{};
+    st.X = c->X.as<double>(); st.resp = c->resp.as<double>(); st.W = c->W.as<double>(); st.flg = c->Flg.as<short>();
+    st.indices = c->Idx.as<unsigned long long>(); st.scal = scal; st.N = N; st.partials = c->i3_spart.as<double>();
+    st.with_stats = with_stats;
+    for (int j = 0; j < FUSED_MAXD; ++j) st.pivot[j] = c->i3_shift[j];
+    if (launch_stats3(p, st, c->stream)) return fail(c, PMCGPU_ERR_CUDA, "statistics kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
+    RC(sink_copy(c, SINK_FINAL));
+    if (launch_comb3(p, c->i3_spart.as<double>(), with_stats, scal, c->i3_out.as<double>(), c->stream))
+      return fail(c, PMCGPU_ERR_CUDA, "combine launch failed");
+    RC(allreduce_dev(c, c->i3_out.as<double>(), nout, 0));
+  }
+  RC(stage(c, (size_t)I3_SCAL_LEN + nout));
+  CU(cudaMemcpyAsync(c->hstage, scal, I3_SCAL_LEN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (stage_limit >= 2)
+    CU(cudaMemcpyAsync(c->hstage + I3_SCAL_LEN, c->i3_out.p, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(o.scal, c->hstage, sizeof o.scal);
+  o.clean = o.scal[I3_CLEAN] != 0.0;
+  if (stage_limit >= 2) o.out.assign(c->hstage + I3_SCAL_LEN, c->hstage + I3_SCAL_LEN + nout);
+  if (c->timing) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->evd, c->ev1));
+    c->fused_ms += ms;
+    c->fused_launches += 1;
+    if (do_draw) { CU(cudaEventElapsedTime(&ms, c->ev0, c->evd)); c->draw_ms += ms; }
+    if (stage_limit >= 2) { CU(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats_ms += ms; }
+  }
+  (void)D;
   return 0;
 }
 
@@ -1046,7 +1253,8 @@ void pmcgpu_destroy(pmcgpu_ctx *c) {
   if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
   DevBuf *bufs[] = {&c->dprop.buf, &c->dprop_pack, &c->dtmix.buf, &c->dt_pack, &c->ddef, &c->dfaces, &c->X, &c->W, &c->R,
                     &c->Idx, &c->Flg, &c->ld, &c->blkmax, &c->partials, &c->stats, &c->small, &c->rbg, &c->rbw, &c->rbacc,
-                    &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll, &c->resp, &c->partials2, &c->dscal, &c->zig};
+                    &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll, &c->resp, &c->partials2, &c->dscal, &c->zig,
+                    &c->i3_gpack, &c->i3_wpart, &c->i3_scal, &c->i3_coll, &c->i3_spart, &c->i3_out};
   for (DevBuf *b : bufs) b->release();
   if (c->hstage) cudaFreeHost(c->hstage);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->evd); }
@@ -1076,6 +1284,9 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "timing")) { c->timing = (int)value; c->fused_ms = 0.0; c->stats_ms = 0.0; c->draw_ms = 0.0; c->fused_launches = 0; }
   else if (!strcmp(name, "split_stats")) c->split_stats = (int)value;
   else if (!strcmp(name, "split_draw")) c->split_draw = (int)value;
+  else if (!strcmp(name, "gen3")) c->gen3 = (int)value;
+  else if (!strcmp(name, "gen3_max_ratio")) c->gen3_max_ratio = value;
+  else if (!strcmp(name, "w3_variant")) c->w3_variant = (int)value;
   else if (!strcmp(name, "mma")) { c->use_mma = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_min_d")) { c->mma_min_d = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_max_chunk")) c->mma_max_chunk = (long)value;
@@ -1123,6 +1334,7 @@ int pmcgpu_set_band_limit(pmcgpu_ctx *c, const size_t *band_limit) {
 
 int pmcgpu_set_target_banana(pmcgpu_ctx *c, int d, double b, double sig1) {
   if (!c || d < 2) return fail(c, PMCGPU_ERR_USAGE, "bentGauss needs d >= 2");
+  c->i3_dirty = true;
   c->tkind = PMCGPU_TGT_BANANA;
   c->td = d;
   c->tb = b;
@@ -1146,6 +1358,7 @@ int pmcgpu_set_target_mix(pmcgpu_ctx *c, int kind, int K, int d, const double *w
   if (rc) return rc;
   c->mtgt.valid = false;
   c->mtgt.dirty = true;
+  c->i3_dirty = true;
   return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles, c->tgt_pack_host);
 }
 
@@ -1397,6 +1610,17 @@ static int weights_common(pmcgpu_ctx *c, int mode, const double *post, const sho
   WeightOut o;
   const int saved_kind = c->tkind;
   if (mode == 1) c->tkind = PMCGPU_TGT_HOST;
+  const Iter3Plan p3 = (c->nranks <= 1) ? plan3_for(c) : Iter3Plan{};  // the phase entry points return rank-local maxima
+  if (p3.valid) {
+    Iter3Out o3;
+    rc = run_iter3(c, p3, 0, 1, 0, 0, 0, first_index, c->N, t_temper, dpost, dok, o3);
+    c->tkind = saved_kind;
+    if (rc) return rc;
+    if (nok) *nok = (long)o3.scal[I3_NOK_W];
+    if (maxW) *maxW = o3.scal[I3_MAXW];
+    if (maxR) *maxR = o3.scal[I3_MAXR];
+    return 0;
+  }
   const FusedPlan p = plan_for(c);
   if (p.valid) rc = run_fused(c, p, 0, 0, 0, 0, first_index, t_temper, dpost, dok, o);
   else rc = run_weights_generic(c, mode, dpost, dok, t_temper, first_index, o);
@@ -1429,6 +1653,20 @@ static int draw_weights_core(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long f
   if (t_temper < 0) return fail(c, -6019, "t_iter_tempered=%g should be > 0", t_temper);
   rc = ensure_cwght_normalised(c);
   if (rc) return rc;
+  const Iter3Plan p3 = (c->nranks <= 1) ? plan3_for(c) : Iter3Plan{};
+  if (p3.valid) {
+    Iter3Out o3;
+    rc = run_iter3(c, p3, 1, 1, 0, seed, iter, first_index, c->N, t_temper, nullptr, nullptr, o3);
+    if (rc) return rc;
+    RC(sink_copy(c, SINK_FINAL));
+    if (n_reject) *n_reject = (long)o3.scal[I3_NREJ];
+    if (o3.scal[I3_NFAIL] > 0 || o3.scal[I3_NREJ] > 5.0 * (double)c->N)
+      return fail(c, kErrTooManySteps, "Too many points (%ld) outside of box", (long)o3.scal[I3_NREJ]);
+    if (nok) *nok = (long)o3.scal[I3_NOK_W];
+    if (maxW) *maxW = o3.scal[I3_MAXW];
+    if (maxR) *maxR = o3.scal[I3_MAXR];
+    return 0;
+  }
   const FusedPlan p = plan_for(c);
   WeightOut o;
   if (p.valid) {
@@ -1752,10 +1990,18 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   if (do_draw) { rc = ensure_cwght_normalised(c); if (rc) return rc; }
   const HostMix &m0 = c->prop;
   const int K = m0.K, d = m0.d;
-  const FusedPlan p = plan_for(c);
+  // third generation first: one host synchronisation per iteration, normalisation fused into the statistics kernel
+  const Iter3Plan p3 = (c->filt_nbins == 0) ? plan3_for(c) : Iter3Plan{};  // a filter changes the flags between weights and statistics
+  Iter3Out o3;
+  const bool have3 = p3.valid != 0;
+  const bool stats3 = have3 && do_update && !c->force_precise;
+  const FusedPlan p = have3 ? FusedPlan{} : plan_for(c);
   WeightOut o;
-  const bool fused_stats = p.valid && do_update && !c->force_precise && c->filt_nbins == 0;  // a filter changes the flags between weights and statistics
-  if (p.valid) {
+  const bool fused_stats = p.valid && do_update && !c->force_precise && c->filt_nbins == 0;
+  if (have3) {
+    rc = run_iter3(c, p3, do_draw, 2, stats3 ? 1 : 0, seed, iter, first_index, N_total, t_temper, nullptr, nullptr, o3);
+    if (rc) return rc;
+  } else if (p.valid) {
     rc = run_fused(c, p, do_draw, fused_stats ? 1 : 0, seed, iter, first_index, t_temper, nullptr, nullptr, o);
     if (rc) return rc;
   } else {
@@ -1774,18 +2020,28 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   }
   tick("draw+weights");
   // ---- global maxima (pmc_mpi.c:502-508 keeps the max over ranks) with the i==0 quirk carried as a flag
-  double mx[6];
+  double mx[6] = {0, 0, 0, 0, 0, 0};
+  double maxW = 0.0, maxR = 0.0;
+  const double M_local = o.M_all;
+  if (have3) {
+    maxW = o3.scal[I3_MAXW];
+    maxR = o3.scal[I3_MAXR];
+    r.maxW = maxW;
+    r.maxR = maxR;
+    r.n_reject = (long)o3.scal[I3_NREJ];
+    if (do_draw && (o3.scal[I3_NFAIL] > 0 || o3.scal[I3_NREJ] > 5.0 * (double)N_total))
+      return fail(c, kErrTooManySteps, "Too many points (%ld) outside of box", r.n_reject);
+  } else {
   mx[0] = o.counters[CNT_POSINF] ? INFINITY : o.M_all;
   mx[1] = o.R_all;
   mx[2] = (o.has_first && o.first[3] != 0.0 && std::isnan(o.first[2])) ? 1.0 : 0.0;  // maxW poisoned by NaN at i==0
   mx[3] = (o.has_first && o.first[1] != 0.0 && std::isnan(o.first[0])) ? 1.0 : 0.0;
   mx[4] = (o.has_first && o.first[3] != 0.0) ? 1.0 : 0.0;  // sample 0 reached the weight assignment
   mx[5] = (o.has_first && o.first[1] != 0.0) ? 1.0 : 0.0;
-  const double M_local = o.M_all;
   rc = allreduce_host(c, mx, 6, 1);
   if (rc) return rc;
-  double maxW = mx[2] != 0.0 ? NAN : (mx[4] != 0.0 ? mx[0] : (mx[0] > kNegInit ? mx[0] : kNegInit));
-  double maxR = mx[3] != 0.0 ? NAN : (mx[5] != 0.0 ? mx[1] : (mx[1] > kNegInit ? mx[1] : kNegInit));
+  maxW = mx[2] != 0.0 ? NAN : (mx[4] != 0.0 ? mx[0] : (mx[0] > kNegInit ? mx[0] : kNegInit));
+  maxR = mx[3] != 0.0 ? NAN : (mx[5] != 0.0 ? mx[1] : (mx[1] > kNegInit ? mx[1] : kNegInit));
   r.maxW = maxW;
   r.maxR = maxR;
   {
@@ -1796,6 +2052,7 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
     if (do_draw && (cnt[1] > 0 || cnt[0] > 5.0 * (double)N_total))
       return fail(c, kErrTooManySteps, "Too many points (%ld) outside of box", r.n_reject);
   }
+  }
   // ---- pmc_filter hook (pmc.c:203-206): filter_histogram on the log-weights
   if (c->filt_nbins > 0) {
     long nf = 0;
@@ -1805,27 +2062,39 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   // ---- normalise (pmc.c:641-697), literally: S = sum exp(lw - maxW + 500)
   double S = 0.0;
   long cnt_ok = 0;
-  rc = normalize_impl(c, maxW, &S, &cnt_ok, true);
-  if (rc) return rc;
+  double H = 0, Q = 0;
+  long nexit = 0;
+  const int nstat3 = stats3 ? p3.K * p3.E : 0;
+  if (have3 && o3.clean) {  // the statistics kernel normalised the weights and summed w log w, w^2 and the counts
+    S = o3.scal[I3_SREF];
+    cnt_ok = (long)o3.out[nstat3 + 2];
+    H = o3.out[nstat3 + 0];
+    Q = o3.out[nstat3 + 1];
+    nexit = (long)o3.out[nstat3 + 3];
+  } else {
+    rc = normalize_impl(c, maxW, &S, &cnt_ok, true);
+    if (rc) return rc;
+  }
   if (cnt_ok == 0) return fail(c, kErrNoSample, "Not a single point in sample with flag=ok.");
   if (!(S > 0)) return fail(c, kErrNegWeight, "Sum of weights <= 0 (got %g)", S);
   r.logSum = std::log(S) + maxW - kDynMax;
   r.nok = cnt_ok;
-  double H = 0, Q = 0;
-  long nexit = 0;
-  rc = scale_perp_impl(c, S, true, &H, &Q, &nexit, true);
-  if (rc) return rc;
+  if (!(have3 && o3.clean)) {
+    rc = scale_perp_impl(c, S, true, &H, &Q, &nexit, true);
+    if (rc) return rc;
+  }
   if (nexit == N_total) return fail(c, kErrUndef, "all points are flagged");
   r.ess = 1 / Q;
   r.perplexity = std::exp(-H) / (double)(N_total - nexit);
   r.ln_evidence = r.logSum - std::log((double)(N_total - nexit));
-  RC(sink_copy(c, SINK_FINAL));  // weights and flags are final; they travel while the update runs
+  if (!(have3 && o3.clean)) RC(sink_copy(c, SINK_FINAL));  // weights and flags are final; they travel while the update runs
   tick("normalise+perplexity");
   // ---- update
   if (do_update) {
     // a NaN maximum (the i==0 quirk) poisons the reference's responsibilities: only the literal path reproduces that
-    const bool mma_stats = !p.valid && !c->force_precise && c->q_resident && mma_usable(c, 0);
-    bool precise = !(fused_stats || mma_stats) || std::isnan(maxR) || std::isnan(maxW);
+    const bool mma_stats = !p.valid && !have3 && !c->force_precise && c->q_resident && mma_usable(c, 0);
+    const bool use_stats3 = stats3 && o3.clean;
+    bool precise = !(fused_stats || mma_stats || use_stats3) || std::isnan(maxR) || std::isnan(maxW);
     std::vector<double> &W = c->hW, &s1 = c->hs1, &S2 = c->hS2;
     StatView sv;
     std::vector<double> pivot(d);
@@ -1840,10 +2109,15 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
           pivot[j] = s / sw;
         }
       }
-      if (fused_stats) {
-        // reduce the statistics over ranks: rescale to the global maximum, then sum
+      if (fused_stats || use_stats3) {
         const int E = 1 + d + d * (d + 1) / 2;
-        std::vector<double> st(o.stats);
+        std::vector<double> st;
+        if (use_stats3) {  // already reduced over ranks on the device
+          st.assign(o3.out.begin(), o3.out.begin() + (size_t)K * E);
+          for (int k = 0; k < K; ++k) count[k] = (size_t)o3.out[nstat3 + 4 + k];
+        } else {
+        // reduce the statistics over ranks: rescale to the global maximum, then sum
+        st = o.stats;
         const double Mg = mx[0];
         const double sc = (M_local == -INFINITY) ? 0.0 : std::exp(M_local - Mg);
         if (c->nranks > 1) for (double &v : st) v *= sc;
@@ -1854,6 +2128,7 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
         rc = allreduce_host(c, cntk.data(), K, 0);
         if (rc) return rc;
         for (int k = 0; k < K; ++k) count[k] = (size_t)cntk[k];
+        }
         // unpack canonical statistics -> W (= G for Gaussian components), s1, S2 about the pivot
         W.resize(K);
         s1.resize((size_t)K * d);

@@ -1,0 +1,1045 @@
+// pmc_iter3.cu — third-generation kernels of the small-d PMC iteration (the ones bench.py times).
+//
+// What changed against pmc_fused2.cu, and which round-1 ncu finding each change answers (profiles/r01_final_ncu.txt):
+//
+//   k_draw3     The second-generation draw picked the component per lane, so every load of a Cholesky-factor entry was a
+//               divergent LDS (62 % of the shared-memory wavefront peak, 2.3e8 bank conflicts, FP64 pipe 22 %).  Here a
+//               block picks the components of a chunk of samples first (Philox call 0, ranindx as mvdens.c:766-782),
+//               buckets the chunk by component in shared memory, and every warp then draws 32 samples of ONE component:
+//               mu_k and L_k are warp-uniform constant-bank operands of the DFMAs, no shared-memory traffic besides the
+//               ziggurat table.  Sample i keeps its position, its Philox counters and its component: the output is the
+//               same i.i.d. sequence whatever the chunking or the sharding.
+//   k_weights3  (mvdens.c:784-825, 354-385, 319-349; pmc.c:537-592)  The triangular solve runs on pre-scaled factors
+//               (t_j = x'_j/L_jj - mu'_j/L_jj,  y_j = t_j - sum_i (L_ji/L_jj) y_i): 65 instead of 75 FP64 instructions per
+//               component at d = 10.  exp() is table-driven (2^(j/64) in shared memory + degree-5 polynomial, 11 FP64
+//               instructions instead of ~23 slots), log() likewise (128-entry reciprocal table, 10 instead of ~53), dead
+//               components are neutralised in the pack instead of by selects, and the kernel carries no draw code.  It
+//               also accumulates sum exp(lw - max) with per-lane online rescaling, so the normaliser is known when the
+//               kernel ends and no separate pass over the log-weights is needed.
+//   k_stats3    (pmc.c:641-697, 1041-1077, 1323-1469)  The DMMA statistics kernel now also writes the normalised weights and
+//               the final flags and accumulates sum w log w, sum w^2, the ok count and the component histogram: the two
+//               normalisation passes (0.83 ms and 2.8 GB of traffic per 1e8 samples) are gone.
+//   k_red3      block partials -> maxima, normaliser, the i==0 quirk of pmc.c:552,579 and the "clean" flag, all on the
+//               device: the host synchronises once per iteration, and with ranks attached the three all-reduces run on
+//               device buffers between these launches.
+//
+// Non-finite corner cases keep the reference's behaviour through two escape hatches: a sample whose fast log-density
+// is not finite is re-evaluated by a literal restatement of mix_mvdens_log_pdf, and an iteration whose maxima are
+// poisoned (NaN at sample 0, +inf log-weight, no usable sample) is flagged "not clean": k_stats3 then leaves the store
+// untouched and the host runs the literal normalise/update sequence of pmc_generic.cu instead.
+#include "pmc_kernels.h"
+
+namespace pmcb200 {
+
+// ---- constant-bank parameter blocks ---------------------------------------------------------------------------------
+constexpr int I3_CW = 2048, I3_CT = 1024, I3_CD = 2048;
+__constant__ double c3_w[I3_CW];   // whitening pack of the proposal
+__constant__ double c3_t[I3_CT];   // whitening pack of a Gaussian / Gaussian-mixture target
+__constant__ double c3_d[I3_CD];   // draw pack of the proposal
+__constant__ double c3_cw[64];     // cumulative weights (mvdens.c:748-750)
+__constant__ double c3_box[2 * FUSED_MAXD];  // slab box: (-lo_thr_j, hi_thr_j) pairs, +-inf when absent
+__constant__ double c3_exptab[64];     // 2^(j/64)
+__constant__ double2 c3_logtab[128];   // (rc_j, -log rc_j), rc_j ~ 1/(1 + (j+0.5)/128)
+
+__host__ __device__ constexpr int i3_ev2(int n) { return (n + 1) & ~1; }
+// whitening pack, per component: (1/L_jj, -mu'_j/L_jj) pairs | -L_ij/L_ii column by column | c' = -0.5 d ln2pi - log detL | alpha
+__host__ __device__ constexpr int i3_wstride(int D) { return i3_ev2(2 * D + D * (D - 1) / 2 + 2); }
+__host__ __device__ constexpr int i3_woC(int D) { return 2 * D + D * (D - 1) / 2; }
+// draw pack, per component: rows (mu_i, L_i0 .. L_ii)
+__host__ __device__ constexpr int i3_dstride(int D) { return i3_ev2(D + D * (D + 1) / 2); }
+
+int iter3_wstride(int D) { return i3_wstride(D); }
+int iter3_dstride(int D) { return i3_dstride(D); }
+
+void iter3_pack_w(int K, int D, const double *wght, const double *mean, const double *L, const double *logdet,
+                  const double *shift, double *out) {
+  const int st = i3_wstride(D);
+  for (int k = 0; k < K; ++k) {
+    double *o = out + (size_t)k * st;
+    for (int i = 0; i < st; ++i) o[i] = 0.0;
+    if (!(wght[k] > 0.0)) {  // dead component: q = 0, log-density -1e300, weight 0 -> contributes exactly nothing
+      o[i3_woC(D)] = -1.0e300;
+      continue;
+    }
+    const double *Lk = L + (size_t)k * D * D;
+    for (int j = 0; j < D; ++j) {
+      const double r = 1.0 / Lk[j * D + j];
+      o[2 * j] = r;
+      o[2 * j + 1] = -(mean[(size_t)k * D + j] - shift[j]) * r;
+    }
+    int e = 2 * D;
+    for (int j = 0; j < D; ++j)
+      for (int i = j + 1; i < D; ++i) o[e++] = -Lk[i * D + j] / Lk[i * D + i];
+    o[i3_woC(D)] = -0.5 * (D * kLn2Pi) - logdet[k];
+    o[i3_woC(D) + 1] = wght[k];
+  }
+}
+
+void iter3_pack_d(int K, int D, const double *mean, const double *L, double *out) {
+  const int st = i3_dstride(D);
+  for (int k = 0; k < K; ++k) {
+    double *o = out + (size_t)k * st;
+    for (int i = 0; i < st; ++i) o[i] = 0.0;
+    int e = 0;
+    for (int i = 0; i < D; ++i) {
+      o[e++] = mean[(size_t)k * D + i];
+      for (int j = 0; j <= i; ++j) o[e++] = L[(size_t)k * D * D + (size_t)i * D + j];
+    }
+  }
+}
+
+// the largest |mu'_j / L_jj| of the live components: the pre-scaled solve loses ~eps times this in relative accuracy
+double iter3_shift_ratio(int K, int D, const double *wght, const double *mean, const double *L, const double *shift) {
+  double worst = 0.0;
+  for (int k = 0; k < K; ++k) {
+    if (!(wght[k] > 0.0)) continue;
+    for (int j = 0; j < D; ++j) {
+      const double v = fabs((mean[(size_t)k * D + j] - shift[j]) / L[(size_t)k * D * D + (size_t)j * D + j]);
+      if (!(v <= worst)) worst = v;
+    }
+  }
+  return worst;
+}
+
+static std::atomic<unsigned long long> g_tables_done{0};
+static int upload_tables() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (g_tables_done.load(std::memory_order_acquire) & bit) return 0;
+  double et[64];
+  double2 lt[128];
+  for (int j = 0; j < 64; ++j) et[j] = (double)exp2l((long double)j / 64.0L);
+  for (int j = 0; j < 128; ++j) {
+    const double rc = (double)(1.0L / (1.0L + ((long double)j + 0.5L) / 128.0L));
+    lt[j].x = rc;
+    lt[j].y = (double)(-logl((long double)rc));
+  }
+  if (cudaMemcpyToSymbol(c3_exptab, et, sizeof et) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(c3_logtab, lt, sizeof lt) != cudaSuccess) return -1;
+  g_tables_done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+
+// ---- table-driven exp and log ---------------------------------------------------------------------------------------
+// exp(x) for x <= 709; arguments below -700 (and NaN) return exp(-700) ~ 1e-304: callers only add the result to sums
+// whose largest term is >= 1, and catch non-finite inputs separately.  x = n ln2/64 + r, |r| <= ln2/128; 2^(n/64) from
+// the table, exp(r) - 1 = r P4(r) (truncation 3.5e-17 relative).
+__device__ __forceinline__ double exp_tab(double x, const double *tab) {
+  constexpr double kMagic = 6755399441055744.0;
+  constexpr double kInv = 92.332482616893657;
+  constexpr double kHi = 6.93147180369123816490e-01 / 64.0, kLo = 1.90821492927058770002e-10 / 64.0;
+  const double xc = (x > -700.0) ? x : -700.0;
+  const double t = fma(xc, kInv, kMagic);
+  const int ni = __double2loint(t);
+  const double n = t - kMagic;
+  double r = fma(n, -kHi, xc);
+  r = fma(n, -kLo, r);
+  const double T = tab[ni & 63];
+  double p = fma(r, 1.0 / 120, 1.0 / 24);
+  p = fma(p, r, 1.0 / 6);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  const double s = p * r;
+  const double v = fma(T, s, T);
+  return __hiloint2double(__double2hiint(v) + ((ni >> 6) << 20), __double2loint(v));
+}
+
+// log(x) for positive normal x: x = 2^e m, m in [1,2); r = m rc_j - 1 with |r| < 1/256 from the table indexed by the
+// top 7 mantissa bits; log1p(r) to degree 6 (truncation 2e-18 absolute)
+__device__ __forceinline__ double log_tab(double x, const double2 *tab) {
+  constexpr double kLn2 = 0.693147180559945309417;
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double2 tb = tab[(hi >> 13) & 127];
+  const double r = fma(m, tb.x, -1.0);
+  double p = fma(r, -1.0 / 6, 0.2);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 1.0 / 3);
+  p = fma(p, r, -0.5);
+  const double lp = fma(r * r, p, r);
+  const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;  // (double)e
+  return fma(ed, kLn2, tb.y + lp);
+}
+
+// ---- pre-scaled triangular solve: q = |L^-1 (x - mu)|^2, every parameter a constant-bank operand -----------------------
+template <int D, int SPL, bool TGT>
+__device__ __forceinline__ void whiten3(int base, const double (&xs)[SPL][D], double (&q)[SPL]) {
+  const double *cp = (TGT ? c3_t : c3_w) + base;
+  double t[SPL][D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) t[s][j] = fma(xs[s][j], cp[2 * j], cp[2 * j + 1]);
+  }
+  int off = 2 * D;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) q[s] = (j == 0) ? t[s][0] * t[s][0] : fma(t[s][j], t[s][j], q[s]);
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) t[s][i] = fma(cp[off + (i - j - 1)], t[s][j], t[s][i]);
+    }
+    off += D - 1 - j;
+  }
+}
+
+// mix_mvdens_log_pdf (mvdens.c:784-825) of KK Gaussian components packed at c3_w / c3_t: e[k] = alpha_k exp(ld_k - max + 500),
+// lpos = sum_k e[k] in component order, returns (max + log lpos) - 500
+template <int D, int KK, int SPL, bool TGT>
+__device__ __forceinline__ void mix_fast(const double (&xs)[SPL][D], const double *s_exp, const double2 *s_log,
+                                         double (&e)[SPL][KK], double (&lpos)[SPL], double (&out)[SPL]) {
+  constexpr int ST = i3_wstride(D);
+  const double *cp = TGT ? c3_t : c3_w;
+  double mx[SPL];
+#pragma unroll
+  for (int k = 0; k < KK; ++k) {
+    double q[SPL];
+    whiten3<D, SPL, TGT>(k * ST, xs, q);
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+      e[s][k] = fma(-0.5, q[s], cp[k * ST + i3_woC(D)]);
+      mx[s] = (k == 0) ? e[s][0] : ((mx[s] < e[s][k]) ? e[s][k] : mx[s]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < SPL; ++s) {
+    lpos[s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      e[s][k] = exp_tab((e[s][k] - mx[s]) + kDynMax, s_exp) * cp[k * ST + i3_woC(D) + 1];
+      lpos[s] = lpos[s] + e[s][k];
+    }
+    out[s] = (mx[s] + log_tab(lpos[s], s_log)) - kDynMax;
+  }
+}
+
+// ---- literal restatements for the non-finite corner (reference layout in global memory) --------------------------------
+static __device__ __noinline__ double mix_log_pdf_literal(const MixDev m, const double *x) {
+  double ld[64], y[FUSED_MAXD];
+  int iloc = 0;
+  while (iloc < m.K && m.alpha[iloc] <= 0) iloc++;
+  if (iloc >= m.K) return nan("");
+  double mx = 0.0;
+  for (int k = iloc; k < m.K; ++k) {
+    if (!(m.alpha[k] > 0.0)) continue;
+    const double *L = m.L + (size_t)k * m.d * m.d, *mu = m.mean + (size_t)k * m.d;
+    for (int i = 0; i < m.d; ++i) y[i] = x[i] - mu[i];
+    y[0] = y[0] / L[0];
+    for (int i = 1; i < m.d; ++i) {
+      double t = y[i];
+      for (int j = 0; j < i; ++j) t -= L[(size_t)i * m.d + j] * y[j];
+      y[i] = t / L[(size_t)i * m.d + i];
+    }
+    double q = 0.0;
+    for (int i = 0; i < m.d; ++i) q += y[i] * y[i];
+    const double v = -0.5 * (m.d * kLn2Pi + q) - m.logdet[k];
+    ld[k] = v;
+    if (k == iloc || mx < v) mx = v;
+  }
+  double lpos = 0.0;
+  for (int k = 0; k < m.K; ++k)
+    if (m.alpha[k] > 0.0) lpos = lpos + exp(ld[k] - mx + kDynMax) * m.alpha[k];
+  return mx + log(lpos) - kDynMax;
+}
+
+template <int D>
+struct RegVec3 {
+  const double (&v)[D];
+  __device__ __forceinline__ double operator[](int i) const { return v[i]; }
+};
+
+// =====================================================================================================================
+// weights
+// =====================================================================================================================
+struct W3Args {
+  const double *X;
+  long N, first_index;
+  int tgt_kind;
+  double b, sig1, t_temper;
+  const double *post_in;
+  const short *ok_in;
+  double shift[FUSED_MAXD];
+  double *lw, *log_rho, *resp;
+  short *flg;
+  double *partials;  // [grid][4]: max log-weight over usable samples, sum exp(lw - max), max log_rho, spare
+  unsigned long long *counters;
+  double *first_vals;
+  MixDev mix, tmix;  // reference layout, for the literal re-evaluation of non-finite samples
+};
+
+template <int D, int K, int KT, int SPL, bool RESP, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_weights3(const W3Args a) {
+  constexpr int ST = i3_wstride(D);
+  static_assert(K * ST <= I3_CW && KT * ST <= I3_CT, "constant memory budget");
+  __shared__ double s_exp[64];
+  __shared__ double2 s_log[128];
+  __shared__ double s_m[4], s_S[4], s_r[4];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_exp[i] = c3_exptab[i];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_log[i] = c3_logtab[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int TS = 32 * SPL;
+  const long ntiles = (a.N + TS - 1) / TS;
+  double m_lane = -INFINITY, S_lane = 0.0, r_lane = -INFINITY;
+  unsigned int nok_lane = 0, posinf_lane = 0;
+
+  for (long tile = (long)blockIdx.x * 4 + wid; tile < ntiles; tile += (long)gridDim.x * 4) {
+    const long tbase = tile * TS;
+    double x[SPL][D], xs[SPL][D];
+    bool valid[SPL];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+      const long i = tbase + s * 32 + lane;
+      valid[s] = i < a.N;
+      const long il = valid[s] ? i : a.N - 1;
+      if ((D & 1) == 0) {
+        const double2 *xi = reinterpret_cast<const double2 *>(a.X + (size_t)il * D);
+#pragma unroll
+        for (int j = 0; j < D; j += 2) { const double2 t = xi[j / 2]; x[s][j] = t.x; x[s][j + 1] = t.y; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[s][j] = a.X[(size_t)il * D + j];
+      }
+#pragma unroll
+      for (int j = 0; j < D; ++j) xs[s][j] = x[s][j] - a.shift[j];
+    }
+
+    // ---- target --------------------------------------------------------------------------------------------------
+    double post[SPL];
+    bool tok[SPL];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) { post[s] = 0.0; tok[s] = true; }
+    if (a.tgt_kind == PMCGPU_TGT_BANANA) {
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) post[s] = bent_gauss(RegVec3<D>{x[s]}, D, a.b, a.sig1);
+    } else if (KT > 0 && a.tgt_kind == PMCGPU_TGT_MVDENS) {
+      double q[SPL];
+      whiten3<D, SPL, true>(0, xs, q);
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) post[s] = fma(-0.5, q[s], c3_t[i3_woC(D)]);
+    } else if (KT > 0 && a.tgt_kind == PMCGPU_TGT_MIX) {
+      double te[SPL][KT > 0 ? KT : 1], tl[SPL];
+      mix_fast<D, (KT > 0 ? KT : 1), SPL, true>(xs, s_exp, s_log, te, tl, post);
+#pragma unroll
+      for (int s = 0; s < SPL; ++s)
+        if (!(fabs(post[s]) < INFINITY)) post[s] = mix_log_pdf_literal(a.tmix, a.X + (size_t)(valid[s] ? tbase + s * 32 + lane : a.N - 1) * D);
+    } else if (a.tgt_kind == PMCGPU_TGT_HOST) {
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) {
+        const long i = tbase + s * 32 + lane;
+        if (i < a.N) { post[s] = a.post_in[i]; tok[s] = a.ok_in ? (a.ok_in[i] != 0) : true; }
+      }
+    }
+
+    // ---- proposal log-density ----------------------------------------------------------------------------------------
+    double e[SPL][K], lpos[SPL], rloc[SPL];
+    mix_fast<D, K, SPL, false>(xs, s_exp, s_log, e, lpos, rloc);
+
+    // ---- log-weight, flags, maxima (pmc.c:546-583) -------------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+      const long i = tbase + s * 32 + lane;
+      bool fastok = fabs(rloc[s]) < INFINITY;
+      if (!fastok) rloc[s] = mix_log_pdf_literal(a.mix, a.X + (size_t)(valid[s] ? i : a.N - 1) * D);  // non-finite: the reference's own operation sequence decides
+      const bool rfin = !(isnan(rloc[s]) || isinf(rloc[s]));
+      const bool reached = valid[s] && rfin && tok[s];
+      const double lw = reached ? (a.t_temper * post[s] - rloc[s]) : 0.0;
+      if (valid[s]) {
+        a.log_rho[i] = rloc[s];
+        a.lw[i] = lw;
+        a.flg[i] = reached ? 1 : 0;
+        if (a.first_index + i == 0) {
+          a.first_vals[0] = rloc[s]; a.first_vals[1] = 1.0; a.first_vals[2] = lw; a.first_vals[3] = reached ? 1.0 : 0.0;
+        }
+        if (rloc[s] > r_lane) r_lane = rloc[s];
+      }
+      const bool wfin = reached && !isnan(lw) && !(lw == INFINITY);
+      if (reached && lw == INFINITY) ++posinf_lane;
+      if (wfin) {
+        ++nok_lane;
+        if (lw > -INFINITY) {  // online sum of exp(lw - running max): one exp per sample
+          const double dlt = lw - m_lane;
+          const double ex = exp_tab(-fabs(dlt), s_exp);
+          if (dlt > 0.0) { S_lane = fma(S_lane, ex, 1.0); m_lane = lw; }
+          else S_lane += ex;
+        }
+      }
+      if (RESP && valid[s]) {  // responsibilities alpha_k phi_k(x)/q(x), component-major: coalesced 256-byte rows
+        const double rs = fastok ? 1.0 / lpos[s] : 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.resp[(size_t)k * a.N + i] = e[s][k] * rs;
+      }
+    }
+  }
+
+  // ---- block partial: (max, sum relative to it, max log_rho), combined in lane/warp order -> deterministic ------------
+  double mw = warp_max_nan_ignoring(m_lane);
+  double sw = (m_lane == -INFINITY) ? 0.0 : S_lane * exp(m_lane - mw);
+  sw = warp_sum(sw);
+  const double rw = warp_max_nan_ignoring(r_lane);
+  if (lane == 0) { s_m[wid] = mw; s_S[wid] = sw; s_r[wid] = rw; }
+  const unsigned long long n1 = (unsigned long long)warp_sum_ll(nok_lane), n2 = (unsigned long long)warp_sum_ll(posinf_lane);
+  if (lane == 0) {
+    if (n1) atomicAdd(&a.counters[CNT_NOK], n1);
+    if (n2) atomicAdd(&a.counters[CNT_POSINF], n2);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double Mb = -INFINITY, Rb = -INFINITY, Sb = 0.0;
+    for (int w = 0; w < 4; ++w) { if (s_m[w] > Mb) Mb = s_m[w]; if (s_r[w] > Rb) Rb = s_r[w]; }
+    for (int w = 0; w < 4; ++w) Sb += (s_m[w] == -INFINITY) ? 0.0 : s_S[w] * exp(s_m[w] - Mb);
+    double *out = a.partials + (size_t)blockIdx.x * 4;
+    out[0] = Mb; out[1] = Sb; out[2] = Rb; out[3] = 0.0;
+  }
+}
+
+// =====================================================================================================================
+// reductions between the kernels (one block): scal[] is the device-resident scalar block of the iteration
+// =====================================================================================================================
+// coll[0..7]  (all-reduce max):  M, maxR-candidate, NaN-at-0 flags (W, R), reached-at-0 flags (W, R), +inf seen, spare
+// coll[8..15] (all-reduce sum):  S relative to the global M, usable samples, box rejections, failed draws
+// scal: I3_* below
+__global__ void k_red3(const double *__restrict__ partials, int nblocks, const unsigned long long *__restrict__ counters,
+                       const double *__restrict__ first_vals, int has_first, double *coll, double *scal, int phases,
+                       double n_total) {
+  __shared__ double sa[256], sb[256];
+  const int t = threadIdx.x;
+  if (phases & 1) {
+    double M = -INFINITY, R = -INFINITY;
+    for (int b = t; b < nblocks; b += blockDim.x) {
+      const double mb = partials[(size_t)b * 4], rb = partials[(size_t)b * 4 + 2];
+      if (mb > M) M = mb;
+      if (rb > R) R = rb;
+    }
+    sa[t] = M; sb[t] = R;
+    __syncthreads();
+    if (t == 0) {
+      for (int i = 1; i < (int)blockDim.x; ++i) { if (sa[i] > M) M = sa[i]; if (sb[i] > R) R = sb[i]; }
+      const bool r0w = has_first && first_vals[3] != 0.0, r0r = has_first && first_vals[1] != 0.0;
+      scal[I3_MLOC] = M;
+      coll[0] = M;
+      coll[1] = R;
+      coll[2] = (r0w && isnan(first_vals[2])) ? 1.0 : 0.0;
+      coll[3] = (r0r && isnan(first_vals[0])) ? 1.0 : 0.0;
+      coll[4] = r0w ? 1.0 : 0.0;
+      coll[5] = r0r ? 1.0 : 0.0;
+      coll[6] = counters[CNT_POSINF] ? 1.0 : 0.0;
+      coll[7] = 0.0;
+    }
+    __syncthreads();
+  }
+  if (phases & 2) {
+    const double Mg = coll[0];
+    double S = 0.0;
+    if (t == 0) {  // fixed order
+      for (int b = 0; b < nblocks; ++b) {
+        const double mb = partials[(size_t)b * 4];
+        if (mb > -INFINITY) S += partials[(size_t)b * 4 + 1] * exp(mb - Mg);
+      }
+      coll[8] = S;
+      coll[9] = (double)counters[CNT_NOK];
+      coll[10] = (double)counters[CNT_REJECT];
+      coll[11] = (double)counters[CNT_DRAWFAIL];
+      coll[12] = coll[13] = coll[14] = coll[15] = 0.0;
+    }
+    __syncthreads();
+  }
+  if ((phases & 4) && t == 0) {
+    const double M = coll[0], R = coll[1], S = coll[8];
+    // the reference's running maxima with their unconditional assignment at i == 0 (pmc.c:535,552,579)
+    const double maxW = coll[2] != 0.0 ? NAN : ((coll[6] != 0.0) ? INFINITY : (coll[4] != 0.0 ? M : (M > kNegInit ? M : kNegInit)));
+    const double maxR = coll[3] != 0.0 ? NAN : (coll[5] != 0.0 ? R : (R > kNegInit ? R : kNegInit));
+    const bool draw_ok = !(coll[11] > 0.0) && !(coll[10] > 5.0 * n_total);
+    const bool clean = draw_ok && coll[2] == 0.0 && coll[3] == 0.0 && coll[6] == 0.0 && M > kNegInit && M < INFINITY && S > 0.0 && S < INFINITY &&
+                       maxW == M;
+    const double Sref = S * exp(kDynMax);  // sum exp(lw - maxW + 500), what pmc.c:660-674 accumulates
+    scal[I3_MAXW] = maxW;
+    scal[I3_MAXR] = maxR;
+    scal[I3_M] = M;
+    scal[I3_SREF] = Sref;
+    scal[I3_INVS] = 1.0 / Sref;
+    scal[I3_LOGSREF] = log(S) + kDynMax;
+    scal[I3_CLEAN] = clean ? 1.0 : 0.0;
+    scal[I3_NOK_W] = coll[9];
+    scal[I3_NREJ] = coll[10];
+    scal[I3_NFAIL] = coll[11];
+  }
+}
+
+// =====================================================================================================================
+// statistics + normalisation
+// =====================================================================================================================
+__device__ __forceinline__ void dmma884_3(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cpa8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cpa16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cpa4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
+struct S3Args {
+  const double *X, *resp;
+  double *W;   // in: log-weights, out: normalised weights (pmc.c:660-682)
+  short *flg;  // in/out: samples whose weight is not finite are flagged out (pmc.c:667-672)
+  const unsigned long long *indices;
+  const double *scal;
+  double pivot[FUSED_MAXD];
+  long N;
+  double *partials;  // [grid][partial_len]: DMMA accumulator fragments | H, Q, ok, flagged-out | count_k[64]
+  int partial_len;
+};
+
+template <int D, int K>
+struct S3Cfg {
+  static constexpr int E = 1 + D + D * (D + 1) / 2;
+  static constexpr int NT = (E + 7) / 8, MT = (K + 7) / 8;
+  static constexpr int XS = (D + 1) | 1;
+  static constexpr int GS = (MT * 8) | 1;
+  static constexpr int ACC = MT * NT * 64;
+  static constexpr int STAGE = 32 * D + 32 * K + 32 + 32 + 8;  // X rows | resp (k-major) | lw | indices | flg (32 shorts)
+  static constexpr int WARP_DOUBLES = 32 * XS + 32 * GS + STAGE;
+  static constexpr int PLEN = ACC + 4 + 64;
+};
+
+// per-sample normalisation shared by k_stats3 and k_norm3; returns the normalised weight if the sample is usable, else 0
+__device__ __forceinline__ double norm_sample(double lwv, short f, double maxW, double invS, double logSref,
+                                              const double *s_exp, double *Wout, short *Fout, double &H, double &Q,
+                                              unsigned int &nok, unsigned int &nflag, bool &ok) {
+  ok = false;
+  if (f != 0 && lwv == lwv) {
+    const double t2 = (lwv - maxW) + kDynMax;
+    const double w = exp_tab(t2, s_exp) * invS;
+    *Wout = w;
+    ok = true;
+    ++nok;
+    if (w >= kPerpZero) { H = fma(w, t2 - logSref, H); Q = fma(w, w, Q); }
+    return w;
+  }
+  if (f != 0) *Fout = 0;  // NaN log-weight: exp is not finite, the reference flags the sample out and skips it
+  *Wout = lwv * invS;     // pmc.c:680-682 divides every entry, flagged or not
+  ++nflag;
+  return 0.0;
+}
+
+template <int D, int K, bool STATS>
+__global__ void __launch_bounds__(256, 2) k_stats3(const S3Args a) {
+  using C = S3Cfg<D, K>;
+  constexpr int NT = C::NT, MT = C::MT, GS = C::GS, XS = C::XS;
+  constexpr int WARPS = 8;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double s_exp[64];
+  __shared__ double s_red[WARPS][2];
+  __shared__ unsigned int s_cnt[WARPS][2];
+  __shared__ unsigned int s_count[64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (a.scal[I3_CLEAN] == 0.0) return;  // poisoned maxima: the host runs the literal sequence instead
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) { s_exp[i] = c3_exptab[i]; s_count[i] = 0; }
+  const double maxW = a.scal[I3_MAXW], invS = a.scal[I3_INVS], logSref = a.scal[I3_LOGSREF];
+  double *xh = smem + (size_t)wid * C::WARP_DOUBLES;
+  double *gt = xh + 32 * XS;
+  double *stx = gt + 32 * GS;
+  double *str = stx + 32 * D;
+  double *stw = str + 32 * K;
+  unsigned long long *sti = reinterpret_cast<unsigned long long *>(stw + 32);
+  short *stf = reinterpret_cast<short *>(sti + 32);
+  for (int i = lane; i < C::WARP_DOUBLES; i += 32) xh[i] = 0.0;
+  __syncthreads();
+  const int fr = lane >> 2, fc = lane & 3;
+  int oa[NT], ob[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int e = 8 * n + fr;
+    int pa = 0, pb = 0;
+    if (e >= 1 && e <= D) pb = e;
+    else if (e > D && e < C::E) {
+      int q = e - 1 - D, r = 0;
+      while (q >= D - r) { q -= D - r; ++r; }
+      pa = 1 + r;
+      pb = 1 + r + q;
+    }
+    oa[n] = pa;
+    ob[n] = pb;
+  }
+  double acc[STATS ? MT : 1][STATS ? NT : 1][2];
+#pragma unroll
+  for (int m = 0; m < (STATS ? MT : 1); ++m)
+#pragma unroll
+    for (int n = 0; n < (STATS ? NT : 1); ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+  double H = 0.0, Q = 0.0;
+  unsigned int nok = 0, nflag = 0;
+  const long ntiles = (a.N + 31) / 32;
+  const long tstep = (long)gridDim.x * WARPS;
+
+  auto prefetch = [&](long tile) {
+    const long base = tile * 32;
+    const int tn = (a.N - base) < 32 ? (int)(a.N - base) : 32;
+    if (STATS) {
+      if ((D & 1) == 0) {
+        for (int c = lane; c < tn * D / 2; c += 32) cpa16(stx + 2 * c, a.X + (size_t)base * D + 2 * c);
+      } else {
+        for (int c = lane; c < tn * D; c += 32) cpa8(stx + c, a.X + (size_t)base * D + c);
+      }
+    }
+    if (lane < tn) {
+      if (STATS) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) cpa8(str + k * 32 + lane, a.resp + (size_t)k * a.N + base + lane);
+      }
+      cpa8(stw + lane, a.W + base + lane);
+      cpa8(sti + lane, a.indices + base + lane);
+    }
+    if (2 * lane + 1 < tn) cpa4(stf + 2 * lane, a.flg + base + 2 * lane);
+    else if (2 * lane < tn) stf[2 * lane] = a.flg[base + 2 * lane];
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  long tile = (long)blockIdx.x * WARPS + wid;
+  if (tile < ntiles) prefetch(tile);
+  for (; tile < ntiles; tile += tstep) {
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncwarp();
+    const long i = tile * 32 + lane;
+    double w = 0.0;
+    double xr[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) xr[j] = 0.0;
+    if (i < a.N) {
+      bool ok;
+      w = norm_sample(stw[lane], stf[lane], maxW, invS, logSref, s_exp, a.W + i, a.flg + i, H, Q, nok, nflag, ok);
+      if (ok) atomicAdd(&s_count[(int)sti[lane] & 63], 1u);
+      if (STATS && w != 0.0) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) xr[j] = stx[lane * D + j] - a.pivot[j];
+      }
+    }
+    if (STATS) {
+      double *xrow = xh + lane * XS, *grow = gt + lane * GS;
+      xrow[0] = 1.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) xrow[1 + j] = xr[j];
+#pragma unroll
+      for (int k = 0; k < K; ++k) grow[k] = (w != 0.0) ? w * str[k * 32 + lane] : 0.0;
+    }
+    __syncwarp();
+    if (tile + tstep < ntiles) prefetch(tile + tstep);
+    if (STATS) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int smp = 16 * h + t + 4 * fc;
+          double af[MT];
+#pragma unroll
+          for (int m = 0; m < MT; ++m) af[m] = gt[smp * GS + 8 * m + fr];
+          const double *xs = xh + smp * XS;
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const double bf = xs[oa[n]] * xs[ob[n]];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) dmma884_3(acc[m][n][0], acc[m][n][1], af[m], bf);
+          }
+        }
+    }
+    __syncwarp();
+  }
+  // ---- block combine in warp order -------------------------------------------------------------------------------
+  __syncthreads();
+  {
+    const double Hw = warp_sum(H), Qw = warp_sum(Q);
+    const unsigned int c1 = (unsigned int)warp_sum_ll(nok), c2 = (unsigned int)warp_sum_ll(nflag);
+    if (lane == 0) { s_red[wid][0] = Hw; s_red[wid][1] = Qw; s_cnt[wid][0] = c1; s_cnt[wid][1] = c2; }
+  }
+  double *out = a.partials + (size_t)blockIdx.x * a.partial_len;
+  if (STATS) {
+    double *comb = smem;
+    for (int w2 = 0; w2 < WARPS; ++w2) {
+      __syncthreads();
+      if (wid == w2) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int idx = ((m * NT + n) * 32 + lane) * 2 + c;
+              comb[idx] = (w2 == 0 ? 0.0 : comb[idx]) + acc[m][n][c];
+            }
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < C::ACC; idx += blockDim.x) out[idx] = comb[idx];
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double Hb = 0.0, Qb = 0.0, n1 = 0.0, n2 = 0.0;
+    for (int w2 = 0; w2 < WARPS; ++w2) { Hb += s_red[w2][0]; Qb += s_red[w2][1]; n1 += (double)s_cnt[w2][0]; n2 += (double)s_cnt[w2][1]; }
+    out[C::ACC + 0] = Hb;
+    out[C::ACC + 1] = Qb;
+    out[C::ACC + 2] = n1;
+    out[C::ACC + 3] = n2;
+  }
+  if (threadIdx.x < 64) out[C::ACC + 4 + threadIdx.x] = (double)s_count[threadIdx.x];
+}
+
+// canonical statistics from the block partials, in block order: out = stats[K*E] | H, Q, ok, flagged-out | count_k[K]
+__global__ void k_comb3(const double *__restrict__ partials, int nblocks, int partial_len, int acc_len, int K, int E, int NT,
+                        int with_stats, const double *__restrict__ scal, double *__restrict__ out) {
+  const int nstat = with_stats ? K * E : 0;
+  const int total = nstat + 4 + K;
+  const bool clean = scal[I3_CLEAN] != 0.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int idx;
+    if (t < nstat) {
+      const int k = t / E, e = t - k * E;
+      const int m = k >> 3, r = k & 7, n = e >> 3, cc = e & 7;
+      idx = ((m * NT + n) * 32 + (r * 4 + (cc >> 1))) * 2 + (cc & 1);
+    } else {
+      idx = acc_len + (t - nstat);
+    }
+    double s = 0.0;
+    if (clean)
+      for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * partial_len + idx];
+    out[t] = s;
+  }
+}
+
+// =====================================================================================================================
+// draw
+// =====================================================================================================================
+struct D3Args {
+  long N, first_index;
+  uint64_t seed;
+  uint32_t iter;
+  int max_attempts, chunk;
+  int has_box;
+  double *X;
+  unsigned long long *indices;
+  short *flg;
+  const double2 *zig;
+  const double *gpack;  // the draw pack in global memory: per-lane component of a redraw
+  unsigned long long *counters;
+};
+
+// attempts >= 1 of a sample whose first draw fell outside the box (pmc.c:281-295: a fresh component every time)
+template <int D, int K>
+static __device__ __noinline__ bool redraw3(const D3Args &a, const Philox ph, uint32_t ilo, uint32_t ihi, const double2 *zts,
+                                            double *x, int &kout, unsigned int &rej) {
+  constexpr int DS = i3_dstride(D);
+  for (int attempt = 1; attempt < a.max_attempts; ++attempt) {
+    const uint32_t cb = (uint32_t)attempt << 12;
+    const uint4 r0 = ph(ilo, ihi, cb, a.iter);
+    const double u = u01_co(r0.x, r0.y);
+    int k = 0;
+    for (int kk = 0; kk < K - 1; ++kk) k += (c3_cw[kk] < u) ? 1 : 0;
+    double g[D + 1];
+    uint32_t spare;
+    zig_normals<D>(ph, ilo, ihi, cb, a.iter, zts, g, spare);
+    const double *cp = a.gpack + (size_t)k * DS;
+    bool inb = true;
+    int e = 0;
+    for (int i = 0; i < D; ++i) {
+      double t = cp[e++];
+      for (int j = 0; j <= i; ++j) t = fma(g[j], cp[e++], t);
+      x[i] = t;
+      inb = inb && isfinite(t);
+      if (a.has_box) inb = inb && !(t < c3_box[2 * i]) && !(t > c3_box[2 * i + 1]);
+    }
+    kout = k;
+    if (inb) return true;
+    ++rej;
+  }
+  return false;
+}
+
+// x = mu_k + L_k g for a warp-uniform k: one straight-line copy per component so that every parameter is a constant-bank
+// operand at a compile-time offset (a register-indexed constant load per entry cost an instruction and two registers each)
+template <int D, int K>
+__device__ __forceinline__ void apply_L3(int k, const double (&g)[D + 1], double (&x)[D]) {
+  constexpr int DS = i3_dstride(D);
+#pragma unroll
+  for (int kk = 0; kk < K; ++kk) {
+    if (k == kk) {
+      int e = kk * DS;
+#pragma unroll
+      for (int i2 = 0; i2 < D; ++i2) {
+        double t = c3_d[e++];
+#pragma unroll
+        for (int j2 = 0; j2 <= i2; ++j2) t = fma(g[j2], c3_d[e++], t);
+        x[i2] = t;
+      }
+    }
+  }
+}
+
+template <int D, int K>
+__global__ void __launch_bounds__(256, 2) k_draw3(const D3Args a) {
+  constexpr int DS = i3_dstride(D);
+  static_assert(K * DS <= I3_CD && K <= 64, "constant memory budget");
+  extern __shared__ __align__(16) unsigned char sm3[];
+  double2 *zts = reinterpret_cast<double2 *>(sm3);
+  unsigned int *tmp = reinterpret_cast<unsigned int *>(zts + kZigLayers);
+  unsigned short *perm = reinterpret_cast<unsigned short *>(tmp + a.chunk);
+  __shared__ unsigned int s_hist[64], s_base[65];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < kZigLayers; i += blockDim.x) zts[i] = a.zig[i];
+  const Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+  unsigned int rej_lane = 0, fail_lane = 0;
+  const long nchunks = (a.N + a.chunk - 1) / a.chunk;
+  for (long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const long cbase = c * a.chunk;
+    const int cn = (a.N - cbase) < a.chunk ? (int)(a.N - cbase) : a.chunk;
+    if (tid < 64) s_hist[tid] = 0;
+    __syncthreads();
+    // ---- component of the first attempt of every sample of the chunk (mvdens.c:775-776), rank inside its bucket --------
+    for (int o = tid; o < cn; o += blockDim.x) {
+      const uint64_t gi = (uint64_t)(a.first_index + cbase + o);
+      const uint4 r0 = ph((uint32_t)gi, (uint32_t)(gi >> 32), 0u, a.iter);
+      const double u = u01_co(r0.x, r0.y);
+      int k = 0;
+#pragma unroll
+      for (int kk = 0; kk < K - 1; ++kk) k += (c3_cw[kk] < u) ? 1 : 0;
+      const unsigned int rank = atomicAdd(&s_hist[k], 1u);
+      tmp[o] = ((unsigned int)k << 16) | rank;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int acc = 0;
+      for (int k = 0; k < K; ++k) { s_base[k] = acc; acc += s_hist[k]; }
+      s_base[K] = acc;
+    }
+    __syncthreads();
+    for (int o = tid; o < cn; o += blockDim.x) {
+      const unsigned int v = tmp[o];
+      perm[s_base[v >> 16] + (v & 0xffffu)] = (unsigned short)o;
+    }
+    __syncthreads();
+    // ---- one component per warp tile: x = mu_k + L_k g with warp-uniform constant-bank operands ------------------------
+    for (int k = 0; k < K; ++k) {
+      const int nk = (int)s_hist[k], b = (int)s_base[k];
+      for (int t0 = wid * 32; t0 < nk; t0 += (int)(blockDim.x >> 5) * 32) {
+        const int j = t0 + lane;
+        const bool active = j < nk;
+        const int o = (int)perm[b + (active ? j : 0)];
+        const long i = cbase + o;
+        const uint64_t gi = (uint64_t)(a.first_index + i);
+        const uint32_t ilo = (uint32_t)gi, ihi = (uint32_t)(gi >> 32);
+        double g[D + 1];
+        uint32_t spare;
+        zig_normals<D>(ph, ilo, ihi, 0u, a.iter, zts, g, spare);
+        double x[D];
+        apply_L3<D, K>(k, g, x);
+        bool inb = true;
+#pragma unroll
+        for (int i2 = 0; i2 < D; ++i2) {
+          inb = inb && isfinite(x[i2]);
+          // thr - c*x < 0 (parabox.c:125-131) for c = -1 / +1 equals a direct comparison with the (negated) threshold
+          if (a.has_box) inb = inb && !(x[i2] < c3_box[2 * i2]) && !(x[i2] > c3_box[2 * i2 + 1]);
+        }
+        if (active) {
+          int kk = k;
+          bool ok = inb;
+          if (!inb) {
+            ++rej_lane;
+            ok = redraw3<D, K>(a, ph, ilo, ihi, zts, x, kk, rej_lane);
+            if (!ok) ++fail_lane;
+          }
+          a.indices[i] = (unsigned long long)kk;
+          a.flg[i] = ok ? 1 : 0;
+          if ((D & 1) == 0) {
+            double2 *xo = reinterpret_cast<double2 *>(a.X + (size_t)i * D);
+#pragma unroll
+            for (int i2 = 0; i2 < D; i2 += 2) xo[i2 / 2] = make_double2(x[i2], x[i2 + 1]);
+          } else {
+#pragma unroll
+            for (int i2 = 0; i2 < D; ++i2) a.X[(size_t)i * D + i2] = x[i2];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const unsigned long long n2 = (unsigned long long)warp_sum_ll(rej_lane), n3 = (unsigned long long)warp_sum_ll(fail_lane);
+  if (lane == 0) {
+    if (n2) atomicAdd(&a.counters[CNT_REJECT], n2);
+    if (n3) atomicAdd(&a.counters[CNT_DRAWFAIL], n3);
+  }
+}
+
+// =====================================================================================================================
+// host side: instantiation table and launchers
+// =====================================================================================================================
+#define PMC_ITER3_TABLE(X) \
+  X(10, 10, 0)             \
+  X(10, 20, 0)             \
+  X(10, 5, 0)              \
+  X(5, 20, 4)              \
+  X(5, 10, 0)              \
+  X(2, 9, 0)
+
+Iter3Plan iter3_plan(int d, int K, int Kt, int tgt_kind, int sm_count) {
+  Iter3Plan best{};
+  const int kt_needed = (tgt_kind == PMCGPU_TGT_MVDENS || tgt_kind == PMCGPU_TGT_MIX) ? Kt : 0;
+  // the smallest instantiation with K_ >= K serves the mixture: the extra components are packed as dead ones
+#define X(D_, K_, KT_)                                                                                          \
+  if (d == D_ && K <= K_ && (kt_needed == 0 || (KT_ > 0 && kt_needed <= KT_)) && (!best.valid || K_ < best.K)) { \
+    using C = S3Cfg<D_, K_>;                                                                                     \
+    best.valid = 1; best.D = D_; best.K = K_; best.KT = KT_; best.sm_count = sm_count;                           \
+    best.E = C::E; best.NT = C::NT; best.acc_len = C::ACC; best.partial_len = C::PLEN;                           \
+    best.stats_blocks = sm_count * 2; best.weights_blocks = sm_count * 4; /* upper bound over the variants */                                        \
+  }
+  PMC_ITER3_TABLE(X)
+#undef X
+  return best;
+}
+
+// variant 0: one sample per lane, 4 blocks/SM (128 registers); 1: one sample per lane, 3 blocks/SM (168 registers);
+// 2: two samples per lane, 2 blocks/SM (255 registers).  Variants 1 and 2 are instantiated for the headline shape only.
+template <int D, int K, int KT>
+static int launch_w3(const Iter3Plan &p, const W3Args &a, int variant, bool resp, int *nblocks, cudaStream_t s) {
+  constexpr bool kHead = (D == 10 && K == 10 && KT == 0);
+  if (!kHead) variant = 0;
+  const int spl = variant == 2 ? 2 : 1, minb = variant == 0 ? 4 : (variant == 1 ? 3 : 2);
+  const long ntiles = (a.N + 32 * spl - 1) / (32 * spl);
+  int grid = p.sm_count * minb;
+  if ((long)grid * 4 > ntiles) grid = (int)((ntiles + 3) / 4);
+  if (grid < 1) grid = 1;
+  *nblocks = grid;
+  if (variant == 0) {
+    if (resp) k_weights3<D, K, KT, 1, true, 4><<<grid, 128, 0, s>>>(a);
+    else k_weights3<D, K, KT, 1, false, 4><<<grid, 128, 0, s>>>(a);
+  }
+  if constexpr (kHead) {
+    if (variant == 1) {
+      if (resp) k_weights3<D, K, KT, 1, true, 3><<<grid, 128, 0, s>>>(a);
+      else k_weights3<D, K, KT, 1, false, 3><<<grid, 128, 0, s>>>(a);
+    } else if (variant == 2) {
+      if (resp) k_weights3<D, K, KT, 2, true, 2><<<grid, 128, 0, s>>>(a);
+      else k_weights3<D, K, KT, 2, false, 2><<<grid, 128, 0, s>>>(a);
+    }
+  }
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int iter3_upload(const Iter3Plan &p, const double *h_w, int nw, const double *h_t, int nt, const double *h_d, int nd,
+                 const double *h_cw, int ncw, cudaStream_t s) {
+  (void)p;
+  if (upload_tables()) return -1;
+  if (h_w && cudaMemcpyToSymbolAsync(c3_w, h_w, sizeof(double) * nw, 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+  if (h_t && nt && cudaMemcpyToSymbolAsync(c3_t, h_t, sizeof(double) * nt, 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+  if (h_d && cudaMemcpyToSymbolAsync(c3_d, h_d, sizeof(double) * nd, 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+  if (h_cw && cudaMemcpyToSymbolAsync(c3_cw, h_cw, sizeof(double) * ncw, 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+  return 0;
+}
+
+int launch_weights3(const Iter3Plan &p, const Iter3Weights &w, int *nblocks, cudaStream_t s) {
+  W3Args a{};
+  a.X = w.X; a.N = w.N; a.first_index = w.first_index; a.tgt_kind = w.tgt_kind; a.b = w.b; a.sig1 = w.sig1; a.t_temper = w.t_temper;
+  a.post_in = w.post_in; a.ok_in = w.ok_in;
+  for (int j = 0; j < FUSED_MAXD; ++j) a.shift[j] = w.shift[j];
+  a.lw = w.lw; a.log_rho = w.log_rho; a.resp = w.resp; a.flg = w.flg; a.partials = w.partials; a.counters = w.counters;
+  a.first_vals = w.first_vals; a.mix = w.mix; a.tmix = w.tmix;
+  const bool resp = w.resp != nullptr;
+#define X(D_, K_, KT_) \
+  if (p.D == D_ && p.K == K_ && p.KT == KT_) return launch_w3<D_, K_, KT_>(p, a, w.variant, resp, nblocks, s);
+  PMC_ITER3_TABLE(X)
+#undef X
+  return -1;
+}
+
+int launch_red3(const double *partials, int nblocks, const unsigned long long *counters, const double *first_vals,
+                int has_first, double *coll, double *scal, int phases, double n_total, cudaStream_t s) {
+  k_red3<<<1, 256, 0, s>>>(partials, nblocks, counters, first_vals, has_first, coll, scal, phases, n_total);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <int D, int K>
+static int launch_s3(const Iter3Plan &p, const S3Args &a, bool stats, cudaStream_t s) {
+  using C = S3Cfg<D, K>;
+  size_t smem = (size_t)8 * C::WARP_DOUBLES * sizeof(double);
+  if (smem < (size_t)C::ACC * sizeof(double)) smem = (size_t)C::ACC * sizeof(double);
+  static std::atomic<unsigned long long> set1{0}, set0{0};
+  if (stats) {
+    if (!set_max_smem_once(k_stats3<D, K, true>, smem, set1)) return -1;
+    k_stats3<D, K, true><<<p.stats_blocks, 256, smem, s>>>(a);
+  } else {
+    if (!set_max_smem_once(k_stats3<D, K, false>, smem, set0)) return -1;
+    k_stats3<D, K, false><<<p.stats_blocks, 256, smem, s>>>(a);
+  }
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_stats3(const Iter3Plan &p, const Iter3Stats &st, cudaStream_t s) {
+  S3Args a{};
+  a.X = st.X; a.resp = st.resp; a.W = st.W; a.flg = st.flg; a.indices = st.indices; a.scal = st.scal; a.N = st.N;
+  a.partials = st.partials; a.partial_len = p.partial_len;
+  for (int j = 0; j < FUSED_MAXD; ++j) a.pivot[j] = st.pivot[j];
+#define X(D_, K_, KT_) \
+  if (p.D == D_ && p.K == K_ && p.KT == KT_) return launch_s3<D_, K_>(p, a, st.with_stats != 0, s);
+  PMC_ITER3_TABLE(X)
+#undef X
+  return -1;
+}
+
+int launch_comb3(const Iter3Plan &p, const double *partials, int with_stats, const double *scal, double *out, cudaStream_t s) {
+  const int total = (with_stats ? p.K * p.E : 0) + 4 + p.K;
+  k_comb3<<<(total + 63) / 64, 64, 0, s>>>(partials, p.stats_blocks, p.partial_len, p.acc_len, p.K, p.E, p.NT, with_stats, scal, out);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+struct D3Host { D3Args a; double lo_thr[FUSED_MAXD], hi_thr[FUSED_MAXD]; };
+template <int D, int K>
+static int launch_d3(const Iter3Plan &p, const D3Host &a0, cudaStream_t s) {
+  D3Args a = a0.a;
+  // chunk: as large as shared memory comfortably allows (few partially filled warp tiles), but small enough that
+  // every SM gets work when N is small
+  long chunk = 8192;
+  const long want = (a.N + (long)p.sm_count * 2 - 1) / ((long)p.sm_count * 2);
+  if (want < chunk) chunk = ((want + 255) / 256) * 256;
+  if (chunk < 256) chunk = 256;
+  a.chunk = (int)chunk;
+  const size_t smem = (size_t)kZigLayers * sizeof(double2) + (size_t)chunk * 6;
+  static std::atomic<unsigned long long> set{0};
+  if (!set_max_smem_once(k_draw3<D, K>, (size_t)kZigLayers * sizeof(double2) + 8192 * 6, set)) return -1;
+  const long nchunks = (a.N + chunk - 1) / chunk;
+  long grid = (long)p.sm_count * 2;
+  if (grid > nchunks) grid = nchunks;
+  {
+    double hb[2 * FUSED_MAXD];
+    for (int j = 0; j < FUSED_MAXD; ++j) { hb[2 * j] = -a0.lo_thr[j]; hb[2 * j + 1] = a0.hi_thr[j]; }
+    if (cudaMemcpyToSymbolAsync(c3_box, hb, sizeof hb, 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+  }
+  k_draw3<D, K><<<(int)grid, 256, smem, s>>>(a);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_draw3(const Iter3Plan &p, const Iter3Draw &d, cudaStream_t s) {
+  D3Host h{};
+  D3Args &a = h.a;
+  a.N = d.N; a.first_index = d.first_index; a.seed = d.seed; a.iter = d.iter; a.max_attempts = d.max_attempts;
+  a.has_box = d.has_box;
+  for (int j = 0; j < FUSED_MAXD; ++j) { h.lo_thr[j] = d.lo_thr[j]; h.hi_thr[j] = d.hi_thr[j]; }
+  a.X = d.X; a.indices = d.indices; a.flg = d.flg; a.zig = d.zig; a.gpack = d.gpack; a.counters = d.counters;
+#define X(D_, K_, KT_) \
+  if (p.D == D_ && p.K == K_ && p.KT == KT_) return launch_d3<D_, K_>(p, h, s);
+  PMC_ITER3_TABLE(X)
+#undef X
+  return -1;
+}
+
+}  // namespace pmcb200

@@ -194,6 +194,76 @@ int launch_fused2_stats(const FusedPlan &p, const double *X, const double *lw, c
                         const double *Mdev, const double *pivot, long N, double *partials, cudaStream_t s);
 int launch_fused2_combine(const FusedPlan &p, const double *partials, int nblocks, double *stats_out, cudaStream_t s);
 
+// ---- third-generation small-d iteration (pmc_iter3.cu): grouped draw, table-driven weights kernel, statistics kernel
+// with the normalisation fused in, device-side reductions ----------------------------------------------------------------
+enum { I3_MAXW = 0, I3_MAXR, I3_M, I3_SREF, I3_INVS, I3_LOGSREF, I3_CLEAN, I3_NOK_W, I3_NREJ, I3_NFAIL, I3_MLOC, I3_SCAL_LEN = 16 };
+constexpr int I3_COLL_LEN = 16;  // [0..7] all-reduce(max) block, [8..15] all-reduce(sum) block
+
+struct Iter3Plan {
+  int valid;
+  int D, K, KT;      // instantiation; K >= the mixture's K (extra components are packed as dead ones)
+  int E, NT, acc_len, partial_len;
+  int stats_blocks, weights_blocks, sm_count;
+};
+struct Iter3Weights {
+  const double *X;
+  long N, first_index;
+  int tgt_kind;
+  double b, sig1, t_temper;
+  const double *post_in;
+  const short *ok_in;
+  double shift[FUSED_MAXD];
+  double *lw, *log_rho, *resp;  // resp == nullptr: no responsibilities
+  short *flg;
+  double *partials;
+  unsigned long long *counters;
+  double *first_vals;
+  MixDev mix, tmix;
+  int variant;  // launch shape of the weights kernel (pmc_iter3.cu:launch_w3)
+};
+struct Iter3Stats {
+  const double *X, *resp;
+  double *W;
+  short *flg;
+  const unsigned long long *indices;
+  const double *scal;
+  double pivot[FUSED_MAXD];
+  long N;
+  double *partials;
+  int with_stats;  // 0: normalisation, perplexity sums and the component histogram only
+};
+struct Iter3Draw {
+  long N, first_index;
+  uint64_t seed;
+  uint32_t iter;
+  int max_attempts, has_box;
+  double lo_thr[FUSED_MAXD], hi_thr[FUSED_MAXD];
+  double *X;
+  unsigned long long *indices;
+  short *flg;
+  const double2 *zig;
+  const double *gpack;
+  unsigned long long *counters;
+};
+Iter3Plan iter3_plan(int d, int K, int Kt, int tgt_kind, int sm_count);
+int iter3_wstride(int D);
+int iter3_dstride(int D);
+void iter3_pack_w(int K, int D, const double *wght, const double *mean, const double *L, const double *logdet,
+                  const double *shift, double *out);
+void iter3_pack_d(int K, int D, const double *mean, const double *L, double *out);
+double iter3_shift_ratio(int K, int D, const double *wght, const double *mean, const double *L, const double *shift);
+// constant-bank uploads on the stream (any pointer may be null = unchanged)
+int iter3_upload(const Iter3Plan &p, const double *h_w, int nw, const double *h_t, int nt, const double *h_d, int nd,
+                 const double *h_cw, int ncw, cudaStream_t s);
+int launch_draw3(const Iter3Plan &p, const Iter3Draw &d, cudaStream_t s);
+int launch_weights3(const Iter3Plan &p, const Iter3Weights &w, int *nblocks, cudaStream_t s);
+// phases: 1 = local maxima -> coll[0..7], 2 = normaliser relative to the (global) maximum -> coll[8..15], 4 = scalars
+int launch_red3(const double *partials, int nblocks, const unsigned long long *counters, const double *first_vals,
+                int has_first, double *coll, double *scal, int phases, double n_total, cudaStream_t s);
+int launch_stats3(const Iter3Plan &p, const Iter3Stats &st, cudaStream_t s);
+// out: stats[K*E] (with_stats) | H, Q, ok, flagged-out | count_k[K]
+int launch_comb3(const Iter3Plan &p, const double *partials, int with_stats, const double *scal, double *out, cudaStream_t s);
+
 // ---- large-d tensor-path kernels (pmc_mma.cu): DMMA whitening and DMMA sufficient statistics, 16 < d <= 128 --------
 int mma_nt(int d);                    // number of 8-row tiles the dimension is padded to (0 = not supported)
 size_t mma_comp_stride(int d);        // doubles of one packed component

@@ -33,6 +33,27 @@ def test_oracle_reproduces_golden(name):
             assert relerr(o[k], g[k]) == 0.0, k
 
 
+def test_oracle_reproduces_c5_update_digest():
+    """configs[4] shape with every component above MINCOUNT: the restatement's RB update equals the compiled reference's
+    (digest made by tests/golden/make_golden.py:update_digest; ~40 s of denormal-bound CPU work)."""
+    import hashlib
+    from golden.make_golden import sample_entries
+    g = np.load(os.path.join(GOLD, "c5_update_d128_K64.npz"))
+    wl = W.gauss128()
+    X, idx = O.orc_simulate(int(g["N"]), wl, seed=int(g["seed"]))
+    assert hashlib.sha256(X.tobytes()).hexdigest() == str(g["x_sha"]) and hashlib.sha256(idx.tobytes()).hexdigest() == str(g["idx_sha"])
+    o = O.orc_iteration(X, idx, wl, do_update=1)
+    assert o["rc"] == int(g["rc"]) == 0 and o["nok"] == int(g["nok"]) and o["retry"] == int(g["retry"])
+    for k in ["maxW", "maxR", "logSum", "perp", "ess", "ln_evidence", "o_wght", "o_mean", "o_detL"]:
+        assert relerr(o[k], g[k]) == 0.0, k
+    S = o["o_std"]
+    kk, aa, bb = sample_entries(wl["K"], wl["d"], len(g["o_std_sel"]))
+    assert np.array_equal(np.array([np.diag(S[k]) for k in range(wl["K"])]), g["o_std_diag"])
+    assert np.array_equal(S[kk, aa, bb], g["o_std_sel"])
+    assert np.array_equal(np.sqrt((np.tril(S) ** 2).sum((1, 2))), g["o_std_fro"])
+    assert np.array_equal(o["w_norm"][:512], g["w_norm_head"]) and np.array_equal(o["log_rho"][:512], g["log_rho_head"])
+
+
 def test_oracle_misc_golden():
     g = np.load(os.path.join(GOLD, "misc.npz"))
     L = O.orc()

@@ -19,13 +19,14 @@ def _mix(rng, K, d):
     return w / w.sum(), rng.normal(0, 2, (K, d)), cov
 
 
-@pytest.mark.parametrize("path,d,K", [("fused_v2", 10, 10), ("fused_v1", 10, 10), ("generic", 10, 10), ("fused_v2", 5, 20),
-                                      ("generic", 7, 3)])
+@pytest.mark.parametrize("path,d,K", [("fused_v3", 10, 10), ("fused_v3", 5, 20), ("fused_v3", 2, 9), ("fused_v3", 10, 7),
+                                      ("fused_v2", 10, 10), ("fused_v1", 10, 10), ("generic", 10, 10),
+                                      ("fused_v2", 5, 20), ("generic", 7, 3)])
 def test_draw_distribution(gpu, path, d, K):
     rng = np.random.default_rng(100 + d + K)
     w, mean, cov = _mix(rng, K, d)
     gpu.set_option("force_generic", 1 if path == "generic" else 0)
-    gpu.set_option("fused_version", {"fused_v1": 1, "fused_v2": 2}.get(path, 0))
+    gpu.set_option("fused_version", {"fused_v1": 1, "fused_v2": 2, "fused_v3": 3}.get(path, 0))
     gpu.set_proposal_cov(w, mean, cov)
     gpu.set_target_banana(d, 0.1, 10.0) if d >= 2 else None
     gpu.set_box(None)

@@ -57,7 +57,7 @@ def oracle_runs():
     return get
 
 
-PATHS = {"generic": (1, 0), "fused_v1": (0, 1), "fused_v2": (0, 2)}
+PATHS = {"generic": (1, 0), "fused_v1": (0, 1), "fused_v2": (0, 2), "fused_v3": (0, 3)}
 
 
 @pytest.mark.parametrize("path", list(PATHS))
@@ -106,8 +106,8 @@ def test_update_rb_two_pass(gpu, oracle_runs, name):
     print(name, "two-pass update errors", errs)
 
 
-# (kernel generation, samples per lane): the second-generation kernels are instantiated for one sample per lane only
-@pytest.mark.parametrize("ver,spl", [(1, 1), (1, 2), (2, 1)])
+# (kernel generation, samples per lane): the second- and third-generation kernels are instantiated for one sample per lane only
+@pytest.mark.parametrize("ver,spl", [(1, 1), (1, 2), (2, 1), (3, 1)])
 @pytest.mark.parametrize("name", ["c1_banana_d10_K10", "c2_gmm_d5_K20", "shipped_d2_K9", "ragged_d10_K10", "tiny_d10_K10",
                                   "d3_K4", "d4_K6", "d6_K12", "d8_K20", "d10_K20", "d10_K5", "d5_K10", "d7_K3_generic_only"])
 def test_fused_iteration_given_samples(gpu, oracle_runs, name, ver, spl):

@@ -66,7 +66,8 @@ def test_fused_update_equals_two_pass_at_scale(gpu):
     two = gpu.pmc_step(seed=11, it=5, retry=0)
     gpu.set_option("force_precise", 0)
     assert two.used_precise_path == 1
-    assert one.perplexity == two.perplexity and one.logSum == two.logSum
+    # same samples, same weights kernel; the perplexity sums run in two different instantiations of the statistics kernel
+    assert abs(one.perplexity - two.perplexity) <= 1e-13 * two.perplexity and one.logSum == two.logSum
     errs = compare_mixture(one.wght, one.mean, one.L, two.wght, two.mean, two.L, rtol=1e-11, what="one-pass vs two-pass")
     print("one-pass vs two-pass at 5e6:", errs)
 
