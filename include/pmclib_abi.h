@@ -43,6 +43,8 @@ error *initError(void);
 void endError(error **err);
 int _isError(error *err);
 #define isError(err) (_isError(err))
+int pickleError(error *err, void **buf);   /* errorlist.c:126-150 */
+error *unpickleError(void *buf, int len);  /* errorlist.c:152-169 */
 #endif
 
 /* ---- GSL types that appear by value in the ABI (mvdens.h:83-110, pmc.h:133) ---------------------------------- */
@@ -80,6 +82,7 @@ void add_slab(parabox *bx, int coord, double vmin, double vmax, error **err);
 void add_face(parabox *bx, double *dirvec, double threshold, error **err);
 void add_halfspace(parabox *bx, int coord, double sign, double val, error **err);
 void free_parabox(parabox **bx);
+void print_parabox(parabox *bx, FILE *mstream);                                        /* parabox.c:147-186 */
 #endif
 
 /* ---- mvdens / mix_mvdens (pmctools/include/mvdens.h:83-155) -------------------------------------------------------- */
@@ -135,6 +138,20 @@ void mix_mvdens_cholesky_decomp(mix_mvdens *self, error **err);
 size_t ranindx(double *cw, size_t nE, gsl_rng *r, error **err);
 double mix_mvdens_log_pdf(mix_mvdens *m, const double *x, error **err);
 double mix_mvdens_log_pdf_void(void *m, const double *x, error **err);
+/* second half of mvdens.h:113-155 (pmc_dropin2.cpp) */
+mvdens *mvdens_dwnp(FILE *where, error **err);                                         /* mvdens.c:146-188 */
+mvdens *mvdens_read_and_chol(FILE *where, error **err);                                /* mvdens.c:190-204 */
+void mvdens_chdump(const char *name, mvdens *what, error **err);                       /* mvdens.c:136-144 */
+void mvdens_from_meanvar(mvdens *m, const double *pmean, const double *pvar, double correct); /* mvdens.c:62-71 */
+double ln_determinant(const double *L, size_t ndim, error **err);                      /* mvdens.c:215-227 */
+double *mvdens_ran(double *dest, mvdens *g, gsl_rng *r, error **err);                  /* mvdens.c:279-317 */
+double mvdens_inverse(mvdens *m, error **err);                                         /* mvdens.c:393-410 */
+void mix_mvdens_copy(mix_mvdens *target, const mix_mvdens *source, error **err);       /* mvdens.c:418-431 */
+double effective_number_of_components(const mix_mvdens *self, error **err);            /* mvdens.c:500-511 */
+size_t mix_mvdens_size(size_t ncomp, size_t ndim);                                     /* mvdens.c:585-594 */
+void *serialize_mix_mvdens(mix_mvdens *self, size_t *sz, error **err);                 /* mvdens.c:596-660 */
+mix_mvdens *deserialize_mix_mvdens(void *serialized, size_t sz, error **err);          /* mvdens.c:662-720 */
+double *mix_mvdens_ran(double *dest, size_t *index, mix_mvdens *m, gsl_rng *r, error **err); /* mvdens.c:730-764 */
 #endif
 
 /* ---- plugin interface (pmclib/include/allmc.h:21-33, distribution.h:25-41) ------------------------------------------ */
@@ -177,6 +194,29 @@ void free_distribution(distribution **pdist);
 double distribution_lkl(void *pdist, const double *pars, error **err);
 void distribution_retrieve(const void *pdist, double *pars, error **err);
 void distribution_set_default(distribution *dist, int ndef, int *idef, double *vdef, error **err);
+/* names, broadcast hook, combined targets and Gaussian priors (distribution.h:66-119, pmc_dropin2.cpp) */
+int distribution_get_name(distribution *dist, char *name, error **err);
+int *distribution_get_names(distribution *dist, int nname, char **name, int includeded, error **err);
+void distribution_set_names(distribution *dist, char **name, error **err);
+void distribution_set_broadcast(distribution *dist, mpi_exchange_func *broadcast, error **err);
+void distribution_set_default_name(distribution *dist, int ndef, char **idef, double *vdef, error **err);
+typedef struct {
+  double *pars, *pded, *dummy;
+  int *ded_from, **dim, **ded;
+  distribution **dist;
+  int ndim, nded, ndist, ndummy;
+} comb_dist_data;
+distribution *combine_distribution_init(int ndim, int nded, error **err);
+distribution *combine_distribution_simple_init(int ndim, error **err);
+double combine_lkl(void *pcbd, const double *pars, error **err);
+void combine_retrieve(const void *pcbd, double *pded, error **err);
+void combine_free(void **pcbd);
+void add_to_combine_distribution(distribution *comb, distribution *addon, int *dim_idx, int *ded_idx, error **err);
+void add_to_combine_distribution_name(distribution *comb, distribution *addon, error **err);
+distribution *add_gaussian_prior(distribution *orig, int ndim, int *idim, double *loc, double *var, error **err);
+distribution *add_gaussian_prior_2(distribution *orig, int ndim, int *idim, double *loc, double *var, error **err);
+distribution *add_gaussian_prior_name(distribution *orig, int ndim, char **idim, double *loc, double *var, error **err);
+distribution *add_gaussian_prior_2_name(distribution *orig, int ndim, char **idim, double *loc, double *var, error **err);
 #endif
 
 /* ---- pmc_simu (pmclib/include/pmc.h:76-205) --------------------------------------------------------------------------- */
@@ -257,6 +297,10 @@ void pmc_simu_print(FILE *where, pmc_simu *psim, double nrm);                   
 void clip_weights(pmc_simu *psim, int n, FILE *OUT, error **err);                        /* pmc.c:1134-1188 */
 size_t *sample_from_pmc_simu(const pmc_simu *psim, const gsl_rng *rng, error **err);     /* pmc.c:1585-1601 */
 unsigned int *resample_residual(const pmc_simu *psim, const gsl_rng *rng, error **err);  /* pmc.c:1605-1626 */
+pmc_simu *pmc_simu_from_file(FILE *PMCSIM, int this_nsamples, int npar, int n_ded, mix_mvdens *proposal, int nclipw,
+                             error **err);                                               /* pmc.c:373-396 */
+double fill_read_pmc_simu(pmc_simu *psim, mix_mvdens *proposal, error **err);            /* pmc.c:400-445 */
+size_t *sort_indices(double *list, size_t size, size_t *in_ind, size_t *buf, int order, error **err); /* pmc.c:881-1034 */
 #endif
 
 /* ---- example target shipped with the reference (examples/target/sampleTarget.h) ---------------------------------------- */

@@ -20,6 +20,7 @@
 #include <vector>
 #include "../../include/pmcb200.h"
 #include "../../include/pmclib_abi.h"
+#include "pmc_dropin_internal.h"
 #include "pmc_hostonly.h"
 
 namespace {
@@ -288,6 +289,15 @@ pmcgpu_ctx *point_ctx(error **err) {
 }
 
 }  // namespace
+
+namespace pmcb200 {
+std::mutex &dropin_point_mutex() {
+  static std::mutex m;
+  return m;
+}
+pmcgpu_ctx *dropin_point_ctx(error **err) { return point_ctx(err); }
+uint64_t dropin_seed_from(gsl_rng *r) { return seed_from(r); }
+}  // namespace pmcb200
 
 extern "C" {
 

@@ -9,11 +9,13 @@
 //               mu_k and L_k are warp-uniform constant-bank operands of the DFMAs, no shared-memory traffic besides the
 //               ziggurat table.  Sample i keeps its position, its Philox counters and its component: the output is the
 //               same i.i.d. sequence whatever the chunking or the sharding.
-//   k_weights3  (mvdens.c:784-825, 354-385, 319-349; pmc.c:537-592)  The triangular solve runs on pre-scaled factors
-//               (t_j = x'_j/L_jj - mu'_j/L_jj,  y_j = t_j - sum_i (L_ji/L_jj) y_i): 65 instead of 75 FP64 instructions per
-//               component at d = 10.  exp() is table-driven (2^(j/64) in shared memory + degree-5 polynomial, 11 FP64
-//               instructions instead of ~23 slots), log() likewise (128-entry reciprocal table, 10 instead of ~53), dead
-//               components are neutralised in the pack instead of by selects, and the kernel carries no draw code.  It
+//   k_weights3  (mvdens.c:784-825, 354-385, 319-349; pmc.c:537-592)  Same forward substitution as before (75 FP64
+//               instructions per component at d = 10, each with exactly one constant-bank operand: a second constant in
+//               one instruction costs a register load whose latency the scoreboard showed).  exp() is table-driven
+//               (2^(j/64) in shared memory + degree-5 polynomial, 11 FP64 instructions instead of ~23 slots), log() likewise
+//               (128-entry reciprocal table, 10 instead of ~53), dead components are neutralised in the pack instead of by
+//               selects, the kernel carries no draw code, the next tile's samples are loaded while the current one is
+//               computed, and the kernel parameters are __grid_constant__ (ptxas had copied them to local memory).  It
 //               also accumulates sum exp(lw - max) with per-lane online rescaling, so the normaliser is known when the
 //               kernel ends and no separate pass over the log-weights is needed.
 //   k_stats3    (pmc.c:641-697, 1041-1077, 1323-1469)  The DMMA statistics kernel now also writes the normalised weights and
@@ -27,14 +29,20 @@
 // is not finite is re-evaluated by a literal restatement of mix_mvdens_log_pdf, and an iteration whose maxima are
 // poisoned (NaN at sample 0, +inf log-weight, no usable sample) is flagged "not clean": k_stats3 then leaves the store
 // untouched and the host runs the literal normalise/update sequence of pmc_generic.cu instead.
+#include <type_traits>
 #include "pmc_kernels.h"
+
+// ---- constant-bank parameter blocks (C linkage: the whitening loads address them by symbol from inline PTX) ----------
+constexpr int I3_CW = 2048, I3_CT = 1024, I3_CD = 2048;
+extern "C" {
+__constant__ __align__(16) double pmcb200_c3_w[I3_CW];   // whitening pack of the proposal
+__constant__ __align__(16) double pmcb200_c3_t[I3_CT];   // whitening pack of a Gaussian / Gaussian-mixture target
+}
+#define c3_w pmcb200_c3_w
+#define c3_t pmcb200_c3_t
 
 namespace pmcb200 {
 
-// ---- constant-bank parameter blocks ---------------------------------------------------------------------------------
-constexpr int I3_CW = 2048, I3_CT = 1024, I3_CD = 2048;
-__constant__ double c3_w[I3_CW];   // whitening pack of the proposal
-__constant__ double c3_t[I3_CT];   // whitening pack of a Gaussian / Gaussian-mixture target
 __constant__ double c3_d[I3_CD];   // draw pack of the proposal
 __constant__ double c3_cw[64];     // cumulative weights (mvdens.c:748-750)
 __constant__ double c3_box[2 * FUSED_MAXD];  // slab box: (-lo_thr_j, hi_thr_j) pairs, +-inf when absent
@@ -42,9 +50,14 @@ __constant__ double c3_exptab[64];     // 2^(j/64)
 __constant__ double2 c3_logtab[128];   // (rc_j, -log rc_j), rc_j ~ 1/(1 + (j+0.5)/128)
 
 __host__ __device__ constexpr int i3_ev2(int n) { return (n + 1) & ~1; }
-// whitening pack, per component: (1/L_jj, -mu'_j/L_jj) pairs | -L_ij/L_ii column by column | c' = -0.5 d ln2pi - log detL | alpha
-__host__ __device__ constexpr int i3_wstride(int D) { return i3_ev2(2 * D + D * (D - 1) / 2 + 2); }
-__host__ __device__ constexpr int i3_woC(int D) { return 2 * D + D * (D - 1) / 2; }
+// whitening pack, per component: -mu_j | 1/L_jj | -L_ij column by column | c' = -0.5 d ln2pi - log detL | alpha
+// Every FP64 instruction of the solve takes exactly one of these as its constant-bank operand; entries that are consumed
+// together sit in the same 16-byte pair (one LDCU.128 fills two uniform-register pairs: a pair whose halves are needed far
+// apart costs two UMOVs to keep the second half alive).
+__host__ __device__ constexpr int i3_woR(int D) { return i3_ev2(D); }
+__host__ __device__ constexpr int i3_woL(int D) { return 2 * i3_ev2(D); }
+__host__ __device__ constexpr int i3_woC(int D) { return i3_woL(D) + D * (D - 1) / 2; }
+__host__ __device__ constexpr int i3_wstride(int D) { return i3_ev2(i3_woC(D) + 2); }
 // draw pack, per component: rows (mu_i, L_i0 .. L_ii)
 __host__ __device__ constexpr int i3_dstride(int D) { return i3_ev2(D + D * (D + 1) / 2); }
 
@@ -57,19 +70,18 @@ void iter3_pack_w(int K, int D, const double *wght, const double *mean, const do
   for (int k = 0; k < K; ++k) {
     double *o = out + (size_t)k * st;
     for (int i = 0; i < st; ++i) o[i] = 0.0;
-    if (!(wght[k] > 0.0)) {  // dead component: q = 0, log-density -1e300, weight 0 -> contributes exactly nothing
+    if (!(wght[k] > 0.0)) {  // dead component: finite q, log-density -1e300, weight 0 -> contributes exactly nothing
       o[i3_woC(D)] = -1.0e300;
       continue;
     }
     const double *Lk = L + (size_t)k * D * D;
     for (int j = 0; j < D; ++j) {
-      const double r = 1.0 / Lk[j * D + j];
-      o[2 * j] = r;
-      o[2 * j + 1] = -(mean[(size_t)k * D + j] - shift[j]) * r;
+      o[j] = -(mean[(size_t)k * D + j] - shift[j]);
+      o[i3_woR(D) + j] = 1.0 / Lk[j * D + j];
     }
-    int e = 2 * D;
+    int e = i3_woL(D);
     for (int j = 0; j < D; ++j)
-      for (int i = j + 1; i < D; ++i) o[e++] = -Lk[i * D + j] / Lk[i * D + i];
+      for (int i = j + 1; i < D; ++i) o[e++] = -Lk[i * D + j];
     o[i3_woC(D)] = -0.5 * (D * kLn2Pi) - logdet[k];
     o[i3_woC(D) + 1] = wght[k];
   }
@@ -88,7 +100,8 @@ void iter3_pack_d(int K, int D, const double *mean, const double *L, double *out
   }
 }
 
-// the largest |mu'_j / L_jj| of the live components: the pre-scaled solve loses ~eps times this in relative accuracy
+// the largest |mu'_j / L_jj| of the live components: subtracting the common shift first costs ~eps times this in
+// relative accuracy of the whitened coordinates
 double iter3_shift_ratio(int K, int D, const double *wght, const double *mean, const double *L, const double *shift) {
   double worst = 0.0;
   for (int k = 0; k < K; ++k) {
@@ -164,53 +177,86 @@ __device__ __forceinline__ double log_tab(double x, const double2 *tab) {
 }
 
 // ---- pre-scaled triangular solve: q = |L^-1 (x - mu)|^2, every parameter a constant-bank operand -----------------------
-template <int D, int SPL, bool TGT>
-__device__ __forceinline__ void whiten3(int base, const double (&xs)[SPL][D], double (&q)[SPL]) {
-  const double *cp = (TGT ? c3_t : c3_w) + base;
-  double t[SPL][D];
-#pragma unroll
-  for (int j = 0; j < D; ++j) {
-#pragma unroll
-    for (int s = 0; s < SPL; ++s) t[s][j] = fma(xs[s][j], cp[2 * j], cp[2 * j + 1]);
+// compile-time loop: f(std::integral_constant<int, i>) for i in [B, E)
+template <int B, int E, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
   }
-  int off = 2 * D;
+}
+
+// Two consecutive pack entries as ONE constant load (LDCU.128 into uniform registers).  The tile body that uses these lives
+// in a __noinline__ function (tile3) because both nvvm and ptxas treat constant loads as loop-invariant: inlined into the
+// persistent tile loop, hundreds of them were hoisted in front of the loop and spilled, so that the hot loop read its
+// parameters back from local memory (long-scoreboard stalls on 20 % of the warp samples, ncu r2_prof4).
+template <bool TGT, int OFF>
+__device__ __forceinline__ void ldc2(double &a, double &b) {
+  static_assert((OFF & 1) == 0, "pairs are 16-byte aligned");
+  if (TGT) asm volatile("ld.const.v2.f64 {%0, %1}, [pmcb200_c3_t + %2];" : "=d"(a), "=d"(b) : "n"(OFF * 8));
+  else asm volatile("ld.const.v2.f64 {%0, %1}, [pmcb200_c3_w + %2];" : "=d"(a), "=d"(b) : "n"(OFF * 8));
+}
+
+// one component: q = |L^-1 (x - mu)|^2 by forward substitution, lv = -q/2 + c'; al = alpha.  Every FP64 instruction has
+// exactly one pack entry as operand (ptxas keeps them in uniform registers: DFMA R, R, UR, R)
+template <int D, int SPL, bool TGT, int BASE>
+__device__ __forceinline__ void comp3(const double (&x)[SPL][D], double (&lv)[SPL], double &al) {
+  constexpr int ST = i3_wstride(D);
+  double c[ST];
+  static_for<0, ST / 2>([&](auto pc) {
+    constexpr int p = decltype(pc)::value;
+    ldc2<TGT, BASE + 2 * p>(c[2 * p], c[2 * p + 1]);
+  });
+  double v[SPL][D], q[SPL];
 #pragma unroll
   for (int j = 0; j < D; ++j) {
 #pragma unroll
-    for (int s = 0; s < SPL; ++s) q[s] = (j == 0) ? t[s][0] * t[s][0] : fma(t[s][j], t[s][j], q[s]);
+    for (int s = 0; s < SPL; ++s) v[s][j] = x[s][j] + c[j];
+  }
+  int off = i3_woL(D);
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double y[SPL];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+      y[s] = v[s][j] * c[i3_woR(D) + j];
+      q[s] = (j == 0) ? y[s] * y[s] : fma(y[s], y[s], q[s]);
+    }
 #pragma unroll
     for (int i = j + 1; i < D; ++i) {
 #pragma unroll
-      for (int s = 0; s < SPL; ++s) t[s][i] = fma(cp[off + (i - j - 1)], t[s][j], t[s][i]);
+      for (int s = 0; s < SPL; ++s) v[s][i] = fma(c[off + (i - j - 1)], y[s], v[s][i]);
     }
     off += D - 1 - j;
   }
+#pragma unroll
+  for (int s = 0; s < SPL; ++s) lv[s] = fma(-0.5, q[s], c[i3_woC(D)]);
+  al = c[i3_woC(D) + 1];
 }
 
 // mix_mvdens_log_pdf (mvdens.c:784-825) of KK Gaussian components packed at c3_w / c3_t: e[k] = alpha_k exp(ld_k - max + 500),
 // lpos = sum_k e[k] in component order, returns (max + log lpos) - 500
 template <int D, int KK, int SPL, bool TGT>
-__device__ __forceinline__ void mix_fast(const double (&xs)[SPL][D], const double *s_exp, const double2 *s_log,
-                                         double (&e)[SPL][KK], double (&lpos)[SPL], double (&out)[SPL]) {
+__device__ __forceinline__ void mix_fast(const double (&xs)[SPL][D], const double *s_exp,
+                                         const double2 *s_log, double (&e)[SPL][KK], double (&lpos)[SPL], double (&out)[SPL]) {
   constexpr int ST = i3_wstride(D);
-  const double *cp = TGT ? c3_t : c3_w;
-  double mx[SPL];
-#pragma unroll
-  for (int k = 0; k < KK; ++k) {
-    double q[SPL];
-    whiten3<D, SPL, TGT>(k * ST, xs, q);
+  double mx[SPL], al[KK];
+  static_for<0, KK>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    double lv[SPL];
+    comp3<D, SPL, TGT, k * ST>(xs, lv, al[k]);
 #pragma unroll
     for (int s = 0; s < SPL; ++s) {
-      e[s][k] = fma(-0.5, q[s], cp[k * ST + i3_woC(D)]);
-      mx[s] = (k == 0) ? e[s][0] : ((mx[s] < e[s][k]) ? e[s][k] : mx[s]);
+      e[s][k] = lv[s];
+      mx[s] = (k == 0) ? lv[s] : ((mx[s] < lv[s]) ? lv[s] : mx[s]);
     }
-  }
+  });
 #pragma unroll
   for (int s = 0; s < SPL; ++s) {
     lpos[s] = 0.0;
 #pragma unroll
     for (int k = 0; k < KK; ++k) {
-      e[s][k] = exp_tab((e[s][k] - mx[s]) + kDynMax, s_exp) * cp[k * ST + i3_woC(D) + 1];
+      e[s][k] = exp_tab((e[s][k] - mx[s]) + kDynMax, s_exp) * al[k];
       lpos[s] = lpos[s] + e[s][k];
     }
     out[s] = (mx[s] + log_tab(lpos[s], s_log)) - kDynMax;
@@ -262,7 +308,6 @@ struct W3Args {
   double b, sig1, t_temper;
   const double *post_in;
   const short *ok_in;
-  double shift[FUSED_MAXD];
   double *lw, *log_rho, *resp;
   short *flg;
   double *partials;  // [grid][4]: max log-weight over usable samples, sum exp(lw - max), max log_rho, spare
@@ -270,11 +315,110 @@ struct W3Args {
   double *first_vals;
   MixDev mix, tmix;  // reference layout, for the literal re-evaluation of non-finite samples
 };
+__constant__ W3Args c3_wargs;  // the launch's arguments: read at compile-time offsets from every function of the kernel
+
+struct TileAcc {  // per-lane running values of the kernel, updated by tile3 through local memory
+  double m, S, r;
+  unsigned int nok, posinf;
+};
+
+// One tile of 32*SPL samples: target, proposal density, log-weight, flags, responsibilities (pmc.c:537-592).
+template <int D, int K, int KT, int SPL, bool RESP>
+static __device__ __noinline__ void tile3(long tile, int lane, const double *s_exp, const double2 *s_log, TileAcc *acc) {
+  const W3Args &a = c3_wargs;
+  constexpr int TS = 32 * SPL;
+  const long tbase = tile * TS;
+  double x[SPL][D];
+  bool valid[SPL];
+#pragma unroll
+  for (int s = 0; s < SPL; ++s) {
+    const long i = tbase + s * 32 + lane;
+    valid[s] = i < a.N;
+    const long il = valid[s] ? i : a.N - 1;
+    if ((D & 1) == 0) {
+      const double2 *xi = reinterpret_cast<const double2 *>(a.X + (size_t)il * D);
+#pragma unroll
+      for (int j = 0; j < D; j += 2) { const double2 t2 = xi[j / 2]; x[s][j] = t2.x; x[s][j + 1] = t2.y; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < D; ++j) x[s][j] = a.X[(size_t)il * D + j];
+    }
+  }
+
+  // ---- target ----------------------------------------------------------------------------------------------------
+  double post[SPL];
+  bool tok[SPL];
+#pragma unroll
+  for (int s = 0; s < SPL; ++s) { post[s] = 0.0; tok[s] = true; }
+  if (a.tgt_kind == PMCGPU_TGT_BANANA) {
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) post[s] = bent_gauss(RegVec3<D>{x[s]}, D, a.b, a.sig1);
+  } else if (KT > 0 && a.tgt_kind == PMCGPU_TGT_MVDENS) {
+    double talpha;
+    comp3<D, SPL, true, 0>(x, post, talpha);
+  } else if (KT > 0 && a.tgt_kind == PMCGPU_TGT_MIX) {
+    double te[SPL][KT > 0 ? KT : 1], tl[SPL];
+    mix_fast<D, (KT > 0 ? KT : 1), SPL, true>(x, s_exp, s_log, te, tl, post);
+#pragma unroll
+    for (int s = 0; s < SPL; ++s)
+      if (!(fabs(post[s]) < INFINITY)) post[s] = mix_log_pdf_literal(a.tmix, a.X + (size_t)(valid[s] ? tbase + s * 32 + lane : a.N - 1) * D);
+  } else if (a.tgt_kind == PMCGPU_TGT_HOST) {
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+      const long i = tbase + s * 32 + lane;
+      if (i < a.N) { post[s] = a.post_in[i]; tok[s] = a.ok_in ? (a.ok_in[i] != 0) : true; }
+    }
+  }
+
+  // ---- proposal log-density ------------------------------------------------------------------------------------------
+  double e[SPL][K], lpos[SPL], rloc[SPL];
+  mix_fast<D, K, SPL, false>(x, s_exp, s_log, e, lpos, rloc);
+
+  // ---- log-weight, flags, maxima (pmc.c:546-583) ---------------------------------------------------------------------
+  double m_lane = acc->m, S_lane = acc->S, r_lane = acc->r;
+  unsigned int nok_lane = acc->nok, posinf_lane = acc->posinf;
+#pragma unroll
+  for (int s = 0; s < SPL; ++s) {
+    const long i = tbase + s * 32 + lane;
+    bool fastok = fabs(rloc[s]) < INFINITY;
+    if (!fastok) rloc[s] = mix_log_pdf_literal(a.mix, a.X + (size_t)(valid[s] ? i : a.N - 1) * D);  // non-finite: the reference's own operation sequence decides
+    const bool rfin = !(isnan(rloc[s]) || isinf(rloc[s]));
+    const bool reached = valid[s] && rfin && tok[s];
+    const double lw = reached ? (a.t_temper * post[s] - rloc[s]) : 0.0;
+    if (valid[s]) {
+      a.log_rho[i] = rloc[s];
+      a.lw[i] = lw;
+      a.flg[i] = reached ? 1 : 0;
+      if (a.first_index + i == 0) {
+        a.first_vals[0] = rloc[s]; a.first_vals[1] = 1.0; a.first_vals[2] = lw; a.first_vals[3] = reached ? 1.0 : 0.0;
+      }
+      if (rloc[s] > r_lane) r_lane = rloc[s];
+    }
+    const bool wfin = reached && !isnan(lw) && !(lw == INFINITY);
+    if (reached && lw == INFINITY) ++posinf_lane;
+    if (wfin) {
+      ++nok_lane;
+      if (lw > -INFINITY) {  // online sum of exp(lw - running max): one exp per sample
+        const double dlt = lw - m_lane;
+        const double ex = exp_tab(-fabs(dlt), s_exp);
+        if (dlt > 0.0) { S_lane = fma(S_lane, ex, 1.0); m_lane = lw; }
+        else S_lane += ex;
+      }
+    }
+    if (RESP && valid[s]) {  // responsibilities alpha_k phi_k(x)/q(x), component-major: coalesced 256-byte rows
+      const double rs = fastok ? 1.0 / lpos[s] : 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) a.resp[(size_t)k * a.N + i] = e[s][k] * rs;
+    }
+  }
+  acc->m = m_lane; acc->S = S_lane; acc->r = r_lane; acc->nok = nok_lane; acc->posinf = posinf_lane;
+}
 
 template <int D, int K, int KT, int SPL, bool RESP, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_weights3(const W3Args a) {
+__global__ void __launch_bounds__(128, MINB) k_weights3() {
   constexpr int ST = i3_wstride(D);
   static_assert(K * ST <= I3_CW && KT * ST <= I3_CT, "constant memory budget");
+  const W3Args &a = c3_wargs;
   __shared__ double s_exp[64];
   __shared__ double2 s_log[128];
   __shared__ double s_m[4], s_S[4], s_r[4];
@@ -284,97 +428,21 @@ __global__ void __launch_bounds__(128, MINB) k_weights3(const W3Args a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int TS = 32 * SPL;
   const long ntiles = (a.N + TS - 1) / TS;
-  double m_lane = -INFINITY, S_lane = 0.0, r_lane = -INFINITY;
-  unsigned int nok_lane = 0, posinf_lane = 0;
-
-  for (long tile = (long)blockIdx.x * 4 + wid; tile < ntiles; tile += (long)gridDim.x * 4) {
-    const long tbase = tile * TS;
-    double x[SPL][D], xs[SPL][D];
-    bool valid[SPL];
-#pragma unroll
-    for (int s = 0; s < SPL; ++s) {
-      const long i = tbase + s * 32 + lane;
-      valid[s] = i < a.N;
-      const long il = valid[s] ? i : a.N - 1;
-      if ((D & 1) == 0) {
-        const double2 *xi = reinterpret_cast<const double2 *>(a.X + (size_t)il * D);
-#pragma unroll
-        for (int j = 0; j < D; j += 2) { const double2 t = xi[j / 2]; x[s][j] = t.x; x[s][j + 1] = t.y; }
-      } else {
-#pragma unroll
-        for (int j = 0; j < D; ++j) x[s][j] = a.X[(size_t)il * D + j];
-      }
-#pragma unroll
-      for (int j = 0; j < D; ++j) xs[s][j] = x[s][j] - a.shift[j];
-    }
-
-    // ---- target --------------------------------------------------------------------------------------------------
-    double post[SPL];
-    bool tok[SPL];
-#pragma unroll
-    for (int s = 0; s < SPL; ++s) { post[s] = 0.0; tok[s] = true; }
-    if (a.tgt_kind == PMCGPU_TGT_BANANA) {
-#pragma unroll
-      for (int s = 0; s < SPL; ++s) post[s] = bent_gauss(RegVec3<D>{x[s]}, D, a.b, a.sig1);
-    } else if (KT > 0 && a.tgt_kind == PMCGPU_TGT_MVDENS) {
-      double q[SPL];
-      whiten3<D, SPL, true>(0, xs, q);
-#pragma unroll
-      for (int s = 0; s < SPL; ++s) post[s] = fma(-0.5, q[s], c3_t[i3_woC(D)]);
-    } else if (KT > 0 && a.tgt_kind == PMCGPU_TGT_MIX) {
-      double te[SPL][KT > 0 ? KT : 1], tl[SPL];
-      mix_fast<D, (KT > 0 ? KT : 1), SPL, true>(xs, s_exp, s_log, te, tl, post);
-#pragma unroll
-      for (int s = 0; s < SPL; ++s)
-        if (!(fabs(post[s]) < INFINITY)) post[s] = mix_log_pdf_literal(a.tmix, a.X + (size_t)(valid[s] ? tbase + s * 32 + lane : a.N - 1) * D);
-    } else if (a.tgt_kind == PMCGPU_TGT_HOST) {
+  TileAcc acc{-INFINITY, 0.0, -INFINITY, 0u, 0u};
+  const long tstep = (long)gridDim.x * 4;
+  for (long tile = (long)blockIdx.x * 4 + wid; tile < ntiles; tile += tstep) {
+    if (tile + tstep < ntiles) {  // the next tile's rows into L1/L2 while this one is computed: 80-byte rows, two lines at most each
+      const char *nx = reinterpret_cast<const char *>(a.X + (size_t)((tile + tstep) * TS + lane) * D);
 #pragma unroll
       for (int s = 0; s < SPL; ++s) {
-        const long i = tbase + s * 32 + lane;
-        if (i < a.N) { post[s] = a.post_in[i]; tok[s] = a.ok_in ? (a.ok_in[i] != 0) : true; }
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + (size_t)s * 32 * D * 8));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + (size_t)s * 32 * D * 8 + D * 8 - 8));
       }
     }
-
-    // ---- proposal log-density ----------------------------------------------------------------------------------------
-    double e[SPL][K], lpos[SPL], rloc[SPL];
-    mix_fast<D, K, SPL, false>(xs, s_exp, s_log, e, lpos, rloc);
-
-    // ---- log-weight, flags, maxima (pmc.c:546-583) -------------------------------------------------------------------
-#pragma unroll
-    for (int s = 0; s < SPL; ++s) {
-      const long i = tbase + s * 32 + lane;
-      bool fastok = fabs(rloc[s]) < INFINITY;
-      if (!fastok) rloc[s] = mix_log_pdf_literal(a.mix, a.X + (size_t)(valid[s] ? i : a.N - 1) * D);  // non-finite: the reference's own operation sequence decides
-      const bool rfin = !(isnan(rloc[s]) || isinf(rloc[s]));
-      const bool reached = valid[s] && rfin && tok[s];
-      const double lw = reached ? (a.t_temper * post[s] - rloc[s]) : 0.0;
-      if (valid[s]) {
-        a.log_rho[i] = rloc[s];
-        a.lw[i] = lw;
-        a.flg[i] = reached ? 1 : 0;
-        if (a.first_index + i == 0) {
-          a.first_vals[0] = rloc[s]; a.first_vals[1] = 1.0; a.first_vals[2] = lw; a.first_vals[3] = reached ? 1.0 : 0.0;
-        }
-        if (rloc[s] > r_lane) r_lane = rloc[s];
-      }
-      const bool wfin = reached && !isnan(lw) && !(lw == INFINITY);
-      if (reached && lw == INFINITY) ++posinf_lane;
-      if (wfin) {
-        ++nok_lane;
-        if (lw > -INFINITY) {  // online sum of exp(lw - running max): one exp per sample
-          const double dlt = lw - m_lane;
-          const double ex = exp_tab(-fabs(dlt), s_exp);
-          if (dlt > 0.0) { S_lane = fma(S_lane, ex, 1.0); m_lane = lw; }
-          else S_lane += ex;
-        }
-      }
-      if (RESP && valid[s]) {  // responsibilities alpha_k phi_k(x)/q(x), component-major: coalesced 256-byte rows
-        const double rs = fastok ? 1.0 / lpos[s] : 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) a.resp[(size_t)k * a.N + i] = e[s][k] * rs;
-      }
-    }
+    tile3<D, K, KT, SPL, RESP>(tile, lane, s_exp, s_log, &acc);
   }
+  const double m_lane = acc.m, S_lane = acc.S, r_lane = acc.r;
+  const unsigned int nok_lane = acc.nok, posinf_lane = acc.posinf;
 
   // ---- block partial: (max, sum relative to it, max log_rho), combined in lane/warp order -> deterministic ------------
   double mw = warp_max_nan_ignoring(m_lane);
@@ -532,7 +600,7 @@ __device__ __forceinline__ double norm_sample(double lwv, short f, double maxW, 
 }
 
 template <int D, int K, bool STATS>
-__global__ void __launch_bounds__(256, 2) k_stats3(const S3Args a) {
+__global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Args a) {
   using C = S3Cfg<D, K>;
   constexpr int NT = C::NT, MT = C::MT, GS = C::GS, XS = C::XS;
   constexpr int WARPS = 8;
@@ -773,25 +841,29 @@ __device__ __forceinline__ void apply_L3(int k, const double (&g)[D + 1], double
       int e = kk * DS;
 #pragma unroll
       for (int i2 = 0; i2 < D; ++i2) {
-        double t = c3_d[e++];
+        const int em = e++;
+        double t = g[0] * c3_d[e++];  // one constant-bank operand per instruction (a second one costs a register load)
 #pragma unroll
-        for (int j2 = 0; j2 <= i2; ++j2) t = fma(g[j2], c3_d[e++], t);
-        x[i2] = t;
+        for (int j2 = 1; j2 <= i2; ++j2) t = fma(g[j2], c3_d[e++], t);
+        x[i2] = t + c3_d[em];
       }
     }
   }
 }
 
 template <int D, int K>
-__global__ void __launch_bounds__(256, 2) k_draw3(const D3Args a) {
+__global__ void __launch_bounds__(256, 2) k_draw3(const __grid_constant__ D3Args a) {
   constexpr int DS = i3_dstride(D);
   static_assert(K * DS <= I3_CD && K <= 64, "constant memory budget");
   extern __shared__ __align__(16) unsigned char sm3[];
   double2 *zts = reinterpret_cast<double2 *>(sm3);
   unsigned int *tmp = reinterpret_cast<unsigned int *>(zts + kZigLayers);
   unsigned short *perm = reinterpret_cast<unsigned short *>(tmp + a.chunk);
-  __shared__ unsigned int s_hist[64], s_base[65];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  __shared__ unsigned int s_hist[64], s_base[65], s_tile[65];
+  __shared__ int s_next;
+  int tid;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));  // read once: ptxas otherwise re-reads the special register in the loop
+  const int lane = tid & 31;
   for (int i = tid; i < kZigLayers; i += blockDim.x) zts[i] = a.zig[i];
   const Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
   unsigned int rej_lane = 0, fail_lane = 0;
@@ -800,6 +872,7 @@ __global__ void __launch_bounds__(256, 2) k_draw3(const D3Args a) {
     const long cbase = c * a.chunk;
     const int cn = (a.N - cbase) < a.chunk ? (int)(a.N - cbase) : a.chunk;
     if (tid < 64) s_hist[tid] = 0;
+    if (tid == 64) s_next = 0;
     __syncthreads();
     // ---- component of the first attempt of every sample of the chunk (mvdens.c:775-776), rank inside its bucket --------
     for (int o = tid; o < cn; o += blockDim.x) {
@@ -814,9 +887,10 @@ __global__ void __launch_bounds__(256, 2) k_draw3(const D3Args a) {
     }
     __syncthreads();
     if (tid == 0) {
-      unsigned int acc = 0;
-      for (int k = 0; k < K; ++k) { s_base[k] = acc; acc += s_hist[k]; }
+      unsigned int acc = 0, tacc = 0;
+      for (int k = 0; k < K; ++k) { s_base[k] = acc; acc += s_hist[k]; s_tile[k] = tacc; tacc += (s_hist[k] + 31) >> 5; }
       s_base[K] = acc;
+      s_tile[K] = tacc;
     }
     __syncthreads();
     for (int o = tid; o < cn; o += blockDim.x) {
@@ -824,11 +898,20 @@ __global__ void __launch_bounds__(256, 2) k_draw3(const D3Args a) {
       perm[s_base[v >> 16] + (v & 0xffffu)] = (unsigned short)o;
     }
     __syncthreads();
-    // ---- one component per warp tile: x = mu_k + L_k g with warp-uniform constant-bank operands ------------------------
-    for (int k = 0; k < K; ++k) {
+    // ---- one component per warp tile: x = mu_k + L_k g with warp-uniform constant-bank operands.  Tiles are handed out
+    // by a shared counter, so the warps of the block stay busy until the chunk is finished.
+    const int ntile = (int)s_tile[K];
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&s_next, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= ntile) break;
+      int k = 0;
+#pragma unroll
+      for (int kk = 1; kk < K; ++kk) k += ((int)s_tile[kk] <= t) ? 1 : 0;
       const int nk = (int)s_hist[k], b = (int)s_base[k];
-      for (int t0 = wid * 32; t0 < nk; t0 += (int)(blockDim.x >> 5) * 32) {
-        const int j = t0 + lane;
+      {
+        const int j = (t - (int)s_tile[k]) * 32 + lane;
         const bool active = j < nk;
         const int o = (int)perm[b + (active ? j : 0)];
         const long i = cbase + o;
@@ -915,17 +998,18 @@ static int launch_w3(const Iter3Plan &p, const W3Args &a, int variant, bool resp
   if ((long)grid * 4 > ntiles) grid = (int)((ntiles + 3) / 4);
   if (grid < 1) grid = 1;
   *nblocks = grid;
+  if (cudaMemcpyToSymbolAsync(c3_wargs, &a, sizeof a, 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
   if (variant == 0) {
-    if (resp) k_weights3<D, K, KT, 1, true, 4><<<grid, 128, 0, s>>>(a);
-    else k_weights3<D, K, KT, 1, false, 4><<<grid, 128, 0, s>>>(a);
+    if (resp) k_weights3<D, K, KT, 1, true, 4><<<grid, 128, 0, s>>>();
+    else k_weights3<D, K, KT, 1, false, 4><<<grid, 128, 0, s>>>();
   }
   if constexpr (kHead) {
     if (variant == 1) {
-      if (resp) k_weights3<D, K, KT, 1, true, 3><<<grid, 128, 0, s>>>(a);
-      else k_weights3<D, K, KT, 1, false, 3><<<grid, 128, 0, s>>>(a);
+      if (resp) k_weights3<D, K, KT, 1, true, 3><<<grid, 128, 0, s>>>();
+      else k_weights3<D, K, KT, 1, false, 3><<<grid, 128, 0, s>>>();
     } else if (variant == 2) {
-      if (resp) k_weights3<D, K, KT, 2, true, 2><<<grid, 128, 0, s>>>(a);
-      else k_weights3<D, K, KT, 2, false, 2><<<grid, 128, 0, s>>>(a);
+      if (resp) k_weights3<D, K, KT, 2, true, 2><<<grid, 128, 0, s>>>();
+      else k_weights3<D, K, KT, 2, false, 2><<<grid, 128, 0, s>>>();
     }
   }
   count_launch();
@@ -947,7 +1031,6 @@ int launch_weights3(const Iter3Plan &p, const Iter3Weights &w, int *nblocks, cud
   W3Args a{};
   a.X = w.X; a.N = w.N; a.first_index = w.first_index; a.tgt_kind = w.tgt_kind; a.b = w.b; a.sig1 = w.sig1; a.t_temper = w.t_temper;
   a.post_in = w.post_in; a.ok_in = w.ok_in;
-  for (int j = 0; j < FUSED_MAXD; ++j) a.shift[j] = w.shift[j];
   a.lw = w.lw; a.log_rho = w.log_rho; a.resp = w.resp; a.flg = w.flg; a.partials = w.partials; a.counters = w.counters;
   a.first_vals = w.first_vals; a.mix = w.mix; a.tmix = w.tmix;
   const bool resp = w.resp != nullptr;
