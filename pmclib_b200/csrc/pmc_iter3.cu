@@ -567,13 +567,33 @@ struct S3Args {
   int partial_len;
 };
 
+// Tiling of the statistics product C[k][e] += g[i][k] P[i][e] with DMMA.8x8x4 (M = components, N = features, K = samples).
+// Full 8-component row tiles cost NT DMMAs per 4 samples.  A remainder of R = K mod 8 components would pad to a whole
+// row tile (K = 10: 37 % of the tensor work was padding, ncu r01).  For R = 1 or 2 the remainder instead uses the product
+// structure of the features: with the augmented row z = (1, x~_1 .. x~_D), P[(a,b)] = z_a z_b, so
+//     D[m = b][n = (r, a)] += sum_i z_i[b] * (g_i[r] z_i[a])
+// gives W, s and S of the remaining components from blocks (a-group of AG = 8/R, b-group of 8); by symmetry only blocks
+// that contain an entry with a >= b are issued (d = 10, K = 10: 4 DMMAs instead of 9 -> 13 instead of 18 per 4 samples).
 template <int D, int K>
 struct S3Cfg {
   static constexpr int E = 1 + D + D * (D + 1) / 2;
-  static constexpr int NT = (E + 7) / 8, MT = (K + 7) / 8;
-  static constexpr int XS = (D + 1) | 1;
-  static constexpr int GS = (MT * 8) | 1;
-  static constexpr int ACC = MT * NT * 64;
+  static constexpr int NT = (E + 7) / 8;
+  static constexpr int R = K % 8;
+  static constexpr bool XT = (R == 1 || R == 2) && K > 8;
+  static constexpr int MT = XT ? K / 8 : (K + 7) / 8;  // full row tiles
+  static constexpr int AG = XT ? 8 / R : 8;
+  static constexpr int NGA = (D + AG) / AG, NGB = (D + 8) / 8;  // ceil((D+1)/AG), ceil((D+1)/8)
+  __host__ __device__ static constexpr bool xinc(int ga, int gb) { return AG * (ga + 1) - 1 >= 8 * gb; }
+  static constexpr int xcount() {
+    int n = 0;
+    for (int ga = 0; ga < NGA; ++ga)
+      for (int gb = 0; gb < NGB; ++gb) n += xinc(ga, gb) ? 1 : 0;
+    return n;
+  }
+  static constexpr int NX = XT ? xcount() : 0;
+  static constexpr int XS = (D + 2) | 1;  // augmented row: 1, x~_1 .. x~_D, 0 (the zero slot pads a- and b-groups)
+  static constexpr int GS = (((K + 7) / 8) * 8) | 1;
+  static constexpr int ACC = (MT * NT + NX) * 64;
   static constexpr int STAGE = 32 * D + 32 * K + 32 + 32 + 8;  // X rows | resp (k-major) | lw | indices | flg (32 shorts)
   static constexpr int WARP_DOUBLES = 32 * XS + 32 * GS + STAGE;
   static constexpr int PLEN = ACC + 4 + 64;
@@ -643,6 +663,17 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
   for (int m = 0; m < (STATS ? MT : 1); ++m)
 #pragma unroll
     for (int n = 0; n < (STATS ? NT : 1); ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+  // remainder components (C::XT): product tiles, see S3Cfg
+  constexpr int NXA = (STATS && C::XT) ? C::NX : 1;
+  double accx[NXA][2];
+#pragma unroll
+  for (int b = 0; b < NXA; ++b) accx[b][0] = accx[b][1] = 0.0;
+  int xao[C::NGA], xbo[C::NGB];
+#pragma unroll
+  for (int g = 0; g < C::NGA; ++g) { const int ai = C::AG * g + (fr % C::AG); xao[g] = ai <= D ? ai : D + 1; }
+#pragma unroll
+  for (int g = 0; g < C::NGB; ++g) { const int bi = 8 * g + fr; xbo[g] = bi <= D ? bi : D + 1; }
+  const int gxo = 8 * MT + fr / C::AG;
   double H = 0.0, Q = 0.0;
   unsigned int nok = 0, nflag = 0;
   const long ntiles = (a.N + 31) / 32;
@@ -716,6 +747,20 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
 #pragma unroll
             for (int m = 0; m < MT; ++m) dmma884_3(acc[m][n][0], acc[m][n][1], af[m], bf);
           }
+          if constexpr (C::XT) {
+            const double gx = gt[smp * GS + gxo];
+            double a2[C::NGB];
+#pragma unroll
+            for (int gb = 0; gb < C::NGB; ++gb) a2[gb] = xs[xbo[gb]];
+            int xb = 0;
+#pragma unroll
+            for (int ga = 0; ga < C::NGA; ++ga) {
+              const double b2 = gx * xs[xao[ga]];
+#pragma unroll
+              for (int gb = 0; gb < C::NGB; ++gb)
+                if (C::xinc(ga, gb)) { dmma884_3(accx[xb][0], accx[xb][1], a2[gb], b2); ++xb; }
+            }
+          }
         }
     }
     __syncwarp();
@@ -742,6 +787,15 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
               const int idx = ((m * NT + n) * 32 + lane) * 2 + c;
               comb[idx] = (w2 == 0 ? 0.0 : comb[idx]) + acc[m][n][c];
             }
+        if constexpr (C::XT) {
+#pragma unroll
+          for (int b = 0; b < C::NX; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int idx = ((MT * NT + b) * 32 + lane) * 2 + c;
+              comb[idx] = (w2 == 0 ? 0.0 : comb[idx]) + accx[b][c];
+            }
+        }
       }
     }
     __syncthreads();
@@ -761,8 +815,9 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
 }
 
 // canonical statistics from the block partials, in block order: out = stats[K*E] | H, Q, ok, flagged-out | count_k[K]
+// Components below 8*MT sit in the (component, feature) row tiles; the others (ag > 0) in the product tiles of S3Cfg.
 __global__ void k_comb3(const double *__restrict__ partials, int nblocks, int partial_len, int acc_len, int K, int E, int NT,
-                        int with_stats, const double *__restrict__ scal, double *__restrict__ out) {
+                        int MT, int D, int ag, int with_stats, const double *__restrict__ scal, double *__restrict__ out) {
   const int nstat = with_stats ? K * E : 0;
   const int total = nstat + 4 + K;
   const bool clean = scal[I3_CLEAN] != 0.0;
@@ -770,8 +825,24 @@ __global__ void k_comb3(const double *__restrict__ partials, int nblocks, int pa
     int idx;
     if (t < nstat) {
       const int k = t / E, e = t - k * E;
-      const int m = k >> 3, r = k & 7, n = e >> 3, cc = e & 7;
-      idx = ((m * NT + n) * 32 + (r * 4 + (cc >> 1))) * 2 + (cc & 1);
+      if (ag == 0 || k < 8 * MT) {
+        const int m = k >> 3, r = k & 7, n = e >> 3, cc = e & 7;
+        idx = ((m * NT + n) * 32 + (r * 4 + (cc >> 1))) * 2 + (cc & 1);
+      } else {
+        int a = e, b = 0;  // feature e = z_a z_b with a >= b (z_0 = 1)
+        if (e > D) {
+          int q = e - 1 - D, r = 0;
+          while (q >= D - r) { q -= D - r; ++r; }
+          b = 1 + r;
+          a = 1 + r + q;
+        }
+        const int ga = a / ag, gb = b >> 3, ngb = (D + 8) / 8;
+        int xb = 0;  // issued blocks before (ga, gb): a-groups outer, b-groups inner, block issued iff ag*(ga+1)-1 >= 8*gb
+        for (int g1 = 0; g1 <= ga; ++g1)
+          for (int g2 = 0; g2 < (g1 < ga ? ngb : gb); ++g2) xb += (ag * (g1 + 1) - 1 >= 8 * g2) ? 1 : 0;
+        const int row = b & 7, col = (k - 8 * MT) * ag + a % ag;
+        idx = ((MT * NT + xb) * 32 + (row * 4 + (col >> 1))) * 2 + (col & 1);
+      }
     } else {
       idx = acc_len + (t - nstat);
     }
@@ -978,7 +1049,8 @@ Iter3Plan iter3_plan(int d, int K, int Kt, int tgt_kind, int sm_count) {
   if (d == D_ && K <= K_ && (kt_needed == 0 || (KT_ > 0 && kt_needed <= KT_)) && (!best.valid || K_ < best.K)) { \
     using C = S3Cfg<D_, K_>;                                                                                     \
     best.valid = 1; best.D = D_; best.K = K_; best.KT = KT_; best.sm_count = sm_count;                           \
-    best.E = C::E; best.NT = C::NT; best.acc_len = C::ACC; best.partial_len = C::PLEN;                           \
+    best.E = C::E; best.NT = C::NT; best.MT = C::MT; best.AG = C::XT ? C::AG : 0;                                \
+    best.acc_len = C::ACC; best.partial_len = C::PLEN;                                                          \
     best.stats_blocks = sm_count * 2; best.weights_blocks = sm_count * 4; /* upper bound over the variants */                                        \
   }
   PMC_ITER3_TABLE(X)
@@ -1079,7 +1151,7 @@ int launch_stats3(const Iter3Plan &p, const Iter3Stats &st, cudaStream_t s) {
 
 int launch_comb3(const Iter3Plan &p, const double *partials, int with_stats, const double *scal, double *out, cudaStream_t s) {
   const int total = (with_stats ? p.K * p.E : 0) + 4 + p.K;
-  k_comb3<<<(total + 63) / 64, 64, 0, s>>>(partials, p.stats_blocks, p.partial_len, p.acc_len, p.K, p.E, p.NT, with_stats, scal, out);
+  k_comb3<<<(total + 63) / 64, 64, 0, s>>>(partials, p.stats_blocks, p.partial_len, p.acc_len, p.K, p.E, p.NT, p.MT, p.D, p.AG, with_stats, scal, out);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
