@@ -33,7 +33,7 @@ typedef struct pmcgpu_ctx pmcgpu_ctx;
 #define PMCGPU_ERR_USAGE (-6023)   /* pmc_base - 23: bad argument / call order */
 #define PMCGPU_ERR_NODEVICE (-6024)
 
-enum { PMCGPU_TGT_NONE = 0, PMCGPU_TGT_BANANA = 1, PMCGPU_TGT_MVDENS = 2, PMCGPU_TGT_MIX = 3, PMCGPU_TGT_HOST = 4 };
+enum { PMCGPU_TGT_NONE = 0, PMCGPU_TGT_BANANA = 1, PMCGPU_TGT_MVDENS = 2, PMCGPU_TGT_MIX = 3, PMCGPU_TGT_HOST = 4, PMCGPU_TGT_COMBINE = 5 };
 
 /* ---- life cycle ------------------------------------------------------------------------------- */
 int pmcgpu_create(int device, pmcgpu_ctx **out);
@@ -79,6 +79,19 @@ int pmcgpu_set_target_mix(pmcgpu_ctx *ctx, int kind, int K, int d, const double 
 int pmcgpu_set_target_defaults(pmcgpu_ctx *ctx, int nfull, const int *is_def, const double *value);
 /* opaque host callback: the caller evaluates the target on the host and passes post[N] to pmcgpu_weights_host_post */
 int pmcgpu_set_target_host(pmcgpu_ctx *ctx, int d);
+/* combined target, replaces combine_lkl (pmclib/src/distribution.c:350-396) and the Gaussian priors built on it
+ * (add_gaussian_prior*, distribution.c:548-606): the target is the SUM of nterms log-densities; term t is a density of
+ * kind PMCGPU_TGT_BANANA (b, sig1), _MVDENS (K = 1) or _MIX evaluated on the ndim coordinates dim_idx[0..ndim) of the
+ * d-dimensional sample.  Arrays as in pmcgpu_set_target_mix.  Evaluated on the device, term by term in the given order. */
+typedef struct {
+  int kind, ndim;
+  const int *dim_idx;
+  double b, sig1;
+  int K;
+  const double *wght, *mean, *L, *detL;
+  const int *df;
+} pmcgpu_combine_term;
+int pmcgpu_set_target_combine(pmcgpu_ctx *ctx, int d, int nterms, const pmcgpu_combine_term *terms);
 /* parabox (parabox.h:22-26): faces[nfaces*(d+1)]; nfaces = 0 removes the box */
 int pmcgpu_set_box(pmcgpu_ctx *ctx, int d, int nfaces, const double *faces);
 
@@ -191,6 +204,13 @@ int pmcgpu_pmc_step(pmcgpu_ctx *ctx, uint64_t seed, uint32_t iter, long first_in
 int pmcgpu_step_given(pmcgpu_ctx *ctx, long first_index, long N_total, double t_temper, int do_update, int *retry,
                       pmcgpu_step_result *res, double *o_wght, double *o_mean, double *o_L, double *o_detL,
                       int *o_alive);
+/* the same for an OPAQUE host target (allmc.h:21 callbacks): the samples are in the store (pmcgpu_draw), the caller has
+ * evaluated post[N_local] (ok[i] = 0 where the callback raised an error, may be NULL) on the host; weights, reductions over
+ * ranks, normalisation, update and perplexity then run as in pmcgpu_pmc_step.  This is what a rank of vanilla_pmc_mpi
+ * does after its likelihood loop. */
+int pmcgpu_step_given_post(pmcgpu_ctx *ctx, const double *post, const short *ok, long first_index, long N_total,
+                           double t_temper, int do_update, int *retry, pmcgpu_step_result *res, double *o_wght,
+                           double *o_mean, double *o_L, double *o_detL, int *o_alive);
 /* read back the proposal currently installed (after a step): reference layout as above */
 int pmcgpu_get_proposal(pmcgpu_ctx *ctx, double *o_wght, double *o_mean, double *o_L, double *o_detL, int *o_alive);
 
@@ -206,6 +226,21 @@ int pmcgpu_comm_init(pmcgpu_ctx *ctx, const void *id, int rank, int nranks);
  * op 0 = sum, 1 = max; must return 0 on success */
 typedef int (*pmcgpu_allreduce_fn)(void *user, double *buf, long n, int op);
 int pmcgpu_comm_set_callback(pmcgpu_ctx *ctx, pmcgpu_allreduce_fn fn, void *user, int rank, int nranks);
+
+/* Collectives for hosts that shard a pmc_simu over ranks the way libpmc_mpi does (pmc_mpi.c:44-125, 334-566), over the
+ * attached communicator (NCCL or the callback).  With one rank they are no-ops / plain copies.
+ *   allreduce: n host doubles in place, op 0 = sum, 1 = max.
+ *   bcast: `bytes` host bytes from rank `root` to every rank (replaces send_mix_mvdens / receive_mix_mvdens and the
+ *          size messages of send_simulation).
+ *   gather_store: the five arrays of this rank's HBM shard [first, first + N_local) land in root's host arrays of the
+ *          whole N_total-sample pmc_simu (replaces send_importance_weight / receive_importance_weight, and delivers the
+ *          samples the master of the reference would have drawn itself).  Null arrays are skipped; non-root ranks may
+ *          pass nulls. */
+int pmcgpu_comm_allreduce(pmcgpu_ctx *ctx, double *buf, long n, int op);
+int pmcgpu_comm_bcast(pmcgpu_ctx *ctx, void *buf, size_t bytes, int root);
+int pmcgpu_comm_gather_store(pmcgpu_ctx *ctx, int root, long N_total, long first, double *X, size_t *indices,
+                             double *weights, double *log_rho, short *flg);
+int pmcgpu_comm_rank(const pmcgpu_ctx *ctx, int *rank, int *nranks);
 
 /* ---- host-side finalisation, exposed for tests and for hosts that reduce the statistics themselves -------- */
 /* number of doubles in the sufficient-statistics block for (K, d): K*(2 + d + d*d) + 8 */

@@ -303,6 +303,31 @@ double fill_read_pmc_simu(pmc_simu *psim, mix_mvdens *proposal, error **err);   
 size_t *sort_indices(double *list, size_t size, size_t *in_ind, size_t *buf, int order, error **err); /* pmc.c:881-1034 */
 #endif
 
+/* ---- libpmc_mpi (pmclib/include/pmc_mpi.h:52-101): one process per GPU, NCCL instead of MPI (pmc_dropin_mpi.cpp) ------- */
+#ifndef __PMC_MPI_H
+pmc_simu *pmc_simu_init_mpi(long nsamples, int ndim, int nded, error **err);
+size_t pmc_simu_importance_mpi(pmc_simu *psim, gsl_rng *r, error **err);
+double pmc_simu_pmc_step_mpi(pmc_simu *psim, gsl_rng *r, error **err);
+void *mvdens_broadcast_mpi(void *, error **err);
+void pmc_simu_realloc_mpi(pmc_simu *psim, long newsamples, error **err);
+void pmc_simu_init_classic_importance_mpi(pmc_simu *psim, distribution *target, parabox *pb, void *prop_data,
+                                          int prop_print_step, error **err);
+void pmc_simu_init_classic_pmc_mpi(pmc_simu *psim, distribution *target, parabox *pb, void *prop_data, int prop_print_step,
+                                   void *filter_data, filter_func *pmc_filter, error **err);
+distribution *init_distribution_full_mpi(int ndim, void *data, posterior_log_pdf_func *log_pdf, posterior_log_free *freef,
+                                         simulate_func *simulate, int nded, retrieve_ded_func *retrieve,
+                                         mpi_exchange_func *broadcast_mpi, error **err);
+distribution *init_distribution_mpi(int ndim, void *data, posterior_log_pdf_func *log_pdf, posterior_log_free *freef,
+                                    simulate_func *simulate, mpi_exchange_func *broadcast_mpi, error **err);
+void distribution_broadcast(distribution *dist, error **err);
+distribution *mix_mvdens_distribution_mpi(int ndim, void *mxmv, error **err);
+void send_mix_mvdens(mix_mvdens *m, int nproc, error **err);
+mix_mvdens *receive_mix_mvdens(int myid, int nproc, error **err);
+#endif
+/* rank / size / rendezvous path resolved from the launcher's environment, and the rendezvous primitive (tests) */
+int pmcb200_mpi_world(int *rank, int *size, char *rdv, int rdv_len);
+int pmcb200_mpi_rendezvous(const char *path, int rank, void *blob, long bytes, double timeout_s);
+
 /* ---- example target shipped with the reference (examples/target/sampleTarget.h) ---------------------------------------- */
 #ifndef __SMP_TARGET__
 typedef struct { int ndim; double b, sig1; } bentGauss;

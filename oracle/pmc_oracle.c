@@ -189,6 +189,18 @@ double orc_bentgauss(int d, double b, double sig1, const double *x) {
 }
 
 double orc_target_log_pdf(const orc_target *t, const double *x, double *tmp, double *ld, int *rc) {
+  if (t->kind == ORC_TGT_COMBINE) { /* distribution.c:350-396: res += distribution_lkl(term, gathered parameters) */
+    double res = 0.0;
+    for (int id = 0; id < t->nterms; ++id) {
+      const orc_target *a = &t->terms[id];
+      double *xs = (double *)malloc(sizeof(double) * a->d), *tm = (double *)malloc(sizeof(double) * a->d);
+      double *l2 = (double *)malloc(sizeof(double) * (a->kind == ORC_TGT_BANANA ? 1 : (a->mix.K > 0 ? a->mix.K : 1)));
+      for (int ip = 0; ip < a->d; ++ip) xs[ip] = x[t->dims[id][ip]];
+      res += orc_target_log_pdf(a, xs, tm, l2, rc);
+      free(xs); free(tm); free(l2);
+    }
+    return res;
+  }
   if (t->kind == ORC_TGT_BANANA) return orc_bentgauss(t->d, t->b, t->sig1, x);
   if (t->kind == ORC_TGT_MVDENS)
     return orc_mvdens_log_pdf(t->d, t->mix.mean, t->mix.L, t->mix.detL[0], t->mix.df[0], x, tmp);
@@ -203,7 +215,7 @@ long orc_weights(long N, int d, const double *X, const orc_mix *prop, const orc_
                  double *weights, double *log_rho, short *flg, double *maxW, double *maxR) {
   double MR = -1.0e30, MW = -1.0e30;
   long cnt = 0;
-  const int tk = (tgt->kind == ORC_TGT_BANANA) ? 0 : tgt->mix.K;
+  const int tk = (tgt->kind == ORC_TGT_BANANA || tgt->kind == ORC_TGT_COMBINE) ? 0 : tgt->mix.K;
   const int kmax = prop->K > tk ? prop->K : tk;
   double *tmp = (double *)malloc(sizeof(double) * d);
   double *ld = (double *)malloc(sizeof(double) * (kmax > 0 ? kmax : 1));

@@ -50,11 +50,16 @@ typedef struct {
   size_t *band_limit;  /* [K] or NULL (= d) */
 } orc_mix;
 
-enum { ORC_TGT_BANANA = 1, ORC_TGT_MVDENS = 2, ORC_TGT_MIX = 3 };
-typedef struct {
+enum { ORC_TGT_BANANA = 1, ORC_TGT_MVDENS = 2, ORC_TGT_MIX = 3, ORC_TGT_COMBINE = 5 };
+typedef struct orc_target_s {
   int kind, d;
   double b, sig1;  /* bentGauss */
   orc_mix mix;     /* kinds 2 (K=1, wght ignored) and 3 */
+  /* kind 5, combine_lkl (distribution.c:350-396): the sum of nterms densities, term t on the coordinates
+   * dims[t][0..terms[t].d) of x; this is what add_gaussian_prior (distribution.c:548-606) builds */
+  int nterms;
+  const struct orc_target_s *terms;
+  const int *const *dims;
 } orc_target;
 
 /* mvdens.c:229-277 + gsl_linalg_cholesky_decomp: in place, restores a[] and returns ORC_MV_CHOLESKY if not PD */

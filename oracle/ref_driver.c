@@ -136,6 +136,27 @@ int ref_target_log_pdf(long N, int d, const double *X, int kind, const double *t
   return rc;
 }
 
+/* A target with Gaussian priors, built by the reference's own add_gaussian_prior / add_gaussian_prior_2
+ * (distribution.c:548-606) around make_target's density, evaluated through distribution_lkl -> combine_lkl (:350-396).
+ * full_cov = 0: var[nprior] (diagonal); 1: var[nprior*nprior]. */
+int ref_prior_log_pdf(long N, int d, const double *X, int kind, const double *tp, int tK, const double *tw,
+                      const double *tmean, const double *tcov, const int *tdf, int nprior, const int *idim,
+                      const double *loc, const double *var, int full_cov, double *out) {
+  error *e = initError(), **err = &e;
+  distribution *t = make_target(kind, d, tp, tK, tw, tmean, tcov, tdf, err);
+  int rc = take_err(err);
+  distribution *c = NULL;
+  if (!rc) {
+    c = full_cov ? add_gaussian_prior_2(t, nprior, (int *)idim, (double *)loc, (double *)var, err)
+                 : add_gaussian_prior(t, nprior, (int *)idim, (double *)loc, (double *)var, err);
+    rc = take_err(err);
+  }
+  for (long i = 0; i < N && !rc; ++i) { out[i] = distribution_lkl(c, X + i * d, err); rc = take_err(err); }
+  if (c) free_distribution(&c);
+  endError(err);
+  return rc;
+}
+
 /* ranindx with injected uniforms (mvdens.c:766-782): a gsl_rng whose get_double replays z[] */
 typedef struct { const double *z; long pos; } replay_state;
 static double replay_get_double(void *s) { replay_state *r = (replay_state *)s; return r->z[r->pos++]; }

@@ -117,12 +117,35 @@ class PmcGpu:
         t = wl["target"]
         if t["kind"] == 1:
             self._ck(self.lib.pmcgpu_set_target_banana(self.h, t["d"], t["b"], t["sig1"]))
+        elif t["kind"] == 5:
+            self.set_target_combine(t["d"], t["terms"])
         else:
             Ls, dets = zip(*[host_cholesky(c) for c in t["cov"]])
             w, m, Lc, dt = _f64(t["wght"]), _f64(t["mean"]), _f64(np.array(Ls)), _f64(np.array(dets))
             df = np.ascontiguousarray(t["df"], np.int32)
             self._ck(self.lib.pmcgpu_set_target_mix(self.h, t["kind"], t["K"], t["d"], _p(w), _p(m), _p(Lc), _p(dt), _p(df)))
         self.set_box(wl["faces"])
+
+    def set_target_combine(self, d, terms):
+        """Sum of densities on index-mapped coordinates (combine_lkl / add_gaussian_prior): terms = list of dicts with
+        kind (1 banana: b, sig1; 2 mvdens / 3 mix: wght, mean, cov, df), d and dims."""
+        from .lib import CombineTermC
+        arr = (CombineTermC * len(terms))()
+        keep = []
+        for i, t in enumerate(terms):
+            dims = np.ascontiguousarray(t["dims"], np.int32)
+            keep.append(dims)
+            arr[i].kind, arr[i].ndim, arr[i].dim_idx = t["kind"], len(dims), dims.ctypes.data
+            if t["kind"] == 1:
+                arr[i].b, arr[i].sig1 = t["b"], t["sig1"]
+            else:
+                Ls, dets = zip(*[host_cholesky(c) for c in t["cov"]])
+                w, m, Lc, dt = _f64(t["wght"]), _f64(t["mean"]), _f64(np.array(Ls)), _f64(np.array(dets))
+                df = np.ascontiguousarray(t["df"], np.int32)
+                keep += [w, m, Lc, dt, df]
+                arr[i].K = len(w)
+                arr[i].wght, arr[i].mean, arr[i].L, arr[i].detL, arr[i].df = (a.ctypes.data for a in (w, m, Lc, dt, df))
+        self._ck(self.lib.pmcgpu_set_target_combine(self.h, d, len(terms), C.addressof(arr)))
 
     def set_target_banana(self, d, b, sig1):
         self._ck(self.lib.pmcgpu_set_target_banana(self.h, d, b, sig1))

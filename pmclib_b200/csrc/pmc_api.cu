@@ -89,7 +89,7 @@ bool load_nccl(std::string &why) {
   }
   return true;
 }
-constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+constexpr int kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
 
 }  // namespace
 
@@ -109,6 +109,11 @@ struct pmcgpu_ctx {
   DevMixBuf dtmix;
   DevBuf dt_pack;
   int t_pack_doubles = 0;
+  // combined target (PMCGPU_TGT_COMBINE): terms in device memory, evaluated into hostpost before the weight kernels
+  struct CombTerm { int kind = 0; std::vector<int> dim; double b = 0, sig1 = 1; HostMix mix; DevMixBuf dmix; };
+  std::vector<CombTerm> comb;
+  DevBuf dcomb, dcombdim;
+  int comb_kmax = 1;
   int nfull = 0;
   std::vector<int> is_def;
   std::vector<double> def_val;
@@ -163,7 +168,7 @@ struct pmcgpu_ctx {
   void *nccl_comm = nullptr;
   pmcgpu_allreduce_fn cb = nullptr;
   void *cb_user = nullptr;
-  DevBuf dcoll;
+  DevBuf dcoll, dshare;
   // third-generation small-d iteration (pmc_iter3.cu)
   int gen3 = 1;                 // option "gen3": 0 = second-generation kernels only
   int w3_variant = 0;           // option "w3_variant": launch shape of the third-generation weights kernel
@@ -341,6 +346,20 @@ TargetDev target_view(const pmcgpu_ctx *c) {
   t.is_def = c->nfull ? c->ddef.as<int>() : nullptr;
   t.def_val = c->nfull ? reinterpret_cast<const double *>(c->ddef.as<char>() + ((c->nfull * sizeof(int) + 15) / 16) * 16) : nullptr;
   return t;
+}
+
+// the combined target (PMCGPU_TGT_COMBINE) of n samples at X (device) -> out (device), in chunks that bound the
+// per-thread scratch of the mixture terms
+int eval_combine(pmcgpu_ctx *c, long n, const double *X, double *out) {
+  const long chunk = n < (1L << 20) ? n : (1L << 20);
+  CU(c->ld.ensure((size_t)chunk * c->comb_kmax * sizeof(double) + 16));
+  for (long base = 0; base < n; base += chunk) {
+    const long m = (n - base) < chunk ? (n - base) : chunk;
+    launch_combine_target(c->dcomb.as<CombTermDev>(), (int)c->comb.size(), c->td, m, X + (size_t)base * c->td, out + base,
+                          c->ld.as<double>(), c->comb_kmax, c->stream);
+  }
+  CU(cudaGetLastError());
+  return 0;
 }
 
 FusedPlan plan_for(const pmcgpu_ctx *c) {
@@ -649,6 +668,8 @@ Iter3Plan plan3_for(pmcgpu_ctx *c) {
     Kt = c->tmix.K;
   } else if (c->tkind == PMCGPU_TGT_BANANA) {
     if (c->td != c->prop.d || c->td < 2) return none;
+  } else if (c->tkind == PMCGPU_TGT_COMBINE) {
+    if (c->td != c->prop.d) return none;  // evaluated by its own kernel, handed to the weights kernel like host values
   } else if (c->tkind != PMCGPU_TGT_HOST) {
     return none;
   }
@@ -749,6 +770,13 @@ int run_iter3(pmcgpu_ctx *c, const Iter3Plan &p, int do_draw, int stage_limit, i
     Iter3Weights w{};
     w.X = c->X.as<double>(); w.N = N; w.first_index = first_index; w.tgt_kind = c->tkind; w.b = c->tb; w.sig1 = c->tsig1;
     w.t_temper = t_temper; w.post_in = post_in; w.ok_in = ok_in;
+    if (c->tkind == PMCGPU_TGT_COMBINE && !post_in) {  // the sum of the terms, computed by k_combine_target
+      CU(c->hostpost.ensure((size_t)N * sizeof(double)));
+      RC(eval_combine(c, N, c->X.as<double>(), c->hostpost.as<double>()));
+      w.post_in = c->hostpost.as<double>();
+      w.ok_in = nullptr;
+    }
+    if (c->tkind == PMCGPU_TGT_COMBINE) w.tgt_kind = PMCGPU_TGT_HOST;
     for (int j = 0; j < FUSED_MAXD; ++j) w.shift[j] = c->i3_shift[j];
     w.lw = c->W.as<double>(); w.log_rho = c->R.as<double>(); w.flg = c->Flg.as<short>();
     w.resp = (stage_limit >= 2 && with_stats) ? c->resp.as<double>() : nullptr;
@@ -968,6 +996,13 @@ int stats_mma(pmcgpu_ctx *c, const std::vector<size_t> &count, const std::vector
 
 int run_weights_generic(pmcgpu_ctx *c, int mode, const double *post_in, const short *ok_in, double t_temper,
                         long first_index, WeightOut &o) {
+  if (mode == 0 && c->tkind == PMCGPU_TGT_COMBINE) {
+    CU(c->hostpost.ensure((size_t)c->N * sizeof(double)));
+    RC(eval_combine(c, c->N, c->X.as<double>(), c->hostpost.as<double>()));
+    mode = 1;
+    post_in = c->hostpost.as<double>();
+    ok_in = nullptr;
+  }
   RC(ensure_mma(c));
   if (mma_usable(c, mode)) return run_weights_mma(c, mode, post_in, ok_in, t_temper, first_index, o);
   c->q_resident = false;
@@ -1277,9 +1312,10 @@ void pmcgpu_destroy(pmcgpu_ctx *c) {
   if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
   DevBuf *bufs[] = {&c->dprop.buf, &c->dprop_pack, &c->dtmix.buf, &c->dt_pack, &c->ddef, &c->dfaces, &c->X, &c->W, &c->R,
                     &c->Idx, &c->Flg, &c->ld, &c->blkmax, &c->partials, &c->stats, &c->small, &c->rbg, &c->rbw, &c->rbacc,
-                    &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll, &c->resp, &c->partials2, &c->dscal, &c->zig,
+                    &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll, &c->dshare, &c->dcomb, &c->dcombdim, &c->resp, &c->partials2, &c->dscal, &c->zig,
                     &c->i3_gpack, &c->i3_wpart, &c->i3_scal, &c->i3_coll, &c->i3_spart, &c->i3_out};
   for (DevBuf *b : bufs) b->release();
+  for (auto &t : c->comb) t.dmix.buf.release();
   if (c->hstage) cudaFreeHost(c->hstage);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->evd); }
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1385,6 +1421,61 @@ int pmcgpu_set_target_mix(pmcgpu_ctx *c, int kind, int K, int d, const double *w
   c->mtgt.dirty = true;
   c->i3_dirty = true;
   return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles, c->tgt_pack_host);
+}
+
+int pmcgpu_set_target_combine(pmcgpu_ctx *c, int d, int nterms, const pmcgpu_combine_term *terms) {
+  if (!c || d < 1 || d > PMCB200_MAXD || nterms < 1 || !terms) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  std::vector<pmcgpu_ctx::CombTerm> comb(nterms);
+  std::vector<int> alldim;
+  int kmax = 1;
+  for (int t = 0; t < nterms; ++t) {
+    const pmcgpu_combine_term &in = terms[t];
+    pmcgpu_ctx::CombTerm &o = comb[t];
+    if (in.ndim < 1 || in.ndim > PMCB200_MAXD || !in.dim_idx) return fail(c, PMCGPU_ERR_USAGE, "combined target: term %d has no coordinates", t);
+    for (int a = 0; a < in.ndim; ++a)
+      if (in.dim_idx[a] < 0 || in.dim_idx[a] >= d) return fail(c, PMCGPU_ERR_USAGE, "combined target: term %d reads coordinate %d of %d", t, in.dim_idx[a], d);
+    o.kind = in.kind;
+    o.dim.assign(in.dim_idx, in.dim_idx + in.ndim);
+    alldim.insert(alldim.end(), o.dim.begin(), o.dim.end());
+    if (in.kind == PMCGPU_TGT_BANANA) {
+      if (in.ndim < 2) return fail(c, PMCGPU_ERR_USAGE, "combined target: bentGauss term needs ndim >= 2");
+      o.b = in.b;
+      o.sig1 = in.sig1;
+    } else if (in.kind == PMCGPU_TGT_MVDENS || in.kind == PMCGPU_TGT_MIX) {
+      const double one = 1.0;
+      const int K = in.kind == PMCGPU_TGT_MVDENS ? 1 : in.K;
+      RC(fill_mix(c, o.mix, K, in.ndim, (in.kind == PMCGPU_TGT_MVDENS && !in.wght) ? &one : in.wght, in.mean, in.L, in.detL, in.df));
+      RC(upload_mix(c, o.mix, o.dmix));
+      if (K > kmax) kmax = K;
+    } else {
+      return fail(c, PMCGPU_ERR_USAGE, "combined target: term %d has kind %d", t, in.kind);
+    }
+  }
+  CU(c->dcombdim.ensure(alldim.size() * sizeof(int)));
+  CU(cudaMemcpy(c->dcombdim.p, alldim.data(), alldim.size() * sizeof(int), cudaMemcpyHostToDevice));
+  std::vector<CombTermDev> dev(nterms);
+  size_t off = 0;
+  for (int t = 0; t < nterms; ++t) {
+    dev[t].kind = comb[t].kind;
+    dev[t].nd = (int)comb[t].dim.size();
+    dev[t].dim = c->dcombdim.as<int>() + off;
+    off += comb[t].dim.size();
+    dev[t].b = comb[t].b;
+    dev[t].sig1 = comb[t].sig1;
+    dev[t].mix = comb[t].dmix.view;
+  }
+  CU(c->dcomb.ensure(dev.size() * sizeof(CombTermDev)));
+  CU(cudaMemcpy(c->dcomb.p, dev.data(), dev.size() * sizeof(CombTermDev), cudaMemcpyHostToDevice));
+  for (auto &t : c->comb) t.dmix.buf.release();
+  c->comb = std::move(comb);
+  c->comb_kmax = kmax;
+  c->tkind = PMCGPU_TGT_COMBINE;
+  c->td = d;
+  c->tmix = HostMix();
+  c->mtgt.valid = false;
+  c->i3_dirty = true;
+  return 0;
 }
 
 int pmcgpu_set_target_host(pmcgpu_ctx *c, int d) {
@@ -1580,7 +1671,10 @@ static int draw_mma(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_inde
   return 0;
 }
 
-int pmcgpu_draw(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, long *n_reject) {
+// The draw of the store's N samples.  local_check: apply the MNOK / failed-draw test of pmc.c:281-297 to this rank's own
+// counters.  Inside the multi-rank iteration the test runs on the REDUCED counters instead (step_core), so that every
+// rank takes the same decision and nobody is left waiting in a collective.
+static int draw_impl(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, long *n_reject, long *n_fail, bool local_check) {
   int rc = check_ready(c, false);
   if (rc) return rc;
   cudaSetDevice(c->device);
@@ -1589,28 +1683,26 @@ int pmcgpu_draw(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, l
   rc = zero_small(c);
   if (rc) return rc;
   rc = draw_mma(c, seed, iter, first_index);
-  if (rc == 0) {
-    unsigned long long cnt[CNT_NUM];
-    rc = read_small(c, cnt, nullptr, nullptr);
-    if (rc) return rc;
-    if (n_reject) *n_reject = (long)cnt[CNT_REJECT];
-    if (cnt[CNT_DRAWFAIL] || (long)cnt[CNT_REJECT] > 5 * c->N)
-      return fail(c, kErrTooManySteps, "Too many points (%llu) outside of box", cnt[CNT_REJECT]);
-    return 0;
+  if (rc != 0 && rc != 1) return rc;
+  if (rc == 1) {
+    BoxDev bx{c->nfaces, c->box_d, c->dfaces.as<double>()};
+    if (c->nfaces > 0 && c->box_d != c->d) return fail(c, PMCGPU_ERR_USAGE, "box dimension %d != %d", c->box_d, c->d);
+    launch_draw_generic(c->dprop.view, bx, seed, iter, first_index, c->N, c->max_attempts, c->X.as<double>(),
+                        c->Idx.as<unsigned long long>(), c->Flg.as<short>(), c->small.as<unsigned long long>() + SM_COUNTERS, c->stream);
+    CU(cudaGetLastError());
   }
-  if (rc != 1) return rc;
-  BoxDev bx{c->nfaces, c->box_d, c->dfaces.as<double>()};
-  if (c->nfaces > 0 && c->box_d != c->d) return fail(c, PMCGPU_ERR_USAGE, "box dimension %d != %d", c->box_d, c->d);
-  launch_draw_generic(c->dprop.view, bx, seed, iter, first_index, c->N, c->max_attempts, c->X.as<double>(),
-                      c->Idx.as<unsigned long long>(), c->Flg.as<short>(), c->small.as<unsigned long long>() + SM_COUNTERS, c->stream);
-  CU(cudaGetLastError());
   unsigned long long cnt[CNT_NUM];
   rc = read_small(c, cnt, nullptr, nullptr);
   if (rc) return rc;
   if (n_reject) *n_reject = (long)cnt[CNT_REJECT];
-  if (cnt[CNT_DRAWFAIL] || (long)cnt[CNT_REJECT] > 5 * c->N)
+  if (n_fail) *n_fail = (long)cnt[CNT_DRAWFAIL];
+  if (local_check && (cnt[CNT_DRAWFAIL] || (long)cnt[CNT_REJECT] > 5 * c->N))
     return fail(c, kErrTooManySteps, "Too many points (%llu) outside of box", cnt[CNT_REJECT]);
   return 0;
+}
+
+int pmcgpu_draw(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, long *n_reject) {
+  return draw_impl(c, seed, iter, first_index, n_reject, nullptr, true);
 }
 
 static int weights_common(pmcgpu_ctx *c, int mode, const double *post, const short *ok, double t_temper,
@@ -1759,6 +1851,14 @@ int pmcgpu_target_log_pdf(pmcgpu_ctx *c, long n, const double *x, double *out) {
   const int K = c->tmix.K > 0 ? c->tmix.K : 1;
   CU(c->tmpx.ensure((size_t)n * d * sizeof(double) + 16));
   CU(c->tmpo.ensure((size_t)n * sizeof(double) + 16));
+  if (c->tkind == PMCGPU_TGT_COMBINE) {
+    if (c->nfull) return fail(c, PMCGPU_ERR_USAGE, "combined target with conditional parameters is not supported on the device");
+    CU(cudaMemcpyAsync(c->tmpx.p, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RC(eval_combine(c, n, c->tmpx.as<double>(), c->tmpo.as<double>()));
+    CU(cudaMemcpyAsync(out, c->tmpo.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
   CU(c->ld.ensure((size_t)n * K * sizeof(double) + 16));
   CU(cudaMemcpyAsync(c->tmpx.p, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   launch_target_log_pdf(target_view(c), d, n, c->tmpx.as<double>(), c->tmpo.as<double>(), c->ld.as<double>(), K, c->stream);
@@ -1995,7 +2095,7 @@ int pmcgpu_isinbox(pmcgpu_ctx *c, long n, const double *x, int *inside) {
 // ---- the iteration ------------------------------------------------------------------------------------------------
 static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, long first_index, long N_total,
                      double t_temper, int do_update, int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean,
-                     double *o_L, double *o_detL, int *o_alive) {
+                     double *o_L, double *o_detL, int *o_alive, const double *post_host = nullptr, const short *ok_host = nullptr) {
   int rc = check_ready(c, true);
   if (rc) return rc;
   cudaSetDevice(c->device);
@@ -2008,8 +2108,22 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
     fprintf(stderr, "[pmcb200] %-22s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
     t_prev = now;
   };
-  if (c->tkind == PMCGPU_TGT_HOST) return fail(c, PMCGPU_ERR_USAGE, "host target: drive the phases separately (draw, download X, weights_host_post, ...)");
+  if (c->tkind == PMCGPU_TGT_HOST && !post_host)
+    return fail(c, PMCGPU_ERR_USAGE, "host target: draw, download X, evaluate, then pmcgpu_step_given_post (or drive the phases separately)");
+  if (post_host && do_draw) return fail(c, PMCGPU_ERR_USAGE, "target values supplied for samples that are still to be drawn");
   if (N_total <= 0) N_total = c->N;
+  const double *dpost = nullptr;
+  const short *dok = nullptr;
+  if (post_host) {  // target values of the store's samples, evaluated by the caller (opaque likelihood callbacks)
+    CU(c->hostpost.ensure((size_t)c->N * sizeof(double)));
+    CU(cudaMemcpyAsync(c->hostpost.p, post_host, (size_t)c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dpost = c->hostpost.as<double>();
+    if (ok_host) {
+      CU(c->hostok.ensure((size_t)c->N * sizeof(short)));
+      CU(cudaMemcpyAsync(c->hostok.p, ok_host, (size_t)c->N * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+      dok = c->hostok.as<short>();
+    }
+  }
   int retry_local = retry ? *retry : 0;
   pmcgpu_step_result r{};
   if (do_draw) { rc = ensure_cwght_normalised(c); if (rc) return rc; }
@@ -2024,24 +2138,26 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   WeightOut o;
   const bool fused_stats = p.valid && do_update && !c->force_precise && c->filt_nbins == 0;
   if (have3) {
-    rc = run_iter3(c, p3, do_draw, 2, stats3 ? 1 : 0, seed, iter, first_index, N_total, t_temper, nullptr, nullptr, o3);
+    rc = run_iter3(c, p3, do_draw, 2, stats3 ? 1 : 0, seed, iter, first_index, N_total, t_temper, dpost, dok, o3);
     if (rc) return rc;
   } else if (p.valid) {
-    rc = run_fused(c, p, do_draw, fused_stats ? 1 : 0, seed, iter, first_index, t_temper, nullptr, nullptr, o);
+    rc = run_fused(c, p, do_draw, fused_stats ? 1 : 0, seed, iter, first_index, t_temper, dpost, dok, o);
     if (rc) return rc;
   } else {
     if (do_draw) {
-      long nrej = 0;
-      rc = pmcgpu_draw(c, seed, iter, first_index, &nrej);
+      long nrej = 0, nfail = 0;
+      rc = draw_impl(c, seed, iter, first_index, &nrej, &nfail, c->nranks <= 1);  // ranks: the reduced counters decide below
       if (rc) return rc;
       o.counters[CNT_REJECT] = (unsigned long long)nrej;
+      o.counters[CNT_DRAWFAIL] = (unsigned long long)nfail;
       RC(sink_copy(c, SINK_DRAWN));
     }
-    const unsigned long long keep_rej = o.counters[CNT_REJECT];
-    rc = run_weights_generic(c, 0, nullptr, nullptr, t_temper, first_index, o);
+    const unsigned long long keep_rej = o.counters[CNT_REJECT], keep_fail = o.counters[CNT_DRAWFAIL];
+    rc = run_weights_generic(c, dpost ? 1 : 0, dpost, dok, t_temper, first_index, o);
     if (rc) return rc;
     RC(sink_copy(c, SINK_RHO));
     o.counters[CNT_REJECT] = keep_rej;
+    o.counters[CNT_DRAWFAIL] = keep_fail;
   }
   tick("draw+weights");
   // ---- global maxima (pmc_mpi.c:502-508 keeps the max over ranks) with the i==0 quirk carried as a flag
@@ -2117,7 +2233,20 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
   // ---- update
   if (do_update) {
     // a NaN maximum (the i==0 quirk) poisons the reference's responsibilities: only the literal path reproduces that
-    const bool mma_stats = !p.valid && !have3 && !c->force_precise && c->q_resident && mma_usable(c, 0);
+    bool mma_stats = !p.valid && !have3 && !c->force_precise && c->q_resident && mma_usable(c, 0);
+    if (!p.valid && !have3 && !c->force_precise) {
+      // q_resident depends on each rank's free memory and the one-pass statistics need a centred copy of the shard: the
+      // ranks agree on the path BEFORE any statistics collective (all take the literal update if one of them cannot),
+      // otherwise they would issue different all-reduce sequences
+      if (mma_stats && c->prop.student && K > 256) mma_stats = false;
+      if (mma_stats && c->xc.ensure((size_t)c->N * d * sizeof(double)) != cudaSuccess) { cudaGetLastError(); mma_stats = false; }
+      if (c->nranks > 1) {
+        double veto = mma_stats ? 0.0 : 1.0;
+        rc = allreduce_host(c, &veto, 1, 1);
+        if (rc) return rc;
+        if (veto != 0.0) mma_stats = false;
+      }
+    }
     const bool use_stats3 = stats3 && o3.clean;
     bool precise = !(fused_stats || mma_stats || use_stats3) || std::isnan(maxR) || std::isnan(maxW);
     std::vector<double> &W = c->hW, &s1 = c->hs1, &S2 = c->hS2;
@@ -2248,11 +2377,11 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
 // the iteration with the host sink armed: whatever happens, no copy into the caller's arrays is in flight on return
 static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, long first_index, long N_total,
                      double t_temper, int do_update, int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean,
-                     double *o_L, double *o_detL, int *o_alive) {
+                     double *o_L, double *o_detL, int *o_alive, const double *post_host = nullptr, const short *ok_host = nullptr) {
   if (!c) return PMCGPU_ERR_USAGE;
   c->sink_active = c->sink.on && do_draw;
   const int rc = step_core(c, do_draw, seed, iter, first_index, N_total, t_temper, do_update, retry, res, o_wght, o_mean,
-                           o_L, o_detL, o_alive);
+                           o_L, o_detL, o_alive, post_host, ok_host);
   if (c->sink_active) {
     c->sink_active = false;
     cudaSetDevice(c->device);
@@ -2283,6 +2412,17 @@ int pmcgpu_step_given(pmcgpu_ctx *c, long first_index, long N_total, double t_te
   return step_impl(c, 0, 0, 0, first_index, N_total, t_temper, do_update, retry, res, o_wght, o_mean, o_L, o_detL, o_alive);
 }
 
+int pmcgpu_step_given_post(pmcgpu_ctx *c, const double *post, const short *ok, long first_index, long N_total, double t_temper,
+                           int do_update, int *retry, pmcgpu_step_result *res, double *o_wght, double *o_mean, double *o_L,
+                           double *o_detL, int *o_alive) {
+  if (!c || !post) return PMCGPU_ERR_USAGE;
+  const int saved_kind = c->tkind;
+  c->tkind = PMCGPU_TGT_HOST;
+  const int rc = step_impl(c, 0, 0, 0, first_index, N_total, t_temper, do_update, retry, res, o_wght, o_mean, o_L, o_detL, o_alive, post, ok);
+  c->tkind = saved_kind == PMCGPU_TGT_NONE ? PMCGPU_TGT_HOST : saved_kind;
+  return rc;
+}
+
 int pmcgpu_get_proposal(pmcgpu_ctx *c, double *o_wght, double *o_mean, double *o_L, double *o_detL, int *o_alive) {
   if (!c || c->prop.K == 0) return PMCGPU_ERR_USAGE;
   export_proposal(c, o_wght, o_mean, o_L, o_detL, o_alive);
@@ -2310,6 +2450,82 @@ void pmcgpu_shard_range(long N_total, int rank, int nranks, long *first, long *l
   const long f = rank * base + (rank < rem ? rank : rem);
   if (first) *first = f;
   if (len) *len = l;
+}
+
+// Every rank contributes the bytes [my_off, my_off + my_len) of a buffer of `total` bytes (ranges of different ranks are
+// disjoint); afterwards host_out (where not null) holds the union.  Chunks travel through a zeroed device staging buffer
+// and a sum all-reduce of 64-bit words: with disjoint non-zero bytes the sum is the union, exact for any bit pattern.
+static int share_bytes(pmcgpu_ctx *c, const void *src, bool src_on_device, size_t total, size_t my_off, size_t my_len, void *host_out) {
+  if (total == 0) return 0;
+  if (c->nranks <= 1) {
+    if (host_out && my_len) {
+      CU(cudaMemcpyAsync((char *)host_out + my_off, src, my_len, src_on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+  }
+  const size_t CH = (size_t)64 << 20;
+  const size_t chunk = total < CH ? ((total + 7) / 8) * 8 : CH;
+  CU(c->dshare.ensure(chunk));
+  for (size_t o = 0; o < total; o += chunk) {
+    const size_t len = (total - o) < chunk ? (total - o) : chunk;
+    const size_t words = (len + 7) / 8;
+    CU(cudaMemsetAsync(c->dshare.p, 0, words * 8, c->stream));
+    const size_t lo = my_off > o ? my_off : o, hi = (my_off + my_len) < (o + len) ? (my_off + my_len) : (o + len);
+    if (hi > lo)
+      CU(cudaMemcpyAsync((char *)c->dshare.p + (lo - o), (const char *)src + (lo - my_off), hi - lo,
+                         src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if (!c->cb) {
+      if (!c->nccl_comm) return fail(c, PMCGPU_ERR_NCCL, "nranks=%d but no communicator attached", c->nranks);
+      const int r = g_nccl.AllReduce(c->dshare.p, c->dshare.p, words, kNcclUint64, kNcclSum, c->nccl_comm, c->stream);
+      if (r != 0) return fail(c, PMCGPU_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+      if (host_out) CU(cudaMemcpyAsync((char *)host_out + o, c->dshare.p, len, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    } else {  // callback ranks reduce doubles on the host: 16-bit pieces as exact doubles
+      std::vector<unsigned short> raw(words * 4);
+      CU(cudaMemcpyAsync(raw.data(), c->dshare.p, words * 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      std::vector<double> dv(raw.begin(), raw.end());
+      if (c->cb(c->cb_user, dv.data(), (long)dv.size(), 0) != 0) return fail(c, PMCGPU_ERR_NCCL, "allreduce callback failed");
+      for (size_t i = 0; i < raw.size(); ++i) raw[i] = (unsigned short)dv[i];
+      if (host_out) memcpy((char *)host_out + o, raw.data(), len);
+    }
+  }
+  return 0;
+}
+
+int pmcgpu_comm_rank(const pmcgpu_ctx *c, int *rank, int *nranks) {
+  if (!c) return PMCGPU_ERR_USAGE;
+  if (rank) *rank = c->rank;
+  if (nranks) *nranks = c->nranks;
+  return 0;
+}
+int pmcgpu_comm_allreduce(pmcgpu_ctx *c, double *buf, long n, int op) {
+  if (!c || !buf || n < 0) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  return allreduce_host(c, buf, n, op);
+}
+int pmcgpu_comm_bcast(pmcgpu_ctx *c, void *buf, size_t bytes, int root) {
+  if (!c || !buf || root < 0 || root >= (c->nranks > 1 ? c->nranks : 1)) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  if (c->nranks <= 1) return 0;
+  return share_bytes(c, buf, false, bytes, 0, c->rank == root ? bytes : 0, buf);
+}
+int pmcgpu_comm_gather_store(pmcgpu_ctx *c, int root, long N_total, long first, double *X, size_t *indices, double *weights,
+                             double *log_rho, short *flg) {
+  if (!c || N_total < 0 || first < 0 || first + c->N > N_total) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  const bool me = c->nranks <= 1 || c->rank == root;
+  const size_t d = (size_t)c->d, N = (size_t)c->N, T = (size_t)N_total, f = (size_t)first;
+  // every rank takes part in every collective: whether an array travels is decided by root's pointers
+  double want[5] = {me && X ? 1.0 : 0.0, me && indices ? 1.0 : 0.0, me && weights ? 1.0 : 0.0, me && log_rho ? 1.0 : 0.0, me && flg ? 1.0 : 0.0};
+  RC(allreduce_host(c, want, 5, 1));
+  if (want[0] != 0.0) RC(share_bytes(c, c->X.p, true, T * d * 8, f * d * 8, N * d * 8, me ? X : nullptr));
+  if (want[1] != 0.0) RC(share_bytes(c, c->Idx.p, true, T * 8, f * 8, N * 8, me ? indices : nullptr));
+  if (want[2] != 0.0) RC(share_bytes(c, c->W.p, true, T * 8, f * 8, N * 8, me ? weights : nullptr));
+  if (want[3] != 0.0) RC(share_bytes(c, c->R.p, true, T * 8, f * 8, N * 8, me ? log_rho : nullptr));
+  if (want[4] != 0.0) RC(share_bytes(c, c->Flg.p, true, T * 2, f * 2, N * 2, me ? flg : nullptr));
+  return 0;
 }
 
 int pmcgpu_nccl_unique_id(void *id_out) {

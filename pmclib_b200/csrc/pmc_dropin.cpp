@@ -218,6 +218,26 @@ int device_kind(const distribution *t) {
   if (t->log_pdf == (posterior_log_pdf_func *)&mix_mvdens_log_pdf_void) return PMCGPU_TGT_MIX;
   if (t->log_pdf == (posterior_log_pdf_func *)&mvdens_log_pdf_void) return PMCGPU_TGT_MVDENS;
   if (t->log_pdf == (posterior_log_pdf_func *)&bentGauss_lkl) return PMCGPU_TGT_BANANA;
+  if (t->log_pdf == &combine_lkl) {
+    // a combine (distribution.c:350-396) is evaluated on the device when every term is a density this library knows,
+    // reads only free parameters and neither side carries deduced or conditional parameters; otherwise the whole
+    // combine is an opaque host target like any user callback
+    const comb_dist_data *cbd = (const comb_dist_data *)t->data;
+    if (!cbd || cbd->nded != 0 || t->ndef != 0 || cbd->ndist < 1) return PMCGPU_TGT_HOST;
+    for (int id = 0; id < cbd->ndist; ++id) {
+      const distribution *a = cbd->dist[id];
+      if (!a || a->ndef != 0 || a->n_ded != 0 || a->log_pdf == &combine_lkl) return PMCGPU_TGT_HOST;
+      const int k = device_kind(a);
+      if (k != PMCGPU_TGT_BANANA && k != PMCGPU_TGT_MVDENS && k != PMCGPU_TGT_MIX) return PMCGPU_TGT_HOST;
+      if (k == PMCGPU_TGT_MVDENS && ((const mvdens *)a->data)->band_limit < ((const mvdens *)a->data)->ndim) return PMCGPU_TGT_HOST;
+      if (k == PMCGPU_TGT_MIX) {
+        const mix_mvdens *mm = (const mix_mvdens *)a->data;
+        for (size_t c = 0; c < mm->ncomp; ++c) if (mm->comp[c]->band_limit < mm->ndim) return PMCGPU_TGT_HOST;
+      }
+      for (int ip = 0; ip < a->ndim; ++ip) if (cbd->dim[id][ip] < 0) return PMCGPU_TGT_HOST;
+    }
+    return PMCGPU_TGT_COMBINE;
+  }
   return PMCGPU_TGT_HOST;
 }
 
@@ -237,11 +257,39 @@ bool push_target(Side *s, distribution *t, error **err) {
     FlatMix f;
     if (!flatten((mix_mvdens *)t->data, f, err)) return false;
     rc = pmcgpu_set_target_mix(s->ctx, kind, f.K, f.d, f.w.data(), f.mean.data(), f.L.data(), f.detL.data(), f.df.data());
+  } else if (kind == PMCGPU_TGT_COMBINE) {
+    const comb_dist_data *cbd = (const comb_dist_data *)t->data;
+    std::vector<pmcgpu_combine_term> terms(cbd->ndist);
+    std::vector<FlatMix> flat(cbd->ndist);
+    const double one = 1.0;
+    for (int id = 0; id < cbd->ndist; ++id) {
+      distribution *a = cbd->dist[id];
+      pmcgpu_combine_term &tm = terms[id];
+      memset(&tm, 0, sizeof tm);
+      tm.kind = device_kind(a);
+      tm.ndim = a->ndim;
+      tm.dim_idx = cbd->dim[id];
+      if (tm.kind == PMCGPU_TGT_BANANA) {
+        const bentGauss *bg = (const bentGauss *)a->data;
+        tm.b = bg->b;
+        tm.sig1 = bg->sig1;
+      } else if (tm.kind == PMCGPU_TGT_MVDENS) {
+        mvdens *g = (mvdens *)a->data;
+        mvdens_cholesky_decomp(g, err);
+        if (isError(*err)) return false;
+        tm.K = 1; tm.wght = &one; tm.mean = g->mean; tm.L = g->std; tm.detL = &g->detL; tm.df = &g->df;
+      } else {
+        FlatMix &f = flat[id];
+        if (!flatten((mix_mvdens *)a->data, f, err)) return false;
+        tm.K = f.K; tm.wght = f.w.data(); tm.mean = f.mean.data(); tm.L = f.L.data(); tm.detL = f.detL.data(); tm.df = f.df.data();
+      }
+    }
+    rc = pmcgpu_set_target_combine(s->ctx, t->ndim, cbd->ndist, terms.data());
   } else {
     rc = pmcgpu_set_target_host(s->ctx, t->ndim);
   }
   if (!rc) {
-    if (kind != PMCGPU_TGT_HOST && t->ndef != 0) rc = pmcgpu_set_target_defaults(s->ctx, t->ndim + t->ndef, t->def, t->pars);
+    if (kind != PMCGPU_TGT_HOST && kind != PMCGPU_TGT_COMBINE && t->ndef != 0) rc = pmcgpu_set_target_defaults(s->ctx, t->ndim + t->ndef, t->def, t->pars);
     else rc = pmcgpu_set_target_defaults(s->ctx, 0, nullptr, nullptr);
   }
   if (rc) { gpu_fail(s, rc, err, "push_target"); return false; }
@@ -297,6 +345,42 @@ std::mutex &dropin_point_mutex() {
 }
 pmcgpu_ctx *dropin_point_ctx(error **err) { return point_ctx(err); }
 uint64_t dropin_seed_from(gsl_rng *r) { return seed_from(r); }
+bool dropin_push_model(pmcgpu_ctx *ctx, mix_mvdens *m, distribution *target, parabox *pb, int d, error **err) {
+  Side tmp;
+  tmp.ctx = ctx;
+  return push_proposal(&tmp, m, err) && (!target || push_target(&tmp, target, err)) && push_box(&tmp, pb, d, err);
+}
+void dropin_unflatten(mix_mvdens *m, const double *w, const double *mean, const double *L, const double *detL) { unflatten(m, w, mean, L, detL); }
+int dropin_device_kind(const distribution *t) { return device_kind(t); }
+// The per-sample loop over an OPAQUE target callback (pmc.c:557-577): errors of a sample are printed (unless quiet),
+// purged and the sample flagged out (ParameterErrorVerb, pmc.h:52-66) - except tls_cosmo_par, which aborts the whole
+// call with the chain forwarded (pmc.c:559-560).  Returns false in that case.
+bool dropin_host_target_values(posterior_log_pdf_func *f, retrieve_ded_func *ret, void *target_data, const double *X, double *X_ded,
+                               long N, int d, int nd, int quiet, double *post, short *ok, error **err) {
+  constexpr int tls_cosmo_par = -8017;  // tools.h:24,42
+  for (long i = 0; i < N; ++i) {
+    const double *x = X + (size_t)i * d;
+    ok[i] = 1;
+    post[i] = f(target_data, x, err);
+    if (isError(*err) && getErrorValue(*err) == tls_cosmo_par) {
+      *err = newError(forwardErr, (char *)__func__, (char *)"", nullptr, *err);
+      return false;
+    }
+    if (!isError(*err) && ret && nd > 0) ret(target_data, X_ded + (size_t)i * nd, err);
+    if (isError(*err)) {
+      if (!quiet) {
+        fprintf(stderr, "*** Error, parameter ***\n");
+        for (int j = 0; j < d; ++j) fprintf(stderr, " %10g", x[j]);
+        fprintf(stderr, "\n*** -- ***\n");
+        printError(stderr, *err);
+      }
+      purgeError(err);
+      ok[i] = 0;
+    }
+  }
+  return true;
+}
+int dropin_device_ordinal() { return device_ordinal(); }
 }  // namespace pmcb200
 
 extern "C" {
@@ -953,21 +1037,9 @@ size_t generic_get_importance_weight_and_deduced_verb(pmc_simu *psim, void *prop
     const int d = psim->ndim, nd = psim->n_ded;
     std::vector<double> post(N, 0.0);
     std::vector<short> ok(N, 1);
-    for (long i = 0; i < N; ++i) {
-      const double *x = psim->X + (size_t)i * d;
-      post[i] = posterior_log_pdf(target_data, x, err);
-      if (!isError(*err) && retrieve_ded && nd > 0) retrieve_ded(target_data, psim->X_ded + (size_t)i * nd, err);
-      if (isError(*err)) {
-        if (!quiet) {
-          fprintf(stderr, "*** Error, parameter ***\n");
-          for (int j = 0; j < d; ++j) fprintf(stderr, " %10g", x[j]);
-          fprintf(stderr, "\n*** -- ***\n");
-          printError(stderr, *err);
-        }
-        purgeError(err);
-        ok[i] = 0;
-      }
-    }
+    if (!pmcb200::dropin_host_target_values(posterior_log_pdf, retrieve_ded, target_data, psim->X, psim->X_ded, N, d, nd, quiet,
+                                            post.data(), ok.data(), err))
+      return 0;
     rc = pmcgpu_set_target_host(s->ctx, d);
     if (!rc) rc = pmcgpu_weights_host_post(s->ctx, post.data(), ok.data(), t_iter_tempered, 0, &nok, &maxW, &maxR);
   }

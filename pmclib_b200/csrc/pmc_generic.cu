@@ -185,6 +185,27 @@ __global__ void k_target_log_pdf(TargetDev tg, int dfree, long n, const double *
   out[i] = target_log_pdf_generic(tg, x, xf, y, ldscratch + (size_t)i * ldstride);
 }
 
+// combine_lkl (distribution.c:350-396) on n points: the terms' log-densities, each on its index-mapped sub-vector, added in
+// term order.  Every term is one of the densities this library evaluates itself (bentGauss, mvdens, mix_mvdens).
+__global__ void k_combine_target(const CombTermDev *__restrict__ terms, int nterms, int d, long n, const double *__restrict__ X,
+                                 double *__restrict__ out, double *__restrict__ ldscratch, int ldstride) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x[MAXD], xs[MAXD], y[MAXD];
+  for (int a = 0; a < d; ++a) x[a] = X[(size_t)i * d + a];
+  double res = 0.0;
+  for (int t = 0; t < nterms; ++t) {
+    const CombTermDev tm = terms[t];
+    for (int a = 0; a < tm.nd; ++a) xs[a] = x[tm.dim[a]];
+    double v;
+    if (tm.kind == PMCGPU_TGT_BANANA) v = bent_gauss(xs, tm.nd, tm.b, tm.sig1);
+    else if (tm.kind == PMCGPU_TGT_MVDENS) v = comp_log_pdf(tm.mix, 0, xs, y, nullptr);
+    else v = mix_log_pdf_generic(tm.mix, xs, y, ldscratch + (size_t)i * ldstride);
+    res += v;
+  }
+  out[i] = res;
+}
+
 __global__ void k_ranindx(const double *__restrict__ cw, int K, long n, const double *__restrict__ z,
                           unsigned long long *__restrict__ idx) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -484,6 +505,10 @@ void launch_weights_generic(const MixDev &m, const TargetDev &tg, int mode, cons
 }
 void launch_mix_log_pdf(const MixDev &m, long n, const double *X, double *out, double *ld, int ldstride, cudaStream_t s) {
   if (n > 0) { k_mix_log_pdf<<<nblk(n, 128), 128, 0, s>>>(m, n, X, out, ld, ldstride); count_launch(); }
+}
+void launch_combine_target(const CombTermDev *terms, int nterms, int d, long n, const double *X, double *out, double *ld,
+                           int ldstride, cudaStream_t s) {
+  if (n > 0) { k_combine_target<<<nblk(n, 128), 128, 0, s>>>(terms, nterms, d, n, X, out, ld, ldstride); count_launch(); }
 }
 void launch_target_log_pdf(const TargetDev &tg, int dfree, long n, const double *X, double *out, double *ld, int ldstride, cudaStream_t s) {
   if (n > 0) { k_target_log_pdf<<<nblk(n, 128), 128, 0, s>>>(tg, dfree, n, X, out, ld, ldstride); count_launch(); }

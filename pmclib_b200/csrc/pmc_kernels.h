@@ -38,6 +38,15 @@ struct TargetDev {
   const double *def_val;
 };
 
+// one term of a combined target (distribution.c:350-396): a density of kind PMCGPU_TGT_BANANA / _MVDENS / _MIX evaluated on
+// the coordinates dim[0..nd) of the full parameter vector
+struct CombTermDev {
+  int kind, nd;
+  const int *dim;
+  double b, sig1;
+  MixDev mix;
+};
+
 #ifdef __CUDACC__
 // Common end of the one-thread-per-sample weight kernels (k_weights_generic, k_weights_q): block maxima of the log-weight
 // and of log_rho with the reference's "v > m" semantics (a NaN never wins, pmc.c:552-554,579) and the count of ok samples.
@@ -83,6 +92,8 @@ void launch_weights_generic(const MixDev &m, const TargetDev &tg, int mode, cons
                             short *flg, double *ldscratch, int ldstride, double *blk_maxw, double *blk_maxr,
                             unsigned long long *counters, double *first_vals, cudaStream_t s);
 void launch_mix_log_pdf(const MixDev &m, long n, const double *X, double *out, double *ld, int ldstride, cudaStream_t s);
+void launch_combine_target(const CombTermDev *terms, int nterms, int d, long n, const double *X, double *out, double *ld,
+                           int ldstride, cudaStream_t s);
 void launch_target_log_pdf(const TargetDev &tg, int dfree, long n, const double *X, double *out, double *ld,
                            int ldstride, cudaStream_t s);
 void launch_ranindx(const double *cw, int K, long n, const double *z, unsigned long long *idx, cudaStream_t s);

@@ -35,7 +35,16 @@ EXPORTS = [
     "pmcgpu_count_indices", "pmcgpu_update_rb", "pmcgpu_update_hard", "pmcgpu_ranindx", "pmcgpu_isinbox",
     "pmcgpu_pmc_step", "pmcgpu_step_given", "pmcgpu_get_proposal", "pmcgpu_shard_range", "pmcgpu_nccl_unique_id",
     "pmcgpu_comm_init", "pmcgpu_comm_set_callback", "pmcgpu_stats_len", "pmcgpu_finalize_update", "pmcgpu_cholesky",
+    "pmcgpu_set_target_combine", "pmcgpu_step_given_post", "pmcgpu_comm_allreduce", "pmcgpu_comm_bcast",
+    "pmcgpu_comm_gather_store", "pmcgpu_comm_rank",
 ]
+
+
+class CombineTermC(C.Structure):
+    """pmcgpu_combine_term (include/pmcb200.h)."""
+    _fields_ = [("kind", C.c_int), ("ndim", C.c_int), ("dim_idx", C.c_void_p), ("b", C.c_double), ("sig1", C.c_double),
+                ("K", C.c_int), ("wght", C.c_void_p), ("mean", C.c_void_p), ("L", C.c_void_p), ("detL", C.c_void_p),
+                ("df", C.c_void_p)]
 
 
 def load_library(build_if_missing: bool = False):
@@ -108,5 +117,11 @@ def load_library(build_if_missing: bool = False):
     L.pmcgpu_stats_len.restype = lng
     L.pmcgpu_finalize_update.argtypes = [i32, i32, vp, vp, vp, vp, vp, i32, vp, lng, vp, C.POINTER(i32), vp, vp, vp, vp, vp]
     L.pmcgpu_cholesky.argtypes = [i32, vp, C.POINTER(dbl)]
+    L.pmcgpu_set_target_combine.argtypes = [vp, i32, i32, vp]
+    L.pmcgpu_step_given_post.argtypes = [vp, vp, vp, lng, lng, dbl, i32, C.POINTER(i32), C.POINTER(StepResultC), vp, vp, vp, vp, vp]
+    L.pmcgpu_comm_allreduce.argtypes = [vp, vp, lng, i32]
+    L.pmcgpu_comm_bcast.argtypes = [vp, vp, C.c_size_t, i32]
+    L.pmcgpu_comm_gather_store.argtypes = [vp, i32, lng, lng, vp, vp, vp, vp, vp]
+    L.pmcgpu_comm_rank.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     _lib = L
     return L

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-TGT_BANANA, TGT_MVDENS, TGT_MIX = 1, 2, 3
+TGT_BANANA, TGT_MVDENS, TGT_MIX, TGT_COMBINE = 1, 2, 3, 5
 
 
 def box_faces(d: int, lo: float, hi: float) -> np.ndarray:
@@ -84,6 +84,32 @@ def shipped_example(seed=5):
     w = banana(d=2, K=9, seed=seed, mean_sigma=np.sqrt(10.0), var=10.0, box=20.0)
     w["name"] = "shipped_test_pmc"
     return w
+
+
+def with_gaussian_prior(wl, idim, loc, var):
+    """The workload's target with a Gaussian prior on the coordinates idim, as add_gaussian_prior (var 1-D: diagonal) /
+    add_gaussian_prior_2 (var 2-D: full covariance) build it (distribution.c:548-606): combine_lkl of [target, mvdens]."""
+    idim = np.asarray(idim, np.int32)
+    var = np.asarray(var, float)
+    cov = np.diag(var) if var.ndim == 1 else var
+    n = len(idim)
+    base = dict(wl["target"], dims=np.arange(wl["d"], dtype=np.int32))
+    prior = _target(TGT_MVDENS, n, K=1, wght=np.ones(1), mean=np.asarray(loc, float)[None], cov=cov[None],
+                    df=np.full(1, -1, np.int32), dims=idim)
+    out = dict(wl)
+    out["name"] = wl["name"] + "_prior"
+    out["target"] = dict(kind=TGT_COMBINE, d=wl["d"], terms=[base, prior], prior=dict(idim=idim, loc=np.asarray(loc, float), var=var))
+    return out
+
+
+def banana_prior(**kw):
+    """10-D banana with a Gaussian prior on coordinates 0, 3, 7 (the shape add_gaussian_prior produces for pmc_rc targets)."""
+    return with_gaussian_prior(banana(**kw), [0, 3, 7], [0.5, -1.0, 2.0], [25.0, 4.0, 9.0])
+
+
+def gmm_prior(**kw):
+    """configs[1] target with a full-covariance prior on coordinates 1 and 4 (add_gaussian_prior_2)."""
+    return with_gaussian_prior(gmm5(**kw), [1, 4], [0.3, -0.2], [[9.0, 1.5], [1.5, 4.0]])
 
 
 CONFIGS = {"c1": banana, "c2": gmm5, "c3": banana, "c4": student30, "c5": gauss128}

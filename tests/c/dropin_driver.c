@@ -8,6 +8,11 @@
  *     functions (simulate, _verb(t=1), normalize, update_prop_rb, perplexity_and_ess, evidence)
  *     mode 2: like 0 but the target is an OPAQUE host callback (user code), exercising the per-sample callback path
  *     mode 3: no-GPU check: object management and the error chain only; pmc_simu_pmc_step must fail loudly
+ *     mode 4: with the shipped histogram filter; mode 5: prepare_update as its own entry point
+ *     mode 6: the target carries a Gaussian prior (add_gaussian_prior -> combine_lkl), evaluated on the device
+ *     mode 7: libpmc_mpi entry points (pmc_simu_init_mpi, pmc_simu_init_classic_pmc_mpi, pmc_simu_pmc_step_mpi), one process
+ *             per GPU; rank and size come from the environment (PMCB200_RANK / PMCB200_WORLD_SIZE); rank 0 writes the file
+ *     mode 8: mode 7 with the opaque host callback target (the likelihood loop each rank runs over its shard)
  */
 #include <math.h>
 #include <stdint.h>
@@ -72,20 +77,29 @@ int main(int argc, char **argv) {
   }
   distribution *tgt;
   user_tgt *ut = NULL;
-  if (mode == 2) {
+  if (mode == 2 || mode == 8) {
     ut = malloc(sizeof(user_tgt)); ut->d = d; ut->b = tp[0]; ut->s1 = tp[1]; ut->calls = 0;
     tgt = init_distribution(d, ut, user_lkl, user_free, NULL, err);
   } else {
     tgt = init_bentGauss_distribution(d, tp[0], tp[1], err);
   }
   CHECK(err, "target");
+  if (mode == 6) { /* distribution.c:548-606: prior on coordinates 0, 3, 7 (pmclib_b200/workloads.py:banana_prior) */
+    int idim[3] = {0, 3, 7};
+    double loc[3] = {0.5, -1.0, 2.0}, var[3] = {25.0, 4.0, 9.0};
+    tgt = add_gaussian_prior(tgt, 3, idim, loc, var, err); CHECK(err, "add_gaussian_prior");
+  }
   parabox *pb = NULL;
   if (nfaces > 0) {
     pb = init_parabox(d, err); CHECK(err, "init_parabox");
     for (int f = 0; f < nfaces; ++f) { add_face(pb, faces + (size_t)f * (d + 1), faces[(size_t)f * (d + 1) + d], err); CHECK(err, "add_face"); }
   }
-  pmc_simu *psim = pmc_simu_init(N, d, err); CHECK(err, "pmc_simu_init");
-  if (mode == 4) { /* the shipped pmc_filter hook (pmc.c:203-206): histogram clipping of the log-weights */
+  const int mpi_mode = (mode == 7 || mode == 8);
+  pmc_simu *psim = mpi_mode ? pmc_simu_init_mpi(N, d, 0, err) : pmc_simu_init(N, d, err); CHECK(err, "pmc_simu_init");
+  if (mpi_mode) {
+    pmc_simu_init_classic_pmc_mpi(psim, tgt, pb, m, 0, NULL, NULL, err);
+    m = (mix_mvdens *)psim->proposal->data; /* clients work on the copy rank 0 broadcast */
+  } else if (mode == 4) { /* the shipped pmc_filter hook (pmc.c:203-206): histogram clipping of the log-weights */
     int *fil = filter_histogram_init(20, 1, 2, err); CHECK(err, "filter_histogram_init");
     pmc_simu_init_classic_pmc(psim, tgt, pb, m, 0, fil, &filter_histogram, err);
   } else {
@@ -105,7 +119,7 @@ int main(int argc, char **argv) {
     return 0;
   }
 
-  FILE *out = fopen(argv[2], "wb");
+  FILE *out = fopen((mpi_mode && psim->mpi_rank != 0) ? "/dev/null" : argv[2], "wb");
   if (!out) return 5;
   for (int it = 0; it < niter; ++it) {
     double perp, ess = 0, lne = 0;
@@ -132,6 +146,20 @@ int main(int argc, char **argv) {
       normalize_importance_weight(psim, err); CHECK(err, "normalize");
       psim->pmc_update(psim->proposal->data, psim, err); CHECK(err, "update");
       perp = perplexity_and_ess(psim, MC_UNORM, &ess, err); CHECK(err, "perplexity");
+    } else if (mpi_mode) {
+      perp = pmc_simu_pmc_step_mpi(psim, &rng, err); CHECK(err, "pmc_simu_pmc_step_mpi");
+      if (psim->mpi_rank != 0) { /* clients hold no sample (pmc_mpi.c:20-34); their proposal must equal the master's: print a digest */
+        double dg = 0;
+        for (int k = 0; k < K; ++k) { dg += m->wght[k] * (k + 1); for (int a = 0; a < d; ++a) dg += m->comp[k]->mean[a] * (a + 1) + m->comp[k]->std[a * d + a]; }
+        printf("rank %d iteration %d proposal digest %.17g\n", psim->mpi_rank, it, dg);
+        continue;
+      }
+      ess = 0;
+      double p2 = perplexity_and_ess(psim, MC_UNORM, &ess, err); CHECK(err, "perplexity_and_ess");
+      if (fabs(p2 - perp) > 1e-9 * fabs(perp)) { fprintf(stderr, "perplexity mismatch %g %g\n", perp, p2); return 11; }
+      { double dg = 0;
+        for (int k = 0; k < K; ++k) { dg += m->wght[k] * (k + 1); for (int a = 0; a < d; ++a) dg += m->comp[k]->mean[a] * (a + 1) + m->comp[k]->std[a * d + a]; }
+        printf("rank 0 iteration %d proposal digest %.17g\n", it, dg); }
     } else {
       perp = pmc_simu_pmc_step(psim, &rng, err); CHECK(err, "pmc_simu_pmc_step");
       double p2 = perplexity_and_ess(psim, MC_NORM, &ess, err); CHECK(err, "perplexity_and_ess"); /* vanilla_pmc.c:117 */

@@ -57,7 +57,21 @@ def update_digest():
     print("c5_update", r["rc"], r["perp"], os.path.getsize(os.path.join(HERE, "c5_update_d128_K64.npz")))
 
 
+def combine_golden():
+    """Targets with Gaussian priors (combine_lkl behind add_gaussian_prior / add_gaussian_prior_2): values of the REAL
+    reference on seeded points."""
+    out = {}
+    for name, f in (("banana_prior", W.banana_prior), ("gmm_prior", W.gmm_prior)):
+        wl = f()
+        X, _ = O.orc_simulate(600, wl, seed=301)
+        out[name + "_X"] = X
+        out[name + "_post"] = O.ref_prior_log_pdf(X, wl)
+    np.savez_compressed(os.path.join(HERE, "combine.npz"), **out)
+    print("combine", {k: v.shape for k, v in out.items()})
+
+
 def main():
+    combine_golden()
     assert O.ref() is not None, "the compiled reference is needed"
     for name, (f, N, seed) in CASES.items():
         wl = f()

@@ -29,7 +29,8 @@ class OrcMix(C.Structure):
 
 
 class OrcTarget(C.Structure):
-    _fields_ = [("kind", C.c_int), ("d", C.c_int), ("b", C.c_double), ("sig1", C.c_double), ("mix", OrcMix)]
+    _fields_ = [("kind", C.c_int), ("d", C.c_int), ("b", C.c_double), ("sig1", C.c_double), ("mix", OrcMix),
+                ("nterms", C.c_int), ("terms", vp), ("dims", vp)]
 
 
 _orc = None
@@ -93,6 +94,18 @@ class Mix:
 def make_target(t):
     if t["kind"] == 1:
         return OrcTarget(1, t["d"], t["b"], t["sig1"], OrcMix()), None
+    if t["kind"] == 5:  # combine_lkl / add_gaussian_prior: terms on index-mapped coordinates
+        n = len(t["terms"])
+        terms = (OrcTarget * n)()
+        dims = (vp * n)()
+        keep = []
+        for i, tt in enumerate(t["terms"]):
+            sub, k = make_target(tt)
+            terms[i] = sub
+            dm = np.ascontiguousarray(tt["dims"], np.int32)
+            dims[i] = dm.ctypes.data
+            keep += [sub, k, dm]
+        return OrcTarget(5, t["d"], 0.0, 0.0, OrcMix(), n, C.cast(terms, vp), C.cast(dims, vp)), (terms, dims, keep)
     m = Mix(t["wght"], t["mean"], t["cov"], t["df"])
     return OrcTarget(t["kind"], t["d"], 0.0, 0.0, m.c), m
 
@@ -164,6 +177,41 @@ def ref_iteration(X, indices, wl, t=1.0, do_update=1, in_retry=0):
     return dict(rc=rc, nok=int(scal[0]), maxW=scal[1], maxR=scal[2], logSum=scal[3], perp=scal[4], ess=scal[5],
                 ln_evidence=scal[6], retry=int(scal[7]), log_rho=lr, logw=lw, w_norm=wn, flg=flg,
                 o_wght=ow, o_mean=om, o_std=os_, o_chol=och, o_detL=od)
+
+
+def ref_prior_log_pdf(X, wl):
+    """The REAL reference: make_target + add_gaussian_prior[_2] + distribution_lkl (oracle/ref_driver.c:ref_prior_log_pdf)."""
+    L = ref()
+    t = wl["target"]
+    base, pr = t["terms"][0], t["prior"]
+    X = np.ascontiguousarray(X, np.float64)
+    N, d = X.shape
+    tp = np.array([base["b"], base["sig1"]])
+    out = np.zeros(N)
+    full = 1 if np.ndim(pr["var"]) == 2 else 0
+    idim = np.ascontiguousarray(pr["idim"], np.int32)
+    loc, var = np.ascontiguousarray(pr["loc"], float), np.ascontiguousarray(pr["var"], float)
+    if base["kind"] == 1:
+        rc = L.ref_prior_log_pdf(C.c_long(N), d, P(X), 1, P(tp), 0, None, None, None, None, len(idim), P(idim), P(loc), P(var), full, P(out))
+    else:
+        tw, tm, tc = (np.ascontiguousarray(base[k], float) for k in ("wght", "mean", "cov"))
+        tdf = np.ascontiguousarray(base["df"], np.int32)
+        rc = L.ref_prior_log_pdf(C.c_long(N), d, P(X), base["kind"], P(tp), len(tw), P(tw), P(tm), P(tc), P(tdf), len(idim), P(idim),
+                                 P(loc), P(var), full, P(out))
+    assert rc == 0, rc
+    return out
+
+
+def orc_target_log_pdf(X, wl):
+    """The restatement's target (any kind, including combined) on the rows of X."""
+    L = orc()
+    tgt, keep = make_target(wl["target"])
+    X = np.ascontiguousarray(X, np.float64)
+    N, d = X.shape
+    tmp = np.zeros(d); ld = np.zeros(64); rc = C.c_int(0)
+    out = np.array([L.orc_target_log_pdf(C.byref(tgt), P(X[i]), P(tmp), P(ld), C.byref(rc)) for i in range(N)])
+    assert rc.value == 0
+    return out
 
 
 def ref_simulate(N, wl, seed=1):

@@ -54,6 +54,20 @@ def test_oracle_reproduces_c5_update_digest():
     assert np.array_equal(o["w_norm"][:512], g["w_norm_head"]) and np.array_equal(o["log_rho"][:512], g["log_rho_head"])
 
 
+@pytest.mark.parametrize("name", ["banana_prior", "gmm_prior"])
+def test_oracle_combined_target_golden(name):
+    """combine_lkl behind add_gaussian_prior / add_gaussian_prior_2 (distribution.c:350-396, 548-606): the restatement's
+    combined target equals the REAL reference's values (tests/golden/combine.npz) bit for bit, and the compiled reference
+    itself where it is present."""
+    g = np.load(os.path.join(GOLD, "combine.npz"))
+    wl = getattr(W, name)()
+    X = g[name + "_X"]
+    o = O.orc_target_log_pdf(X, wl)
+    assert relerr(o, g[name + "_post"]) == 0.0
+    if O.ref() is not None:
+        assert relerr(O.ref_prior_log_pdf(X, wl), o) == 0.0
+
+
 def test_oracle_misc_golden():
     g = np.load(os.path.join(GOLD, "misc.npz"))
     L = O.orc()

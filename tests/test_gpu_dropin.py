@@ -10,7 +10,7 @@ import pytest
 import oracle_py as O
 from pmclib_b200 import workloads as W
 from pmclib_b200.lib import LIB_PATH
-from util import RTOL, assert_close, compare_mixture
+from util import PTOL, RTOL, WTOL, assert_close, compare_mixture
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,6 +22,27 @@ def driver(tmp_path_factory):
     subprocess.run(["gcc", "-O2", "-std=gnu99", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "dropin_driver.c"),
                     "-o", exe, "-L" + os.path.dirname(LIB_PATH), "-lpmcb200", "-Wl,-rpath," + os.path.dirname(LIB_PATH), "-lm"], check=True)
     return exe
+
+
+def _write_cfg(cfg, wl, N, niter, seed):
+    K, d = wl["K"], wl["d"]
+    faces = wl["faces"]
+    with open(cfg, "wb") as f:
+        f.write(np.array([K, d, N, niter, 0 if faces is None else len(faces), seed], np.int64).tobytes())
+        f.write(np.array([wl["target"]["b"], wl["target"]["sig1"]]).tobytes())
+        f.write(np.ascontiguousarray(wl["wght"]).tobytes()); f.write(np.ascontiguousarray(wl["mean"]).tobytes())
+        f.write(np.ascontiguousarray(wl["cov"]).tobytes())
+        if faces is not None:
+            f.write(np.ascontiguousarray(faces).tobytes())
+
+
+def _run_raw(driver, tmp_path, wl, N, niter, mode, env=None, seed=4242):
+    """a client rank: no output file to parse, stdout only"""
+    cfg, out = tmp_path / f"in{mode}.bin", tmp_path / f"out{mode}.bin"
+    _write_cfg(cfg, wl, N, niter, seed)
+    r = subprocess.run([driver, str(cfg), str(out), str(mode)], capture_output=True, text=True, env=dict(os.environ, **(env or {})))
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
 
 
 def _run(driver, tmp_path, wl, N, niter, mode, env=None, seed=4242):
@@ -56,6 +77,82 @@ def _run(driver, tmp_path, wl, N, niter, mode, env=None, seed=4242):
     return rec, r.stdout
 
 
+def _check_against_oracle(rec, wl, what, filt=None):
+    cur = dict(wl)
+    for it, r in enumerate(rec):
+        o = O.orc_iteration(r["X"], r["idx"], cur, do_update=1, in_retry=0 if it == 0 else rec[it - 1]["retry"], filt=filt)
+        assert o["rc"] == 0
+        big = max(np.max(np.abs(o["log_rho"])), 1.0)
+        assert r["isLog"] == 0 and np.array_equal(r["flg"], o["flg"])
+        assert_close(r["lr"], o["log_rho"], RTOL, what=f"{what} it{it} log_rho")
+        assert_close(r["w"], o["w_norm"], WTOL, scale=np.max(o["w_norm"]) * 1e-3, what=f"{what} it{it} weights")
+        assert_close(r["perp"], o["perp"], PTOL, what="perplexity")
+        assert_close(r["ess"], o["ess"], PTOL, what="ess")
+        assert_close(r["logSum"], o["logSum"], RTOL, scale=big, what="logSum")
+        assert_close(r["maxW"], o["maxW"], RTOL, scale=big, what="maxW")
+        assert_close(r["maxR"], o["maxR"], RTOL, what="maxR")
+        assert r["retry"] == o["retry"]
+        errs = compare_mixture(r["wght"], r["mean"], r["L"], o["o_wght"], o["o_mean"], o["o_std"], what=f"{what} it{it}")
+        print(f"{what} iteration {it}: perp {r['perp']:.4f} update errors {errs}")
+        cur = dict(wl, wght=r["wght"], mean=r["mean"], cov=r["L"], is_chol=True)
+
+
+def test_c_driver_target_with_gaussian_prior(driver, tmp_path):
+    """add_gaussian_prior(init_bentGauss_distribution(...)) -> combine_lkl target: the drop-in layer recognises the terms and
+    evaluates the sum on the device (no per-sample host callbacks); every iteration matches the oracle's combined target,
+    which is bit-identical to the real reference's (tests/test_cpu_oracle.py)."""
+    base = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
+    wl = W.with_gaussian_prior(base, [0, 3, 7], [0.5, -1.0, 2.0], [25.0, 4.0, 9.0])
+    rec, stdout = _run(driver, tmp_path, base, 40000, 3, 6)
+    _check_against_oracle(rec, wl, "prior")
+
+
+@pytest.mark.parametrize("mode", [7, 8])
+def test_c_driver_libpmc_mpi_entry_points_one_rank(driver, tmp_path, mode):
+    """pmc_simu_init_mpi / pmc_simu_init_classic_pmc_mpi / pmc_simu_pmc_step_mpi (pmc_mpi.h:52-101) with a world of one rank:
+    mode 7 device target, mode 8 opaque host callback target."""
+    wl = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
+    N, niter = 30000, 3
+    env = {k: "" for k in ()}
+    rec, stdout = _run(driver, tmp_path, wl, N, niter, mode, env=env)
+    _check_against_oracle(rec, wl, f"mpi mode {mode}")
+    if mode == 8:
+        assert f"user callback calls {N * niter}" in stdout
+
+
+@pytest.mark.parametrize("mode", [7, 8])
+def test_c_driver_libpmc_mpi_two_ranks(driver, tmp_path, mode):
+    """Two processes, one GPU each, rank/size from the environment, NCCL id through the rendezvous file: rank 0 ends every
+    iteration with the WHOLE sample in its pmc_simu (as the reference's master does) and it matches the oracle; rank 1's
+    proposal is identical (digest)."""
+    from pmclib_b200.lib import load_library
+    if load_library().pmcgpu_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import threading
+    wl = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
+    N, niter = 30001, 3
+    outs = [None, None]
+
+    def go(rank):
+        env = {"PMCB200_RANK": str(rank), "PMCB200_WORLD_SIZE": "2", "PMCB200_LOCAL_RANK": str(rank),
+               "PMCB200_RENDEZVOUS": str(tmp_path / "rdv")}
+        sub = tmp_path / f"r{rank}"
+        sub.mkdir()
+        outs[rank] = _run(driver, sub, wl, N, niter, mode, env=env) if rank == 0 else _run_raw(driver, sub, wl, N, niter, mode, env)
+    th = [threading.Thread(target=go, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    rec, so0 = outs[0]
+    so1 = outs[1]
+    _check_against_oracle(rec, wl, f"2-rank mpi mode {mode}")
+    d0 = [l.split()[-1] for l in so0.splitlines() if "proposal digest" in l]
+    d1 = [l.split()[-1] for l in so1.splitlines() if "proposal digest" in l]
+    assert len(d0) == niter and d0 == d1
+    if mode == 8:
+        calls = [int(l.split()[-1]) for l in (so0 + so1).splitlines() if l.startswith("user callback calls")]
+        assert sum(calls) == N * niter and min(calls) > 0
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 5])
 def test_c_driver_iterations_match_oracle(driver, tmp_path, mode):
     wl = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
@@ -69,9 +166,9 @@ def test_c_driver_iterations_match_oracle(driver, tmp_path, mode):
         big = max(np.max(np.abs(o["log_rho"])), 1.0)
         assert r["isLog"] == 0 and np.array_equal(r["flg"], o["flg"])
         assert_close(r["lr"], o["log_rho"], RTOL, what=f"it{it} log_rho")
-        assert_close(r["w"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
-        assert_close(r["perp"], o["perp"], 1e-11, what="perplexity")
-        assert_close(r["ess"], o["ess"], 1e-11, what="ess")
+        assert_close(r["w"], o["w_norm"], WTOL, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
+        assert_close(r["perp"], o["perp"], PTOL, what="perplexity")
+        assert_close(r["ess"], o["ess"], PTOL, what="ess")
         assert_close(r["lne"], o["ln_evidence"], RTOL, scale=big, what="ln evidence")
         assert_close(r["logSum"], o["logSum"], RTOL, scale=big, what="logSum")
         assert_close(r["maxW"], o["maxW"], RTOL, scale=big, what="maxW")
@@ -101,8 +198,8 @@ def test_c_driver_with_histogram_filter(driver, tmp_path):
         o = O.orc_iteration(r["X"], r["idx"], cur, do_update=1, in_retry=0 if it == 0 else rec[it - 1]["retry"], filt=(20, 1, 2))
         assert o["rc"] == 0 and o["n_filtered"] > 0
         assert np.array_equal(r["flg"], o["flg"])
-        assert_close(r["w"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
-        assert_close(r["perp"], o["perp"], 1e-11, what="perplexity")
+        assert_close(r["w"], o["w_norm"], WTOL, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
+        assert_close(r["perp"], o["perp"], PTOL, what="perplexity")
         assert r["retry"] == o["retry"]
         compare_mixture(r["wght"], r["mean"], r["L"], o["o_wght"], o["o_mean"], o["o_std"], what=f"filter it{it}")
         cur = dict(wl, wght=r["wght"], mean=r["mean"], cov=r["L"], is_chol=True)
@@ -142,8 +239,8 @@ def test_c_driver_single_process_multi_gpu(driver, tmp_path, mode):
         big = max(np.max(np.abs(o["log_rho"])), 1.0)
         assert np.array_equal(r["flg"], o["flg"])
         assert_close(r["lr"], o["log_rho"], RTOL, what=f"it{it} log_rho")
-        assert_close(r["w"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
-        assert_close(r["perp"], o["perp"], 1e-11, what="perplexity")
+        assert_close(r["w"], o["w_norm"], WTOL, scale=np.max(o["w_norm"]) * 1e-3, what=f"it{it} weights")
+        assert_close(r["perp"], o["perp"], PTOL, what="perplexity")
         assert_close(r["logSum"], o["logSum"], RTOL, scale=big, what="logSum")
         assert r["retry"] == o["retry"]
         compare_mixture(r["wght"], r["mean"], r["L"], o["o_wght"], o["o_mean"], o["o_std"], what=f"2 GPUs it{it}")

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from pmclib_b200 import workloads as W
-from util import RTOL, assert_close, compare_mixture
+from util import PTOL, RTOL, WTOL, assert_close, compare_mixture
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -40,13 +40,13 @@ def test_iteration_matches_reference_golden(gpu, name, path):
     got = gpu.download(X=False, indices=False)
     assert r.nok == int(g["nok"]) and np.array_equal(got["flg"], g["flg"])
     assert_close(got["log_rho"], g["log_rho"], RTOL, what="log_rho")
-    assert_close(got["weights"], g["w_norm"], 2e-12, scale=np.max(g["w_norm"]) * 1e-3, what="normalised weights")
+    assert_close(got["weights"], g["w_norm"], WTOL, scale=np.max(g["w_norm"]) * 1e-3, what="normalised weights")
     assert_close(r.maxW, float(g["maxW"]), RTOL, scale=big, what="maxW")
     assert_close(r.maxR, float(g["maxR"]), RTOL, what="maxR")
     assert_close(r.logSum, float(g["logSum"]), RTOL, scale=big, what="logSum")
     assert_close(r.ln_evidence, float(g["ln_evidence"]), RTOL, scale=big, what="evidence")
-    assert_close(r.perplexity, float(g["perp"]), 1e-11, what="perplexity")
-    assert_close(r.ess, float(g["ess"]), 1e-11, what="ess")
+    assert_close(r.perplexity, float(g["perp"]), PTOL, what="perplexity")
+    assert_close(r.ess, float(g["ess"]), PTOL, what="ess")
     if upd and int(g["rc"]) == 0:
         assert r.retry == int(g["retry"])
         compare_mixture(r.wght, r.mean, r.L, g["o_wght"], g["o_mean"], g["o_std"], what=name)

@@ -8,7 +8,7 @@ import pytest
 
 import oracle_py as O
 from pmclib_b200 import workloads as W
-from util import RTOL, assert_close, compare_mixture
+from util import PTOL, RTOL, WTOL, assert_close, compare_mixture
 
 pytestmark = pytest.mark.gpu
 
@@ -99,10 +99,10 @@ def test_mma_weights(gpu, oracle_runs, name):
     assert_close(logSum, o["logSum"], RTOL, scale=big, what="logSum")
     got = gpu.download(X=False, indices=False, log_rho=False)
     assert np.array_equal(got["flg"], o["flg"])
-    assert_close(got["weights"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
+    assert_close(got["weights"], o["w_norm"], WTOL, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
     perp, ess, nfl = gpu.perplexity_ess()
-    assert_close(perp, o["perp"], 1e-11, what="perplexity")
-    assert_close(ess, o["ess"], 1e-11, what="ESS")
+    assert_close(perp, o["perp"], PTOL, what="perplexity")
+    assert_close(ess, o["ess"], PTOL, what="ESS")
 
 
 @pytest.mark.parametrize("name", [n for n in CASES if not CASES[n][0]()["importance_only"]])
@@ -118,8 +118,8 @@ def test_mma_iteration_given_samples(gpu, oracle_runs, name):
     big = max(np.max(np.abs(o["log_rho"])), 1.0)
     assert r.nok == o["nok"]
     assert_close(r.logSum, o["logSum"], RTOL, scale=big, what="logSum")
-    assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
-    assert_close(r.ess, o["ess"], 1e-11, what="ESS")
+    assert_close(r.perplexity, o["perp"], PTOL, what="perplexity")
+    assert_close(r.ess, o["ess"], PTOL, what="ESS")
     assert r.retry == o["retry"]
     errs = compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
     print(name, f"precise={r.used_precise_path} one-pass DMMA update errors", errs)
@@ -146,7 +146,7 @@ def test_mma_matches_generic_with_dead_component_and_flags(gpu):
     assert g1["flg"][7] == 0 and g1["flg"][11] == 0
     ok = g0["flg"] == 1
     assert_close(g1["log_rho"][ok], g0["log_rho"][ok], RTOL, what="log_rho")
-    assert_close(g1["weights"][ok], g0["weights"][ok], 2e-12, scale=np.max(g0["weights"][ok]) * 1e-3, what="weights")
+    assert_close(g1["weights"][ok], g0["weights"][ok], WTOL, scale=np.max(g0["weights"][ok]) * 1e-3, what="weights")
     assert r0.n_alive == r1.n_alive
     assert np.array_equal(r0.alive, r1.alive)
     compare_mixture(r1.wght, r1.mean, r1.L, r0.wght, r0.mean, r0.L, what="mma vs generic")
@@ -216,8 +216,8 @@ def test_mma_chunked_whitening_when_q_does_not_fit(gpu, oracle_runs):
         gpu.set_option("mma_max_chunk", 0)
     got = gpu.download(X=False, indices=False)
     assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho")
-    assert_close(got["weights"], o["w_norm"], 2e-12, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
-    assert_close(r.perplexity, o["perp"], 1e-11, what="perplexity")
+    assert_close(got["weights"], o["w_norm"], WTOL, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
+    assert_close(r.perplexity, o["perp"], PTOL, what="perplexity")
     assert r.used_precise_path == 1
     compare_mixture(r.wght, r.mean, r.L, o["o_wght"], o["o_mean"], o["o_std"], what=name)
 

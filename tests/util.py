@@ -2,6 +2,12 @@
 import numpy as np
 
 RTOL = 1e-12  # BASELINE.json north_star: "within 1e-12 relative in double precision"
+PTOL = 1e-12  # perplexity, ESS: the same bar (measured errors are printed by tools/ab_step.py: 1e-15 .. 4e-14)
+# Normalised weights w_i = exp(lw_i - maxW + 500) / S.  An ABSOLUTE error delta in a log-weight is a RELATIVE error delta
+# in the weight, and lw_i = t*post - log_rho is a difference of log-densities of size up to `big` (a few hundred at
+# d = 128), each good to a few eps relative: delta <= ~8 eps big = 1e-12 at big = 560.  So the bar is 1e-12 relative for
+# every weight above 1e-3 of the largest (and 1e-12 of that floor below it), on all the shapes the tests run.
+WTOL = 1e-12
 
 
 def relerr(a, b, scale=0.0):
