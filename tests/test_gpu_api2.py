@@ -60,7 +60,8 @@ def test_wire_format_and_helpers(api2, tmp_path):
     assert any(l.startswith("name missing -1 code -6701") for l in lines)       # dist_undef
     v, wv = float(rep["prior_name"][1]), float(rep["prior_name"][3])
     assert abs(v - wv) < 1e-9  # the reference's ln2pi is truncated to 13 digits (maths_base.h:49)
-    assert rep["pickle"][:6] == ["n", "2", "top", "-43", "next", "-42"] and rep["pickle"][-1] == "first"
+    # newError(v, where, text, linkTo, NULL) appends to linkTo's chain and returns linkTo (errorlist.c:44-50)
+    assert rep["pickle"][:6] == ["n", "2", "top", "-42", "next", "-43"] and rep["pickle"][-1] == "second"
     assert any(l.startswith("Face |") for l in lines) and sum(l.strip().startswith(("0 |", "1 |")) for l in lines) == 2
     assert rep["sort"] == ["5", "1", "3", "0", "4", "2"]
 
