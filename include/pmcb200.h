@@ -127,6 +127,8 @@ int pmcgpu_weights_host_post(pmcgpu_ctx *ctx, const double *post, const short *o
 /* mix_mvdens_log_pdf (mvdens.c:784-825) of the PROPOSAL / the device TARGET on n host points: out[n] */
 int pmcgpu_proposal_log_pdf(pmcgpu_ctx *ctx, long n, const double *x, double *out);
 int pmcgpu_target_log_pdf(pmcgpu_ctx *ctx, long n, const double *x, double *out);
+/* scalar_product (pmctools/src/mvdens.c:319-349): q = (x-mu)^T Sigma^-1 (x-mu) of the mvdens installed as the target */
+int pmcgpu_target_scalar_product(pmcgpu_ctx *ctx, long n, const double *x, double *out);
 /* normalize_importance_weight (pmc.c:641-697): weights <- exp(lw - maxW + 500)/S over flg==1, non-finite
  * entries flagged out; logSum = log S + maxW - 500.  count = number of samples summed. */
 int pmcgpu_normalize(pmcgpu_ctx *ctx, double maxW, double *logSum, long *count);

@@ -30,10 +30,15 @@ static int take_err(error **err) {
 }
 
 /* mixture from flat arrays: wght[K], mean[K*d], cov[K*d*d] (covariance, chol=0 -> reference factorises), df[K] */
+/* band limit applied to every mixture make_mix builds (0 = leave the default, band_limit = ndim) */
+static size_t g_band_limit = 0;
+void ref_set_band_limit(size_t b) { g_band_limit = b; }
+
 static mix_mvdens *make_mix(int K, int d, const double *wght, const double *mean, const double *cov,
                             const int *df, int is_chol, error **err) {
   mix_mvdens *m = mix_mvdens_alloc(K, d, err);
   if (isError(*err)) return NULL;
+  if (g_band_limit > 0) mix_mvdens_set_band_limit(m, g_band_limit);
   for (int k = 0; k < K; ++k) {
     m->wght[k] = wght[k];
     memcpy(m->comp[k]->mean, mean + (size_t)k * d, sizeof(double) * d);
@@ -153,6 +158,38 @@ int ref_prior_log_pdf(long N, int d, const double *X, int kind, const double *tp
   }
   for (long i = 0; i < N && !rc; ++i) { out[i] = distribution_lkl(c, X + i * d, err); rc = take_err(err); }
   if (c) free_distribution(&c);
+  endError(err);
+  return rc;
+}
+
+/* the on-disk formats either side of the PMC path, written by the reference's own functions: <prefix>.mix
+ * (mix_mvdens_dump, mvdens.c:513-528), .mvd (mvdens_dump of component 0, :114-134), .psim (pmc_simu_dump, pmc.c:342-371),
+ * .out (out_pmc_simu, pmc.c:306-325) */
+int ref_dump_all(const char *prefix, long N, int d, int K, const double *X, const size_t *indices, const double *w,
+                 const double *log_rho, const short *flg, double logSum, int isLog, const double *wght, const double *mean,
+                 const double *cov, const int *df) {
+  error *e = initError(), **err = &e;
+  char name[4096];
+  mix_mvdens *m = make_mix(K, d, wght, mean, cov, df, 0, err);
+  pmc_simu *ps = pmc_simu_init(N, d, err);
+  int rc = take_err(err);
+  if (!rc) {
+    memcpy(ps->X, X, sizeof(double) * N * d);
+    memcpy(ps->indices, indices, sizeof(size_t) * N);
+    memcpy(ps->weights, w, sizeof(double) * N);
+    memcpy(ps->log_rho, log_rho, sizeof(double) * N);
+    memcpy(ps->flg, flg, sizeof(short) * N);
+    ps->logSum = logSum; ps->isLog = isLog;
+    FILE *f;
+    snprintf(name, sizeof name, "%s.mix", prefix); f = fopen(name, "w"); mix_mvdens_dump(f, m); fclose(f);
+    snprintf(name, sizeof name, "%s.mvd", prefix); f = fopen(name, "w"); mvdens_dump(f, m->comp[0]); fclose(f);
+    snprintf(name, sizeof name, "%s.psim", prefix); f = fopen(name, "w"); pmc_simu_dump(f, ps, err); fclose(f);
+    rc = take_err(err);
+    snprintf(name, sizeof name, "%s.out", prefix);
+    if (!rc) { out_pmc_simu(name, ps, err); rc = take_err(err); }
+  }
+  if (ps) pmc_simu_free(&ps);
+  if (m) mix_mvdens_free(&m);
   endError(err);
   return rc;
 }

@@ -1868,6 +1868,21 @@ int pmcgpu_target_log_pdf(pmcgpu_ctx *c, long n, const double *x, double *out) {
   return 0;
 }
 
+// scalar_product (mvdens.c:319-349) of the mvdens / first mixture component installed as the target, on n points
+int pmcgpu_target_scalar_product(pmcgpu_ctx *c, long n, const double *x, double *out) {
+  if (!c || n < 0 || (c->tkind != PMCGPU_TGT_MVDENS && c->tkind != PMCGPU_TGT_MIX) || c->tmix.K < 1) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  const int d = c->tmix.d;
+  CU(c->tmpx.ensure((size_t)n * d * sizeof(double) + 16));
+  CU(c->tmpo.ensure((size_t)n * sizeof(double) + 16));
+  CU(cudaMemcpyAsync(c->tmpx.p, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_scalar_product(c->dtmix.view, 0, n, c->tmpx.as<double>(), c->tmpo.as<double>(), c->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, c->tmpo.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int pmcgpu_normalize(pmcgpu_ctx *c, double maxW, double *logSum, long *count) {
   if (!c || c->N <= 0) return PMCGPU_ERR_USAGE;
   cudaSetDevice(c->device);

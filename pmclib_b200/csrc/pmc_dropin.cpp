@@ -499,6 +499,7 @@ int isinBox(const parabox *bx, double *pos, error **err) {
       *err = newErrorVA(pb_infnan, __func__, (char *)"", (char *)"Parameter #%d is not finite", *err, nullptr, j);
       return 0;
     }
+  std::lock_guard<std::mutex> lk(pmcb200::dropin_point_mutex());
   pmcgpu_ctx *c = point_ctx(err);
   if (!c) return 0;
   int inside = 0;
@@ -721,16 +722,56 @@ size_t ranindx(double *cw, size_t nE, gsl_rng *r, error **err) {  // mvdens.c:76
   return index;
 }
 
-// point-wise densities: one launch each; bulk evaluation should go through generic_get_importance_weight*
+// Point-wise densities: one upload + one launch + one synchronisation per call (tens of microseconds); bulk evaluation
+// should go through generic_get_importance_weight*.  The calls share one context behind a mutex, and the density that
+// was uploaded last is remembered, so a likelihood that evaluates the SAME mvdens / mixture sample after sample (the
+// usual pattern in pmclib targets) pays for the upload once.
+namespace {
+struct PointCache {
+  FlatMix mix;        // last mixture installed as the proposal of the point context
+  bool have_mix = false;
+  std::vector<double> gm, gL;  // last mvdens installed as its target
+  int gdf = 0;
+  bool have_g = false;
+};
+PointCache g_pc;
+bool same_mix(const FlatMix &a, const FlatMix &b) {
+  return a.K == b.K && a.d == b.d && a.w == b.w && a.mean == b.mean && a.L == b.L && a.detL == b.detL && a.df == b.df;
+}
+// installs g (factorised) as the target of the point context unless it is already there
+int point_install_mvdens(pmcgpu_ctx *c, mvdens *g) {
+  const size_t d = g->ndim;
+  if (g_pc.have_g && g_pc.gdf == g->df && g_pc.gm.size() == d && !memcmp(g_pc.gm.data(), g->mean, d * sizeof(double)) &&
+      !memcmp(g_pc.gL.data(), g->std, d * d * sizeof(double)))
+    return 0;
+  const double one = 1.0;
+  int rc = pmcgpu_set_target_mix(c, PMCGPU_TGT_MVDENS, 1, (int)d, &one, g->mean, g->std, &g->detL, &g->df);
+  if (!rc) rc = pmcgpu_set_target_defaults(c, 0, nullptr, nullptr);
+  g_pc.have_g = rc == 0;
+  if (!rc) { g_pc.gm.assign(g->mean, g->mean + d); g_pc.gL.assign(g->std, g->std + d * d); g_pc.gdf = g->df; }
+  return rc;
+}
+}  // namespace
+}  // extern "C"
+namespace pmcb200 {
+void dropin_point_invalidate() { g_pc.have_mix = false; g_pc.have_g = false; }
+}  // namespace pmcb200
+extern "C" {
 double mix_mvdens_log_pdf(mix_mvdens *m, const double *x, error **err) {
+  std::lock_guard<std::mutex> lk(pmcb200::dropin_point_mutex());
   pmcgpu_ctx *c = point_ctx(err);
   if (!c) return 0;
   FlatMix f;
   if (!flatten(m, f, err)) { FWD(*err, 0); }
   double out = 0.0;
-  int rc = pmcgpu_set_proposal(c, f.K, f.d, f.w.data(), f.mean.data(), f.L.data(), f.detL.data(), f.df.data());
+  int rc = 0;
+  if (!g_pc.have_mix || !same_mix(f, g_pc.mix)) {
+    rc = pmcgpu_set_proposal(c, f.K, f.d, f.w.data(), f.mean.data(), f.L.data(), f.detL.data(), f.df.data());
+    g_pc.have_mix = rc == 0;
+    if (!rc) g_pc.mix = f;
+  }
   if (!rc) rc = pmcgpu_proposal_log_pdf(c, 1, x, &out);
-  if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0; }
+  if (rc) { g_pc.have_mix = false; *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0; }
   return out;
 }
 double mix_mvdens_log_pdf_void(void *m, const double *x, error **err) {
@@ -741,14 +782,13 @@ double mix_mvdens_log_pdf_void(void *m, const double *x, error **err) {
 double mvdens_log_pdf(mvdens *g, const double *x, error **err) {
   mvdens_cholesky_decomp(g, err);
   FWD(*err, -1);
+  std::lock_guard<std::mutex> lk(pmcb200::dropin_point_mutex());
   pmcgpu_ctx *c = point_ctx(err);
   if (!c) return 0;
-  const double one = 1.0;
   double out = 0.0;
-  int rc = pmcgpu_set_target_mix(c, PMCGPU_TGT_MVDENS, 1, (int)g->ndim, &one, g->mean, g->std, &g->detL, &g->df);
-  if (!rc) rc = pmcgpu_set_target_defaults(c, 0, nullptr, nullptr);
+  int rc = point_install_mvdens(c, g);
   if (!rc) rc = pmcgpu_target_log_pdf(c, 1, x, &out);
-  if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0; }
+  if (rc) { g_pc.have_g = false; *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0; }
   return out;
 }
 double mvdens_log_pdf_void(void *g, const double *x, error **err) {
@@ -756,14 +796,19 @@ double mvdens_log_pdf_void(void *g, const double *x, error **err) {
   FWD(*err, 0.0);
   return r;
 }
-// (x-mu)^T Sigma^-1 (x-mu): recovered from the Gaussian log-density the device computes
+// (x-mu)^T Sigma^-1 (x-mu) (mvdens.c:319-349): the forward substitution itself on the device, not a value recovered from
+// the log-density (that would cancel for small q); g is not modified
 double scalar_product(mvdens *g, const double *x, error **err) {
-  const int df = g->df;
-  g->df = -1;
-  const double lp = mvdens_log_pdf(g, x, err);
-  g->df = df;
+  mvdens_cholesky_decomp(g, err);
   FWD(*err, -1);
-  return -2.0 * (lp + std::log(g->detL)) - (double)g->ndim * 1.837877066409;
+  std::lock_guard<std::mutex> lk(pmcb200::dropin_point_mutex());
+  pmcgpu_ctx *c = point_ctx(err);
+  if (!c) return 0;
+  double out = 0.0;
+  int rc = point_install_mvdens(c, g);
+  if (!rc) rc = pmcgpu_target_scalar_product(c, 1, x, &out);
+  if (rc) { g_pc.have_g = false; *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0; }
+  return out;
 }
 
 // text formats (mvdens.c:114-134, 513-583)
@@ -846,8 +891,10 @@ void bentGauss_free(void **pbg) { free(*pbg); *pbg = nullptr; }
 // point-wise value; inside a PMC run the density is evaluated by the kernels, not through this pointer
 double bentGauss_lkl(void *vbg, double *pars, error **err) {
   const bentGauss *bg = (const bentGauss *)vbg;
+  std::lock_guard<std::mutex> lk(pmcb200::dropin_point_mutex());
   pmcgpu_ctx *c = point_ctx(err);
   if (!c) return 0;
+  g_pc.have_g = false;  // the point context's target changes
   double out = 0.0;
   int rc = pmcgpu_set_target_banana(c, bg->ndim, bg->b, bg->sig1);
   if (!rc) rc = pmcgpu_set_target_defaults(c, 0, nullptr, nullptr);

@@ -45,6 +45,7 @@ bool gpu_draw_one(int K, int d, const double *w, const double *mean, const doubl
   std::lock_guard<std::mutex> lk(pmcb200::dropin_point_mutex());
   pmcgpu_ctx *c = pmcb200::dropin_point_ctx(err);
   if (!c) return false;
+  pmcb200::dropin_point_invalidate();
   int rc = pmcgpu_set_proposal(c, K, d, w, mean, L, detL, df);
   if (!rc) rc = pmcgpu_set_box(c, d, 0, nullptr);
   if (!rc) rc = pmcgpu_resize(c, 1, d);
@@ -298,6 +299,7 @@ double fill_read_pmc_simu(pmc_simu *psim, mix_mvdens *proposal, error **err) {
     std::lock_guard<std::mutex> lk(pmcb200::dropin_point_mutex());
     pmcgpu_ctx *c = pmcb200::dropin_point_ctx(err);
     if (!c) return 0.0;
+    pmcb200::dropin_point_invalidate();
     int rc = pmcgpu_set_proposal(c, (int)K, (int)d, proposal->wght, mean.data(), L.data(), det.data(), df.data());
     if (!rc) rc = pmcgpu_proposal_log_pdf(c, N, psim->X, psim->log_rho);
     if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0.0; }

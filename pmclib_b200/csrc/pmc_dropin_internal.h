@@ -11,6 +11,8 @@ std::mutex &dropin_point_mutex();
 pmcgpu_ctx *dropin_point_ctx(error **err);
 // Philox key of one call from the caller's gsl_rng (two 32-bit words), or a process-local counter
 uint64_t dropin_seed_from(gsl_rng *r);
+// whoever installs another proposal / target on the point context (holding the mutex) calls this afterwards
+void dropin_point_invalidate();
 // proposal + target (may be null) + box onto a context; mixture <- flat arrays; which device density evaluates a target
 bool dropin_push_model(pmcgpu_ctx *ctx, mix_mvdens *m, distribution *target, parabox *pb, int d, error **err);
 void dropin_unflatten(mix_mvdens *m, const double *w, const double *mean, const double *L, const double *detL);

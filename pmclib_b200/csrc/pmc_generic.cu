@@ -176,6 +176,14 @@ __global__ void k_mix_log_pdf(MixDev m, long n, const double *__restrict__ X, do
   for (int a = 0; a < m.d; ++a) x[a] = X[(size_t)i * m.d + a];
   out[i] = mix_log_pdf_generic(m, x, y, ldscratch + (size_t)i * ldstride);
 }
+// scalar_product (mvdens.c:319-349) of component k of a mixture on n points: q = |L^-1 (x - mu)|^2
+__global__ void k_scalar_product(MixDev m, int k, long n, const double *__restrict__ X, double *__restrict__ out) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x[MAXD], y[MAXD];
+  for (int a = 0; a < m.d; ++a) x[a] = X[(size_t)i * m.d + a];
+  out[i] = whiten_q(m.L + (size_t)k * m.d * m.d, m.mean + (size_t)k * m.d, x, y, m.d);
+}
 __global__ void k_target_log_pdf(TargetDev tg, int dfree, long n, const double *__restrict__ X, double *__restrict__ out,
                                  double *__restrict__ ldscratch, int ldstride) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -509,6 +517,9 @@ void launch_mix_log_pdf(const MixDev &m, long n, const double *X, double *out, d
 void launch_combine_target(const CombTermDev *terms, int nterms, int d, long n, const double *X, double *out, double *ld,
                            int ldstride, cudaStream_t s) {
   if (n > 0) { k_combine_target<<<nblk(n, 128), 128, 0, s>>>(terms, nterms, d, n, X, out, ld, ldstride); count_launch(); }
+}
+void launch_scalar_product(const MixDev &m, int k, long n, const double *X, double *out, cudaStream_t s) {
+  if (n > 0) { k_scalar_product<<<nblk(n, 128), 128, 0, s>>>(m, k, n, X, out); count_launch(); }
 }
 void launch_target_log_pdf(const TargetDev &tg, int dfree, long n, const double *X, double *out, double *ld, int ldstride, cudaStream_t s) {
   if (n > 0) { k_target_log_pdf<<<nblk(n, 128), 128, 0, s>>>(tg, dfree, n, X, out, ld, ldstride); count_launch(); }

@@ -92,6 +92,7 @@ void launch_weights_generic(const MixDev &m, const TargetDev &tg, int mode, cons
                             short *flg, double *ldscratch, int ldstride, double *blk_maxw, double *blk_maxr,
                             unsigned long long *counters, double *first_vals, cudaStream_t s);
 void launch_mix_log_pdf(const MixDev &m, long n, const double *X, double *out, double *ld, int ldstride, cudaStream_t s);
+void launch_scalar_product(const MixDev &m, int k, long n, const double *X, double *out, cudaStream_t s);
 void launch_combine_target(const CombTermDev *terms, int nterms, int d, long n, const double *X, double *out, double *ld,
                            int ldstride, cudaStream_t s);
 void launch_target_log_pdf(const TargetDev &tg, int dfree, long n, const double *X, double *out, double *ld,

@@ -227,7 +227,95 @@ static int mode_file(const char *inname, const char *outname, int N, int d) {
   return 0;
 }
 
+/* dump <in.bin> <prefix>: the on-disk formats (byte-compared with files the reference's own functions wrote) */
+static int mode_dump(const char *inname, const char *prefix) {
+  error *_err = initError(), **err = &_err;
+  FILE *in = fopen(inname, "rb");
+  if (!in) return 3;
+  long hdr[4]; /* N, d, K, isLog */
+  double logSum;
+  if (fread(hdr, sizeof hdr, 1, in) != 1 || fread(&logSum, sizeof logSum, 1, in) != 1) return 4;
+  const long N = hdr[0];
+  const int d = (int)hdr[1], K = (int)hdr[2];
+  pmc_simu *ps = pmc_simu_init(N, d, err); CHECK(err, "pmc_simu_init");
+  mix_mvdens *m = mix_mvdens_alloc(K, d, err); CHECK(err, "mix_mvdens_alloc");
+  int ok = fread(ps->X, sizeof(double), (size_t)N * d, in) == (size_t)N * d && fread(ps->indices, sizeof(size_t), N, in) == (size_t)N &&
+           fread(ps->weights, sizeof(double), N, in) == (size_t)N && fread(ps->log_rho, sizeof(double), N, in) == (size_t)N &&
+           fread(ps->flg, sizeof(short), N, in) == (size_t)N && fread(m->wght, sizeof(double), K, in) == (size_t)K;
+  for (int k = 0; k < K && ok; ++k) ok = fread(m->comp[k]->mean, sizeof(double), d, in) == (size_t)d;
+  for (int k = 0; k < K && ok; ++k) ok = fread(m->comp[k]->std, sizeof(double), (size_t)d * d, in) == (size_t)d * d;
+  for (int k = 0; k < K && ok; ++k) ok = fread(&m->comp[k]->df, sizeof(int), 1, in) == 1;
+  fclose(in);
+  if (!ok) return 4;
+  ps->logSum = logSum; ps->isLog = (int)hdr[3];
+  char name[4096];
+  FILE *f;
+  snprintf(name, sizeof name, "%s.mix", prefix); f = fopen(name, "w"); mix_mvdens_dump(f, m); fclose(f);
+  snprintf(name, sizeof name, "%s.mvd", prefix); f = fopen(name, "w"); mvdens_dump(f, m->comp[0]); fclose(f);
+  snprintf(name, sizeof name, "%s.psim", prefix); f = fopen(name, "w"); pmc_simu_dump(f, ps, err); fclose(f); CHECK(err, "pmc_simu_dump");
+  snprintf(name, sizeof name, "%s.out", prefix); out_pmc_simu(name, ps, err); CHECK(err, "out_pmc_simu");
+  /* and back: mix_mvdens_dwnp reads what mix_mvdens_dump wrote */
+  snprintf(name, sizeof name, "%s.mix", prefix); f = fopen(name, "r");
+  mix_mvdens *back = mix_mvdens_dwnp(f, err); CHECK(err, "mix_mvdens_dwnp");
+  fclose(f);
+  double worst = 0;
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i < d * d; ++i) { const double e = fabs(back->comp[k]->std[i] - m->comp[k]->std[i]); if (e > worst) worst = e; }
+  printf("dwnp K %zu d %zu worst %.3e df0 %d\n", back->ncomp, back->ndim, worst, back->comp[0]->df);
+  pmc_simu_free(&ps);
+  return 0;
+}
+
+/* point <in.bin> <out.bin>: the point-wise entry points on M points of dimension d: mvdens_log_pdf (Gaussian and
+ * Student-t), scalar_product, mix_mvdens_log_pdf, bentGauss_lkl, isinBox */
+static int mode_point(const char *inname, const char *outname) {
+  error *_err = initError(), **err = &_err;
+  FILE *in = fopen(inname, "rb");
+  if (!in) return 3;
+  long hdr[2]; /* M, d */
+  if (fread(hdr, sizeof hdr, 1, in) != 1) return 4;
+  const long M = hdr[0];
+  const int d = (int)hdr[1];
+  double *X = malloc(sizeof(double) * (size_t)M * d), *mean = malloc(sizeof(double) * d), *cov = malloc(sizeof(double) * d * d);
+  if (fread(X, sizeof(double), (size_t)M * d, in) != (size_t)M * d || fread(mean, sizeof(double), d, in) != (size_t)d ||
+      fread(cov, sizeof(double), (size_t)d * d, in) != (size_t)d * d) return 4;
+  fclose(in);
+  mvdens *g = mvdens_alloc(d, err); CHECK(err, "mvdens_alloc");
+  memcpy(g->mean, mean, sizeof(double) * d); memcpy(g->std, cov, sizeof(double) * d * d);
+  mvdens *t = mvdens_alloc(d, err); CHECK(err, "mvdens_alloc");
+  memcpy(t->mean, mean, sizeof(double) * d); memcpy(t->std, cov, sizeof(double) * d * d);
+  t->df = 4;
+  mix_mvdens *m = mix_mvdens_alloc(2, d, err); CHECK(err, "mix_mvdens_alloc");
+  m->wght[0] = 0.25; m->wght[1] = 0.75;
+  for (int k = 0; k < 2; ++k) {
+    for (int a = 0; a < d; ++a) m->comp[k]->mean[a] = mean[a] + (k ? 0.5 : -0.5);
+    memcpy(m->comp[k]->std, cov, sizeof(double) * d * d);
+  }
+  bentGauss *bg = init_bentGauss(d, 0.1, 10.0, err); CHECK(err, "bentGauss");
+  parabox *pb = init_parabox(d, err); CHECK(err, "parabox");
+  add_slab(pb, 0, -1.0, 1.5, err); add_hibound(pb, 1, 2.0, err); CHECK(err, "box");
+  double *out = malloc(sizeof(double) * (size_t)M * 7);
+  for (long i = 0; i < M; ++i) {
+    double *x = X + (size_t)i * d;
+    out[7 * i + 0] = mvdens_log_pdf(g, x, err);
+    out[7 * i + 1] = scalar_product(g, x, err);
+    out[7 * i + 2] = mvdens_log_pdf(t, x, err);
+    out[7 * i + 3] = scalar_product(t, x, err);  /* must not depend on df nor change it */
+    out[7 * i + 4] = mix_mvdens_log_pdf(m, x, err);
+    out[7 * i + 5] = bentGauss_lkl(bg, x, err);
+    out[7 * i + 6] = (double)isinBox(pb, x, err);
+    CHECK(err, "point-wise");
+  }
+  printf("df_after %d chol %d\n", t->df, t->chol);
+  FILE *f = fopen(outname, "wb");
+  fwrite(out, sizeof(double), (size_t)M * 7, f);
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 4 && !strcmp(argv[1], "point")) return mode_point(argv[2], argv[3]);
+  if (argc >= 4 && !strcmp(argv[1], "dump")) return mode_dump(argv[2], argv[3]);
   if (argc >= 3 && !strcmp(argv[1], "wire")) return mode_wire(argv[2]);
   if (argc >= 5 && !strcmp(argv[1], "ran")) return mode_ran(argv[2], atol(argv[3]), atoi(argv[4]));
   if (argc >= 6 && !strcmp(argv[1], "file")) return mode_file(argv[2], argv[3], atoi(argv[4]), atoi(argv[5]));

@@ -70,8 +70,52 @@ def combine_golden():
     print("combine", {k: v.shape for k, v in out.items()})
 
 
+def updates_golden():
+    """update_prop (hard-assignment EM, pmc.c:1194-1310) and the band-limited update_prop_rb (pmc.c:1444) of the compiled
+    reference on seeded samples: inputs are regenerated from the seed, outputs kept."""
+    out = {}
+    for name, f, N, upd, band in (("hard_c1", W.banana, 4000, 2, None), ("hard_c2", W.gmm5, 6000, 2, None),
+                                  ("band_c1", W.banana, 4000, 1, 3), ("hardband_c2", W.gmm5, 6000, 2, 2)):
+        wl = f()
+        if band is not None:
+            wl["band_limit"] = np.full(wl["K"], band, np.uint64)
+        X, idx = O.orc_simulate(N, wl, seed=401)
+        r = O.ref_iteration(X, idx, wl, do_update=upd)
+        assert r["rc"] == 0, (name, r["rc"])
+        for k in ("o_wght", "o_mean", "o_std", "o_detL", "retry", "perp"):
+            out[f"{name}_{k}"] = np.asarray(r[k])
+    np.savez_compressed(os.path.join(HERE, "updates.npz"), **out)
+    print("updates", sorted(out)[:4], os.path.getsize(os.path.join(HERE, "updates.npz")))
+
+
+def dumps_golden():
+    """The on-disk formats written by the reference's own mix_mvdens_dump / mvdens_dump / pmc_simu_dump / out_pmc_simu
+    (oracle/ref_driver.c:ref_dump_all) for a small seeded object; the input is stored next to the files."""
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    N, d, K = 40, 3, 2
+    X = rng.normal(0, 2, (N, d)); idx = rng.integers(0, K, N).astype(np.uint64)
+    w = rng.random(N); w /= w.sum(); lr = rng.normal(-4, 1, N); flg = (rng.random(N) > 0.2).astype(np.int16)
+    wght = np.array([0.7, 0.3]); mean = rng.normal(0, 1, (K, d))
+    cov = np.array([np.eye(d) * (1.5 + k) + 0.25 for k in range(K)]); df = np.array([-1, 5], np.int32)
+    logSum = -3.25
+    L = O.ref()
+    L.ref_set_band_limit(C.c_size_t(0))
+    prefix = os.path.join(HERE, "dump_ref")
+    rc = L.ref_dump_all(prefix.encode(), C.c_long(N), d, K, O.P(X), O.P(idx), O.P(w), O.P(lr), O.P(flg), C.c_double(logSum), 0,
+                        O.P(wght), O.P(mean), O.P(cov), O.P(df))
+    assert rc == 0
+    with open(prefix + ".in", "wb") as f:
+        f.write(np.array([N, d, K, 0], np.int64).tobytes()); f.write(np.array([logSum]).tobytes())
+        for a in (X, idx, w, lr, flg, wght, mean, cov, df):
+            f.write(np.ascontiguousarray(a).tobytes())
+    print("dumps", [os.path.getsize(prefix + e) for e in (".mix", ".mvd", ".psim", ".out", ".in")])
+
+
 def main():
     combine_golden()
+    updates_golden()
+    dumps_golden()
     assert O.ref() is not None, "the compiled reference is needed"
     for name, (f, N, seed) in CASES.items():
         wl = f()

@@ -74,7 +74,7 @@ def ref():
 class Mix:
     """Mixture on the oracle side: keeps numpy arrays alive and exposes the ctypes struct."""
 
-    def __init__(self, wght, mean, cov, df=None, factorise=True):
+    def __init__(self, wght, mean, cov, df=None, factorise=True, band_limit=None):
         self.K, self.d = mean.shape
         self.wght = np.ascontiguousarray(wght, np.float64).copy()
         self.mean = np.ascontiguousarray(mean, np.float64).copy()
@@ -88,7 +88,8 @@ class Mix:
                 if rc:
                     raise ValueError(f"component {k} not positive definite")
                 self.detL[k] = det.value
-        self.c = OrcMix(self.K, self.d, P(self.wght), P(self.mean), P(self.L), P(self.detL), P(self.df), None)
+        self.band = None if band_limit is None else np.ascontiguousarray(band_limit, np.uint64)
+        self.c = OrcMix(self.K, self.d, P(self.wght), P(self.mean), P(self.L), P(self.detL), P(self.df), P(self.band))
 
 
 def make_target(t):
@@ -116,14 +117,14 @@ def orc_iteration(X, indices, wl, t=1.0, do_update=1, in_retry=0, filt=None):
     X = np.ascontiguousarray(X, np.float64)
     N, d = X.shape
     if wl.get("is_chol"):  # wl["cov"] already holds Cholesky factors (e.g. the proposal a previous update produced)
-        m = Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"], factorise=False)
+        m = Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"], factorise=False, band_limit=wl.get("band_limit"))
         for k in range(m.K):
             det = 1.0
             for a in range(d):
                 det *= m.L[k, a, a]
             m.detL[k] = det
     else:
-        m = Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"])
+        m = Mix(wl["wght"], wl["mean"], wl["cov"], wl["df"], band_limit=wl.get("band_limit"))
     tgt, keep = make_target(wl["target"])
     w = np.zeros(N); lr = np.zeros(N); flg = np.zeros(N, np.int16)
     mw, mr = C.c_double(), C.c_double()
@@ -160,6 +161,8 @@ def orc_iteration(X, indices, wl, t=1.0, do_update=1, in_retry=0, filt=None):
 
 def ref_iteration(X, indices, wl, t=1.0, do_update=1, in_retry=0):
     L = ref()
+    bl = wl.get("band_limit")
+    L.ref_set_band_limit(C.c_size_t(0 if bl is None else int(bl[0])))  # the driver applies one limit to the whole mixture
     X = np.ascontiguousarray(X, np.float64)
     N, d = X.shape
     K = wl["K"]

@@ -214,3 +214,20 @@ def test_shard_range_partitions_like_send_simulation():
             assert f0 + n0 == f1
         lens = [n for _, n in parts]
         assert max(lens) - min(lens) <= 1 and sorted(lens, reverse=True) == lens  # the first N%P ranks get one more
+
+
+def test_on_disk_formats_are_byte_identical_to_the_reference(tmp_path):
+    """mix_mvdens_dump, mvdens_dump, pmc_simu_dump and out_pmc_simu write the bytes the reference's own functions write
+    (tests/golden/dump_ref.*, produced by oracle/ref_driver.c:ref_dump_all from the unmodified reference), and
+    mix_mvdens_dwnp reads them back.  Host-only entry points: no GPU needed."""
+    import subprocess
+    gold = os.path.join(ROOT, "tests", "golden", "dump_ref")
+    exe = str(tmp_path / "api2_driver")
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "api2_driver.c"),
+                    "-o", exe, "-L" + os.path.dirname(LIB_PATH), "-lpmcb200", "-Wl,-rpath," + os.path.dirname(LIB_PATH), "-lm"], check=True)
+    r = subprocess.run([exe, "dump", gold + ".in", str(tmp_path / "ours")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in (".mix", ".mvd", ".psim", ".out"):
+        assert open(str(tmp_path / "ours") + ext, "rb").read() == open(gold + ext, "rb").read(), ext
+    assert "dwnp K 2 d 3" in r.stdout and "df0 -1" in r.stdout
+    assert float(r.stdout.split("worst")[1].split()[0]) < 1e-14

@@ -68,6 +68,24 @@ def test_oracle_combined_target_golden(name):
         assert relerr(O.ref_prior_log_pdf(X, wl), o) == 0.0
 
 
+@pytest.mark.parametrize("name,fact,N,upd,band", [("hard_c1", "banana", 4000, 2, None), ("hard_c2", "gmm5", 6000, 2, None),
+                                                  ("band_c1", "banana", 4000, 1, 3), ("hardband_c2", "gmm5", 6000, 2, 2)])
+def test_oracle_hard_and_band_limited_updates_golden(name, fact, N, upd, band, capfd):
+    """update_prop (hard-assignment EM, pmc.c:1194-1310) and band-limited updates (pmc.c:1288,1444; the band-limited cases
+    end in the retry branch of cleanup_after_update): the restatement equals the compiled reference's outputs
+    (tests/golden/updates.npz, made by make_golden.py:updates_golden) bit for bit."""
+    g = np.load(os.path.join(GOLD, "updates.npz"))
+    wl = getattr(W, fact)()
+    if band is not None:
+        wl["band_limit"] = np.full(wl["K"], band, np.uint64)
+    X, idx = O.orc_simulate(N, wl, seed=401)
+    o = O.orc_iteration(X, idx, wl, do_update=upd)
+    capfd.readouterr()
+    assert o["rc"] == 0 and o["retry"] == int(g[f"{name}_retry"])
+    for k in ("o_wght", "o_mean", "o_std", "o_detL", "perp"):
+        assert relerr(o[k], g[f"{name}_{k}"]) == 0.0, k
+
+
 def test_oracle_misc_golden():
     g = np.load(os.path.join(GOLD, "misc.npz"))
     L = O.orc()

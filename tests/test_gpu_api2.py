@@ -142,3 +142,46 @@ def test_pmc_simu_from_file(api2, tmp_path):
     e = np.exp(lw - lw.max() + 500.0)
     assert_close(gw, e / e.sum(), WTOL, what="normalised weights")
     assert_close(sc[1], np.log(e.sum()) + lw.max() - 500.0, RTOL, scale=10.0, what="logSum")
+
+
+def test_point_wise_entry_points(api2, tmp_path):
+    """mvdens_log_pdf (Gaussian and Student-t), scalar_product, mix_mvdens_log_pdf, bentGauss_lkl and isinBox called one
+    point at a time, as an opaque user likelihood would (pmc_dropin.cpp): against the oracle's restatements.  Points close
+    to the mean are included: scalar_product is the forward substitution itself, so small q keeps its relative accuracy."""
+    rng = np.random.default_rng(3)
+    M, d = 160, 6
+    a = rng.normal(0, 1, (d, d))
+    cov = a @ a.T / d + 0.7 * np.eye(d)
+    mean = rng.normal(0, 1, d)
+    X = mean + rng.normal(0, 1.2, (M, d))
+    X[:20] = mean + rng.normal(0, 1e-4, (20, d))   # tiny q
+    with open(tmp_path / "pt.in", "wb") as f:
+        f.write(np.array([M, d], np.int64).tobytes()); f.write(X.tobytes()); f.write(mean.tobytes()); f.write(cov.tobytes())
+    r = subprocess.run([api2, "point", str(tmp_path / "pt.in"), str(tmp_path / "pt.out")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "df_after 4 chol 1" in r.stdout
+    got = np.fromfile(tmp_path / "pt.out").reshape(M, 7)
+    L = O.orc()
+    g = O.Mix(np.ones(1), mean[None], cov[None], np.array([-1], np.int32))
+    t = O.Mix(np.ones(1), mean[None], cov[None], np.array([4], np.int32))
+    mm = O.Mix(np.array([0.25, 0.75]), np.array([mean - 0.5, mean + 0.5]), np.array([cov, cov]), np.full(2, -1, np.int32))
+    tmp, ld, rc = np.zeros(d), np.zeros(2), O.C.c_int(0)
+    want = np.zeros((M, 7))
+    for i in range(M):
+        x = np.ascontiguousarray(X[i])
+        want[i, 0] = L.orc_mvdens_log_pdf(d, O.P(g.mean), O.P(g.L), O.C.c_double(g.detL[0]), -1, O.P(x), O.P(tmp))
+        want[i, 1] = L.orc_scalar_product(d, O.P(g.mean), O.P(g.L), O.P(x), O.P(tmp))
+        want[i, 2] = L.orc_mvdens_log_pdf(d, O.P(t.mean), O.P(t.L), O.C.c_double(t.detL[0]), 4, O.P(x), O.P(tmp))
+        want[i, 3] = want[i, 1]
+        want[i, 4] = L.orc_mix_log_pdf(O.C.byref(mm.c), O.P(x), O.P(tmp), O.P(ld), O.C.byref(rc))
+        want[i, 5] = L.orc_bentgauss(d, O.C.c_double(0.1), O.C.c_double(10.0), O.P(x))
+        want[i, 6] = float(-1.0 <= x[0] <= 1.5 and x[1] <= 2.0)
+    for j, name in enumerate(["mvdens_log_pdf", "scalar_product", "mvdens_log_pdf student-t", "scalar_product (t)",
+                              "mix_mvdens_log_pdf", "bentGauss_lkl"]):
+        if "scalar" in name:
+            e = float(np.max(np.abs(got[:, j] - want[:, j]) / want[:, j]))   # element-wise relative, tiny q included
+            assert e <= 1e-11, (name, e)   # q = |y|^2 of a forward substitution: error ~ eps * cond(L), independent of |q|
+        else:
+            e = assert_close(got[:, j], want[:, j], RTOL, what=name)
+        print(name, "max rel err", e)
+    assert np.array_equal(got[:, 6], want[:, 6])

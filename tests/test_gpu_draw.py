@@ -124,3 +124,61 @@ def test_box_rejection(gpu, path):
     Xb, _ = O.orc_simulate(200_000, wl, seed=2)
     se = np.sqrt(X.var(0) / len(X) + Xb.var(0) / len(Xb))
     assert np.all(np.abs(X.mean(0) - Xb.mean(0)) < 5 * se)
+
+
+@pytest.mark.parametrize("path,d,K,nu", [("tensor", 30, 50, 9), ("tensor", 8, 6, 4), ("generic", 30, 12, 9), ("generic", 5, 4, 3),
+                                         ("tensor_mixed_df", 12, 5, 7)])
+def test_student_t_draw_distribution(gpu, path, d, K, nu):
+    """Student-t components (mvdens.c:305-310: x = mu + L g sqrt(nu / chi2_nu), one chi2 per sample): configs[3]'s whole
+    proposal.  Per component the whitened residual r = L^-1 (x - mu) must be a multivariate t: |r|^2 / d ~ F(d, nu),
+    every coordinate a univariate t_nu, directions uniform (coordinates uncorrelated, unit scale matrix), and the heavy
+    tails must be there.  `tensor` = the grouped DMMA draw kernels (k_draw_pick/perm/mma), `generic` = the literal kernel;
+    tensor_mixed_df mixes Gaussian (df = -1) and Student-t components in one mixture."""
+    rng = np.random.default_rng(500 + d + K + nu)
+    w, mean, cov = _mix(rng, K, d)
+    df = np.full(K, nu, np.int32)
+    if path == "tensor_mixed_df":
+        df[::2] = -1
+    gpu.set_option("force_generic", 1 if path == "generic" else 0)
+    gpu.set_option("fused_version", 0)
+    gpu.set_proposal_cov(w, mean, cov, df)
+    gpu.set_target_banana(d, 0.1, 10.0)
+    gpu.set_box(None)
+    N = 600_000
+    gpu.resize(N, d)
+    gpu.draw(seed=4321, it=1)
+    got = gpu.download(weights=False, log_rho=False)
+    X, idx = got["X"], got["indices"].astype(np.int64)
+    assert np.all(got["flg"] == 1) and np.all(np.isfinite(X))
+    cnt = np.bincount(idx, minlength=K)
+    chi2 = np.sum((cnt - N * w) ** 2 / (N * w))
+    assert stats.chi2.sf(chi2, K - 1) > 1e-4, f"component frequencies off (chi2={chi2:.1f})"
+    for fam, sel in (("t", df > 0), ("gauss", df <= 0)):
+        ks = [k for k in range(K) if sel[k]]
+        if not ks:
+            continue
+        zs = []
+        for k in ks:
+            L = np.linalg.cholesky(cov[k])
+            zs.append(np.linalg.solve(L, (X[idx == k] - mean[k]).T).T)
+        z = np.concatenate(zs)
+        n = len(z)
+        q = (z ** 2).sum(1)
+        if fam == "gauss":
+            assert stats.kstest(q, "chi2", args=(d,)).pvalue > 1e-4
+            continue
+        assert stats.kstest(q / d, stats.f(d, nu).cdf).pvalue > 1e-4, "radius law F(d, nu)"
+        for j in range(0, d, max(1, d // 6)):
+            assert stats.kstest(z[:, j], stats.t(nu).cdf).pvalue > 1e-4, f"marginal t_nu, dim {j}"
+        # directions: u = z / |z| is uniform on the sphere whatever the radius law -> E[u_a u_b] = delta_ab / d
+        u = z / np.sqrt(q)[:, None]
+        C2 = u.T @ u / n
+        assert np.max(np.abs(C2 - np.eye(d) / d)) < 6.0 / (d * np.sqrt(n)) * np.sqrt(2.0)
+        # tails: P(|z_j| > 6) for t_nu against a Gaussian's 2e-9
+        p = 2 * stats.t.sf(6.0, nu)
+        frac = (np.abs(z) > 6.0).mean()
+        assert abs(frac - p) < 6 * np.sqrt(p / z.size) + 1e-7, (frac, p)
+        # the chi2 is shared by the coordinates of a sample: squared coordinates are positively correlated
+        if nu > 4:
+            r = np.corrcoef(z[:, 0] ** 2, z[:, 1] ** 2)[0, 1]
+            assert r > 0.02, r  # independent coordinates would give 0 +- 0.002
