@@ -159,6 +159,38 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def other_configs(g, stream, torch):
+    """Short runs of the other BASELINE.json configurations on the same GPU (not the bench metric: reported beside it so that
+    the driver's record holds them too).  Per configuration: full iterations (importance-only for configs[3]) timed with CUDA
+    events on the library's stream after 3 warm-up iterations."""
+    from pmclib_b200.workloads import banana, gmm5, student30, gauss128
+    plan = [("configs[0]", banana, 10_000, 1, 20), ("configs[1]", gmm5, 1_000_000, 1, 20),
+            ("configs[3]", student30, 10_000_000, 0, 4), ("configs[4]", gauss128, 1_250_000, 1, 4)]
+    out = {}
+    for name, fac, n, upd, steps in plan:
+        try:
+            wl = fac()
+            g.set_workload(wl)
+            g.resize(n, wl["d"])
+            it, retry = 0, 0
+            for _ in range(3):
+                r = g.pmc_step(777, it, 0, n, upd, retry); retry = r.retry; it += 1
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                r = g.pmc_step(777, it, 0, n, upd, retry); retry = r.retry; it += 1
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"workload": wl["name"], "samples_per_step": n, "update": bool(upd), "ms_per_step": ms,
+                         "samples_per_s": n / (ms * 1e-3), "perplexity_last": float(r.perplexity), "steps": steps}
+        except Exception as ex:  # pragma: no cover
+            out[name] = {"error": str(ex)}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,6 +200,9 @@ def main():
     ap.add_argument("--samples", type=int, default=100_000_000, help="proposal samples per GPU per iteration")
     ap.add_argument("--ref-samples", type=int, default=1_000_000, help="samples per iteration for the CPU reference arm")
     ap.add_argument("--cpu-baseline-samples", type=int, default=1_000_000)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --samples per GPU (default); strong: --samples in total, sharded over the GPUs (configs[2] as written)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of configs[0], [1], [3], [4]")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spl", type=int, default=None)
@@ -204,7 +239,7 @@ def main():
         k_, v_ = kv.split("=")
         g.set_option(k_, float(v_))
     g.set_workload(wl)
-    N_total = args.samples * world
+    N_total = args.samples * world if args.scaling == "weak" else args.samples
     first, n_local = shard_range(N_total, rank, world)
     g.resize(n_local)
     if world > 1:
@@ -279,7 +314,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         e0.record(stream)
-        nst = max(1, min(args.steps, 5))
+        nst = max(1, args.steps)
         for _ in range(nst):
             rr = e2e_step(it, rr.retry); it += 1
         e1.record(stream)
@@ -316,7 +351,7 @@ def main():
         if split and msd > 0:
             bytes_k1 = 8.0 * wl["d"] + 8 + 18 + 8.0 * wl["K"]   # reads X and indices, writes weights, log_rho, flg, responsibilities
         roof = {"bound": "tensor", "bound_detail": "FP64 pipe: DFMA and the FP64 tensor instruction DMMA share it on B200 (36.9 / 37.15 TFLOP/s measured, not additive)", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
-                "traffic": None, "kernel": ("k_fused2<MODE 1> (mixture log-density + target + log-weights)" if msd > 0 else "k_fused2 (draw + mixture log-density + target + log-weights)") if split else "k_fused2 (single pass)",
+                "traffic": None, "kernel": ("k_weights3 (mixture log-density + target + log-weights + running normaliser)" if msd > 0 else "k_fused2 (draw + mixture log-density + target + log-weights)") if split else "k_fused2 (single pass)",
                 "kernel_ms": ms, "kernel_share_of_step": fused_ms / ev_ms, "algorithmic_flop_per_sample": flop,
                 "peak_source": "measured DFMA peak, profiles/r01_fp64_peak.md (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm": {"achieved": bytes_k1 * n_local / (ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
@@ -329,7 +364,7 @@ def main():
                 roof["draw_kernel"] = {"kernel": "k_fused2<MODE 3> (Philox + ziggurat + L g + box)", "kernel_ms": msd,
                                        "kernel_share_of_step": draw_ms / ev_ms,
                                        "hbm_gbs": (8.0 * wl["d"] + 8) * n_local / (msd * 1e-3) * 1e-9}
-            roof["stats_kernel"] = {"kernel": "k_stats2 (DMMA sufficient statistics)", "kernel_ms": ms2, "achieved": tf2,
+            roof["stats_kernel"] = {"kernel": "k_stats3 (normalisation + perplexity sums + DMMA sufficient statistics)", "kernel_ms": ms2, "achieved": tf2,
                                     "frac": tf2 / FP64_PEAK_TFLOPS, "algorithmic_flop_per_sample": FLOP_K2,
                                     "kernel_share_of_step": stats_ms / ev_ms}
             roof["pipeline"] = {"achieved": tfp, "frac": tfp / FP64_PEAK_TFLOPS, "algorithmic_flop_per_sample": FLOP_PER_SAMPLE,
@@ -355,9 +390,13 @@ def main():
         except Exception as ex:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {ex}"}
 
+    others = None
+    if not args.no_other_configs and world == 1:
+        others = other_configs(g, stream, torch)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[2]: 10-D banana (b=0.1, sig1^2=10), 10-component Gaussian mixture proposal, box +-40",
                    "samples_per_gpu_per_step": n_local, "samples_per_step": N_total, "parallelism": f"sample shards x{world}",
@@ -366,6 +405,7 @@ def main():
                    "precise_path_steps": int(precise), "wall_ms_per_step": wall_ms / args.steps},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(launches1 - launches0),
+        "other_configs": others,
     }
     print(json.dumps(line))
     if world > 1:

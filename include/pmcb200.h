@@ -52,6 +52,9 @@ void *pmcgpu_stream(pmcgpu_ctx *ctx);
  * "t_temper" (t_iter_tempered used by pmcgpu_pmc_step, pmc.c:570; default 1), "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass update),
  * "guard_ratio" (pivot guard threshold of the one-pass update), "timing" (see pmcgpu_get_timing) */
 int pmcgpu_set_option(pmcgpu_ctx *ctx, const char *name, double value);
+/* read-only diagnostics: "mma_active", "mma_inverse_discrepancy" (conditioning guard of the tensor path: explicit inverse
+ * factors are used only while they agree with the reference's forward substitution to option "mma_inv_tol", default 1e-13) */
+int pmcgpu_get_info(pmcgpu_ctx *ctx, const char *name, double *value);
 
 /* timing of the dominant (fused) kernel, measured with CUDA events on the launching stream while option "timing" = 1:
  * accumulated milliseconds and launches since the option was set; total_launches = kernels launched by the library

@@ -126,6 +126,11 @@ class PmcGpu:
             self._ck(self.lib.pmcgpu_set_target_mix(self.h, t["kind"], t["K"], t["d"], _p(w), _p(m), _p(Lc), _p(dt), _p(df)))
         self.set_box(wl["faces"])
 
+    def get_info(self, name):
+        v = C.c_double()
+        self._ck(self.lib.pmcgpu_get_info(self.h, name.encode(), C.byref(v)))
+        return v.value
+
     def set_target_combine(self, d, terms):
         """Sum of densities on index-mapped coordinates (combine_lkl / add_gaussian_prior): terms = list of dicts with
         kind (1 banana: b, sig1; 2 mvdens / 3 mix: wght, mean, cov, df), d and dims."""

@@ -146,7 +146,7 @@ struct pmcgpu_ctx {
   int force_generic = 0, spl = 1, max_attempts = 10000, force_precise = 0;
   double guard_ratio = 200.0;
   // large-d tensor path (pmc_mma.cu)
-  struct MmaMix { DevBuf pack, lpack, kmap, dfj; int J = 0; bool valid = false, dirty = false; std::vector<int> alive; };
+  struct MmaMix { DevBuf pack, lpack, kmap, dfj; int J = 0; bool valid = false, dirty = false; std::vector<int> alive; double inv_discrepancy = 0.0; };
   MmaMix mprop, mtgt;
   DevBuf Q, Qt, mpart, mstats, mpivot, dperm, dtiles, dcnt, xc;
   HostMix trial;  // scratch of the update (kept to reuse its storage)
@@ -156,6 +156,7 @@ struct pmcgpu_ctx {
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 2;  // any shape without a fused small-d instantiation goes to the tensor path (30x the literal kernels at d = 7..16)
   double t_temper = 1.0;  // t_iter_tempered of pmcgpu_pmc_step (pmc.c:570: weight = t * post - rloc)
+  double mma_inv_tol = 1.0e-13;  // conditioning guard of the explicit inverse factors (pack_mma), option "mma_inv_tol"
   long mma_max_chunk = 0;  // test knob: cap of the samples whitened per pass (0 = as many as memory allows)
   int filt_nbins = 0, filt_cl = 0, filt_cr = 0;  // filter_histogram inside the iteration (0 = off)
   // host sink: arrays of the caller that pmcgpu_pmc_step fills while the iteration is still running
@@ -302,11 +303,18 @@ int pack_mma(pmcgpu_ctx *c, const HostMix &m, pmcgpu_ctx::MmaMix &o) {
   const size_t cs = mma_comp_stride(d), nd = (size_t)J * cs;
   RC(stage(c, 2 * nd + J + 2));
   double *h = c->hstage;
+  std::vector<double> disc(J, 0.0);
   parallel_components(J, (double)d * d * d / 3.0, [&](int j) {
     const double *mu = m.mean.data() + (size_t)alive[j] * d, *Lk = m.L.data() + (size_t)alive[j] * d * d;
-    mma_pack_component(d, mu, Lk, 1, h + (size_t)j * cs);        // whitening: inverse factor
-    mma_pack_component(d, mu, Lk, 0, h + nd + (size_t)j * cs);   // draw: the factor itself
+    mma_pack_component(d, mu, Lk, 1, h + (size_t)j * cs, &disc[j]);  // whitening: inverse factor
+    mma_pack_component(d, mu, Lk, 0, h + nd + (size_t)j * cs);       // draw: the factor itself
   });
+  // conditioning guard: the product with an explicit inverse and the reference's forward substitution must agree to well
+  // inside the 1e-12 parity tolerance on every component, otherwise this mixture stays on the literal kernels
+  double worst = 0.0;
+  for (int j = 0; j < J; ++j) if (!(disc[j] <= worst)) worst = disc[j];
+  o.inv_discrepancy = worst;
+  if (!(worst <= c->mma_inv_tol)) return 0;
   int *hi = reinterpret_cast<int *>(h + 2 * nd);
   for (int j = 0; j < J; ++j) { hi[j] = alive[j]; hi[J + j] = m.df[alive[j]]; }
   CU(o.pack.ensure(nd * sizeof(double)));
@@ -1351,9 +1359,21 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "mma")) { c->use_mma = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_min_d")) { c->mma_min_d = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_max_chunk")) c->mma_max_chunk = (long)value;
+  else if (!strcmp(name, "mma_inv_tol")) { c->mma_inv_tol = value; return repack_mma(c); }
   else if (!strcmp(name, "t_temper")) { if (!(value >= 0)) return fail(c, -6019, "t_iter_tempered=%g should be > 0", value); c->t_temper = value; }
   else return fail(c, PMCGPU_ERR_USAGE, "unknown option %s", name);
   return 0;
+}
+
+// read-only diagnostics: "mma_active" (1 if the proposal is packed for the tensor path), "mma_inverse_discrepancy"
+// (largest relative difference between Linv b and the forward substitution over the proposal's components, see
+// pmc_mma.cu:inverse_discrepancy; the tensor path is used only while it is below option "mma_inv_tol")
+int pmcgpu_get_info(pmcgpu_ctx *c, const char *name, double *value) {
+  if (!c || !name || !value) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  if (!strcmp(name, "mma_active")) { RC(ensure_mma(c)); *value = c->mprop.valid ? 1.0 : 0.0; return 0; }
+  if (!strcmp(name, "mma_inverse_discrepancy")) { RC(ensure_mma(c)); *value = c->mprop.inv_discrepancy; return 0; }
+  return fail(c, PMCGPU_ERR_USAGE, "unknown info %s", name);
 }
 
 int pmcgpu_get_timing(pmcgpu_ctx *c, double *fused_ms, long *fused_launches, long *total_launches) {

@@ -280,7 +280,8 @@ int launch_comb3(const Iter3Plan &p, const double *partials, int with_stats, con
 int mma_nt(int d);                    // number of 8-row tiles the dimension is padded to (0 = not supported)
 size_t mma_comp_stride(int d);        // doubles of one packed component
 // host: mean + (invert ? inverse factor : factor) of one component in B-fragment order
-void mma_pack_component(int d, const double *mean, const double *L, int invert, double *out);
+// inv_discrepancy (invert only, may be null): conditioning probe, see pmc_mma.cu:inverse_discrepancy
+void mma_pack_component(int d, const double *mean, const double *L, int invert, double *out, double *inv_discrepancy = nullptr);
 // q[kmap[j]][i] = |L_j^-1 (x_i - mu_j)|^2 for the J packed components, i < n; Q row stride qs
 int launch_q_mma(const double *X, long n, int d, const double *pack, int J, const int *kmap, double *Q, long qs,
                  int sm_count, cudaStream_t s);

@@ -668,7 +668,44 @@ size_t mma_comp_stride(int d) {
 
 // One component in kernel order: mu[8 NT] (zero padded), then for ks ascending, nt = ks/2 .. NT-1, the 32 B-fragment
 // values  Linv[8 nt + lane/4][4 ks + lane%4].  Linv is formed column by column in extended precision.
-void mma_pack_component(int d, const double *mean, const double *L, int invert, double *out) {
+// Conditioning probe of the explicit inverse (host, O(d^2)): for a few vectors b = L z the whitened vector is computed
+// both ways in plain double - the product Linv b the tensor kernel forms, and the forward substitution of mvdens.c:341
+// the reference (and the literal kernels) use - and the largest difference relative to |y| is returned.  Both have the
+// forward error bound d eps cond(L); for an ill-conditioned factor their difference can exceed the 1e-12 parity
+// tolerance, and the caller then keeps such a mixture off the tensor path.
+static double inverse_discrepancy(int d, const double *L, const std::vector<long double> &inv) {
+  double worst = 0.0;
+  std::vector<double> z(d), b(d), y1(d), y2(d);
+  for (int probe = 0; probe < 3; ++probe) {
+    unsigned long long st = 0x9E3779B97F4A7C15ull * (unsigned long long)(probe + 1);
+    for (int i = 0; i < d; ++i) {
+      st = st * 6364136223846793005ull + 1442695040888963407ull;
+      const double u = (double)(st >> 11) / 9007199254740992.0;
+      z[i] = probe == 0 ? ((i & 1) ? -1.0 : 1.0) : (probe == 1 ? 2.0 * u - 1.0 : ((u < 0.5) ? -3.0 * u : 3.0 * u));
+    }
+    for (int r = 0; r < d; ++r) {
+      long double acc = 0.0L;
+      for (int c = 0; c <= r; ++c) acc += (long double)L[(size_t)r * d + c] * (long double)z[c];
+      b[r] = (double)acc;
+    }
+    double ymax = 0.0;
+    for (int r = 0; r < d; ++r) {
+      double a1 = 0.0, t = b[r];
+      for (int c = 0; c <= r; ++c) a1 += (double)inv[(size_t)r * d + c] * b[c];
+      for (int c = 0; c < r; ++c) t -= L[(size_t)r * d + c] * y2[c];
+      y1[r] = a1;
+      y2[r] = t / L[(size_t)r * d + r];
+      if (std::fabs(y2[r]) > ymax) ymax = std::fabs(y2[r]);
+    }
+    for (int r = 0; r < d; ++r) {
+      const double e = std::fabs(y1[r] - y2[r]) / (ymax > 0.0 ? ymax : 1.0);
+      if (!(e <= worst)) worst = e;
+    }
+  }
+  return worst;
+}
+
+void mma_pack_component(int d, const double *mean, const double *L, int invert, double *out, double *inv_discrepancy) {
   const int NT = mma_nt(d), DP = 8 * NT;
   // Linv L = I, row r of Linv from the diagonal leftwards: inv[r][c] = -(sum_{m=c+1..r} inv[r][m] L[m][c]) / L[c][c];
   // Lt holds L transposed so that both operands of the dot product are contiguous
@@ -690,6 +727,7 @@ void mma_pack_component(int d, const double *mean, const double *L, int invert, 
       ir[c] = -(acc0 + acc1) / (long double)lc[c];
     }
   }
+  if (invert && inv_discrepancy) *inv_discrepancy = inverse_discrepancy(d, L, inv);
   for (int a = 0; a < DP; ++a) out[a] = a < d ? mean[a] : 0.0;
   double *tp = out + DP;
   for (int ks = 0; ks < 2 * NT; ++ks)

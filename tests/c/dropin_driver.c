@@ -19,7 +19,19 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef PMCLIB_REFERENCE_HEADERS
+/* compiled against the REFERENCE's own headers (pmclib/include, pmctools/include, examples/target) instead of the
+ * mirror in include/pmclib_abi.h: proves that struct layouts and prototypes agree (tests/test_cpu_abi.py) */
+#include "pmc.h"
+#include "sampleTarget.h"
+/* pmc_mpi.h needs <mpi.h>, which this image does not have: the three prototypes the driver uses, as pmc_mpi.h:52-66 has them */
+pmc_simu *pmc_simu_init_mpi(long nsamples, int ndim, int nded, error **err);
+double pmc_simu_pmc_step_mpi(pmc_simu *psim, gsl_rng *r, error **err);
+void pmc_simu_init_classic_pmc_mpi(pmc_simu *psim, distribution *target, parabox *pb, void *prop_data, int prop_print_step,
+                                   void *filter_data, filter_func *pmc_filter, error **err);
+#else
 #include "pmclib_abi.h"
+#endif
 
 /* a tiny gsl_rng-compatible generator owned by the caller (the library only calls r->type->get) */
 typedef struct { uint64_t s; } sm_state;

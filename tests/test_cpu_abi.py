@@ -231,3 +231,60 @@ def test_on_disk_formats_are_byte_identical_to_the_reference(tmp_path):
         assert open(str(tmp_path / "ours") + ext, "rb").read() == open(gold + ext, "rb").read(), ext
     assert "dwnp K 2 d 3" in r.stdout and "df0 -1" in r.stdout
     assert float(r.stdout.split("worst")[1].split()[0]) < 1e-14
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pmclib", "include")), reason="reference headers not present on this machine")
+def test_c_driver_compiles_against_the_reference_headers(tmp_path):
+    """The C driver — a pmclib caller — built with the REFERENCE's own headers (pmc.h, mvdens.h, distribution.h, parabox.h,
+    errorlist.h, sampleTarget.h; GSL types from oracle/gslshim) instead of include/pmclib_abi.h, linked against
+    libpmcb200.so: prototypes and struct layouts of the drop-in agree with the reference.  Without a GPU the run must fail
+    loudly through the reference's error chain (mode 3)."""
+    exe = str(tmp_path / "dropin_driver_ref")
+    inc = ["-I" + os.path.join(ROOT, "oracle", "gslshim"), "-I" + os.path.join(ROOT, "oracle", "gslshim", "luastub"),
+           "-I" + os.path.join(REF, "pmctools", "include"), "-I" + os.path.join(REF, "pmclib", "include"),
+           "-I" + os.path.join(REF, "examples", "target")]
+    r = subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-DPMCLIB_REFERENCE_HEADERS", "-D_NOFFTW_", "-D_GNU_SOURCE"] + inc +
+                       [os.path.join(ROOT, "tests", "c", "dropin_driver.c"), "-o", exe, "-L" + os.path.dirname(LIB_PATH), "-lpmcb200",
+                        "-Wl,-rpath," + os.path.dirname(LIB_PATH), "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "conflicting types" not in r.stderr and "incompatible" not in r.stderr, r.stderr
+    # sizes and offsets the driver relies on, as the reference headers define them vs the mirror
+    probe = tmp_path / "probe.c"
+    body = r'''
+#include <stdio.h>
+#include <stddef.h>
+#ifdef PMCLIB_REFERENCE_HEADERS
+#include "pmc.h"
+#include "sampleTarget.h"
+#else
+#include "pmclib_abi.h"
+#endif
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu ", sizeof(pmc_simu), sizeof(mvdens), sizeof(mix_mvdens), sizeof(distribution), sizeof(parabox), sizeof(error));
+  printf("%zu %zu %zu %zu %zu %zu ", offsetof(pmc_simu, X), offsetof(pmc_simu, flg), offsetof(pmc_simu, indices), offsetof(pmc_simu, logSum), offsetof(pmc_simu, proposal), offsetof(pmc_simu, mpi_size));
+  printf("%zu %zu %zu %zu %zu ", offsetof(mvdens, std), offsetof(mvdens, band_limit), offsetof(mvdens, chol), offsetof(mvdens, detL), offsetof(mvdens, x_tmp));
+  printf("%zu %zu %zu %zu\n", offsetof(mix_mvdens, comp), offsetof(mix_mvdens, cwght), offsetof(distribution, broadcast_mpi), offsetof(distribution, name));
+  return 0;
+}
+'''
+    probe.write_text(body)
+    outs = []
+    for flags in (["-DPMCLIB_REFERENCE_HEADERS", "-D_NOFFTW_", "-D_GNU_SOURCE"] + inc, ["-I" + os.path.join(ROOT, "include")]):
+        e = str(tmp_path / ("probe" + str(len(outs))))
+        subprocess.run(["gcc", "-std=gnu99"] + flags + [str(probe), "-o", e], check=True, capture_output=True)
+        outs.append(subprocess.run([e], capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1], outs
+    import torch
+    if torch.cuda.is_available():
+        return
+    K, d, N = 4, 3, 50
+    cfg = tmp_path / "in.bin"
+    with open(cfg, "wb") as f:
+        f.write(np.array([K, d, N, 1, 0, 1], np.int64).tobytes())
+        f.write(np.array([0.1, 10.0]).tobytes())
+        f.write(np.full(K, 1 / K).tobytes()); f.write(np.zeros((K, d)).tobytes()); f.write(np.tile(np.eye(d), (K, 1, 1)).tobytes())
+    r = subprocess.run([exe, str(cfg), str(tmp_path / "out.bin"), "3"], capture_output=True, text=True, check=True)
+    assert '"is_error": 1' in r.stdout and "-6024" in r.stdout

@@ -251,3 +251,43 @@ def test_mma_tiny_samples(gpu, N):
         gpu.pmc_step(3, 0, do_update=0)
     except Exception as e:   # all-flagged / no-sample errors of the reference are legitimate at N = 1
         assert "-60" in str(e)
+
+
+def test_ill_conditioned_component_stays_off_the_tensor_path(gpu):
+    """Conditioning guard of the explicit inverse factors (pack_mma / pmc_mma.cu:inverse_discrepancy): a product with
+    L^-1 and the reference's forward substitution both carry a forward error ~ d eps cond(L); for a badly conditioned
+    component their DIFFERENCE can exceed the 1e-12 parity tolerance.  A well-conditioned mixture is served by the tensor
+    path with a tiny measured discrepancy; a mixture with one ill-conditioned component is routed to the literal kernels
+    and still matches the oracle."""
+    d, K, N = 24, 4, 4000
+    wl = _case(d, K, 31)
+    gpu.set_option("force_generic", 0); gpu.set_option("fused_version", 0); gpu.set_option("force_precise", 0)
+    gpu.set_workload(wl)
+    assert gpu.get_info("mma_active") == 1.0
+    good = gpu.get_info("mma_inverse_discrepancy")
+    assert good < 2e-14, good
+    # strongly correlated coordinates with scales from 1 to 1e-7: cond(L) ~ 1e9
+    rng = np.random.default_rng(9)
+    a = rng.normal(0, 1, (d, d))
+    s = np.logspace(0, -7, d)
+    bad = (a * s) @ (a * s).T + 1e-15 * np.eye(d)
+    wl2 = dict(wl, cov=wl["cov"].copy())
+    wl2["cov"][1] = bad
+    gpu.set_workload(wl2)
+    disc = gpu.get_info("mma_inverse_discrepancy")
+    assert disc > 1e-13, disc
+    assert gpu.get_info("mma_active") == 0.0
+    X, idx = O.orc_simulate(N, wl2, seed=3)
+    o = O.orc_iteration(X, idx, wl2, do_update=0)
+    gpu.resize(N, d)
+    gpu.upload(X=X, indices=idx, flg=np.ones(N, np.int16))
+    nok, maxW, maxR = gpu.weights(1.0)
+    got = gpu.download(X=False, indices=False)
+    assert nok == o["nok"]
+    e = assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho through the literal kernels")
+    print("well-conditioned discrepancy", good, "ill-conditioned", disc, "log_rho error on the literal path", e)
+    # with the guard disabled the tensor path would be used (and may miss the tolerance): the knob exists for that check
+    gpu.set_option("mma_inv_tol", 1.0)
+    assert gpu.get_info("mma_active") == 1.0
+    gpu.set_option("mma_inv_tol", 1e-13)
+    assert gpu.get_info("mma_active") == 0.0
