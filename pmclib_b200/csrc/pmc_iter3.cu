@@ -591,11 +591,21 @@ struct S3Cfg {
     return n;
   }
   static constexpr int NX = XT ? xcount() : 0;
-  static constexpr int XS = (D + 2) | 1;  // augmented row: 1, x~_1 .. x~_D, 0 (the zero slot pads a- and b-groups)
-  static constexpr int GS = (((K + 7) / 8) * 8) | 1;
+  // cyclic feature layout: the NI (NI + 1) / 2 products z_a z_b as (a, s) = z_a z_{(a+s) mod NI} with s < SH = NI/2 + 1;
+  // tile s holds a = 0..7 (lane row fr = a), the a >= 8 take NHI further tiles with lane row fr = s.  A lane then needs
+  // only the SH consecutive values z_fr .. z_{fr+SH-1} for its first SH products (6 loads instead of 12 at d = 10).
+  // Used when it needs no more tiles than the row-major layout (d = 6, 8, 10).  The rows are then stored periodically
+  // extended (z_{i mod NI}, i < RL), so that every fragment operand of every k-step is ONE per-lane base address plus a
+  // compile-time offset: no address arithmetic in the DMMA loop and no registers spent on per-tile offsets.
+  static constexpr int NI = D + 1, SH = NI / 2 + 1, NHI = NI > 8 ? NI - 8 : 0;
+  static constexpr bool CYC = (SH + NHI == (1 + D + D * (D + 1) / 2 + 7) / 8) && SH <= 8;
+  static constexpr int RL = CYC ? (NI > 8 ? NI + 7 : 7 + SH) : D + 2;  // row length: largest index read + 1
+  static constexpr int XS = RL | 1;  // odd stride: conflict-free fragment loads (non-cyclic: 1, x~_1 .. x~_D, 0)
+  static constexpr int GS = (XT ? K : ((K + 7) / 8) * 8) | 1;  // g row stride (odd): full row tiles read 8 MT entries, the product tiles K
   static constexpr int ACC = (MT * NT + NX) * 64;
-  static constexpr int STAGE = 32 * D + 32 * K + 32 + 32 + 8;  // X rows | resp (k-major) | lw | indices | flg (32 shorts)
+  static constexpr int STAGE = 32 * D + 32 * K + 32 + 32 + 8;  // next tile, by cp.async: X rows | resp (k-major) | lw | indices | flg
   static constexpr int WARP_DOUBLES = 32 * XS + 32 * GS + STAGE;
+
   static constexpr int PLEN = ACC + 4 + 64;
 };
 
@@ -622,7 +632,7 @@ __device__ __forceinline__ double norm_sample(double lwv, short f, double maxW, 
 template <int D, int K, bool STATS>
 __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Args a) {
   using C = S3Cfg<D, K>;
-  constexpr int NT = C::NT, MT = C::MT, GS = C::GS, XS = C::XS;
+  constexpr int NT = C::NT, MT = C::MT, GS = C::GS, XS = C::XS, NI = C::NI, SH = C::SH, NHI = C::NHI;
   constexpr int WARPS = 8;
   extern __shared__ __align__(16) double smem[];
   __shared__ double s_exp[64];
@@ -633,9 +643,9 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
   if (a.scal[I3_CLEAN] == 0.0) return;  // poisoned maxima: the host runs the literal sequence instead
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { s_exp[i] = c3_exptab[i]; s_count[i] = 0; }
   const double maxW = a.scal[I3_MAXW], invS = a.scal[I3_INVS], logSref = a.scal[I3_LOGSREF];
-  double *xh = smem + (size_t)wid * C::WARP_DOUBLES;
-  double *gt = xh + 32 * XS;
-  double *stx = gt + 32 * GS;
+  double *xh = smem + (size_t)wid * C::WARP_DOUBLES;  // augmented rows z = (1, x~_1 .. x~_D, 0) of the warp's 32 samples
+  double *gt = xh + 32 * XS;                          // g rows: w_i * responsibility_k
+  double *stx = gt + 32 * GS;                         // staging of the NEXT tile (cp.async, no registers held across the DMMA phase)
   double *str = stx + 32 * D;
   double *stw = str + 32 * K;
   unsigned long long *sti = reinterpret_cast<unsigned long long *>(stw + 32);
@@ -643,17 +653,25 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
   for (int i = lane; i < C::WARP_DOUBLES; i += 32) xh[i] = 0.0;
   __syncthreads();
   const int fr = lane >> 2, fc = lane & 3;
+  // B-fragment operands.  Cyclic layout (C::CYC): feature (a, s) = z_a z_{(a+s) mod NI}, s < SH; a lane loads the SH values
+  // z_{fr}, z_{fr+1}, .. once per k-step and forms SH products from them, the features with a >= 8 take NHI more tiles
+  // (lane fr <-> shift s = fr).  Otherwise the row-major upper-triangular layout with two loads per product.
   int oa[NT], ob[NT];
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
-    const int e = 8 * n + fr;
     int pa = 0, pb = 0;
-    if (e >= 1 && e <= D) pb = e;
-    else if (e > D && e < C::E) {
-      int q = e - 1 - D, r = 0;
-      while (q >= D - r) { q -= D - r; ++r; }
-      pa = 1 + r;
-      pb = 1 + r + q;
+    if (C::CYC) {
+      if (n < SH) { pa = fr % NI; pb = (fr + n) % NI; }
+      else { pa = 8 + (n - SH); pb = (pa + fr) % NI; }
+    } else {
+      const int e = 8 * n + fr;
+      if (e >= 1 && e <= D) pb = e;
+      else if (e > D && e < C::E) {
+        int q = e - 1 - D, r = 0;
+        while (q >= D - r) { q -= D - r; ++r; }
+        pa = 1 + r;
+        pb = 1 + r + q;
+      }
     }
     oa[n] = pa;
     ob[n] = pb;
@@ -709,61 +727,96 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
     __syncwarp();
     const long i = tile * 32 + lane;
     double w = 0.0;
-    double xr[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) xr[j] = 0.0;
     if (i < a.N) {
       bool ok;
       w = norm_sample(stw[lane], stf[lane], maxW, invS, logSref, s_exp, a.W + i, a.flg + i, H, Q, nok, nflag, ok);
       if (ok) atomicAdd(&s_count[(int)sti[lane] & 63], 1u);
-      if (STATS && w != 0.0) {
-#pragma unroll
-        for (int j = 0; j < D; ++j) xr[j] = stx[lane * D + j] - a.pivot[j];
-      }
     }
     if (STATS) {
       double *xrow = xh + lane * XS, *grow = gt + lane * GS;
-      xrow[0] = 1.0;
+      const bool use = w != 0.0;
+      auto put = [&](int idx, double v) {  // z_idx, and its periodic copies in the cyclic layout
+        xrow[idx] = v;
+        if (C::CYC && idx + NI < C::RL) xrow[idx + NI] = v;
+      };
+      put(0, 1.0);
+      if ((D & 1) == 0) {
+        const double2 *xi = reinterpret_cast<const double2 *>(stx + lane * D);  // 80-byte rows: conflict-free 16-byte loads
 #pragma unroll
-      for (int j = 0; j < D; ++j) xrow[1 + j] = xr[j];
+        for (int j = 0; j < D; j += 2) {
+          const double2 t2 = xi[j / 2];
+          put(1 + j, use ? t2.x - a.pivot[j] : 0.0);
+          put(2 + j, use ? t2.y - a.pivot[j + 1] : 0.0);
+        }
+      } else {
 #pragma unroll
-      for (int k = 0; k < K; ++k) grow[k] = (w != 0.0) ? w * str[k * 32 + lane] : 0.0;
+        for (int j = 0; j < D; ++j) put(1 + j, use ? stx[lane * D + j] - a.pivot[j] : 0.0);
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) grow[k] = use ? w * str[k * 32 + lane] : 0.0;
     }
     __syncwarp();
-    if (tile + tstep < ntiles) prefetch(tile + tstep);
+    if (tile + tstep < ntiles) prefetch(tile + tstep);  // lands while the DMMA phase below runs
     if (STATS) {
+      // per-lane bases: sample 4 fc of the k-step, row element fr; every operand below is base + compile-time offset
+      const double *xb0 = xh + (4 * fc) * XS + fr, *xb1 = xh + (4 * fc) * XS + (fr % C::AG);
+      const double *gb0 = gt + (4 * fc) * GS + fr, *gb1 = gt + (4 * fc) * GS + gxo;
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int smp = 16 * h + t + 4 * fc;
+          const int so = 16 * h + t;  // sample offset of the k-step (added to 4 fc)
+          const int smp = so + 4 * fc;
           double af[MT];
 #pragma unroll
-          for (int m = 0; m < MT; ++m) af[m] = gt[smp * GS + 8 * m + fr];
+          for (int m = 0; m < MT; ++m) af[m] = gb0[so * GS + 8 * m];
           const double *xs = xh + smp * XS;
+          double u0 = 0.0;
+          if constexpr (C::CYC) {
+            double u[SH];
 #pragma unroll
-          for (int n = 0; n < NT; ++n) {
-            const double bf = xs[oa[n]] * xs[ob[n]];
+            for (int n = 0; n < SH; ++n) u[n] = xb0[so * XS + n];
+            u0 = u[0];
 #pragma unroll
-            for (int m = 0; m < MT; ++m) dmma884_3(acc[m][n][0], acc[m][n][1], af[m], bf);
+            for (int n = 0; n < SH; ++n) {
+              const double bf = u[0] * u[n];
+#pragma unroll
+              for (int m = 0; m < MT; ++m) dmma884_3(acc[m][n][0], acc[m][n][1], af[m], bf);
+            }
+#pragma unroll
+            for (int n = SH; n < NT; ++n) {
+              const double bf = xs[8 + (n - SH)] * xb0[so * XS + 8 + (n - SH)];
+#pragma unroll
+              for (int m = 0; m < MT; ++m) dmma884_3(acc[m][n][0], acc[m][n][1], af[m], bf);
+            }
+          } else {
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              const double bf = xs[oa[n]] * xs[ob[n]];
+#pragma unroll
+              for (int m = 0; m < MT; ++m) dmma884_3(acc[m][n][0], acc[m][n][1], af[m], bf);
+            }
           }
           if constexpr (C::XT) {
-            const double gx = gt[smp * GS + gxo];
+            const double gx = gb1[so * GS];
             double a2[C::NGB];
 #pragma unroll
-            for (int gb = 0; gb < C::NGB; ++gb) a2[gb] = xs[xbo[gb]];
+            for (int gb = 0; gb < C::NGB; ++gb) {
+              if (C::CYC) a2[gb] = (gb == 0) ? u0 : xb0[so * XS + 8 * gb];  // rows beyond D carry periodic copies: those output rows are never read
+              else a2[gb] = xs[xbo[gb]];
+            }
             int xb = 0;
 #pragma unroll
             for (int ga = 0; ga < C::NGA; ++ga) {
-              const double b2 = gx * xs[xao[ga]];
+              const double b2 = gx * (C::CYC ? xb1[so * XS + C::AG * ga] : xs[xao[ga]]);
 #pragma unroll
               for (int gb = 0; gb < C::NGB; ++gb)
                 if (C::xinc(ga, gb)) { dmma884_3(accx[xb][0], accx[xb][1], a2[gb], b2); ++xb; }
             }
           }
         }
+      __syncwarp();
     }
-    __syncwarp();
   }
   // ---- block combine in warp order -------------------------------------------------------------------------------
   __syncthreads();
@@ -817,7 +870,7 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
 // canonical statistics from the block partials, in block order: out = stats[K*E] | H, Q, ok, flagged-out | count_k[K]
 // Components below 8*MT sit in the (component, feature) row tiles; the others (ag > 0) in the product tiles of S3Cfg.
 __global__ void k_comb3(const double *__restrict__ partials, int nblocks, int partial_len, int acc_len, int K, int E, int NT,
-                        int MT, int D, int ag, int with_stats, const double *__restrict__ scal, double *__restrict__ out) {
+                        int MT, int D, int ag, int cyc, int with_stats, const double *__restrict__ scal, double *__restrict__ out) {
   const int nstat = with_stats ? K * E : 0;
   const int total = nstat + 4 + K;
   const bool clean = scal[I3_CLEAN] != 0.0;
@@ -825,17 +878,25 @@ __global__ void k_comb3(const double *__restrict__ partials, int nblocks, int pa
     int idx;
     if (t < nstat) {
       const int k = t / E, e = t - k * E;
+      int pa = 0, pb = e;  // canonical feature e = z_pa z_pb, pa <= pb (z_0 = 1): W, s_1..s_D, then the upper triangle row by row
+      if (e > D) {
+        int q = e - 1 - D, r = 0;
+        while (q >= D - r) { q -= D - r; ++r; }
+        pa = 1 + r;
+        pb = 1 + r + q;
+      }
       if (ag == 0 || k < 8 * MT) {
-        const int m = k >> 3, r = k & 7, n = e >> 3, cc = e & 7;
+        const int m = k >> 3, r = k & 7;
+        int n = e >> 3, cc = e & 7;
+        if (cyc) {  // cyclic layout of S3Cfg: (a, s) with z_b = z_{(a+s) mod NI}
+          const int NI = D + 1, SH = NI / 2 + 1, s1 = pb - pa;
+          const int a_ = s1 < SH ? pa : pb, s_ = s1 < SH ? s1 : NI - s1;
+          n = a_ < 8 ? s_ : SH + a_ - 8;
+          cc = a_ < 8 ? a_ : s_;
+        }
         idx = ((m * NT + n) * 32 + (r * 4 + (cc >> 1))) * 2 + (cc & 1);
       } else {
-        int a = e, b = 0;  // feature e = z_a z_b with a >= b (z_0 = 1)
-        if (e > D) {
-          int q = e - 1 - D, r = 0;
-          while (q >= D - r) { q -= D - r; ++r; }
-          b = 1 + r;
-          a = 1 + r + q;
-        }
+        const int a = pb, b = pa;  // a >= b
         const int ga = a / ag, gb = b >> 3, ngb = (D + 8) / 8;
         int xb = 0;  // issued blocks before (ga, gb): a-groups outer, b-groups inner, block issued iff ag*(ga+1)-1 >= 8*gb
         for (int g1 = 0; g1 <= ga; ++g1)
@@ -1049,7 +1110,7 @@ Iter3Plan iter3_plan(int d, int K, int Kt, int tgt_kind, int sm_count) {
   if (d == D_ && K <= K_ && (kt_needed == 0 || (KT_ > 0 && kt_needed <= KT_)) && (!best.valid || K_ < best.K)) { \
     using C = S3Cfg<D_, K_>;                                                                                     \
     best.valid = 1; best.D = D_; best.K = K_; best.KT = KT_; best.sm_count = sm_count;                           \
-    best.E = C::E; best.NT = C::NT; best.MT = C::MT; best.AG = C::XT ? C::AG : 0;                                \
+    best.E = C::E; best.NT = C::NT; best.MT = C::MT; best.AG = C::XT ? C::AG : 0; best.CYC = C::CYC ? 1 : 0;                                \
     best.acc_len = C::ACC; best.partial_len = C::PLEN;                                                          \
     best.stats_blocks = sm_count * 2; best.weights_blocks = sm_count * 4; /* upper bound over the variants */                                        \
   }
@@ -1151,7 +1212,7 @@ int launch_stats3(const Iter3Plan &p, const Iter3Stats &st, cudaStream_t s) {
 
 int launch_comb3(const Iter3Plan &p, const double *partials, int with_stats, const double *scal, double *out, cudaStream_t s) {
   const int total = (with_stats ? p.K * p.E : 0) + 4 + p.K;
-  k_comb3<<<(total + 63) / 64, 64, 0, s>>>(partials, p.stats_blocks, p.partial_len, p.acc_len, p.K, p.E, p.NT, p.MT, p.D, p.AG, with_stats, scal, out);
+  k_comb3<<<(total + 63) / 64, 64, 0, s>>>(partials, p.stats_blocks, p.partial_len, p.acc_len, p.K, p.E, p.NT, p.MT, p.D, p.AG, p.CYC, with_stats, scal, out);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

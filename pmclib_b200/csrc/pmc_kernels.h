@@ -214,7 +214,7 @@ constexpr int I3_COLL_LEN = 16;  // [0..7] all-reduce(max) block, [8..15] all-re
 struct Iter3Plan {
   int valid;
   int D, K, KT;      // instantiation; K >= the mixture's K (extra components are packed as dead ones)
-  int E, NT, MT, AG, acc_len, partial_len;  // AG > 0: remainder components in product tiles (S3Cfg)
+  int E, NT, MT, AG, CYC, acc_len, partial_len;  // AG > 0: remainder components in product tiles; CYC: cyclic feature layout (S3Cfg)
   int stats_blocks, weights_blocks, sm_count;
 };
 struct Iter3Weights {
