@@ -66,7 +66,10 @@ def test_reference_vanilla_pmc_runs_on_the_gpu(tmp_path):
     perp_lines = [l.split() for l in open(tmp_path / "pmc_exploration.perp").read().splitlines()]
     assert len(perp_lines) == niter
     prev = read_mix(tmp_path / "proposal.mix_mvdens")         # the initial proposal (draw_from), saved by rc_mix_mvdens
-    assert prev["K"] == 9 and prev["d"] == 2 and np.allclose(prev["wght"], 1 / 9) and np.all(prev["chol"] == 0)
+    # mvdens_ran factorises component 0 in place before the first draw (mvdens.c:287), and the flag and the factor are copied
+    # to the other components (pmc_rc.c:548-553): the saved initial proposal already holds Cholesky factors
+    assert prev["K"] == 9 and prev["d"] == 2 and np.allclose(prev["wght"], 1 / 9) and np.all(prev["chol"] == 1)
+    assert np.allclose(prev["std"][:, 0, 0], np.sqrt(10.0)) and np.allclose(prev["std"][:, 1, 0], 0.0)
     assert np.all(prev["mean"][0] == 0.0) and np.all(np.abs(prev["mean"][1:]) < 20) and len(np.unique(prev["mean"][:, 0])) == 9
     tgt4 = W._target(W.TGT_BANANA, 4, b=0.1, sig1=10.0)
     pins = np.array([0.5, -1.5])
