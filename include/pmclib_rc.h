@@ -82,6 +82,13 @@ gsl_rng *rc_gsl_rng(confFile *rc, char *root, error **err);                     
 char *get_itername(confFile *rc, char *key, int iter, error **err);               /* pmc_rc.c:770-794 */
 void *rcinit_bentGauss(confFile *rc, char *root, error **err);                    /* examples/target/sampleTarget.c:61-84 */
 #endif
+#ifndef __PMC_MPI_H
+/* libpmc_mpi's config functions (pmc_mpi.h:94-99; the parameter-file name "mix_mvdens_mpi" selects the broadcast proposal) */
+mix_mvdens *rc_mix_mvdens_mpi(confFile *rc, error **err);                         /* pmc_mpi.c:236-250 */
+distribution *rcinit_mix_mvdens_mpi(confFile *rc, error **err);                   /* pmc_mpi.c:252-272 */
+pmc_simu *init_importance_mpi_from_rc(confFile *rc, char *root, error **err);     /* pmc_mpi.c:274-318 */
+pmc_simu *init_pmc_mpi_from_rc(confFile *rc, char *root, error **err);            /* pmc_mpi.c:320-330 */
+#endif
 
 /* rc_gsl_rng hands out a gsl_rng of GSL's own layout (type, state) backed by an MT19937 of this library (the default
  * generator of pmc_rc.c:733), so hosts without GSL can run the drivers; release it with gsl_rng_free or this function */

@@ -351,10 +351,14 @@ unsigned long mt_get(void *vs) {
 double mt_get_double(void *vs) { return mt_get(vs) / 4294967296.0; }
 const gsl_rng_type mt_type = {"mt19937", 0xffffffffUL, 0, sizeof(MtState), &mt_set, &mt_get, &mt_get_double};
 
+}  // namespace
+extern "C" { static void *rcinit_mix_mvdens_mpi3(confFile *rc, char *root, error **err); }
+namespace {
 // INIT_FROM_RC (pmc_rc.h:31-63): initfunc or rcinit_<name>, from libpath if given, else from the process, else built in
 rcinit_smthng *builtin_init(const char *fn) {
   if (!strcmp(fn, "rcinit_bentGauss")) return &rcinit_bentGauss;
   if (!strcmp(fn, "rcinit_mix_mvdens")) return (rcinit_smthng *)&rcinit_mix_mvdens;
+  if (!strcmp(fn, "rcinit_mix_mvdens_mpi")) return &rcinit_mix_mvdens_mpi3;
   if (!strcmp(fn, "rcinit_combine_distributions")) return &rcinit_combine_distributions;
   if (!strcmp(fn, "rcinit_add_gaussian_prior")) return &rcinit_add_gaussian_prior;
   return nullptr;
@@ -967,6 +971,66 @@ void pmcb200_rng_free(gsl_rng *r) {
   if (!r) return;
   free(r->state);
   free(r);
+}
+
+// ---- libpmc_mpi's config functions (pmc_mpi.c:236-330, compiled there only with Lua) ---------------------------------
+// rank 0 builds the mixture from the parameter file (the draw_from initialisation draws on ITS GPU), the others receive it
+mix_mvdens *rc_mix_mvdens_mpi(confFile *rc, error **err) {  // pmc_mpi.c:236-250
+  mix_mvdens *mmv = nullptr;
+  int rank = 0, size = 1;
+  pmcb200_mpi_world(&rank, &size, nullptr, 0);
+  if (rank == 0) {
+    mmv = rc_mix_mvdens(rc, err);
+    RCFWD(*err, nullptr);
+  }
+  mmv = (mix_mvdens *)mvdens_broadcast_mpi(mmv, err);
+  RCFWD(*err, nullptr);
+  return mmv;
+}
+static void *rcinit_mix_mvdens_mpi3(confFile *rc, char *root, error **err) {
+  confFile *rca = rc_alias(rc, root, err);
+  RCFWD(*err, nullptr);
+  mix_mvdens *mmv = rc_mix_mvdens_mpi(rca, err);
+  RCFWD(*err, nullptr);
+  distribution *dist = init_distribution_full((int)mmv->ndim, mmv, &mix_mvdens_log_pdf_void, &mix_mvdens_free_void, &simulate_mix_mvdens_void, 0, nullptr, err);
+  RCFWD(*err, nullptr);
+  dist->broadcast_mpi = &mvdens_broadcast_mpi;
+  rc_close(&rca);
+  return dist;
+}
+// pmc_mpi.h:96 declares two arguments although INIT_FROM_RC calls every rcinit_* with three (rc, "", err); the parameter
+// file name "mix_mvdens_mpi" is served by the three-argument form above, this symbol keeps the header's prototype
+distribution *rcinit_mix_mvdens_mpi(confFile *rc, error **err) { return (distribution *)rcinit_mix_mvdens_mpi3(rc, (char *)"", err); }
+
+pmc_simu *init_importance_mpi_from_rc(confFile *rc, char *root, error **err) {  // pmc_mpi.c:274-318
+  confFile *rca = rc_alias(rc, root, err);
+  RCFWD(*err, nullptr);
+  distribution *target = init_distribution_from_rc(rca, (char *)"target", err);
+  RCFWD(*err, nullptr);
+  distribution *proposal = init_distribution_from_rc(rca, (char *)"proposal", err);
+  RCFWD(*err, nullptr);
+  if (proposal->ndim != target->ndim) { RCERR(*err, pmc_dimension, "incompatible dim for proposal (%d) and target (%d)", *err, nullptr, proposal->ndim, target->ndim); return nullptr; }
+  const long nsamples = rc_get_integer(rca, (char *)"nsample", err);
+  RCFWD(*err, nullptr);
+  pmc_simu *psim = pmc_simu_init_mpi(nsamples, target->ndim, target->n_ded, err);
+  RCFWD(*err, nullptr);
+  parabox *pb = parabox_from_rc(rca, (char *)"pb", err);
+  RCFWD(*err, nullptr);
+  if (pb->ndim != target->ndim) { RCERR(*err, pmc_dimension, "incompatible dim for pb (got %d expected %d)", *err, nullptr, pb->ndim, target->ndim); return nullptr; }
+  pmc_simu_init_target(psim, target, pb, err);
+  RCFWD(*err, nullptr);
+  const int pstep = (int)rc_safeget_integer(rca, (char *)"print_pc", 0, err);
+  RCFWD(*err, nullptr);
+  pmc_simu_init_proposal(psim, proposal, pstep, err);
+  RCFWD(*err, nullptr);
+  rc_close(&rca);
+  return psim;
+}
+pmc_simu *init_pmc_mpi_from_rc(confFile *rc, char *root, error **err) {  // pmc_mpi.c:320-330
+  pmc_simu *psim = init_importance_mpi_from_rc(rc, root, err);
+  RCFWD(*err, nullptr);
+  pmc_simu_init_pmc(psim, nullptr, nullptr, &update_prop_rb_void);
+  return psim;
 }
 
 char *get_itername(confFile *rc, char *key, int iter, error **err) {  // pmc_rc.c:770-794

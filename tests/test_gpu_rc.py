@@ -62,7 +62,35 @@ def test_reference_vanilla_pmc_runs_on_the_gpu(tmp_path):
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "c", "test_pmc.par")], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "----- end" in r.stdout
-    niter, N = 4, 30000
+    _check_pmc_run(tmp_path, 4, 30000)
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_reference_vanilla_pmc_mpi_runs_on_the_gpu(tmp_path, nranks):
+    """pmcexec/vanilla_pmc_mpi.c unmodified (MPI_Init / MPI_Comm_rank from the test-only mpi.h stub, everything else through
+    libpmc_mpi = libpmcb200.so over NCCL): one process per GPU; rank 0 builds the proposal from the parameter file and
+    broadcasts it, every rank draws and weighs its shard, rank 0 writes the reference's files with the WHOLE sample."""
+    exe = _driver("vanilla_pmc_mpi")
+    from pmclib_b200.lib import load_library
+    if load_library().pmcgpu_device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    import threading
+    res = [None] * nranks
+
+    def go(rank):
+        env = dict(os.environ, PMCB200_RANK=str(rank), PMCB200_WORLD_SIZE=str(nranks), PMCB200_LOCAL_RANK=str(rank),
+                   PMCB200_RENDEZVOUS=str(tmp_path / "rdv"))
+        res[rank] = subprocess.run([exe, os.path.join(ROOT, "tests", "c", "test_pmc_mpi.par")], cwd=tmp_path, capture_output=True, text=True, env=env)
+    th = [threading.Thread(target=go, args=(r,)) for r in range(nranks)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for r in res:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "----- end" in res[0].stdout
+    _check_pmc_run(tmp_path, 4, 30001)
+
+
+def _check_pmc_run(tmp_path, niter, N):
     perp_lines = [l.split() for l in open(tmp_path / "pmc_exploration.perp").read().splitlines()]
     assert len(perp_lines) == niter
     prev = read_mix(tmp_path / "proposal.mix_mvdens")         # the initial proposal (draw_from), saved by rc_mix_mvdens
