@@ -263,6 +263,40 @@ __device__ __forceinline__ void mix_fast(const double (&xs)[SPL][D], const doubl
   }
 }
 
+// The same for SPL samples per lane with the K component log-densities STREAMED through shared memory instead of held in
+// registers: during the component loop a lane keeps only x and the running solve of its SPL samples (one LDCU.128 now
+// feeds 2 SPL FP64 instructions), afterwards one sample at a time is finished from the stored values.  lvs: this warp's
+// [KK][SPL*32] doubles; on return it holds e[k] = alpha_k exp(ld_k - max + 500) of every sample.
+template <int D, int KK, int SPL, bool TGT>
+__device__ __forceinline__ void mix_stream(const double (&xs)[SPL][D], const double *s_exp, const double2 *s_log, double *lvs, int lane,
+                                           double (&lpos)[SPL], double (&out)[SPL]) {
+  constexpr int ST = i3_wstride(D);
+  double mx[SPL];
+  static_for<0, KK>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    double lv[SPL], al;
+    comp3<D, SPL, TGT, k * ST>(xs, lv, al);
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+      lvs[(k * SPL + s) * 32 + lane] = lv[s];
+      mx[s] = (k == 0) ? lv[s] : ((mx[s] < lv[s]) ? lv[s] : mx[s]);
+    }
+  });
+#pragma unroll
+  for (int s = 0; s < SPL; ++s) {
+    double lp = 0.0;
+    static_for<0, KK>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      const double al = TGT ? c3_t[k * ST + i3_woC(D) + 1] : c3_w[k * ST + i3_woC(D) + 1];
+      const double e = exp_tab((lvs[(k * SPL + s) * 32 + lane] - mx[s]) + kDynMax, s_exp) * al;
+      lvs[(k * SPL + s) * 32 + lane] = e;
+      lp = lp + e;
+    });
+    lpos[s] = lp;
+    out[s] = (mx[s] + log_tab(lp, s_log)) - kDynMax;
+  }
+}
+
 // ---- literal restatements for the non-finite corner (reference layout in global memory) --------------------------------
 static __device__ __noinline__ double mix_log_pdf_literal(const MixDev m, const double *x) {
   double ld[64], y[FUSED_MAXD];
@@ -324,7 +358,7 @@ struct TileAcc {  // per-lane running values of the kernel, updated by tile3 thr
 
 // One tile of 32*SPL samples: target, proposal density, log-weight, flags, responsibilities (pmc.c:537-592).
 template <int D, int K, int KT, int SPL, bool RESP>
-static __device__ __noinline__ void tile3(long tile, int lane, const double *s_exp, const double2 *s_log, TileAcc *acc) {
+static __device__ __noinline__ void tile3(long tile, int lane, const double *s_exp, const double2 *s_log, TileAcc *acc, double *lvs) {
   const W3Args &a = c3_wargs;
   constexpr int TS = 32 * SPL;
   const long tbase = tile * TS;
@@ -371,8 +405,10 @@ static __device__ __noinline__ void tile3(long tile, int lane, const double *s_e
   }
 
   // ---- proposal log-density ------------------------------------------------------------------------------------------
-  double e[SPL][K], lpos[SPL], rloc[SPL];
-  mix_fast<D, K, SPL, false>(x, s_exp, s_log, e, lpos, rloc);
+  constexpr bool STREAM = SPL > 1;  // two samples per lane: the component log-densities live in shared memory (mix_stream)
+  double e[STREAM ? 1 : SPL][STREAM ? 1 : K], lpos[SPL], rloc[SPL];
+  if constexpr (STREAM) mix_stream<D, K, SPL, false>(x, s_exp, s_log, lvs, lane, lpos, rloc);
+  else mix_fast<D, K, SPL, false>(x, s_exp, s_log, e, lpos, rloc);
 
   // ---- log-weight, flags, maxima (pmc.c:546-583) ---------------------------------------------------------------------
   double m_lane = acc->m, S_lane = acc->S, r_lane = acc->r;
@@ -408,7 +444,7 @@ static __device__ __noinline__ void tile3(long tile, int lane, const double *s_e
     if (RESP && valid[s]) {  // responsibilities alpha_k phi_k(x)/q(x), component-major: coalesced 256-byte rows
       const double rs = fastok ? 1.0 / lpos[s] : 0.0;
 #pragma unroll
-      for (int k = 0; k < K; ++k) a.resp[(size_t)k * a.N + i] = e[s][k] * rs;
+      for (int k = 0; k < K; ++k) a.resp[(size_t)k * a.N + i] = (STREAM ? lvs[(k * SPL + s) * 32 + lane] : e[STREAM ? 0 : s][STREAM ? 0 : k]) * rs;
     }
   }
   acc->m = m_lane; acc->S = S_lane; acc->r = r_lane; acc->nok = nok_lane; acc->posinf = posinf_lane;
@@ -427,6 +463,8 @@ __global__ void __launch_bounds__(128, MINB) k_weights3() {
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int TS = 32 * SPL;
+  extern __shared__ __align__(16) double w3_dyn[];  // SPL > 1: [4 warps][K][SPL*32] component log-densities (mix_stream)
+  double *lvs = w3_dyn + (size_t)wid * K * SPL * 32;
   const long ntiles = (a.N + TS - 1) / TS;
   TileAcc acc{-INFINITY, 0.0, -INFINITY, 0u, 0u};
   const long tstep = (long)gridDim.x * 4;
@@ -439,7 +477,7 @@ __global__ void __launch_bounds__(128, MINB) k_weights3() {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + (size_t)s * 32 * D * 8 + D * 8 - 8));
       }
     }
-    tile3<D, K, KT, SPL, RESP>(tile, lane, s_exp, s_log, &acc);
+    tile3<D, K, KT, SPL, RESP>(tile, lane, s_exp, s_log, &acc, lvs);
   }
   const double m_lane = acc.m, S_lane = acc.S, r_lane = acc.r;
   const unsigned int nok_lane = acc.nok, posinf_lane = acc.posinf;
@@ -1120,12 +1158,14 @@ Iter3Plan iter3_plan(int d, int K, int Kt, int tgt_kind, int sm_count) {
 }
 
 // variant 0: one sample per lane, 4 blocks/SM (128 registers); 1: one sample per lane, 3 blocks/SM (168 registers);
-// 2: two samples per lane, 2 blocks/SM (255 registers).  Variants 1 and 2 are instantiated for the headline shape only.
+// 2: two samples per lane with the component log-densities streamed through shared memory, 4 blocks/SM (128 registers).
+// Variants 1 and 2 are instantiated for the headline shape only.
 template <int D, int K, int KT>
 static int launch_w3(const Iter3Plan &p, const W3Args &a, int variant, bool resp, int *nblocks, cudaStream_t s) {
   constexpr bool kHead = (D == 10 && K == 10 && KT == 0);
   if (!kHead) variant = 0;
-  const int spl = variant == 2 ? 2 : 1, minb = variant == 0 ? 4 : (variant == 1 ? 3 : 2);
+  const int spl = variant == 2 ? 2 : 1, minb = variant == 1 ? 3 : 4;
+  const size_t dyn2 = (size_t)4 * K * 2 * 32 * sizeof(double);  // variant 2: the streamed component log-densities
   const long ntiles = (a.N + 32 * spl - 1) / (32 * spl);
   int grid = p.sm_count * minb;
   if ((long)grid * 4 > ntiles) grid = (int)((ntiles + 3) / 4);
@@ -1141,8 +1181,8 @@ static int launch_w3(const Iter3Plan &p, const W3Args &a, int variant, bool resp
       if (resp) k_weights3<D, K, KT, 1, true, 3><<<grid, 128, 0, s>>>();
       else k_weights3<D, K, KT, 1, false, 3><<<grid, 128, 0, s>>>();
     } else if (variant == 2) {
-      if (resp) k_weights3<D, K, KT, 2, true, 2><<<grid, 128, 0, s>>>();
-      else k_weights3<D, K, KT, 2, false, 2><<<grid, 128, 0, s>>>();
+      if (resp) k_weights3<D, K, KT, 2, true, 4><<<grid, 128, dyn2, s>>>();
+      else k_weights3<D, K, KT, 2, false, 4><<<grid, 128, dyn2, s>>>();
     }
   }
   count_launch();
