@@ -243,6 +243,9 @@ int pmcgpu_comm_set_callback(pmcgpu_ctx *ctx, pmcgpu_allreduce_fn fn, void *user
  *          pass nulls. */
 int pmcgpu_comm_allreduce(pmcgpu_ctx *ctx, double *buf, long n, int op);
 int pmcgpu_comm_bcast(pmcgpu_ctx *ctx, void *buf, size_t bytes, int root);
+/* every rank owns the bytes [my_off, my_off + my_len) of a host buffer of `total` bytes (disjoint ranges); afterwards all
+ * ranks hold the whole buffer.  The scatter / gather messages of pmc_mpi.c:334-520 are expressed with it. */
+int pmcgpu_comm_allgather_bytes(pmcgpu_ctx *ctx, void *buf, size_t total, size_t my_off, size_t my_len);
 int pmcgpu_comm_gather_store(pmcgpu_ctx *ctx, int root, long N_total, long first, double *X, size_t *indices,
                              double *weights, double *log_rho, short *flg);
 int pmcgpu_comm_rank(const pmcgpu_ctx *ctx, int *rank, int *nranks);

@@ -301,6 +301,7 @@ pmc_simu *pmc_simu_from_file(FILE *PMCSIM, int this_nsamples, int npar, int n_de
                              error **err);                                               /* pmc.c:373-396 */
 double fill_read_pmc_simu(pmc_simu *psim, mix_mvdens *proposal, error **err);            /* pmc.c:400-445 */
 size_t *sort_indices(double *list, size_t size, size_t *in_ind, size_t *buf, int order, error **err); /* pmc.c:881-1034 */
+void filter_importance_weight(pmc_simu *psim, double nsig, error **err);                 /* pmc.c:829-873 (a stub there too) */
 #endif
 
 /* ---- libpmc_mpi (pmclib/include/pmc_mpi.h:52-101): one process per GPU, NCCL instead of MPI (pmc_dropin_mpi.cpp) ------- */
@@ -323,6 +324,11 @@ void distribution_broadcast(distribution *dist, error **err);
 distribution *mix_mvdens_distribution_mpi(int ndim, void *mxmv, error **err);
 void send_mix_mvdens(mix_mvdens *m, int nproc, error **err);
 mix_mvdens *receive_mix_mvdens(int myid, int nproc, error **err);
+/* the message-level functions (pmc_mpi.c:334-520), for hand-written master / client loops: same slice layout */
+size_t send_simulation(pmc_simu *psim, int nproc, error **err);
+void receive_simulation(pmc_simu *psim, int basetag, int myid, error **err);
+void send_importance_weight(int myid, int basetag, pmc_simu *psim, size_t nok);
+size_t receive_importance_weight(pmc_simu *psim, int nproc, int master_cnt, int master_sample, error **err);
 #endif
 /* rank / size / rendezvous path resolved from the launcher's environment, and the rendezvous primitive (tests) */
 int pmcb200_mpi_world(int *rank, int *size, char *rdv, int rdv_len);

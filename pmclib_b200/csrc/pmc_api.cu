@@ -172,11 +172,13 @@ struct pmcgpu_ctx {
   DevBuf dcoll, dshare;
   // third-generation small-d iteration (pmc_iter3.cu)
   int gen3 = 1;                 // option "gen3": 0 = second-generation kernels only
-  int w3_variant = 0;           // option "w3_variant": launch shape of the third-generation weights kernel
+  int w3_variant = 3;           // option "w3_variant": 3 = row-scaled solve (default, guarded by gen3_max_ratio), 0 = exact subtraction, 1 / 2 = launch-shape experiments
   int draw3 = 0;                // option "draw3": 1 = grouped draw kernel k_draw3 even where the second-generation draw exists
   double gen3_max_ratio = 100;  // largest |mu' / L_jj| the pre-scaled solve is trusted with (option "gen3_max_ratio")
   bool i3_dirty = true;         // packs must be rebuilt (proposal or target changed)
   double i3_ratio = 0.0;
+  double i3_pre_ratio = 0.0;    // largest |mu'_j / L_jj| over the live components about the common shift
+  bool i3_pre = false;          // the proposal's whitening pack is in row-scaled form (w3_variant 3 and the ratio guard passed)
   double i3_shift[FUSED_MAXD] = {0};
   std::vector<double> i3_hw, i3_ht, i3_hd, i3_hcw;
   DevBuf i3_gpack, i3_wpart, i3_scal, i3_coll, i3_spart, i3_out;
@@ -643,7 +645,11 @@ int pack_iter3(pmcgpu_ctx *c, const Iter3Plan &p) {
   c->i3_hd.assign((size_t)p.K * ds, 0.0);
   // the whitening subtracts each component's mean exactly (no common shift): i3_shift is the pivot of the statistics only
   const double noshift[FUSED_MAXD] = {0};
-  iter3_pack_w(p.K, D, wg.data(), mu.data(), L.data(), ld.data(), noshift, c->i3_hw.data());
+  // w3_variant 3: the row-scaled solve about the common shift, trusted while no live component has |mu'_j / L_jj| above
+  // gen3_max_ratio (its offsets m_j = -mu'_j / L_jj carry a relative rounding error); otherwise the exact subtraction
+  c->i3_pre_ratio = iter3_shift_ratio(p.K, D, wg.data(), mu.data(), L.data(), c->i3_shift);
+  c->i3_pre = c->w3_variant == 3 && c->i3_pre_ratio <= c->gen3_max_ratio;
+  iter3_pack_w(p.K, D, wg.data(), mu.data(), L.data(), ld.data(), c->i3_pre ? c->i3_shift : noshift, c->i3_hw.data(), c->i3_pre ? 1 : 0);
   iter3_pack_d(p.K, D, mu.data(), L.data(), c->i3_hd.data());
   c->i3_ratio = 0.0;
   // ranindx (mvdens.c:776): the index is the number of the first K-1 cumulative weights below z
@@ -789,7 +795,7 @@ int run_iter3(pmcgpu_ctx *c, const Iter3Plan &p, int do_draw, int stage_limit, i
     w.lw = c->W.as<double>(); w.log_rho = c->R.as<double>(); w.flg = c->Flg.as<short>();
     w.resp = (stage_limit >= 2 && with_stats) ? c->resp.as<double>() : nullptr;
     w.partials = c->i3_wpart.as<double>(); w.counters = sm + SM_COUNTERS; w.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
-    w.mix = c->dprop.view; w.tmix = c->dtmix.view; w.variant = c->w3_variant;
+    w.mix = c->dprop.view; w.tmix = c->dtmix.view; w.variant = c->i3_pre ? 3 : (c->w3_variant == 3 ? 0 : c->w3_variant);
     if (launch_weights3(p, w, &wblocks, c->stream)) return fail(c, PMCGPU_ERR_CUDA, "weights kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
@@ -1353,8 +1359,8 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "split_stats")) c->split_stats = (int)value;
   else if (!strcmp(name, "split_draw")) c->split_draw = (int)value;
   else if (!strcmp(name, "gen3")) c->gen3 = (int)value;
-  else if (!strcmp(name, "gen3_max_ratio")) c->gen3_max_ratio = value;
-  else if (!strcmp(name, "w3_variant")) c->w3_variant = (int)value;
+  else if (!strcmp(name, "gen3_max_ratio")) { c->gen3_max_ratio = value; c->i3_dirty = true; }
+  else if (!strcmp(name, "w3_variant")) { c->w3_variant = (int)value; c->i3_dirty = true; }
   else if (!strcmp(name, "draw3")) c->draw3 = (int)value;
   else if (!strcmp(name, "mma")) { c->use_mma = (int)value; return repack_mma(c); }
   else if (!strcmp(name, "mma_min_d")) { c->mma_min_d = (int)value; return repack_mma(c); }
@@ -1373,6 +1379,9 @@ int pmcgpu_get_info(pmcgpu_ctx *c, const char *name, double *value) {
   cudaSetDevice(c->device);
   if (!strcmp(name, "mma_active")) { RC(ensure_mma(c)); *value = c->mprop.valid ? 1.0 : 0.0; return 0; }
   if (!strcmp(name, "mma_inverse_discrepancy")) { RC(ensure_mma(c)); *value = c->mprop.inv_discrepancy; return 0; }
+  // third-generation weights kernel: 1 if the current proposal is packed for the row-scaled solve, and the guard's ratio
+  if (!strcmp(name, "w3_rowscaled")) { const Iter3Plan p = plan3_for(c); *value = (p.valid && c->i3_pre) ? 1.0 : 0.0; return 0; }
+  if (!strcmp(name, "w3_shift_ratio")) { const Iter3Plan p = plan3_for(c); *value = p.valid ? c->i3_pre_ratio : -1.0; return 0; }
   return fail(c, PMCGPU_ERR_USAGE, "unknown info %s", name);
 }
 
@@ -2545,6 +2554,12 @@ int pmcgpu_comm_bcast(pmcgpu_ctx *c, void *buf, size_t bytes, int root) {
   cudaSetDevice(c->device);
   if (c->nranks <= 1) return 0;
   return share_bytes(c, buf, false, bytes, 0, c->rank == root ? bytes : 0, buf);
+}
+int pmcgpu_comm_allgather_bytes(pmcgpu_ctx *c, void *buf, size_t total, size_t my_off, size_t my_len) {
+  if (!c || !buf || my_off + my_len > total) return PMCGPU_ERR_USAGE;
+  cudaSetDevice(c->device);
+  if (c->nranks <= 1) return 0;
+  return share_bytes(c, (const char *)buf + my_off, false, total, my_off, my_len, buf);
 }
 int pmcgpu_comm_gather_store(pmcgpu_ctx *c, int root, long N_total, long first, double *X, size_t *indices, double *weights,
                              double *log_rho, short *flg) {

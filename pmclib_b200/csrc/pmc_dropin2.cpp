@@ -360,6 +360,14 @@ pmc_simu *pmc_simu_from_file(FILE *PMCSIM, int nsamples, int npar, int n_ded, mi
   return psim;
 }
 
+// pmc.c:829-873: an unfinished function in the reference — it sorts a copy of the log-weights, computes nothing from the
+// order and leaves the pmc_simu untouched (the median / variance code is commented out).  Exported so that callers that
+// reference pmc.h:174 link; observable behaviour (the warning for normalised weights, no change of psim) is kept.
+void filter_importance_weight(pmc_simu *psim, double nsig, error **err) {
+  (void)nsig; (void)err;
+  if (psim->isLog != 1) fprintf(stderr, "Filtering normalized importance weights... It is probably too late...\n");
+}
+
 // pmc.c:881-1034: permutation that sorts list (order > 0 ascending, else descending).  in_ind == NULL allocates the
 // identity first.  Ties keep their input order (the reference's quick-sort leaves them in an unspecified order).
 size_t *sort_indices(double *list, size_t size, size_t *in_ind, size_t *buf, int order, error **err) {

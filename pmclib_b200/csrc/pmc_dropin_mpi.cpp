@@ -417,6 +417,142 @@ mix_mvdens *receive_mix_mvdens(int myid, int nproc, error **err) {
   return (mix_mvdens *)mvdens_broadcast_mpi(nullptr, err);
 }
 
+// ---- the message-level functions of pmc_mpi.c:334-520, for callers that write their own master / client loop ---------
+// Same slice layout as the reference: the master keeps the first N/nproc samples, client i the next N/nproc (+1 for the
+// first N mod nproc clients).  Each MPI_Send / MPI_Recv pair becomes a collective every rank takes part in: the master
+// enters it from send_simulation / receive_importance_weight, the clients from receive_simulation / send_importance_weight.
+namespace {
+struct Slices { std::vector<long> first, len; };
+Slices ref_slices(long N, int nproc) {  // pmc_mpi.c:344-352, 366-372
+  Slices s;
+  s.first.assign(nproc, 0);
+  s.len.assign(nproc, 0);
+  const long per = N / nproc;
+  long remaining = N - per * nproc, cur = per;
+  s.len[0] = per;
+  for (int i = 1; i < nproc; ++i) {
+    long b = per;
+    if (remaining > 0) { b = per + 1; --remaining; }
+    s.first[i] = cur;
+    s.len[i] = b;
+    cur += b;
+  }
+  return s;
+}
+pmcgpu_ctx *msg_ctx(pmc_simu *psim, error **err) {
+  MpiSide *s = mside_for(psim, err);
+  return s ? s->ctx : nullptr;
+}
+// one array of the master's pmc_simu <-> the clients' slices: everybody ends with the whole array in `full`
+bool exchange(pmcgpu_ctx *c, std::vector<char> &full, size_t elem, long N, const Slices &sl, int rank, const void *mine, long nmine, error **err) {
+  full.assign((size_t)N * elem + 8, 0);
+  if (mine && nmine > 0) memcpy(full.data() + (size_t)sl.first[rank] * elem, mine, (size_t)nmine * elem);
+  const int rc = pmcgpu_comm_allgather_bytes(c, full.data(), (size_t)N * elem, (size_t)sl.first[rank] * elem, (size_t)nmine * elem);
+  if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return false; }
+  return true;
+}
+}  // namespace
+
+// master: the slices of X, X_ded and flg leave for the clients; returns the master's own sample count
+size_t send_simulation(pmc_simu *psim, int nproc, error **err) {
+  const World &w = world();
+  pmcgpu_ctx *c = msg_ctx(psim, err);
+  if (!c) return 0;
+  long hdr[3] = {psim->nsamples, psim->ndim, psim->n_ded};
+  int rc = pmcgpu_comm_bcast(c, hdr, sizeof hdr, 0);
+  if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0; }
+  const long N = hdr[0];
+  const Slices sl = ref_slices(N, nproc);
+  std::vector<char> full;
+  // the master owns everything: it contributes the whole arrays (first = 0, len = N in the collective)
+  Slices all = sl;
+  all.first[w.rank] = 0;
+  if (!exchange(c, full, sizeof(double) * psim->ndim, N, all, w.rank, psim->X, N, err)) return 0;
+  if (psim->n_ded > 0 && !exchange(c, full, sizeof(double) * psim->n_ded, N, all, w.rank, psim->X_ded, N, err)) return 0;
+  if (!exchange(c, full, sizeof(short), N, all, w.rank, psim->flg, N, err)) return 0;
+  return (size_t)sl.len[0];
+}
+// client: receives its slice (the pmc_simu is re-allocated to the slice size, pmc_mpi.c:392-395)
+void receive_simulation(pmc_simu *psim, int basetag, int myid, error **err) {
+  const int nproc = basetag;  // the reference passes mpi_size as the tag base (pmc_mpi.c:66)
+  pmcgpu_ctx *c = msg_ctx(psim, err);
+  if (!c) return;
+  long hdr[3] = {0, 0, 0};
+  int rc = pmcgpu_comm_bcast(c, hdr, sizeof hdr, 0);
+  if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return; }
+  const long N = hdr[0];
+  const Slices sl = ref_slices(N, nproc);
+  const long mine = sl.len[myid];
+  if (mine != psim->nsamples) {
+    pmc_simu_realloc(psim, mine, err);
+    if (isError(*err)) { *err = newError(forwardErr, (char *)__func__, (char *)"", nullptr, *err); return; }
+  }
+  std::vector<char> full;
+  Slices none = sl;  // a client contributes nothing
+  if (!exchange(c, full, sizeof(double) * psim->ndim, N, none, myid, nullptr, 0, err)) return;
+  memcpy(psim->X, full.data() + (size_t)sl.first[myid] * psim->ndim * sizeof(double), (size_t)mine * psim->ndim * sizeof(double));
+  if (psim->n_ded > 0) {
+    if (!exchange(c, full, sizeof(double) * psim->n_ded, N, none, myid, nullptr, 0, err)) return;
+    memcpy(psim->X_ded, full.data() + (size_t)sl.first[myid] * psim->n_ded * sizeof(double), (size_t)mine * psim->n_ded * sizeof(double));
+  }
+  if (!exchange(c, full, sizeof(short), N, none, myid, nullptr, 0, err)) return;
+  memcpy(psim->flg, full.data() + (size_t)sl.first[myid] * sizeof(short), (size_t)mine * sizeof(short));
+}
+
+namespace {
+// the gather of pmc_mpi.c:410-520, entered by all ranks: weights, X_ded, log_rho, flags, and (nok, maxW, maxR) per rank
+size_t gather_weights(pmc_simu *psim, int nproc, int rank, size_t nok, long N_master_total, error **err) {
+  pmcgpu_ctx *c = msg_ctx(psim, err);
+  if (!c) return 0;
+  long hdr[1] = {N_master_total};
+  int rc = pmcgpu_comm_bcast(c, hdr, sizeof hdr, 0);
+  if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0; }
+  const long N = hdr[0];
+  const Slices sl = ref_slices(N, nproc);
+  const long mine = sl.len[rank];
+  std::vector<double> slot((size_t)3 * nproc, 0.0);
+  slot[3 * rank] = (double)nok; slot[3 * rank + 1] = psim->maxW; slot[3 * rank + 2] = psim->maxR;
+  rc = pmcgpu_comm_allreduce(c, slot.data(), (long)slot.size(), 0);
+  if (rc) { *err = newErrorVA(rc, __func__, (char *)"", (char *)"%s", *err, nullptr, pmcgpu_last_error(c)); return 0; }
+  std::vector<char> fw, fd, fr, ff;
+  if (!exchange(c, fw, sizeof(double), N, sl, rank, psim->weights, mine, err)) return 0;
+  if (psim->n_ded > 0 && !exchange(c, fd, sizeof(double) * psim->n_ded, N, sl, rank, psim->X_ded, mine, err)) return 0;
+  if (!exchange(c, fr, sizeof(double), N, sl, rank, psim->log_rho, mine, err)) return 0;
+  if (!exchange(c, ff, sizeof(short), N, sl, rank, psim->flg, mine, err)) return 0;
+  if (rank != 0) return nok;
+  size_t cnt = (size_t)slot[0];
+  for (int i = 1; i < nproc; ++i) {
+    const long f = sl.first[i], n = sl.len[i];
+    const size_t inok = (size_t)slot[3 * i];
+    cnt += inok;
+    if (inok == 0) {  // pmc_mpi.c:466-474: a client without a single valid sample
+      for (long j = 0; j < n; ++j) { psim->weights[f + j] = 0; psim->log_rho[f + j] = 0; psim->flg[f + j] = 0; }
+      continue;
+    }
+    memcpy(psim->weights + f, fw.data() + (size_t)f * sizeof(double), (size_t)n * sizeof(double));
+    if (psim->n_ded > 0) memcpy(psim->X_ded + (size_t)f * psim->n_ded, fd.data() + (size_t)f * psim->n_ded * sizeof(double), (size_t)n * psim->n_ded * sizeof(double));
+    memcpy(psim->log_rho + f, fr.data() + (size_t)f * sizeof(double), (size_t)n * sizeof(double));
+    memcpy(psim->flg + f, ff.data() + (size_t)f * sizeof(short), (size_t)n * sizeof(short));
+    if (slot[3 * i + 1] > psim->maxW) psim->maxW = slot[3 * i + 1];  // pmc_mpi.c:502-508
+    if (slot[3 * i + 2] > psim->maxR) psim->maxR = slot[3 * i + 2];
+  }
+  return cnt;
+}
+}  // namespace
+
+// client: un-normalised weights, deduced parameters, log_rho, flags and the running maxima go to the master
+void send_importance_weight(int myid, int basetag, pmc_simu *psim, size_t nok) {
+  error *e = initError();
+  gather_weights(psim, basetag, myid, nok, 0, &e);
+  if (isError(e)) printError(stderr, e);  // the reference's prototype has no error argument
+  endError(&e);
+}
+// master: psim->nsamples must be the whole sample again (pmc_mpi.c:84-86); master_cnt / master_sample describe its own slice
+size_t receive_importance_weight(pmc_simu *psim, int nproc, int master_cnt, int master_sample, error **err) {
+  (void)master_sample;
+  return gather_weights(psim, nproc, 0, (size_t)master_cnt, psim->nsamples, err);
+}
+
 /* test hook: rank, size and rendezvous path this process resolved from its environment */
 int pmcb200_mpi_world(int *rank, int *size, char *rdv, int rdv_len) {
   const World &w = world();

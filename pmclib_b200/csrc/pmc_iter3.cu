@@ -64,8 +64,11 @@ __host__ __device__ constexpr int i3_dstride(int D) { return i3_ev2(D + D * (D +
 int iter3_wstride(int D) { return i3_wstride(D); }
 int iter3_dstride(int D) { return i3_dstride(D); }
 
+// pre = 1: row-scaled form for the PRE kernels — m_j = -(mu_j - shift_j)/L_jj | 1/L_jj | -L_ij/L_ii — so that
+// y_i = x~_i/L_ii + m_i - sum_j (L_ij/L_ii) y_j needs no separate subtraction and scaling (65 instead of 75 FP64
+// instructions per component at d = 10); x~ = x - shift is formed once per sample.
 void iter3_pack_w(int K, int D, const double *wght, const double *mean, const double *L, const double *logdet,
-                  const double *shift, double *out) {
+                  const double *shift, double *out, int pre) {
   const int st = i3_wstride(D);
   for (int k = 0; k < K; ++k) {
     double *o = out + (size_t)k * st;
@@ -76,13 +79,16 @@ void iter3_pack_w(int K, int D, const double *wght, const double *mean, const do
     }
     const double *Lk = L + (size_t)k * D * D;
     for (int j = 0; j < D; ++j) {
-      o[j] = -(mean[(size_t)k * D + j] - shift[j]);
-      o[i3_woR(D) + j] = 1.0 / Lk[j * D + j];
+      const double dj = 1.0 / Lk[j * D + j];
+      o[j] = pre ? -(mean[(size_t)k * D + j] - shift[j]) * dj : -(mean[(size_t)k * D + j] - shift[j]);
+      o[i3_woR(D) + j] = dj;
     }
     int e = i3_woL(D);
     for (int j = 0; j < D; ++j)
-      for (int i = j + 1; i < D; ++i) o[e++] = -Lk[i * D + j];
-    o[i3_woC(D)] = -0.5 * (D * kLn2Pi) - logdet[k];
+      for (int i = j + 1; i < D; ++i) o[e++] = pre ? -Lk[i * D + j] * (1.0 / Lk[i * D + i]) : -Lk[i * D + j];
+    // pre: log alpha_k is folded into the constant, so the log-sum-exp runs over log(alpha_k phi_k) without the K products
+    // alpha_k exp(.) and without the DYNMAX offsets (mvdens.c:805-822 shifts by max ld_k + 500: any pivot gives the same sum)
+    o[i3_woC(D)] = -0.5 * (D * kLn2Pi) - logdet[k] + (pre ? log(wght[k]) : 0.0);
     o[i3_woC(D) + 1] = wght[k];
   }
 }
@@ -142,7 +148,9 @@ __device__ __forceinline__ double exp_tab(double x, const double *tab) {
   constexpr double kMagic = 6755399441055744.0;
   constexpr double kInv = 92.332482616893657;
   constexpr double kHi = 6.93147180369123816490e-01 / 64.0, kLo = 1.90821492927058770002e-10 / 64.0;
-  const double xc = (x > -700.0) ? x : -700.0;
+  // clamp on the high word (x <= 709 by contract: "below -700" is then an unsigned comparison of the sign-magnitude bits;
+  // an FP64 max costs a DSETP on the FP64 pipe plus NaN plumbing)
+  const double xc = ((unsigned)__double2hiint(x) >= 0xC085E000u) ? -700.0 : x;
   const double t = fma(xc, kInv, kMagic);
   const int ni = __double2loint(t);
   const double n = t - kMagic;
@@ -199,19 +207,33 @@ __device__ __forceinline__ void ldc2(double &a, double &b) {
 
 // one component: q = |L^-1 (x - mu)|^2 by forward substitution, lv = -q/2 + c'; al = alpha.  Every FP64 instruction has
 // exactly one pack entry as operand (ptxas keeps them in uniform registers: DFMA R, R, UR, R)
-template <int D, int SPL, bool TGT, int BASE>
-__device__ __forceinline__ void comp3(const double (&x)[SPL][D], double (&lv)[SPL], double &al) {
+// PRE: the row-scaled pack (iter3_pack_w, pre = 1).  The offsets m_j are the one operand that cannot come from the constant
+// bank (an FP64 instruction takes one constant operand): they are read from shared memory, two per warp-uniform LDS.128.
+template <int D, int SPL, bool TGT, int BASE, bool PRE = false>
+__device__ __forceinline__ void comp3(const double (&x)[SPL][D], double (&lv)[SPL], double &al, const double2 *s_mu = nullptr) {
   constexpr int ST = i3_wstride(D);
+  constexpr int H = i3_ev2(D) / 2;
   double c[ST];
-  static_for<0, ST / 2>([&](auto pc) {
+  static_for<(PRE ? H : 0), ST / 2>([&](auto pc) {
     constexpr int p = decltype(pc)::value;
     ldc2<TGT, BASE + 2 * p>(c[2 * p], c[2 * p + 1]);
   });
   double v[SPL][D], q[SPL];
+  if constexpr (PRE) {
+    double mm[2 * H];
 #pragma unroll
-  for (int j = 0; j < D; ++j) {
+    for (int p = 0; p < H; ++p) { const double2 t2 = s_mu[(BASE / ST) * H + p]; mm[2 * p] = t2.x; mm[2 * p + 1] = t2.y; }
 #pragma unroll
-    for (int s = 0; s < SPL; ++s) v[s][j] = x[s][j] + c[j];
+    for (int j = 0; j < D; ++j) {
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) v[s][j] = fma(x[s][j], c[i3_woR(D) + j], mm[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) v[s][j] = x[s][j] + c[j];
+    }
   }
   int off = i3_woL(D);
 #pragma unroll
@@ -219,7 +241,7 @@ __device__ __forceinline__ void comp3(const double (&x)[SPL][D], double (&lv)[SP
     double y[SPL];
 #pragma unroll
     for (int s = 0; s < SPL; ++s) {
-      y[s] = v[s][j] * c[i3_woR(D) + j];
+      y[s] = PRE ? v[s][j] : v[s][j] * c[i3_woR(D) + j];
       q[s] = (j == 0) ? y[s] * y[s] : fma(y[s], y[s], q[s]);
     }
 #pragma unroll
@@ -236,15 +258,16 @@ __device__ __forceinline__ void comp3(const double (&x)[SPL][D], double (&lv)[SP
 
 // mix_mvdens_log_pdf (mvdens.c:784-825) of KK Gaussian components packed at c3_w / c3_t: e[k] = alpha_k exp(ld_k - max + 500),
 // lpos = sum_k e[k] in component order, returns (max + log lpos) - 500
-template <int D, int KK, int SPL, bool TGT>
+template <int D, int KK, int SPL, bool TGT, bool PRE = false>
 __device__ __forceinline__ void mix_fast(const double (&xs)[SPL][D], const double *s_exp,
-                                         const double2 *s_log, double (&e)[SPL][KK], double (&lpos)[SPL], double (&out)[SPL]) {
+                                         const double2 *s_log, double (&e)[SPL][KK], double (&lpos)[SPL], double (&out)[SPL],
+                                         const double2 *s_mu = nullptr) {
   constexpr int ST = i3_wstride(D);
   double mx[SPL], al[KK];
   static_for<0, KK>([&](auto kc) {
     constexpr int k = decltype(kc)::value;
     double lv[SPL];
-    comp3<D, SPL, TGT, k * ST>(xs, lv, al[k]);
+    comp3<D, SPL, TGT, k * ST, PRE>(xs, lv, al[k], s_mu);
 #pragma unroll
     for (int s = 0; s < SPL; ++s) {
       e[s][k] = lv[s];
@@ -256,10 +279,11 @@ __device__ __forceinline__ void mix_fast(const double (&xs)[SPL][D], const doubl
     lpos[s] = 0.0;
 #pragma unroll
     for (int k = 0; k < KK; ++k) {
-      e[s][k] = exp_tab((e[s][k] - mx[s]) + kDynMax, s_exp) * al[k];
+      if constexpr (PRE) e[s][k] = exp_tab(e[s][k] - mx[s], s_exp);  // log alpha_k is part of the pack's constant
+      else e[s][k] = exp_tab((e[s][k] - mx[s]) + kDynMax, s_exp) * al[k];
       lpos[s] = lpos[s] + e[s][k];
     }
-    out[s] = (mx[s] + log_tab(lpos[s], s_log)) - kDynMax;
+    out[s] = PRE ? mx[s] + log_tab(lpos[s], s_log) : (mx[s] + log_tab(lpos[s], s_log)) - kDynMax;
   }
 }
 
@@ -348,6 +372,7 @@ struct W3Args {
   unsigned long long *counters;
   double *first_vals;
   MixDev mix, tmix;  // reference layout, for the literal re-evaluation of non-finite samples
+  double shift[FUSED_MAXD];  // PRE kernels: the common shift of the row-scaled pack
 };
 __constant__ W3Args c3_wargs;  // the launch's arguments: read at compile-time offsets from every function of the kernel
 
@@ -357,8 +382,9 @@ struct TileAcc {  // per-lane running values of the kernel, updated by tile3 thr
 };
 
 // One tile of 32*SPL samples: target, proposal density, log-weight, flags, responsibilities (pmc.c:537-592).
-template <int D, int K, int KT, int SPL, bool RESP>
-static __device__ __noinline__ void tile3(long tile, int lane, const double *s_exp, const double2 *s_log, TileAcc *acc, double *lvs) {
+template <int D, int K, int KT, int SPL, bool RESP, bool PRE>
+static __device__ __noinline__ void tile3(long tile, int lane, const double *s_exp, const double2 *s_log, TileAcc *acc, double *lvs,
+                                          const double2 *s_mu) {
   const W3Args &a = c3_wargs;
   constexpr int TS = 32 * SPL;
   const long tbase = tile * TS;
@@ -407,8 +433,15 @@ static __device__ __noinline__ void tile3(long tile, int lane, const double *s_e
   // ---- proposal log-density ------------------------------------------------------------------------------------------
   constexpr bool STREAM = SPL > 1;  // two samples per lane: the component log-densities live in shared memory (mix_stream)
   double e[STREAM ? 1 : SPL][STREAM ? 1 : K], lpos[SPL], rloc[SPL];
+  if constexpr (PRE) {
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) x[s][j] -= a.shift[j];
+    }
+  }
   if constexpr (STREAM) mix_stream<D, K, SPL, false>(x, s_exp, s_log, lvs, lane, lpos, rloc);
-  else mix_fast<D, K, SPL, false>(x, s_exp, s_log, e, lpos, rloc);
+  else mix_fast<D, K, SPL, false, PRE>(x, s_exp, s_log, e, lpos, rloc, s_mu);
 
   // ---- log-weight, flags, maxima (pmc.c:546-583) ---------------------------------------------------------------------
   double m_lane = acc->m, S_lane = acc->S, r_lane = acc->r;
@@ -450,16 +483,25 @@ static __device__ __noinline__ void tile3(long tile, int lane, const double *s_e
   acc->m = m_lane; acc->S = S_lane; acc->r = r_lane; acc->nok = nok_lane; acc->posinf = posinf_lane;
 }
 
-template <int D, int K, int KT, int SPL, bool RESP, int MINB>
+template <int D, int K, int KT, int SPL, bool RESP, int MINB, bool PRE = false>
 __global__ void __launch_bounds__(128, MINB) k_weights3() {
   constexpr int ST = i3_wstride(D);
   static_assert(K * ST <= I3_CW && KT * ST <= I3_CT, "constant memory budget");
+  static_assert(!PRE || SPL == 1, "the row-scaled solve is built for one sample per lane");
   const W3Args &a = c3_wargs;
   __shared__ double s_exp[64];
   __shared__ double2 s_log[128];
   __shared__ double s_m[4], s_S[4], s_r[4];
+  constexpr int H = i3_ev2(D) / 2;
+  __shared__ double2 s_mu[PRE ? K * H : 1];  // PRE: the offsets m_j of every component (the pack's first ev2(D) entries)
   for (int i = threadIdx.x; i < 64; i += blockDim.x) s_exp[i] = c3_exptab[i];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) s_log[i] = c3_logtab[i];
+  if constexpr (PRE) {
+    for (int i = threadIdx.x; i < K * H; i += blockDim.x) {
+      const int k = i / H, p = i - k * H;
+      s_mu[i] = make_double2(c3_w[k * ST + 2 * p], c3_w[k * ST + 2 * p + 1]);
+    }
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int TS = 32 * SPL;
@@ -477,7 +519,7 @@ __global__ void __launch_bounds__(128, MINB) k_weights3() {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + (size_t)s * 32 * D * 8 + D * 8 - 8));
       }
     }
-    tile3<D, K, KT, SPL, RESP>(tile, lane, s_exp, s_log, &acc, lvs);
+    tile3<D, K, KT, SPL, RESP, PRE>(tile, lane, s_exp, s_log, &acc, lvs, s_mu);
   }
   const double m_lane = acc.m, S_lane = acc.S, r_lane = acc.r;
   const unsigned int nok_lane = acc.nok, posinf_lane = acc.posinf;
@@ -1163,7 +1205,7 @@ Iter3Plan iter3_plan(int d, int K, int Kt, int tgt_kind, int sm_count) {
 template <int D, int K, int KT>
 static int launch_w3(const Iter3Plan &p, const W3Args &a, int variant, bool resp, int *nblocks, cudaStream_t s) {
   constexpr bool kHead = (D == 10 && K == 10 && KT == 0);
-  if (!kHead) variant = 0;
+  if (!kHead && variant != 3) variant = 0;
   const int spl = variant == 2 ? 2 : 1, minb = variant == 1 ? 3 : 4;
   const size_t dyn2 = (size_t)4 * K * 2 * 32 * sizeof(double);  // variant 2: the streamed component log-densities
   const long ntiles = (a.N + 32 * spl - 1) / (32 * spl);
@@ -1175,6 +1217,9 @@ static int launch_w3(const Iter3Plan &p, const W3Args &a, int variant, bool resp
   if (variant == 0) {
     if (resp) k_weights3<D, K, KT, 1, true, 4><<<grid, 128, 0, s>>>();
     else k_weights3<D, K, KT, 1, false, 4><<<grid, 128, 0, s>>>();
+  } else if (variant == 3) {  // row-scaled solve (the pack was built with pre = 1)
+    if (resp) k_weights3<D, K, KT, 1, true, 4, true><<<grid, 128, 0, s>>>();
+    else k_weights3<D, K, KT, 1, false, 4, true><<<grid, 128, 0, s>>>();
   }
   if constexpr (kHead) {
     if (variant == 1) {
@@ -1206,6 +1251,7 @@ int launch_weights3(const Iter3Plan &p, const Iter3Weights &w, int *nblocks, cud
   a.post_in = w.post_in; a.ok_in = w.ok_in;
   a.lw = w.lw; a.log_rho = w.log_rho; a.resp = w.resp; a.flg = w.flg; a.partials = w.partials; a.counters = w.counters;
   a.first_vals = w.first_vals; a.mix = w.mix; a.tmix = w.tmix;
+  for (int j = 0; j < FUSED_MAXD; ++j) a.shift[j] = w.shift[j];
   const bool resp = w.resp != nullptr;
 #define X(D_, K_, KT_) \
   if (p.D == D_ && p.K == K_ && p.KT == KT_) return launch_w3<D_, K_, KT_>(p, a, w.variant, resp, nblocks, s);

@@ -261,7 +261,7 @@ Iter3Plan iter3_plan(int d, int K, int Kt, int tgt_kind, int sm_count);
 int iter3_wstride(int D);
 int iter3_dstride(int D);
 void iter3_pack_w(int K, int D, const double *wght, const double *mean, const double *L, const double *logdet,
-                  const double *shift, double *out);
+                  const double *shift, double *out, int pre = 0);
 void iter3_pack_d(int K, int D, const double *mean, const double *L, double *out);
 double iter3_shift_ratio(int K, int D, const double *wght, const double *mean, const double *L, const double *shift);
 // constant-bank uploads on the stream (any pointer may be null = unchanged)

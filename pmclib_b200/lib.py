@@ -36,7 +36,7 @@ EXPORTS = [
     "pmcgpu_pmc_step", "pmcgpu_step_given", "pmcgpu_get_proposal", "pmcgpu_shard_range", "pmcgpu_nccl_unique_id",
     "pmcgpu_comm_init", "pmcgpu_comm_set_callback", "pmcgpu_stats_len", "pmcgpu_finalize_update", "pmcgpu_cholesky",
     "pmcgpu_set_target_combine", "pmcgpu_step_given_post", "pmcgpu_comm_allreduce", "pmcgpu_comm_bcast",
-    "pmcgpu_comm_gather_store", "pmcgpu_comm_rank", "pmcgpu_target_scalar_product", "pmcgpu_get_info",
+    "pmcgpu_comm_gather_store", "pmcgpu_comm_rank", "pmcgpu_target_scalar_product", "pmcgpu_get_info", "pmcgpu_comm_allgather_bytes",
 ]
 
 
@@ -125,5 +125,6 @@ def load_library(build_if_missing: bool = False):
     L.pmcgpu_comm_rank.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.pmcgpu_target_scalar_product.argtypes = [vp, lng, vp, vp]
     L.pmcgpu_get_info.argtypes = [vp, C.c_char_p, C.POINTER(dbl)]
+    L.pmcgpu_comm_allgather_bytes.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t]
     _lib = L
     return L

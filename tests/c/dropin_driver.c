@@ -106,7 +106,7 @@ int main(int argc, char **argv) {
     pb = init_parabox(d, err); CHECK(err, "init_parabox");
     for (int f = 0; f < nfaces; ++f) { add_face(pb, faces + (size_t)f * (d + 1), faces[(size_t)f * (d + 1) + d], err); CHECK(err, "add_face"); }
   }
-  const int mpi_mode = (mode == 7 || mode == 8);
+  const int mpi_mode = (mode == 7 || mode == 8 || mode == 9);
   pmc_simu *psim = mpi_mode ? pmc_simu_init_mpi(N, d, 0, err) : pmc_simu_init(N, d, err); CHECK(err, "pmc_simu_init");
   if (mpi_mode) {
     pmc_simu_init_classic_pmc_mpi(psim, tgt, pb, m, 0, NULL, NULL, err);
@@ -159,7 +159,37 @@ int main(int argc, char **argv) {
       psim->pmc_update(psim->proposal->data, psim, err); CHECK(err, "update");
       perp = perplexity_and_ess(psim, MC_UNORM, &ess, err); CHECK(err, "perplexity");
     } else if (mpi_mode) {
-      perp = pmc_simu_pmc_step_mpi(psim, &rng, err); CHECK(err, "pmc_simu_pmc_step_mpi");
+      if (mode == 9) {
+        /* a hand-written master / client iteration on the message-level functions, laid out as pmc_mpi.c:44-125 */
+        size_t nok, mys, all = 0;
+        if (psim->mpi_rank == 0) {
+          psim->proposal->simulate(psim, psim->proposal->data, &rng, psim->pb, err); CHECK(err, "simulate");
+          mys = send_simulation(psim, psim->mpi_size, err); CHECK(err, "send_simulation");
+          all = psim->nsamples;
+          psim->nsamples = mys;
+        } else {
+          receive_simulation(psim, psim->mpi_size, psim->mpi_rank, err); CHECK(err, "receive_simulation");
+        }
+        nok = generic_get_importance_weight_and_deduced(psim, psim->proposal->data, psim->proposal->log_pdf, psim->target->log_pdf,
+                                                        psim->target->retrieve, psim->target->data, err); CHECK(err, "weights");
+        if (psim->mpi_rank == 0) {
+          mys = psim->nsamples;
+          psim->nsamples = all;
+          nok = receive_importance_weight(psim, psim->mpi_size, nok, mys, err); CHECK(err, "receive_importance_weight");
+          printf("message-level iteration %d nok %zu of %ld\n", it, nok, psim->nsamples);
+          normalize_importance_weight(psim, err); CHECK(err, "normalize");
+          psim->pmc_update(psim->proposal->data, psim, err); CHECK(err, "update");
+          perp = perplexity_and_ess(psim, MC_UNORM, &ess, err); CHECK(err, "perplexity");
+        } else {
+          printf("rank %d slice %ld nok %zu\n", psim->mpi_rank, psim->nsamples, nok);
+          send_importance_weight(psim->mpi_rank, psim->mpi_size, psim, nok);
+          perp = 0;
+        }
+        distribution_broadcast(psim->proposal, err); CHECK(err, "distribution_broadcast");
+        m = (mix_mvdens *)psim->proposal->data;
+      } else {
+        perp = pmc_simu_pmc_step_mpi(psim, &rng, err); CHECK(err, "pmc_simu_pmc_step_mpi");
+      }
       if (psim->mpi_rank != 0) { /* clients hold no sample (pmc_mpi.c:20-34); their proposal must equal the master's: print a digest */
         double dg = 0;
         for (int k = 0; k < K; ++k) { dg += m->wght[k] * (k + 1); for (int a = 0; a < d; ++a) dg += m->comp[k]->mean[a] * (a + 1) + m->comp[k]->std[a * d + a]; }

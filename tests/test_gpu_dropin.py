@@ -107,10 +107,11 @@ def test_c_driver_target_with_gaussian_prior(driver, tmp_path):
     _check_against_oracle(rec, wl, "prior")
 
 
-@pytest.mark.parametrize("mode", [7, 8])
+@pytest.mark.parametrize("mode", [7, 8, 9])
 def test_c_driver_libpmc_mpi_entry_points_one_rank(driver, tmp_path, mode):
     """pmc_simu_init_mpi / pmc_simu_init_classic_pmc_mpi / pmc_simu_pmc_step_mpi (pmc_mpi.h:52-101) with a world of one rank:
-    mode 7 device target, mode 8 opaque host callback target."""
+    mode 7 device target, mode 8 opaque host callback target, mode 9 a hand-written master loop on send_simulation /
+    receive_importance_weight / distribution_broadcast (pmc_mpi.c:334-520)."""
     wl = W.banana(d=10, K=10, seed=321, mean_sigma=2.0, var=6.0, box=40.0)
     N, niter = 30000, 3
     env = {k: "" for k in ()}
@@ -120,7 +121,7 @@ def test_c_driver_libpmc_mpi_entry_points_one_rank(driver, tmp_path, mode):
         assert f"user callback calls {N * niter}" in stdout
 
 
-@pytest.mark.parametrize("mode", [7, 8])
+@pytest.mark.parametrize("mode", [7, 8, 9])
 def test_c_driver_libpmc_mpi_two_ranks(driver, tmp_path, mode):
     """Two processes, one GPU each, rank/size from the environment, NCCL id through the rendezvous file: rank 0 ends every
     iteration with the WHOLE sample in its pmc_simu (as the reference's master does) and it matches the oracle; rank 1's
@@ -148,6 +149,8 @@ def test_c_driver_libpmc_mpi_two_ranks(driver, tmp_path, mode):
     d0 = [l.split()[-1] for l in so0.splitlines() if "proposal digest" in l]
     d1 = [l.split()[-1] for l in so1.splitlines() if "proposal digest" in l]
     assert len(d0) == niter and d0 == d1
+    if mode == 9:  # the reference's slice layout (pmc_mpi.c:344-352): master N/2, client the rest; every sample valid here
+        assert f"rank 1 slice {N - N // 2} nok {N - N // 2}" in so1 and f"nok {N} of {N}" in so0
     if mode == 8:
         calls = [int(l.split()[-1]) for l in (so0 + so1).splitlines() if l.startswith("user callback calls")]
         assert sum(calls) == N * niter and min(calls) > 0

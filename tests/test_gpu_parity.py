@@ -37,7 +37,8 @@ CASES = {
 }
 
 
-def _setup(gpu, wl, X, idx, force_generic, spl=1, ver=0):
+def _setup(gpu, wl, X, idx, force_generic, spl=1, ver=0, w3v=3):
+    gpu.set_option("w3_variant", w3v)
     gpu.set_option("force_generic", force_generic)
     gpu.set_option("fused_version", ver)
     gpu.set_option("force_precise", 0)
@@ -62,14 +63,16 @@ def oracle_runs():
     return get
 
 
-PATHS = {"generic": (1, 0), "fused_v1": (0, 1), "fused_v2": (0, 2), "fused_v3": (0, 3)}
+# fused_v3: the third-generation weights kernel with the row-scaled solve (the default, option w3_variant = 3);
+# fused_v3_exact: the same kernel with the exact per-component mean subtraction (w3_variant = 0, the guard's fallback)
+PATHS = {"generic": (1, 0, 3), "fused_v1": (0, 1, 3), "fused_v2": (0, 2, 3), "fused_v3": (0, 3, 3), "fused_v3_exact": (0, 3, 0)}
 
 
 @pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("name", list(CASES))
 def test_weights_normalise_perplexity(gpu, oracle_runs, name, path):
     wl, X, idx, o = oracle_runs(name)
-    _setup(gpu, wl, X, idx, PATHS[path][0], 1, PATHS[path][1])
+    _setup(gpu, wl, X, idx, PATHS[path][0], 1, PATHS[path][1], PATHS[path][2])
     nok, maxW, maxR = gpu.weights(1.0)
     got = gpu.download(X=False, indices=False)
     assert nok == o["nok"]
@@ -87,6 +90,7 @@ def test_weights_normalise_perplexity(gpu, oracle_runs, name, path):
     assert np.array_equal(got["flg"], o["flg"])
     assert_close(got["weights"], o["w_norm"], WTOL, scale=np.max(o["w_norm"]) * 1e-3, what="normalised weights")
     perp, ess, nfl = gpu.perplexity_ess()
+    gpu.set_option("w3_variant", 3)  # the context is shared by the whole session: back to the default
     assert nfl == int(np.sum(o["flg"] == 0))
     assert_close(perp, o["perp"], PTOL, what="perplexity")
     assert_close(ess, o["ess"], PTOL, what="ESS")
@@ -152,6 +156,35 @@ def test_importance_only_student(gpu, oracle_runs):
     assert_close(r.ln_evidence, o["ln_evidence"], RTOL, scale=big, what="ln evidence")
     assert_close(r.perplexity, o["perp"], PTOL, what="perplexity")
     assert_close(r.ess, o["ess"], PTOL, what="ESS")
+
+
+def test_row_scaled_solve_and_its_guard(gpu):
+    """The third-generation weights kernel uses the row-scaled solve while every live component has |mu'_j / L_jj| (about the
+    mixture mean) below option gen3_max_ratio, and the exact mean subtraction beyond it: two narrow clusters 1000 widths
+    apart trip the guard; both forms are held to the same bar against the oracle."""
+    base = W.banana(seed=31, mean_sigma=2.0, var=6.0, box=40.0)
+    far = dict(base)
+    far["mean"] = base["mean"] * 0.05
+    far["mean"][: base["K"] // 2] += 25.0
+    far["mean"][base["K"] // 2:] -= 25.0
+    far["cov"] = base["cov"] * (0.05 ** 2 / 6.0)
+    for wl, expect in ((base, 1), (far, 0)):
+        X, idx = O.orc_simulate(20000, wl, seed=17)
+        o = O.orc_iteration(X, idx, wl, do_update=0)
+        _setup(gpu, wl, X, idx, 0, 1, 3, 3)
+        assert int(gpu.get_info("w3_rowscaled")) == expect, gpu.get_info("w3_shift_ratio")
+        nok, maxW, maxR = gpu.weights(1.0)
+        got = gpu.download(X=False, indices=False)
+        assert nok == o["nok"]
+        big = max(np.max(np.abs(o["log_rho"])), 1.0)
+        assert_close(got["log_rho"], o["log_rho"], RTOL, what="log_rho")
+        assert_close(got["weights"], o["logw"], RTOL, scale=big, what="log-weights")
+    gpu.set_option("gen3_max_ratio", 1.0)  # the option moves the guard
+    gpu.set_workload(base)
+    assert int(gpu.get_info("w3_rowscaled")) == 0
+    gpu.set_option("gen3_max_ratio", 100.0)
+    gpu.set_workload(base)
+    assert int(gpu.get_info("w3_rowscaled")) == 1
 
 
 def test_ranindx_and_box_bit_exact(gpu):
