@@ -117,28 +117,33 @@ __device__ __forceinline__ bool in_box(const BoxDev &bx, const XT &x) {
 }
 
 
-// ---- ziggurat normal sampler (Marsaglia & Tsang 2000 in Doornik's ZIGNOR form, 1024 layers) -------------------------
+// ---- ziggurat normal sampler (Marsaglia & Tsang 2000 in Doornik's ZIGNOR form, 4096 layers) -------------------------
 // A Box-Muller pair costs ~115 DFMA issue slots in double precision (log + sqrt + sincospi, profiles/r01_fp64_peak.md);
-// the ziggurat's fast path is one table lookup, one DADD, one DMUL and one compare.  With 1024 layers it is taken
-// 99.7 % of the time, which matters on a GPU because one slow lane stalls its whole warp (the 256-layer version
-// spent 27 % of the draw/weights kernel in the slow path, measured by A/B builds).
+// the ziggurat's fast path is one table lookup, one DADD, one DMUL and one compare.  What matters on a GPU is how often a
+// WARP leaves the fast path, because one slow lane stalls the other 31: a 10-D sample is 320 candidates per warp, so the
+// 256-layer version (1.5 % slow candidates) spent 27 % of the draw kernel in the slow path, the 1024-layer version
+// (0.43 %: 75 % of the warps still had a slow lane, ncu profiles/r02_ncu.txt) 20 %, and 4096 layers (0.12 %) bring it
+// to 32 % of the warps.  The 64 KB table lives in shared memory.
 // Table t[i] = (x_i, x_{i+1}/x_i), x_0 = V/f(R), x_1 = R, x_C = 0 (built on the host by the C-ABI layer).
-// R and V solve the closing condition x_{C-1} (1 - f(x_{C-1})) = V; the solver reproduces the published constants
-// for C = 128 and 256.
-constexpr int kZigLayers = 1024;
-constexpr double kZigR = 4.038849846109505;
-constexpr double kZigV = 0.0012263246463530852;
+// R and V solve the closing condition V/x_{C-1} + f(x_{C-1}) = 1 (tools/zig_constants.py, 60-digit bisection; it
+// reproduces the published constants for C = 128 and 256).
+constexpr int kZigBits = 12;
+constexpr int kZigLayers = 1 << kZigBits;
+constexpr double kZigR = 4.3859450348713045;
+constexpr double kZigV = 0.0003061541032784645;
 
-// candidate from 64 random bits (hi:lo): layer = lo[0..9], sign = lo[10], lo[11..13] are left for the caller,
-// |u| = the top 50 bits as a fraction in [0,1)
+// candidate from 64 random bits (hi:lo): layer = lo[0..11], sign = lo[12], lo[13..15] are left for the caller,
+// |u| = the top 48 bits as a fraction in [0,1)
 __device__ __forceinline__ double zig_u(uint32_t lo, uint32_t hi) {
-  return __hiloint2double(0x3ff00000 | (hi >> 12), ((hi << 20) | (lo >> 12)) & ~3u) - 1.0;
+  return __hiloint2double(0x3ff00000 | (hi >> 12), ((hi << 20) | (lo >> 12)) & ~15u) - 1.0;
 }
 __device__ __forceinline__ bool zig_fast(uint32_t lo, uint32_t hi, const double2 *zt, double &x) {
   const double2 t = zt[lo & (kZigLayers - 1)];
   const double u = zig_u(lo, hi);
   const double ax = u * t.x;
-  x = (lo & kZigLayers) ? -ax : ax;
+  // the sign bit of the candidate goes straight into the (non-negative) product: a shift and one three-input logic
+  // operation instead of a negation on the FP64 pipe and two selects
+  x = __hiloint2double(__double2hiint(ax) ^ ((lo << (31 - kZigBits)) & 0x80000000u), __double2loint(ax));
   return u < t.y;
 }
 
@@ -191,13 +196,13 @@ __device__ __forceinline__ void zig_normals(const Philox &ph, uint32_t ilo, uint
 #pragma unroll
   for (int j = 0; j < D; j += 2) {
     const uint4 r = ph(ilo, ihi, cb | (1 + j / 2), iter);
-    spare |= ((r.x >> 11) & 7u) << ((3 * j) & 31);
+    spare |= ((r.x >> (kZigBits + 1)) & 7u) << ((3 * j) & 31);
     if (!zig_fast(r.x, r.y, zt, g[j])) {
       if (!fail) { slo = r.x; shi = r.y; }
       fail |= 1u << j;
     }
     if (j + 1 < D) {
-      spare |= ((r.z >> 11) & 7u) << ((3 * (j + 1)) & 31);
+      spare |= ((r.z >> (kZigBits + 1)) & 7u) << ((3 * (j + 1)) & 31);
       if (!zig_fast(r.z, r.w, zt, g[j + 1])) {
         if (!fail) { slo = r.z; shi = r.w; }
         fail |= 1u << (j + 1);

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
 
   double *mixs = smem;                      // copy of the packed mixture for the draw (per-lane component)
   double *cws = mixs + K * ST;
-  double2 *zts = reinterpret_cast<double2 *>(cws + f2_ev2(K));  // ziggurat table (x_i, x_{i+1}/x_i), 4 KB
+  double2 *zts = reinterpret_cast<double2 *>(cws + f2_ev2(K));  // ziggurat table (x_i, x_{i+1}/x_i), 64 KB
   double *warp0 = cws + f2_ev2(K) + 2 * kZigLayers;
   constexpr int WD = (MODE == 2) ? C::WARP_DOUBLES : f2_ev2(TS * D);
   double *ptile = warp0 + (size_t)wid * WD;

@@ -148,9 +148,10 @@ __device__ __forceinline__ double exp_tab(double x, const double *tab) {
   constexpr double kMagic = 6755399441055744.0;
   constexpr double kInv = 92.332482616893657;
   constexpr double kHi = 6.93147180369123816490e-01 / 64.0, kLo = 1.90821492927058770002e-10 / 64.0;
-  // clamp on the high word (x <= 709 by contract: "below -700" is then an unsigned comparison of the sign-magnitude bits;
-  // an FP64 max costs a DSETP on the FP64 pipe plus NaN plumbing)
-  const double xc = ((unsigned)__double2hiint(x) >= 0xC085E000u) ? -700.0 : x;
+  // clamp on the high word (x <= 709 by contract: "below -700" is then an unsigned minimum of the sign-magnitude bits, which
+  // leaves the low word alone, i.e. clamps to a value in [-700.0000002, -700]; an FP64 max costs a DSETP on the FP64 pipe plus
+  // NaN plumbing)
+  const double xc = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC085E000u), __double2loint(x));  // one VIMNMX: |x| <= 700.00.. for negative x
   const double t = fma(xc, kInv, kMagic);
   const int ni = __double2loint(t);
   const double n = t - kMagic;
