@@ -324,10 +324,10 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         h2d = K * (1 + d + d * d + 1) * 8 + K * 4
-        d2h = n_local * (8 * d + 8 + 8 + 8 + 2)
+        d2h = g.get_info("sink_bytes")  # counted by the library from the copies of the last step
         e2e = {"value": N_total * nst / (float(t[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": nst,
-               "path": "pmcgpu_set_proposal (host mixture) -> pmcgpu_pmc_step with the host sink attached: X, indices, weights, log_rho, flg land in pinned host buffers (D2H on a second stream, overlapped with the kernels)"}
+               "d2h_bytes_per_step": int(d2h), "host_bytes_delivered_per_step": int(n_local * (8 * d + 8 + 8 + 8 + 2)), "steps": nst,
+               "path": "pmcgpu_set_proposal (host mixture) -> pmcgpu_pmc_step with the host sink attached: X, indices, weights, log_rho, flg land in pinned host buffers (D2H on a second stream, overlapped with the kernels; the component indices cross PCIe as bytes and are widened to size_t on the host)"}
         g._ck(g.lib.pmcgpu_set_host_sink(g.h, None, None, None, None, None))
 
     if rank != 0:

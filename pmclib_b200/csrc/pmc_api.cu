@@ -164,6 +164,15 @@ struct pmcgpu_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
   bool sink_active = false;  // inside a drawing iteration with a sink attached
+  // indices travel to the sink as bytes (1 instead of 8 per sample over PCIe) and are widened into the caller's size_t array by
+  // a host thread while the X copy is still in flight (option "sink_idx8", on by default for K <= 256)
+  int sink_idx8 = 1;
+  DevBuf didx8;
+  unsigned char *hidx8 = nullptr;
+  size_t hidx8_cap = 0;
+  cudaEvent_t ev_idx8 = nullptr;
+  std::thread widen;
+  double sink_bytes = 0.0;  // device-to-host bytes the sink copies of the current / last call moved (info "sink_bytes")
   // comm
   int rank = 0, nranks = 1;
   void *nccl_comm = nullptr;
@@ -422,18 +431,55 @@ int allreduce_device_sum(pmcgpu_ctx *c, double *dbuf, size_t n) {
 
 // ---- host sink: device->host copies on a second stream, overlapped with the kernels that follow ------------------------
 enum { SINK_DRAWN = 1, SINK_RHO = 2, SINK_FINAL = 4 };
+void sink_join(pmcgpu_ctx *c) {
+  if (c->widen.joinable()) c->widen.join();
+}
+
 int sink_copy(pmcgpu_ctx *c, int what) {
   if (!c->sink_active) return 0;
   if (!c->copy_stream) {
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_idx8, cudaEventDisableTiming));
+  }
+  const size_t N = c->N;
+  const pmcgpu_ctx::Sink &k = c->sink;
+  bool idx8 = (what & SINK_DRAWN) && k.idx && c->sink_idx8 && c->prop.K <= 256 && N > 0;
+  if (idx8) {  // the byte copy of the indices, made on the compute stream before the copy stream is released
+    sink_join(c);
+    if (c->hidx8_cap < N) {
+      if (c->hidx8) cudaFreeHost(c->hidx8);
+      c->hidx8 = nullptr;
+      c->hidx8_cap = 0;
+      if (cudaHostAlloc((void **)&c->hidx8, N, cudaHostAllocDefault) == cudaSuccess) c->hidx8_cap = N;
+      else { cudaGetLastError(); idx8 = false; }  // no pinned staging: the indices travel as size_t
+    }
+    if (idx8 && c->didx8.ensure(N) != cudaSuccess) { cudaGetLastError(); idx8 = false; }
+    if (idx8) launch_narrow_idx((long)N, c->Idx.as<unsigned long long>(), c->didx8.as<unsigned char>(), c->sm_count, c->stream);
   }
   CU(cudaEventRecord(c->ev_copy, c->stream));
   CU(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
-  const size_t N = c->N;
-  const pmcgpu_ctx::Sink &k = c->sink;
+  if (idx8) {
+    CU(cudaMemcpyAsync(c->hidx8, c->didx8.p, N, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU(cudaEventRecord(c->ev_idx8, c->copy_stream));
+    const int dev = c->device;
+    cudaEvent_t ev = c->ev_idx8;
+    const unsigned char *src = c->hidx8;
+    size_t *dst = k.idx;
+    c->widen = std::thread([dev, ev, src, dst, N]() {
+      cudaSetDevice(dev);
+      if (cudaEventSynchronize(ev) != cudaSuccess) return;
+      for (size_t i = 0; i < N; ++i) dst[i] = src[i];
+    });
+  }
+  if (idx8) c->sink_bytes += (double)N;
+  if ((what & SINK_DRAWN) && k.X) c->sink_bytes += (double)N * c->d * sizeof(double);
+  if ((what & SINK_DRAWN) && k.idx && !idx8) c->sink_bytes += (double)N * sizeof(size_t);
+  if ((what & SINK_RHO) && k.lr) c->sink_bytes += (double)N * sizeof(double);
+  if ((what & SINK_FINAL) && k.w) c->sink_bytes += (double)N * sizeof(double);
+  if ((what & SINK_FINAL) && k.flg) c->sink_bytes += (double)N * sizeof(short);
   if ((what & SINK_DRAWN) && k.X) CU(cudaMemcpyAsync(k.X, c->X.p, N * c->d * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
-  if ((what & SINK_DRAWN) && k.idx) CU(cudaMemcpyAsync(k.idx, c->Idx.p, N * sizeof(size_t), cudaMemcpyDeviceToHost, c->copy_stream));
+  if ((what & SINK_DRAWN) && k.idx && !idx8) CU(cudaMemcpyAsync(k.idx, c->Idx.p, N * sizeof(size_t), cudaMemcpyDeviceToHost, c->copy_stream));
   if ((what & SINK_RHO) && k.lr) CU(cudaMemcpyAsync(k.lr, c->R.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
   if ((what & SINK_FINAL) && k.w) CU(cudaMemcpyAsync(k.w, c->W.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
   if ((what & SINK_FINAL) && k.flg) CU(cudaMemcpyAsync(k.flg, c->Flg.p, N * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
@@ -1319,7 +1365,9 @@ int pmcgpu_create(int device, pmcgpu_ctx **out) {
 }
 
 void pmcgpu_destroy(pmcgpu_ctx *c) {
-  if (c && c->copy_stream) { cudaSetDevice(c->device); cudaStreamDestroy(c->copy_stream); if (c->ev_copy) cudaEventDestroy(c->ev_copy); }
+  if (c) sink_join(c);
+  if (c && c->copy_stream) { cudaSetDevice(c->device); cudaStreamDestroy(c->copy_stream); if (c->ev_copy) cudaEventDestroy(c->ev_copy); if (c->ev_idx8) cudaEventDestroy(c->ev_idx8); }
+  if (c && c->hidx8) { cudaSetDevice(c->device); cudaFreeHost(c->hidx8); c->hidx8 = nullptr; }
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
@@ -1327,7 +1375,7 @@ void pmcgpu_destroy(pmcgpu_ctx *c) {
   DevBuf *bufs[] = {&c->dprop.buf, &c->dprop_pack, &c->dtmix.buf, &c->dt_pack, &c->ddef, &c->dfaces, &c->X, &c->W, &c->R,
                     &c->Idx, &c->Flg, &c->ld, &c->blkmax, &c->partials, &c->stats, &c->small, &c->rbg, &c->rbw, &c->rbacc,
                     &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll, &c->dshare, &c->dcomb, &c->dcombdim, &c->resp, &c->partials2, &c->dscal, &c->zig,
-                    &c->i3_gpack, &c->i3_wpart, &c->i3_scal, &c->i3_coll, &c->i3_spart, &c->i3_out};
+                    &c->i3_gpack, &c->i3_wpart, &c->i3_scal, &c->i3_coll, &c->i3_spart, &c->i3_out, &c->didx8};
   for (DevBuf *b : bufs) b->release();
   for (auto &t : c->comb) t.dmix.buf.release();
   if (c->hstage) cudaFreeHost(c->hstage);
@@ -1360,6 +1408,7 @@ int pmcgpu_set_option(pmcgpu_ctx *c, const char *name, double value) {
   else if (!strcmp(name, "split_draw")) c->split_draw = (int)value;
   else if (!strcmp(name, "gen3")) c->gen3 = (int)value;
   else if (!strcmp(name, "gen3_max_ratio")) { c->gen3_max_ratio = value; c->i3_dirty = true; }
+  else if (!strcmp(name, "sink_idx8")) c->sink_idx8 = (int)value;
   else if (!strcmp(name, "w3_variant")) { c->w3_variant = (int)value; c->i3_dirty = true; }
   else if (!strcmp(name, "draw3")) c->draw3 = (int)value;
   else if (!strcmp(name, "mma")) { c->use_mma = (int)value; return repack_mma(c); }
@@ -1380,6 +1429,7 @@ int pmcgpu_get_info(pmcgpu_ctx *c, const char *name, double *value) {
   if (!strcmp(name, "mma_active")) { RC(ensure_mma(c)); *value = c->mprop.valid ? 1.0 : 0.0; return 0; }
   if (!strcmp(name, "mma_inverse_discrepancy")) { RC(ensure_mma(c)); *value = c->mprop.inv_discrepancy; return 0; }
   // third-generation weights kernel: 1 if the current proposal is packed for the row-scaled solve, and the guard's ratio
+  if (!strcmp(name, "sink_bytes")) { *value = c->sink_bytes; return 0; }
   if (!strcmp(name, "w3_rowscaled")) { const Iter3Plan p = plan3_for(c); *value = (p.valid && c->i3_pre) ? 1.0 : 0.0; return 0; }
   if (!strcmp(name, "w3_shift_ratio")) { const Iter3Plan p = plan3_for(c); *value = p.valid ? c->i3_pre_ratio : -1.0; return 0; }
   return fail(c, PMCGPU_ERR_USAGE, "unknown info %s", name);
@@ -1845,11 +1895,14 @@ int pmcgpu_draw_weights(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_
                         double *maxW, double *maxR, long *n_reject) {
   if (!c) return PMCGPU_ERR_USAGE;
   c->sink_active = c->sink.on;  // with a host sink attached the arrays travel while the weight kernels run
+  c->sink_bytes = 0.0;
   const int rc = draw_weights_core(c, seed, iter, first_index, t_temper, nok, maxW, maxR, n_reject);
   if (c->sink_active) {
     c->sink_active = false;
     cudaSetDevice(c->device);
-    if (c->copy_stream && cudaStreamSynchronize(c->copy_stream) != cudaSuccess && rc == 0)
+    const bool copy_ok = !c->copy_stream || cudaStreamSynchronize(c->copy_stream) == cudaSuccess;
+    sink_join(c);
+    if (!copy_ok && rc == 0)
       return fail(c, PMCGPU_ERR_CUDA, "copy to the host sink failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   return rc;
@@ -2424,12 +2477,15 @@ static int step_impl(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
                      double *o_L, double *o_detL, int *o_alive, const double *post_host = nullptr, const short *ok_host = nullptr) {
   if (!c) return PMCGPU_ERR_USAGE;
   c->sink_active = c->sink.on && do_draw;
+  c->sink_bytes = 0.0;
   const int rc = step_core(c, do_draw, seed, iter, first_index, N_total, t_temper, do_update, retry, res, o_wght, o_mean,
                            o_L, o_detL, o_alive, post_host, ok_host);
   if (c->sink_active) {
     c->sink_active = false;
     cudaSetDevice(c->device);
-    if (c->copy_stream && cudaStreamSynchronize(c->copy_stream) != cudaSuccess && rc == 0)
+    const bool copy_ok = !c->copy_stream || cudaStreamSynchronize(c->copy_stream) == cudaSuccess;
+    sink_join(c);
+    if (!copy_ok && rc == 0)
       return fail(c, PMCGPU_ERR_CUDA, "copy to the host sink failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   return rc;

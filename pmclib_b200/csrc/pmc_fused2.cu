@@ -727,9 +727,13 @@ static int launch_k1(const FusedPlan &p, const FusedArgs &a, int *nblocks_out, c
   const size_t smem = ((size_t)K * C::ST + f2_ev2(K) + 2 * kZigLayers + (size_t)WARPS * wd) * sizeof(double);
   static std::atomic<unsigned long long> smem_set{0};
   if (!set_max_smem_once(kern, smem, smem_set)) return -1;
-  int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
-  if (nb > 5) nb = 5;
+  static std::atomic<int> nb_cached{0};  // the occupancy query costs several microseconds: once per instantiation
+  int nb = nb_cached.load(std::memory_order_relaxed);
+  if (nb == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+    if (nb > 5) nb = 5;
+    nb_cached.store(nb, std::memory_order_relaxed);
+  }
   *nblocks_out = p.grid * nb;
   kern<<<p.grid * nb, WARPS * 32, smem, s>>>(a);
   count_launch();

@@ -129,6 +129,7 @@ void launch_weight_cdf(long N, const double *w, int mode, double *cdf, double *b
 void launch_resample(long N, long ndraw, const double *cdf, uint64_t seed, uint32_t stream, int mode,
                      unsigned long long *isample, unsigned int *counts, cudaStream_t s);
 
+void launch_narrow_idx(long N, const unsigned long long *in, unsigned char *out, int sm_count, cudaStream_t s);
 void launch_count_key_ge(long N, long first, const double *w, const short *flg, unsigned long long key,
                          unsigned long long *cnt, int nblocks, cudaStream_t s);
 void launch_clip_apply(long N, double T, double *w, short *flg, double *partial, unsigned long long *cnt, int nblocks,

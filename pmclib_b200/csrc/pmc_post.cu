@@ -138,6 +138,32 @@ void launch_scale_ok(long N, double S, double *w, const short *flg, int nblocks,
   count_launch();
 }
 
+// component indices (size_t in pmc_simu, values < 256) as bytes: what the host sink sends over PCIe (1 instead of 8 bytes per
+// sample); the host widens them back into the caller's size_t array
+__global__ void k_narrow_idx(long N, const unsigned long long *__restrict__ in, unsigned char *__restrict__ out) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  const long n8 = N >> 3;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(in + 8 * g);
+    unsigned long long packed = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const ulonglong2 v = p[q];
+      packed |= (v.x & 0xffull) << (16 * q) | (v.y & 0xffull) << (16 * q + 8);
+    }
+    reinterpret_cast<unsigned long long *>(out)[g] = packed;
+  }
+  for (long i = 8 * n8 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) out[i] = (unsigned char)in[i];
+}
+void launch_narrow_idx(long N, const unsigned long long *in, unsigned char *out, int sm_count, cudaStream_t s) {
+  if (N <= 0) return;
+  long nb = (N / 8 + 255) / 256;
+  if (nb > (long)sm_count * 8) nb = (long)sm_count * 8;
+  if (nb < 1) nb = 1;
+  k_narrow_idx<<<(int)nb, 256, 0, s>>>(N, in, out);
+  count_launch();
+}
+
 long scan_blocks(long N) { return (N + SCAN_CHUNK - 1) / SCAN_CHUNK; }
 
 // cdf[i] = sum_{j <= i} value_j, value = weights (mode 0) or residual weights (mode 1); blocksum: scan_blocks(N) doubles
