@@ -584,11 +584,21 @@ __global__ void k_red3(const double *__restrict__ partials, int nblocks, const u
   if (phases & 2) {
     const double Mg = coll[0];
     double S = 0.0;
-    if (t == 0) {  // fixed order
-      for (int b = 0; b < nblocks; ++b) {
-        const double mb = partials[(size_t)b * 4];
-        if (mb > -INFINITY) S += partials[(size_t)b * 4 + 1] * exp(mb - Mg);
+    // the terms S_b exp(m_b - M) by all threads (one serial thread took 85 us for 592 blocks: two dependent loads and an exp
+    // each), then summed by one thread in block order from shared memory: same fixed order, 2 us
+    __shared__ double st[1024];
+    for (int base = 0; base < nblocks; base += 1024) {
+      const int nb = (nblocks - base) < 1024 ? (nblocks - base) : 1024;
+      for (int b = t; b < nb; b += blockDim.x) {
+        const double mb = partials[(size_t)(base + b) * 4];
+        st[b] = (mb > -INFINITY) ? partials[(size_t)(base + b) * 4 + 1] * exp(mb - Mg) : 0.0;
       }
+      __syncthreads();
+      if (t == 0)
+        for (int b = 0; b < nb; ++b) S += st[b];
+      __syncthreads();
+    }
+    if (t == 0) {
       coll[8] = S;
       coll[9] = (double)counters[CNT_NOK];
       coll[10] = (double)counters[CNT_REJECT];
@@ -950,12 +960,15 @@ __global__ void __launch_bounds__(256, 2) k_stats3(const __grid_constant__ S3Arg
 
 // canonical statistics from the block partials, in block order: out = stats[K*E] | H, Q, ok, flagged-out | count_k[K]
 // Components below 8*MT sit in the (component, feature) row tiles; the others (ag > 0) in the product tiles of S3Cfg.
+// One WARP per output value: lane l adds the partials of blocks l, l + 32, .. in that order, the 32 lane sums are combined by
+// a fixed shuffle tree -> the same association order every run (one thread per value walking all blocks took 55 us).
 __global__ void k_comb3(const double *__restrict__ partials, int nblocks, int partial_len, int acc_len, int K, int E, int NT,
                         int MT, int D, int ag, int cyc, int with_stats, const double *__restrict__ scal, double *__restrict__ out) {
   const int nstat = with_stats ? K * E : 0;
   const int total = nstat + 4 + K;
   const bool clean = scal[I3_CLEAN] != 0.0;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < total; t += gridDim.x * wpb) {
     int idx;
     if (t < nstat) {
       const int k = t / E, e = t - k * E;
@@ -990,8 +1003,10 @@ __global__ void k_comb3(const double *__restrict__ partials, int nblocks, int pa
     }
     double s = 0.0;
     if (clean)
-      for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * partial_len + idx];
-    out[t] = s;
+      for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * partial_len + idx];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[t] = s;
   }
 }
 
@@ -1299,7 +1314,7 @@ int launch_stats3(const Iter3Plan &p, const Iter3Stats &st, cudaStream_t s) {
 
 int launch_comb3(const Iter3Plan &p, const double *partials, int with_stats, const double *scal, double *out, cudaStream_t s) {
   const int total = (with_stats ? p.K * p.E : 0) + 4 + p.K;
-  k_comb3<<<(total + 63) / 64, 64, 0, s>>>(partials, p.stats_blocks, p.partial_len, p.acc_len, p.K, p.E, p.NT, p.MT, p.D, p.AG, p.CYC, with_stats, scal, out);
+  k_comb3<<<(total + 7) / 8, 256, 0, s>>>(partials, p.stats_blocks, p.partial_len, p.acc_len, p.K, p.E, p.NT, p.MT, p.D, p.AG, p.CYC, with_stats, scal, out);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
