@@ -768,6 +768,36 @@ int allreduce_dev(pmcgpu_ctx *c, double *dbuf, long n, int op) {
 
 // draw (optional) -> weights -> maxima/normaliser -> statistics + normalisation -> one device-to-host copy.
 // stage_limit: 1 = stop after the weights and their reductions (log-weights stay un-normalised), 2 = full.
+// The per-lane-component draw kernel (k_fused2 MODE 3: Philox + ziggurat + mu_k + L_k g + slab box) wherever it is
+// instantiated for the proposal's exact K: measured 4.0 ms per 1e8 samples against 8.7 ms of the grouped k_draw3 and 33 ms of
+// the literal kernel (profiles/r02_*).  c->small must have been zeroed (zero_small).  *done = 0: no instantiation, nothing launched.
+int draw_fused2(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, int *done) {
+  *done = 0;
+  if (!c->prop_pack_doubles || c->prop.student || c->force_generic || c->nfull != 0 || (c->nfaces > 0 && !c->box_slab)) return 0;
+  const FusedPlan p2 = fused2_plan(c->prop.d, c->prop.K, 0, PMCGPU_TGT_BANANA, c->sm_count, 1);
+  if (!p2.valid) return 0;
+  unsigned long long *sm = c->small.as<unsigned long long>();
+  FusedArgs a{};
+  a.K = c->prop.K;
+  a.has_box = c->nfaces > 0;
+  for (int j = 0; j < FUSED_MAXD; ++j) { a.lo_thr[j] = c->lo_thr[j]; a.hi_thr[j] = c->hi_thr[j]; a.pivot[j] = 0.0; }
+  a.zig = c->zig.as<double2>();
+  a.do_draw = 1;
+  a.N = c->N; a.first_index = first_index; a.seed = seed; a.iter = iter; a.max_attempts = c->max_attempts;
+  a.X = c->X.as<double>(); a.lw = c->W.as<double>(); a.log_rho = c->R.as<double>();
+  a.indices = c->Idx.as<unsigned long long>(); a.flg = c->Flg.as<short>();
+  CU(c->partials.ensure((size_t)fused2_max_blocks(p2) * p2.partial_len * sizeof(double)));
+  a.partials = c->partials.as<double>(); a.partial_len = p2.partial_len;
+  a.counters = sm + SM_COUNTERS; a.count_k = sm + SM_COUNTK; a.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
+  int nb2 = 0;
+  if (launch_fused2(p2, a, c->prop_pack_host.data(), nullptr, 3, &nb2, c->stream))
+    return fail(c, PMCGPU_ERR_CUDA, "draw kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  CU(cudaMemsetAsync(sm + SM_COUNTK, 0, 64 * 8, c->stream));
+  CU(cudaMemsetAsync(sm + SM_COUNTERS + CNT_NOK, 0, 8, c->stream));
+  *done = 1;
+  return 0;
+}
+
 int run_iter3(pmcgpu_ctx *c, const Iter3Plan &p, int do_draw, int stage_limit, int with_stats, uint64_t seed, uint32_t iter,
               long first_index, long N_total, double t_temper, const double *post_in, const short *ok_in, Iter3Out &o) {
   const HostMix &m = c->prop;
@@ -791,28 +821,9 @@ int run_iter3(pmcgpu_ctx *c, const Iter3Plan &p, int do_draw, int stage_limit, i
     if (!c->ev0) { CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->ev2)); CU(cudaEventCreate(&c->evd)); }
     CU(cudaEventRecord(c->ev0, c->stream));
   }
-  FusedPlan p2{};
-  if (do_draw && !c->draw3 && c->prop_pack_doubles) p2 = fused2_plan(c->prop.d, c->prop.K, 0, PMCGPU_TGT_BANANA, c->sm_count, 1);
-  if (do_draw && p2.valid) {
-    // second-generation draw kernel (per-lane component, mixture in shared memory): measured 4.4 ms per 1e8 samples against
-    // 8.7 ms of the grouped k_draw3 (profiles/r02_*): kept as the default wherever it is instantiated for the exact K
-    FusedArgs a{};
-    a.K = c->prop.K;
-    a.has_box = c->nfaces > 0;
-    for (int j = 0; j < FUSED_MAXD; ++j) { a.lo_thr[j] = c->lo_thr[j]; a.hi_thr[j] = c->hi_thr[j]; a.pivot[j] = 0.0; }
-    a.zig = c->zig.as<double2>();
-    a.do_draw = 1;
-    a.N = N; a.first_index = first_index; a.seed = seed; a.iter = iter; a.max_attempts = c->max_attempts;
-    a.X = c->X.as<double>(); a.lw = c->W.as<double>(); a.log_rho = c->R.as<double>();
-    a.indices = c->Idx.as<unsigned long long>(); a.flg = c->Flg.as<short>();
-    CU(c->partials.ensure((size_t)fused2_max_blocks(p2) * p2.partial_len * sizeof(double)));
-    a.partials = c->partials.as<double>(); a.partial_len = p2.partial_len;
-    a.counters = sm + SM_COUNTERS; a.count_k = sm + SM_COUNTK; a.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
-    int nb2 = 0;
-    if (launch_fused2(p2, a, c->prop_pack_host.data(), nullptr, 3, &nb2, c->stream))
-      return fail(c, PMCGPU_ERR_CUDA, "draw kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    CU(cudaMemsetAsync(sm + SM_COUNTK, 0, 64 * 8, c->stream));
-    CU(cudaMemsetAsync(sm + SM_COUNTERS + CNT_NOK, 0, 8, c->stream));
+  int drew2 = 0;
+  if (do_draw && !c->draw3) RC(draw_fused2(c, seed, iter, first_index, &drew2));
+  if (drew2) {
     RC(sink_copy(c, SINK_DRAWN));
   } else if (do_draw) {
     Iter3Draw d{};
@@ -1761,7 +1772,12 @@ static int draw_impl(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_ind
   if (rc) return rc;
   rc = zero_small(c);
   if (rc) return rc;
-  rc = draw_mma(c, seed, iter, first_index);
+  int drew2 = 0;
+  if (c->gen3 && c->fused_version != 1 && !c->draw3) {
+    rc = draw_fused2(c, seed, iter, first_index, &drew2);
+    if (rc) return rc;
+  }
+  rc = drew2 ? 0 : draw_mma(c, seed, iter, first_index);
   if (rc != 0 && rc != 1) return rc;
   if (rc == 1) {
     BoxDev bx{c->nfaces, c->box_d, c->dfaces.as<double>()};
