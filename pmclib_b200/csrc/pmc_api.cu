@@ -53,9 +53,43 @@ struct HostMix {
   int n_alive() const { int n = 0; for (double w : wght) n += (w > 0.0); return n; }
 };
 
+// pinned host staging that belongs to ONE upload site: the copy out of it is asynchronous; before the site writes the buffer
+// again it waits for the event recorded behind its previous copy (normally long complete), not for the whole stream
+struct Pinned {
+  double *p = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+  cudaError_t ensure(size_t doubles) {
+    if (pending) { cudaEventSynchronize(ev); pending = false; }
+    if (doubles <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);  // waits for copies in flight
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost((void **)&p, doubles * sizeof(double));
+    if (e == cudaSuccess) cap = doubles;
+    return e;
+  }
+  cudaError_t copied(cudaStream_t st) {  // call right after enqueueing the copy out of p
+    if (!ev) { cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    pending = true;
+    return cudaEventRecord(ev, st);
+  }
+  void release() {
+    if (pending && ev) cudaEventSynchronize(ev);
+    pending = false;
+    if (ev) cudaEventDestroy(ev);
+    ev = nullptr;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
 struct DevMixBuf {
   DevBuf buf;
   MixDev view{};
+  Pinned pin;
 };
 
 // ---- NCCL through dlopen (no link-time dependency) ---------------------------------------------------------------
@@ -101,8 +135,9 @@ struct pmcgpu_ctx {
   HostMix prop;
   DevMixBuf dprop;
   DevBuf dprop_pack;
+  Pinned pin_ppack, pin_tpack;
   int prop_pack_doubles = 0;
-  std::vector<double> prop_pack_host, tgt_pack_host;
+  std::vector<double> prop_pack_host, tgt_pack_host, draw_pack_padded;
   int tkind = PMCGPU_TGT_NONE, td = 0;
   double tb = 0, tsig1 = 1;
   HostMix tmix;
@@ -230,16 +265,16 @@ int upload_mix(pmcgpu_ctx *c, const HostMix &m, DevMixBuf &o) {
   const size_t nd = K * 6 + K * d + K * d * d;  // alpha,cw,logdet,gam,norm + pad | mean | L
   const size_t bytes = nd * sizeof(double) + K * sizeof(int);
   CU(o.buf.ensure(bytes));
-  RC(stage(c, nd + K));
-  double *h = c->hstage;
+  CU(o.pin.ensure(nd + K));
+  double *h = o.pin.p;
   size_t off = 0;
   auto put = [&](const std::vector<double> &v) { memcpy(h + off, v.data(), v.size() * sizeof(double)); size_t r = off; off += v.size(); return r; };
   const size_t oa = put(m.wght), ocw = put(m.cw), old = put(m.logdet), og = put(m.gam), on = put(m.norm);
   off += K;
   const size_t om = put(m.mean), oL = put(m.L);
   memcpy(h + off, m.df.data(), K * sizeof(int));
-  CU(cudaMemcpyAsync(o.buf.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyAsync(o.buf.p, h, bytes, cudaMemcpyHostToDevice, c->stream));  // no host synchronisation: see Pinned
+  CU(o.pin.copied(c->stream));
   double *b = o.buf.as<double>();
   o.view = MixDev{(int)K, (int)d, b + oa, b + ocw, b + om, b + oL, b + old, b + og, b + on, reinterpret_cast<const int *>(b + nd)};
   return 0;
@@ -285,17 +320,17 @@ int fill_mix(pmcgpu_ctx *c, HostMix &m, int K, int d, const double *wght, const 
   return 0;
 }
 
-int pack_small(pmcgpu_ctx *c, const HostMix &m, DevBuf &out, int &ndoubles, std::vector<double> &hostcopy) {
+int pack_small(pmcgpu_ctx *c, const HostMix &m, DevBuf &out, int &ndoubles, std::vector<double> &hostcopy, Pinned &pin) {
   ndoubles = 0;
   hostcopy.clear();
   if (m.d > FUSED_MAXD || m.student) return 0;
   const int n = m.K * fused_comp_stride(m.d);
   CU(out.ensure((size_t)n * sizeof(double)));
-  RC(stage(c, n));
-  fused_pack_mixture(m.K, m.d, m.wght.data(), m.mean.data(), m.L.data(), m.logdet.data(), c->hstage);
-  hostcopy.assign(c->hstage, c->hstage + n);
-  CU(cudaMemcpyAsync(out.p, c->hstage, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(pin.ensure(n));
+  fused_pack_mixture(m.K, m.d, m.wght.data(), m.mean.data(), m.L.data(), m.logdet.data(), pin.p);
+  hostcopy.assign(pin.p, pin.p + n);
+  CU(cudaMemcpyAsync(out.p, pin.p, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));  // no host synchronisation: see Pinned
+  CU(pin.copied(c->stream));
   ndoubles = n;
   return 0;
 }
@@ -351,7 +386,7 @@ int install_proposal(pmcgpu_ctx *c) {
   c->mprop.dirty = true;
   c->q_resident = false;
   c->i3_dirty = true;
-  return pack_small(c, c->prop, c->dprop_pack, c->prop_pack_doubles, c->prop_pack_host);
+  return pack_small(c, c->prop, c->dprop_pack, c->prop_pack_doubles, c->prop_pack_host, c->pin_ppack);
 }
 
 TargetDev target_view(const pmcgpu_ctx *c) {
@@ -774,8 +809,14 @@ int allreduce_dev(pmcgpu_ctx *c, double *dbuf, long n, int op) {
 int draw_fused2(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, int *done) {
   *done = 0;
   if (!c->prop_pack_doubles || c->prop.student || c->force_generic || c->nfull != 0 || (c->nfaces > 0 && !c->box_slab)) return 0;
-  const FusedPlan p2 = fused2_plan(c->prop.d, c->prop.K, 0, PMCGPU_TGT_BANANA, c->sm_count, 1);
+  const FusedPlan p2 = fused2_plan_draw(c->prop.d, c->prop.K, c->sm_count);
   if (!p2.valid) return 0;
+  const double *hpack = c->prop_pack_host.data();
+  if (p2.RK > c->prop.K) {  // a larger instantiation: the extra components are zeros and never picked
+    c->draw_pack_padded.assign((size_t)p2.RK * fused_comp_stride(c->prop.d), 0.0);
+    memcpy(c->draw_pack_padded.data(), c->prop_pack_host.data(), c->prop_pack_host.size() * sizeof(double));
+    hpack = c->draw_pack_padded.data();
+  }
   unsigned long long *sm = c->small.as<unsigned long long>();
   FusedArgs a{};
   a.K = c->prop.K;
@@ -790,7 +831,7 @@ int draw_fused2(pmcgpu_ctx *c, uint64_t seed, uint32_t iter, long first_index, i
   a.partials = c->partials.as<double>(); a.partial_len = p2.partial_len;
   a.counters = sm + SM_COUNTERS; a.count_k = sm + SM_COUNTK; a.first_vals = reinterpret_cast<double *>(sm + SM_FIRST);
   int nb2 = 0;
-  if (launch_fused2(p2, a, c->prop_pack_host.data(), nullptr, 3, &nb2, c->stream))
+  if (launch_fused2(p2, a, hpack, nullptr, 3, &nb2, c->stream))
     return fail(c, PMCGPU_ERR_CUDA, "draw kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   CU(cudaMemsetAsync(sm + SM_COUNTK, 0, 64 * 8, c->stream));
   CU(cudaMemsetAsync(sm + SM_COUNTERS + CNT_NOK, 0, 8, c->stream));
@@ -1388,7 +1429,8 @@ void pmcgpu_destroy(pmcgpu_ctx *c) {
                     &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll, &c->dshare, &c->dcomb, &c->dcombdim, &c->resp, &c->partials2, &c->dscal, &c->zig,
                     &c->i3_gpack, &c->i3_wpart, &c->i3_scal, &c->i3_coll, &c->i3_spart, &c->i3_out, &c->didx8};
   for (DevBuf *b : bufs) b->release();
-  for (auto &t : c->comb) t.dmix.buf.release();
+  for (auto &t : c->comb) { t.dmix.buf.release(); t.dmix.pin.release(); }
+  c->dprop.pin.release(); c->dtmix.pin.release(); c->pin_ppack.release(); c->pin_tpack.release();
   if (c->hstage) cudaFreeHost(c->hstage);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->evd); }
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1510,7 +1552,7 @@ int pmcgpu_set_target_mix(pmcgpu_ctx *c, int kind, int K, int d, const double *w
   c->mtgt.valid = false;
   c->mtgt.dirty = true;
   c->i3_dirty = true;
-  return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles, c->tgt_pack_host);
+  return pack_small(c, c->tmix, c->dt_pack, c->t_pack_doubles, c->tgt_pack_host, c->pin_tpack);
 }
 
 int pmcgpu_set_target_combine(pmcgpu_ctx *c, int d, int nterms, const pmcgpu_combine_term *terms) {
@@ -1557,7 +1599,8 @@ int pmcgpu_set_target_combine(pmcgpu_ctx *c, int d, int nterms, const pmcgpu_com
   }
   CU(c->dcomb.ensure(dev.size() * sizeof(CombTermDev)));
   CU(cudaMemcpy(c->dcomb.p, dev.data(), dev.size() * sizeof(CombTermDev), cudaMemcpyHostToDevice));
-  for (auto &t : c->comb) t.dmix.buf.release();
+  for (auto &t : c->comb) { t.dmix.buf.release(); t.dmix.pin.release(); }
+  c->dprop.pin.release(); c->dtmix.pin.release(); c->pin_ppack.release(); c->pin_tpack.release();
   c->comb = std::move(comb);
   c->comb_kmax = kmax;
   c->tkind = PMCGPU_TGT_COMBINE;

@@ -117,6 +117,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_fused2(const FusedArgs a) 
   if (threadIdx.x == 0) {  // cumulative weights exactly as mvdens.c:748-750 (sequential sum)
     double c = 0.0;
     for (int k = 0; k < K; ++k) { c = (k == 0) ? mixs[f2_oSc(D)] : c + mixs[k * ST + f2_oSc(D)]; cws[k] = c; }
+    // the mixture may have fewer components than this instantiation (a.K <= K, the rest packed as zeros): ranindx stops at
+    // the last component of the MIXTURE (mvdens.c:776, "index < K - 1"), so the pick never looks past cw[a.K - 2]
+    for (int k = (a.K > 0 ? a.K - 1 : 0); k < K; ++k) cws[k] = INFINITY;
   }
   // zero the padding rows/columns of this warp's tiles once (entries E..8NT-1, components K..8MT-1)
   for (int i = lane; i < WD; i += 32) ptile[i] = 0.0;
@@ -778,6 +781,22 @@ FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want
     best.NR = (dbl * 8 <= 227 * 1024) ? 1 : 0; /* does the single-kernel mode (MODE 2) fit in shared memory? */ \
     best.grid = sm_count; best.threads = 256; best.smem_bytes = dbl * 8;                                 \
     best.partial_len = C::ACC + 4; best.nstat = K_ * C::E;                                               \
+  }
+  PMC_FUSED2_TABLE(X)
+#undef X
+  return best;
+}
+
+// the draw-only kernel (MODE 3) of the smallest instantiation with at least K components
+FusedPlan fused2_plan_draw(int d, int K, int sm_count) {
+  FusedPlan best{};
+  best.valid = 0;
+#define X(D_, K_, KT_, SPL_)                                                                  \
+  if (d == D_ && K <= K_ && SPL_ == 1 && (!best.valid || K_ < best.RK)) {                     \
+    using C = F2Cfg<D_, K_, KT_, SPL_>;                                                       \
+    best.valid = 2; best.D = D_; best.RK = K_; best.RE = KT_; best.SPL = SPL_; best.NR = 0;   \
+    best.grid = sm_count; best.threads = 256; best.smem_bytes = 0;                            \
+    best.partial_len = C::ACC + 4; best.nstat = K_ * C::E;                                    \
   }
   PMC_FUSED2_TABLE(X)
 #undef X

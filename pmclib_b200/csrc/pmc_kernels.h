@@ -197,6 +197,7 @@ int launch_fused_combine(const FusedPlan &p, const double *partials, int K, doub
 // second-generation kernel (pmc_fused2.cu): (D, K) templated, mixture in constant memory, DMMA statistics.
 // plan.valid == 2; plan.RK / plan.RE carry K / KT.  h_mix / h_tgt are the host copies of the packed blocks.
 FusedPlan fused2_plan(int d, int K, int Kt, int tgt_kind, int sm_count, int want_spl);
+FusedPlan fused2_plan_draw(int d, int K, int sm_count);
 int fused2_max_blocks(const FusedPlan &p);  // upper bound of the grid of any launch shape (size of the partials buffer)
 // mode 0: weights only, 1: weights + responsibilities (split pipeline), 2: statistics fused.  Returns blocks launched
 // through *nblocks_out.

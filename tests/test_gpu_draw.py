@@ -19,7 +19,10 @@ def _mix(rng, K, d):
     return w / w.sum(), rng.normal(0, 2, (K, d)), cov
 
 
+# (10, 7), (10, 13), (5, 17): no instantiation for the exact K; the draw kernel of the next larger one runs with the extra
+# components packed as zeros (never picked: ranindx stops at the mixture's last component)
 @pytest.mark.parametrize("path,d,K", [("fused_v3", 10, 10), ("fused_v3", 5, 20), ("fused_v3", 2, 9), ("fused_v3", 10, 7),
+                                      ("fused_v3", 10, 13), ("fused_v3", 5, 17),
                                       ("fused_v2", 10, 10), ("fused_v1", 10, 10), ("generic", 10, 10),
                                       ("fused_v2", 5, 20), ("generic", 7, 3)])
 def test_draw_distribution(gpu, path, d, K):
