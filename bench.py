@@ -129,6 +129,69 @@ def cpu_reference_run(N, niter, nworkers, seed=42):
     return dict(kind=kind, per_iter_s=per_iter, wall=wall, phase_s=times.reshape(niter, 5).sum(0), stats=stats.reshape(niter, 3))
 
 
+def parity_check(g, wl, rank, world, shard_range, torch, dist, n_par=200_003):
+    """Outside the timed region: one sharded iteration over n_par samples in total (ragged shards) must give every rank the
+    identical proposal, and - on rank 0, with the shards gathered - must equal the CPU oracle's iteration over the same
+    global sample (log_rho, normalised weights, perplexity, logSum, updated mixture) to 1e-12.  The oracle is the checker
+    only (tests/oracle_py.py -> oracle/liboracle.so); it is not in any timed region."""
+    d, K = wl["d"], wl["K"]
+    first, n = shard_range(n_par, rank, world)
+    g.set_workload(wl)
+    g.resize(n)
+    r = g.pmc_step(777, 0, first, n_par, 1, 0)
+    got = g.download()
+    same = True
+    shards = [got]
+    if world > 1:
+        vec = torch.from_numpy(np.concatenate([r.wght, r.mean.ravel(), r.L.ravel(), [r.perplexity, r.logSum]])).cuda()
+        vmax, vmin = vec.clone(), vec.clone()
+        dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
+        same = bool(torch.equal(vmax, vmin))
+        nmax = (n_par + world - 1) // world + 1
+        buf = torch.zeros((nmax, d + 4), dtype=torch.float64, device="cuda")
+        pack = np.concatenate([got["X"], got["indices"].astype(np.float64)[:, None], got["weights"][:, None],
+                               got["log_rho"][:, None], got["flg"].astype(np.float64)[:, None]], axis=1)
+        buf[:n] = torch.from_numpy(pack).cuda()
+        allb = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(allb, buf)
+        shards = []
+        for q in range(world):
+            _, nq = shard_range(n_par, q, world)
+            a = allb[q][:nq].cpu().numpy()
+            shards.append(dict(X=np.ascontiguousarray(a[:, :d]), indices=a[:, d].astype(np.uint64), weights=a[:, d + 1].copy(),
+                               log_rho=a[:, d + 2].copy(), flg=a[:, d + 3].astype(np.int16)))
+    out = None
+    if rank == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_py as O
+            from util import relerr, cov_from_L
+            X = np.concatenate([s_["X"] for s_ in shards]); idx = np.concatenate([s_["indices"] for s_ in shards])
+            w = np.concatenate([s_["weights"] for s_ in shards]); lr = np.concatenate([s_["log_rho"] for s_ in shards])
+            fl = np.concatenate([s_["flg"] for s_ in shards])
+            o = O.orc_iteration(X, idx, wl, do_update=1)
+            big = max(float(np.max(np.abs(o["log_rho"]))), 1.0)
+            errs = {"log_rho": relerr(lr, o["log_rho"]),
+                    "weights": relerr(w, o["w_norm"], scale=float(np.max(o["w_norm"])) * 1e-3),
+                    "perplexity": abs(r.perplexity - o["perp"]) / o["perp"],
+                    "logSum": abs(r.logSum - o["logSum"]) / big,
+                    "mixture_weights": relerr(r.wght, o["o_wght"], scale=float(np.max(o["o_wght"]))),
+                    "mixture_means": relerr(r.mean, o["o_mean"], scale=float(np.max(np.abs(o["o_mean"])))),
+                    "mixture_covariances": max(relerr(cov_from_L(r.L[k:k + 1]), cov_from_L(o["o_std"][k:k + 1]),
+                                                      scale=float(np.max(np.abs(cov_from_L(o["o_std"][k:k + 1])))))
+                                               for k in range(K) if o["o_wght"][k] > 0)}
+            flags_equal = bool(np.array_equal(fl, o["flg"])) and bool(np.array_equal(r.wght > 0, o["o_wght"] > 0))
+            worst = max(errs.values())
+            out = {"ok": bool(same and flags_equal and worst <= 1e-12), "tolerance": 1e-12, "samples": n_par, "ranks": world,
+                   "identical_proposal_on_all_ranks": same, "flags_and_live_components_bit_exact": flags_equal,
+                   "max_rel_err_vs_oracle": {k_: float(v_) for k_, v_ in errs.items()},
+                   "checker": "CPU oracle (oracle/pmc_oracle.c, pinned bit-identical to the compiled reference) on the gathered shards, outside the timed region"}
+        except Exception as ex:  # pragma: no cover
+            out = {"ok": False, "error": repr(ex)}
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -204,6 +267,7 @@ def main():
                     help="weak: --samples per GPU (default); strong: --samples in total, sharded over the GPUs (configs[2] as written)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of configs[0], [1], [3], [4]")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded-iteration-vs-oracle check made before the warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spl", type=int, default=None)
     ap.add_argument("--opts", default="", help="comma separated pmcgpu_set_option pairs, e.g. split_stats=0,split_draw=0")
@@ -248,6 +312,11 @@ def main():
         g.comm_init_nccl(ids[0], rank, world)
     stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local_rank))
     seed = 20261019
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(g, wl, rank, world, shard_range, torch, dist)
+        g.set_workload(wl)
+        g.resize(n_local)
 
     def reset():
         g.set_workload(wl)
@@ -405,6 +474,7 @@ def main():
                    "precise_path_steps": int(precise), "wall_ms_per_step": wall_ms / args.steps},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(launches1 - launches0),
+        "parity": parity,
         "other_configs": others,
     }
     print(json.dumps(line))
