@@ -188,6 +188,7 @@ struct pmcgpu_ctx {
   std::vector<double> hW, hG, hs1, hS2;
   DevBuf wpart, cdf, cdfsum, rsout;
   long q_stride = 0;
+  int mma_store_ld = 1;     // 0 inside an importance-only iteration: the tensor path's tail does not write the component log-densities back
   bool q_resident = false;  // Q holds the component log-densities of all N samples of the store (left by the weights pass)
   int use_mma = 1, mma_min_d = 2;  // any shape without a fused small-d instantiation goes to the tensor path (30x the literal kernels at d = 7..16)
   double t_temper = 1.0;  // t_iter_tempered of pmcgpu_pmc_step (pmc.c:570: weight = t * post - rloc)
@@ -1009,7 +1010,7 @@ int run_weights_mma(pmcgpu_ctx *c, int mode, const double *post_in, const short 
     launch_weights_q(c->dprop.view, tv, mode, post_in ? post_in + base : nullptr, ok_in ? ok_in + base : nullptr, t_temper,
                      first_index + base, n, Xb, c->Q.as<double>(), c->Qt.as<double>(), qs, c->W.as<double>() + base,
                      c->R.as<double>() + base, c->Flg.as<short>() + base, c->blkmax.as<double>(), c->blkmax.as<double>() + nb,
-                     sm + SM_COUNTERS, reinterpret_cast<double *>(sm + SM_FIRST), c->stream);
+                     sm + SM_COUNTERS, reinterpret_cast<double *>(sm + SM_FIRST), c->mma_store_ld, c->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->hstage, c->blkmax.p, (size_t)2 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1025,7 +1026,7 @@ int run_weights_mma(pmcgpu_ctx *c, int mode, const double *post_in, const short 
     }
   }
   c->q_stride = qs;
-  c->q_resident = (chunk == N);
+  c->q_resident = (chunk == N) && c->mma_store_ld != 0;
   rc = read_small(c, o.counters, nullptr, o.first);
   o.has_first = (first_index == 0);
   return rc;
@@ -2309,7 +2310,9 @@ static int step_core(pmcgpu_ctx *c, int do_draw, uint64_t seed, uint32_t iter, l
       RC(sink_copy(c, SINK_DRAWN));
     }
     const unsigned long long keep_rej = o.counters[CNT_REJECT], keep_fail = o.counters[CNT_DRAWFAIL];
+    c->mma_store_ld = do_update ? 1 : 0;  // importance only: nothing reads the component log-densities afterwards
     rc = run_weights_generic(c, dpost ? 1 : 0, dpost, dok, t_temper, first_index, o);
+    c->mma_store_ld = 1;
     if (rc) return rc;
     RC(sink_copy(c, SINK_RHO));
     o.counters[CNT_REJECT] = keep_rej;

@@ -140,50 +140,7 @@ static int upload_tables() {
   return 0;
 }
 
-// ---- table-driven exp and log ---------------------------------------------------------------------------------------
-// exp(x) for x <= 709; arguments below -700 (and NaN) return exp(-700) ~ 1e-304: callers only add the result to sums
-// whose largest term is >= 1, and catch non-finite inputs separately.  x = n ln2/64 + r, |r| <= ln2/128; 2^(n/64) from
-// the table, exp(r) - 1 = r P4(r) (truncation 3.5e-17 relative).
-__device__ __forceinline__ double exp_tab(double x, const double *tab) {
-  constexpr double kMagic = 6755399441055744.0;
-  constexpr double kInv = 92.332482616893657;
-  constexpr double kHi = 6.93147180369123816490e-01 / 64.0, kLo = 1.90821492927058770002e-10 / 64.0;
-  // clamp on the high word (x <= 709 by contract: "below -700" is then an unsigned minimum of the sign-magnitude bits, which
-  // leaves the low word alone, i.e. clamps to a value in [-700.0000002, -700]; an FP64 max costs a DSETP on the FP64 pipe plus
-  // NaN plumbing)
-  const double xc = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC085E000u), __double2loint(x));  // one VIMNMX: |x| <= 700.00.. for negative x
-  const double t = fma(xc, kInv, kMagic);
-  const int ni = __double2loint(t);
-  const double n = t - kMagic;
-  double r = fma(n, -kHi, xc);
-  r = fma(n, -kLo, r);
-  const double T = tab[ni & 63];
-  double p = fma(r, 1.0 / 120, 1.0 / 24);
-  p = fma(p, r, 1.0 / 6);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  const double s = p * r;
-  const double v = fma(T, s, T);
-  return __hiloint2double(__double2hiint(v) + ((ni >> 6) << 20), __double2loint(v));
-}
-
-// log(x) for positive normal x: x = 2^e m, m in [1,2); r = m rc_j - 1 with |r| < 1/256 from the table indexed by the
-// top 7 mantissa bits; log1p(r) to degree 6 (truncation 2e-18 absolute)
-__device__ __forceinline__ double log_tab(double x, const double2 *tab) {
-  constexpr double kLn2 = 0.693147180559945309417;
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  const int e = (hi >> 20) - 1023;
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-  const double2 tb = tab[(hi >> 13) & 127];
-  const double r = fma(m, tb.x, -1.0);
-  double p = fma(r, -1.0 / 6, 0.2);
-  p = fma(p, r, -0.25);
-  p = fma(p, r, 1.0 / 3);
-  p = fma(p, r, -0.5);
-  const double lp = fma(r * r, p, r);
-  const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;  // (double)e
-  return fma(ed, kLn2, tb.y + lp);
-}
+// table-driven exp_tab / log_tab: pmc_dev.cuh (shared with the tensor path's importance tail)
 
 // ---- pre-scaled triangular solve: q = |L^-1 (x - mu)|^2, every parameter a constant-bank operand -----------------------
 // compile-time loop: f(std::integral_constant<int, i>) for i in [B, E)

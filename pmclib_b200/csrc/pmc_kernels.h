@@ -290,7 +290,7 @@ int launch_q_mma(const double *X, long n, int d, const double *pack, int J, cons
 void launch_weights_q(const MixDev &m, const TargetDev &tg, int mode, const double *post_in, const short *ok_in,
                       double t_temper, long first_index, long N, const double *X, double *Q, double *Qt,
                       long qs, double *lw, double *log_rho, short *flg, double *blk_maxw, double *blk_maxr,
-                      unsigned long long *counters, double *first_vals, cudaStream_t s);
+                      unsigned long long *counters, double *first_vals, int store_ld, cudaStream_t s);
 void launch_lse_q(const MixDev &m, long n, double *Q, long qs, double *out, cudaStream_t s);
 // wpart (Student-t mixtures only, else nullptr): [resp_q_blocks(N)][K] block sums of the un-gamma-weighted responsibilities
 int resp_q_blocks(long N);

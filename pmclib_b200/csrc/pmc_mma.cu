@@ -56,6 +56,11 @@ __host__ __device__ constexpr int q_mt(int NT) { return NT <= 4 ? 4 : (NT <= 8 ?
 // components per shared-memory stage of the whitening kernel: small factors are staged several at a time so that the
 // block-wide barrier and the cp.async round trip are paid once per 640+ DMMAs per warp group
 __host__ __device__ constexpr int q_cps(int NT) { return NT <= 4 ? 4 : (NT <= 8 ? 2 : 1); }
+// draw kernel: samples per warp (x 8) and blocks per SM.  Each sample costs ~1800 FP64 issue slots of Box-Muller latency chains,
+// so the kernel wants warps, not register tiles: two blocks of 8 warps per SM where the fragments fit in 128 registers (one
+// block per SM ran the configs[3] draw at 3.95 ms per 1e7 samples with the FP64 pipe a quarter busy)
+__host__ __device__ constexpr int d_mt(int NT) { return NT <= 2 ? 4 : (NT <= 4 ? 2 : 1); }
+__host__ __device__ constexpr int d_blocks(int NT) { return NT <= 8 ? 2 : 1; }
 // warps per block of the whitening kernel: as many as the register file allows (NT = 16 needs 162 registers: 12 warps)
 __host__ __device__ constexpr int q_warps(int NT) { return NT == 16 ? 12 : 8; }
 
@@ -156,19 +161,90 @@ __device__ __forceinline__ double mix_lse_q(const MixDev &m, double *__restrict_
   return mx + log(lpos) - kDynMax;
 }
 
-// same outputs and flag/maximum semantics as k_weights_generic (pmc.c:528-590)
-__global__ void k_weights_q(MixDev m, TargetDev tg, int mode, const double *__restrict__ post_in,
+// The same value without storing the component log-densities (importance-only iterations: nothing reads them afterwards),
+// with the table-driven exp / log of pmc_dev.cuh and the per-component constants hoisted into shared memory by the block:
+//     ld_k = c0_k - hq_k q - hnp_k log(1 + q invn_k)
+// Gaussian component: c0 = -d ln2pi / 2 - log detL, hq = 1/2, hnp = invn = 0; Student-t (mvdens.c:376-379): c0 = lgamma((n+d)/2)
+// - lgamma(n/2) - d/2 log(n pi) - log detL, hq = 0, hnp = (n+d)/2, invn = 1/n.  Pass 1 finds the maximum, pass 2 recomputes each
+// log-density from q and accumulates.  ncu of the literal tail at configs[3] (K = 50, nu = 9): 206 warp instructions per
+// (sample, component) pair - a libm log, a libm exp, a double division 1/n, int-to-double conversions and five parameter
+// loads with 64-bit address arithmetic per pair - issue-bound at 4.2 ms per 1e7 samples.
+// Returns false if a q is not finite or negative: the caller then takes the literal function (the reference's NaN flow).
+struct LseTabParams { const double *c0, *hq, *hnp, *invn, *alpha; };
+__device__ __forceinline__ bool mix_lse_q_tab(int K, const LseTabParams &P, const double *__restrict__ Q, long qs, long i,
+                                              const double *s_exp, const double2 *s_log, double &out) {
+  constexpr int U = 8;
+  double mx = -INFINITY;
+  bool fin = true;
+  for (int k0 = 0; k0 < K; k0 += U) {
+    double q[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) q[j] = (k0 + j < K) ? Q[(size_t)(k0 + j) * qs + i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int k = k0 + j;
+      if (k < K && P.alpha[k] > 0.0) {
+        fin = fin && (q[j] >= 0.0) && (q[j] < INFINITY);
+        const double v = fma(-P.hnp[k], log_tab(fma(q[j], P.invn[k], 1.0), s_log), fma(-P.hq[k], q[j], P.c0[k]));
+        mx = (mx < v) ? v : mx;
+      }
+    }
+  }
+  if (!fin || !(mx > -INFINITY) || !(mx < INFINITY)) return false;
+  double lpos = 0.0;
+  for (int k0 = 0; k0 < K; k0 += U) {
+    double q[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) q[j] = (k0 + j < K) ? Q[(size_t)(k0 + j) * qs + i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int k = k0 + j;
+      if (k < K && P.alpha[k] > 0.0) {
+        const double v = fma(-P.hnp[k], log_tab(fma(q[j], P.invn[k], 1.0), s_log), fma(-P.hq[k], q[j], P.c0[k]));
+        lpos = fma(exp_tab(v - mx + kDynMax, s_exp), P.alpha[k], lpos);
+      }
+    }
+  }
+  out = mx + log_tab(lpos, s_log) - kDynMax;
+  return true;
+}
+
+// same outputs and flag/maximum semantics as k_weights_generic (pmc.c:528-590); store_ld = 0: the component log-densities are
+// not written back over q (importance-only iterations)
+__global__ void k_weights_q(int store_ld, MixDev m, TargetDev tg, int mode, const double *__restrict__ post_in,
                             const short *__restrict__ ok_in, double t_temper, long first_index, long N,
                             const double *__restrict__ X, double *__restrict__ Q, double *__restrict__ Qt,
                             long qs, double *__restrict__ lw, double *__restrict__ log_rho, short *__restrict__ flg,
                             double *blk_maxw, double *blk_maxr, unsigned long long *counters, double *first_vals) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  __shared__ double s_exp[64];
+  __shared__ double2 s_log[128];
+  extern __shared__ double s_par[];  // store_ld == 0: [5][K] per-component constants of mix_lse_q_tab
+  LseTabParams P{s_par, s_par + m.K, s_par + 2 * m.K, s_par + 3 * m.K, s_par + 4 * m.K};
+  if (!store_ld) {  // tables of exp_tab / log_tab (pmc_dev.cuh), built by the block: 2^(j/64); (rc_j, -log rc_j)
+    for (int t = threadIdx.x; t < 128; t += blockDim.x) {
+      if (t < 64) s_exp[t] = exp2((double)t / 64.0);
+      const double rc = 1.0 / (1.0 + ((double)t + 0.5) / 128.0);
+      s_log[t] = make_double2(rc, -log(rc));
+    }
+    for (int k = threadIdx.x; k < m.K; k += blockDim.x) {
+      const bool st = m.df[k] != -1;
+      const double n = (double)m.df[k];
+      s_par[k] = st ? (m.gam[k] - m.norm[k]) - m.logdet[k] : -0.5 * (m.d * kLn2Pi) - m.logdet[k];
+      s_par[m.K + k] = st ? 0.0 : 0.5;
+      s_par[2 * m.K + k] = st ? 0.5 * (n + m.d) : 0.0;
+      s_par[3 * m.K + k] = st ? 1.0 / n : 0.0;
+      s_par[4 * m.K + k] = m.alpha[k];
+    }
+    __syncthreads();
+  }
   double my_w = -INFINITY, my_r = -INFINITY;
   bool okflag = false;
   if (i < N) {
     flg[i] = 0;
     lw[i] = 0;
-    const double rloc = mix_lse_q(m, Q, qs, i);
+    double rloc;
+    if (store_ld || !mix_lse_q_tab(m.K, P, Q, qs, i, s_exp, s_log, rloc)) rloc = mix_lse_q(m, Q, qs, i);
     my_r = rloc;
     log_rho[i] = rloc;
     bool reached_w = false;
@@ -500,12 +576,12 @@ k_draw_perm(long N, int K, const unsigned long long *__restrict__ indices, unsig
 }
 
 template <int NT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, d_blocks(NT))
 k_draw_mma(const double *__restrict__ pack, const int4 *__restrict__ tiles, int ntiles, const unsigned int *__restrict__ perm,
            const int *__restrict__ dfj, int d, uint64_t seed, uint32_t iter, long first_index, double *__restrict__ X,
            short *__restrict__ flg, unsigned long long *counters, const double *__restrict__ thr,
            unsigned int *__restrict__ redo, unsigned int *__restrict__ nredo) {
-  constexpr int KS = 2 * NT, MT = q_mt(NT), CS = q_comp_stride(NT);
+  constexpr int KS = 2 * NT, MT = d_mt(NT), CS = q_comp_stride(NT);
   extern __shared__ double sm[];  // [CS]: mean and factor tiles of the current component
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
   const int per = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -616,7 +692,7 @@ int launch_draw_t(const double *pack, const int4 *tiles, int ntiles, const unsig
   const size_t smem = (size_t)q_comp_stride(NT) * sizeof(double);
   static std::atomic<unsigned long long> smem_set{0};
   if (!set_max_smem_once(k_draw_mma<NT>, smem, smem_set)) return 1;
-  const int grid = ntiles < sm_count ? ntiles : sm_count;
+  const int grid = ntiles < sm_count * d_blocks(NT) ? ntiles : sm_count * d_blocks(NT);
   k_draw_mma<NT><<<grid, 256, smem, s>>>(pack, tiles, ntiles, perm, dfj, d, seed, iter, first_index, X, flg, counters, thr, redo, nredo);
   count_launch();
   return cudaGetLastError() != cudaSuccess;
@@ -755,10 +831,10 @@ int launch_q_mma(const double *X, long n, int d, const double *pack, int J, cons
 void launch_weights_q(const MixDev &m, const TargetDev &tg, int mode, const double *post_in, const short *ok_in,
                       double t_temper, long first_index, long N, const double *X, double *Q, double *Qt,
                       long qs, double *lw, double *log_rho, short *flg, double *blk_maxw, double *blk_maxr,
-                      unsigned long long *counters, double *first_vals, cudaStream_t s) {
+                      unsigned long long *counters, double *first_vals, int store_ld, cudaStream_t s) {
   if (N <= 0) return;
   const int nb = (int)((N + GEN_WEIGHT_THREADS - 1) / GEN_WEIGHT_THREADS);
-  k_weights_q<<<nb, GEN_WEIGHT_THREADS, 0, s>>>(m, tg, mode, post_in, ok_in, t_temper, first_index, N, X, Q, Qt, qs, lw,
+  k_weights_q<<<nb, GEN_WEIGHT_THREADS, store_ld ? 0 : (size_t)5 * m.K * sizeof(double), s>>>(store_ld, m, tg, mode, post_in, ok_in, t_temper, first_index, N, X, Q, Qt, qs, lw,
                                                 log_rho, flg, blk_maxw, blk_maxr, counters, first_vals);
   count_launch();
 }
@@ -804,10 +880,10 @@ int mma_stats_chunks(long n, int J, int sm_count) {
 
 int mma_draw_tile_samples(int d) {
   switch (mma_nt(d)) {
-    case 2: return 64 * q_mt(2);
-    case 4: return 64 * q_mt(4);
-    case 8: return 64 * q_mt(8);
-    case 16: return 64 * q_mt(16);
+    case 2: return 64 * d_mt(2);
+    case 4: return 64 * d_mt(4);
+    case 8: return 64 * d_mt(8);
+    case 16: return 64 * d_mt(16);
   }
   return 0;
 }
