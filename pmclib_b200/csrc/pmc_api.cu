@@ -226,7 +226,7 @@ struct pmcgpu_ctx {
   bool i3_pre = false;          // the proposal's whitening pack is in row-scaled form (w3_variant 3 and the ratio guard passed)
   double i3_shift[FUSED_MAXD] = {0};
   std::vector<double> i3_hw, i3_ht, i3_hd, i3_hcw;
-  DevBuf i3_gpack, i3_wpart, i3_scal, i3_coll, i3_spart, i3_out;
+  DevBuf i3_gpack, i3_wpart, i3_scal, i3_coll, i3_spart, i3_out, i3_gath;
 };
 
 namespace {
@@ -906,13 +906,14 @@ int run_iter3(pmcgpu_ctx *c, const Iter3Plan &p, int do_draw, int stage_limit, i
     if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 7, (double)N_total, c->stream))
       return fail(c, PMCGPU_ERR_CUDA, "reduction launch failed");
   } else {
-    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 1, (double)N_total, c->stream))
+    // one collective for the maxima and the normaliser: every rank publishes its 16 local values in its slot of a zeroed
+    // [nranks][16] buffer, the sum all-reduce gathers the slots, k_red3 folds them in rank order (see k_red3)
+    CU(c->i3_gath.ensure((size_t)c->nranks * 16 * sizeof(double)));
+    double *gath = c->i3_gath.as<double>();
+    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 1 | 2 | 16, (double)N_total, c->stream, gath, c->rank, c->nranks))
       return fail(c, PMCGPU_ERR_CUDA, "reduction launch failed");
-    RC(allreduce_dev(c, coll, 8, 1));
-    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 2, (double)N_total, c->stream))
-      return fail(c, PMCGPU_ERR_CUDA, "reduction launch failed");
-    RC(allreduce_dev(c, coll + 8, 8, 0));
-    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 4, (double)N_total, c->stream))
+    RC(allreduce_dev(c, gath, (long)c->nranks * 16, 0));
+    if (launch_red3(c->i3_wpart.as<double>(), wblocks, sm + SM_COUNTERS, fv, has_first, coll, scal, 8 | 4, (double)N_total, c->stream, gath, c->rank, c->nranks))
       return fail(c, PMCGPU_ERR_CUDA, "reduction launch failed");
   }
   if (stage_limit >= 2) {
@@ -1428,7 +1429,7 @@ void pmcgpu_destroy(pmcgpu_ctx *c) {
   DevBuf *bufs[] = {&c->dprop.buf, &c->dprop_pack, &c->dtmix.buf, &c->dt_pack, &c->ddef, &c->dfaces, &c->X, &c->W, &c->R,
                     &c->Idx, &c->Flg, &c->ld, &c->blkmax, &c->partials, &c->stats, &c->small, &c->rbg, &c->rbw, &c->rbacc,
                     &c->rbpart, &c->newmean, &c->hostpost, &c->hostok, &c->tmpx, &c->tmpo, &c->dcoll, &c->dshare, &c->dcomb, &c->dcombdim, &c->resp, &c->partials2, &c->dscal, &c->zig,
-                    &c->i3_gpack, &c->i3_wpart, &c->i3_scal, &c->i3_coll, &c->i3_spart, &c->i3_out, &c->didx8};
+                    &c->i3_gpack, &c->i3_wpart, &c->i3_scal, &c->i3_coll, &c->i3_spart, &c->i3_out, &c->didx8, &c->i3_gath};
   for (DevBuf *b : bufs) b->release();
   for (auto &t : c->comb) { t.dmix.buf.release(); t.dmix.pin.release(); }
   c->dprop.pin.release(); c->dtmix.pin.release(); c->pin_ppack.release(); c->pin_tpack.release();

@@ -509,9 +509,13 @@ __global__ void __launch_bounds__(128, MINB) k_weights3() {
 // coll[0..7]  (all-reduce max):  M, maxR-candidate, NaN-at-0 flags (W, R), reached-at-0 flags (W, R), +inf seen, spare
 // coll[8..15] (all-reduce sum):  S relative to the global M, usable samples, box rejections, failed draws
 // scal: I3_* below
+// With ranks attached the two blocks travel in ONE collective: phases 1|2|16 leave the rank-local values (S relative to the
+// LOCAL maximum) in this rank's 16-double slot of gath[nranks][16], all other slots zero, so that a sum all-reduce of gath is
+// an all-gather; phase 8 then folds the slots in rank order - M = max M_r, S = sum_r S_r exp(M_r - M), flags by max, counters
+// by sum - identically on every rank, and phase 4 finishes as in the single-rank case.
 __global__ void k_red3(const double *__restrict__ partials, int nblocks, const unsigned long long *__restrict__ counters,
                        const double *__restrict__ first_vals, int has_first, double *coll, double *scal, int phases,
-                       double n_total) {
+                       double n_total, double *gath, int rank, int nranks) {
   __shared__ double sa[256], sb[256];
   const int t = threadIdx.x;
   if (phases & 1) {
@@ -561,6 +565,30 @@ __global__ void k_red3(const double *__restrict__ partials, int nblocks, const u
       coll[10] = (double)counters[CNT_REJECT];
       coll[11] = (double)counters[CNT_DRAWFAIL];
       coll[12] = coll[13] = coll[14] = coll[15] = 0.0;
+    }
+    __syncthreads();
+  }
+  if (phases & 16) {  // publish: own slot = coll[0..15], the others zero
+    for (int j = t; j < nranks * 16; j += blockDim.x) gath[j] = (j >> 4) == rank ? coll[j & 15] : 0.0;
+  }
+  if (phases & 8) {  // combine the gathered slots (after the all-reduce), rank order
+    if (t == 0) {
+      double M = -INFINITY, R = -INFINITY, f[5] = {0, 0, 0, 0, 0}, S = 0.0, cnt[3] = {0, 0, 0};
+      for (int r = 0; r < nranks; ++r) {
+        const double *g = gath + 16 * r;
+        if (g[0] > M) M = g[0];
+        if (g[1] > R) R = g[1];
+        for (int j = 0; j < 5; ++j) if (g[2 + j] > f[j]) f[j] = g[2 + j];
+      }
+      for (int r = 0; r < nranks; ++r) {
+        const double *g = gath + 16 * r;
+        if (g[0] > -INFINITY) S += g[8] * exp(g[0] - M);
+        for (int j = 0; j < 3; ++j) cnt[j] += g[9 + j];
+      }
+      coll[0] = M; coll[1] = R;
+      for (int j = 0; j < 5; ++j) coll[2 + j] = f[j];
+      coll[7] = 0.0;
+      coll[8] = S; coll[9] = cnt[0]; coll[10] = cnt[1]; coll[11] = cnt[2];
     }
     __syncthreads();
   }
@@ -1234,8 +1262,9 @@ int launch_weights3(const Iter3Plan &p, const Iter3Weights &w, int *nblocks, cud
 }
 
 int launch_red3(const double *partials, int nblocks, const unsigned long long *counters, const double *first_vals,
-                int has_first, double *coll, double *scal, int phases, double n_total, cudaStream_t s) {
-  k_red3<<<1, 256, 0, s>>>(partials, nblocks, counters, first_vals, has_first, coll, scal, phases, n_total);
+                int has_first, double *coll, double *scal, int phases, double n_total, cudaStream_t s, double *gath, int rank,
+                int nranks) {
+  k_red3<<<1, 256, 0, s>>>(partials, nblocks, counters, first_vals, has_first, coll, scal, phases, n_total, gath, rank, nranks);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -273,7 +273,8 @@ int launch_draw3(const Iter3Plan &p, const Iter3Draw &d, cudaStream_t s);
 int launch_weights3(const Iter3Plan &p, const Iter3Weights &w, int *nblocks, cudaStream_t s);
 // phases: 1 = local maxima -> coll[0..7], 2 = normaliser relative to the (global) maximum -> coll[8..15], 4 = scalars
 int launch_red3(const double *partials, int nblocks, const unsigned long long *counters, const double *first_vals,
-                int has_first, double *coll, double *scal, int phases, double n_total, cudaStream_t s);
+                int has_first, double *coll, double *scal, int phases, double n_total, cudaStream_t s, double *gath = nullptr,
+                int rank = 0, int nranks = 1);
 int launch_stats3(const Iter3Plan &p, const Iter3Stats &st, cudaStream_t s);
 // out: stats[K*E] (with_stats) | H, Q, ok, flagged-out | count_k[K]
 int launch_comb3(const Iter3Plan &p, const double *partials, int with_stats, const double *scal, double *out, cudaStream_t s);
