@@ -50,10 +50,17 @@ void *pmcgpu_stream(pmcgpu_ctx *ctx);
  * "mma" (0 = do not use the large-d tensor path), "mma_min_d" (smallest dimension routed to it when no fused small-d kernel is instantiated for the shape, default 2),
  * "mma_max_chunk" (test knob: samples whitened per pass; 0 = as many as memory allows),
  * "t_temper" (t_iter_tempered used by pmcgpu_pmc_step, pmc.c:570; default 1), "max_attempts" (per-sample cap on box rejections), "force_precise" (1 = always take the two-pass update),
- * "guard_ratio" (pivot guard threshold of the one-pass update), "timing" (see pmcgpu_get_timing) */
+ * "guard_ratio" (pivot guard threshold of the one-pass update), "timing" (see pmcgpu_get_timing),
+ * "gen3" (0 = without the third-generation small-d kernels), "w3_variant" (third-generation weights kernel: 3 = row-scaled
+ * triangular solve, the default; 0 = exact per-component mean subtraction; 1, 2 = launch-shape experiments), "gen3_max_ratio"
+ * (largest |mu_j - c_j| / L_jj the row-scaled solve is used for, default 100; beyond it the exact form runs), "draw3" (1 = the
+ * block-grouped draw kernel), "sink_idx8" (0 = the host sink receives the component indices as size_t over PCIe instead of as
+ * bytes widened on the host) */
 int pmcgpu_set_option(pmcgpu_ctx *ctx, const char *name, double value);
 /* read-only diagnostics: "mma_active", "mma_inverse_discrepancy" (conditioning guard of the tensor path: explicit inverse
- * factors are used only while they agree with the reference's forward substitution to option "mma_inv_tol", default 1e-13) */
+ * factors are used only while they agree with the reference's forward substitution to option "mma_inv_tol", default 1e-13),
+ * "w3_rowscaled" (1 if the current proposal is packed for the row-scaled solve), "w3_shift_ratio" (the guard's ratio),
+ * "sink_bytes" (device-to-host bytes the host-sink copies of the last call moved) */
 int pmcgpu_get_info(pmcgpu_ctx *ctx, const char *name, double *value);
 
 /* timing of the dominant (fused) kernel, measured with CUDA events on the launching stream while option "timing" = 1:
