@@ -192,6 +192,7 @@ distribution *init_distribution(int ndim, void *data, posterior_log_pdf_func *lo
                                 simulate_func *simulate, error **err);
 void free_distribution(distribution **pdist);
 double distribution_lkl(void *pdist, const double *pars, error **err);
+double *distribution_fill_pars(distribution *dist, double *pars, error **err); /* distribution.c:193-209 (global, undeclared there) */
 void distribution_retrieve(const void *pdist, double *pars, error **err);
 void distribution_set_default(distribution *dist, int ndef, int *idef, double *vdef, error **err);
 /* names, broadcast hook, combined targets and Gaussian priors (distribution.h:66-119, pmc_dropin2.cpp) */
@@ -302,6 +303,7 @@ pmc_simu *pmc_simu_from_file(FILE *PMCSIM, int this_nsamples, int npar, int n_de
 double fill_read_pmc_simu(pmc_simu *psim, mix_mvdens *proposal, error **err);            /* pmc.c:400-445 */
 size_t *sort_indices(double *list, size_t size, size_t *in_ind, size_t *buf, int order, error **err); /* pmc.c:881-1034 */
 void filter_importance_weight(pmc_simu *psim, double nsig, error **err);                 /* pmc.c:829-873 (a stub there too) */
+void filter_importance_weight_sig(pmc_simu *psim, double nsig, error **err);             /* pmc.c:772-827 (global, undeclared in pmc.h) */
 #endif
 
 /* ---- libpmc_mpi (pmclib/include/pmc_mpi.h:52-101): one process per GPU, NCCL instead of MPI (pmc_dropin_mpi.cpp) ------- */

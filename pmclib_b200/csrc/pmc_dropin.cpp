@@ -586,16 +586,20 @@ void distribution_set_default(distribution *dist, int ndef, int *idef, double *v
   dist->ndim -= ndef;
 }
 // distribution.c:193-225: scatter the free parameters into the full vector, then the density
+// distribution.c:193-209 (a global symbol of libpmc, not declared in distribution.h): the free parameters scattered into the
+// full vector of a distribution with conditional ("default") parameters; without defaults the caller's vector itself
+double *distribution_fill_pars(distribution *dist, double *pars, error **err) {
+  (void)err;
+  if (dist->ndef == 0) return pars;
+  int ir = 0;
+  for (int ik = 0; ik < dist->ndim + dist->ndef; ++ik)
+    if (dist->def[ik] == 0) dist->pars[ik] = pars[ir++];
+  return dist->pars;
+}
 double distribution_lkl(void *pdist, const double *pars, error **err) {
   distribution *dist = (distribution *)pdist;
   if (!dist->log_pdf) { ERR_HERE(*err, dist_undef, "undefined log pdf function for distribution", *err, nullptr); return 0; }
-  const double *p = pars;
-  if (dist->ndef != 0) {
-    int ir = 0;
-    for (int ik = 0; ik < dist->ndim + dist->ndef; ++ik)
-      if (dist->def[ik] == 0) dist->pars[ik] = pars[ir++];
-    p = dist->pars;
-  }
+  const double *p = distribution_fill_pars(dist, const_cast<double *>(pars), err);
   const double res = dist->log_pdf(dist->data, p, err);
   FWD(*err, 0);
   return res;

@@ -368,6 +368,39 @@ void filter_importance_weight(pmc_simu *psim, double nsig, error **err) {
   if (psim->isLog != 1) fprintf(stderr, "Filtering normalized importance weights... It is probably too late...\n");
 }
 
+// pmc.c:772-827 (not declared in pmc.h, but a global symbol of libpmc): weights back to log scale with outliers flagged out.
+// Normalises first if needed (GPU), then on the host arrays: mean and standard deviation of the usable weights, every usable
+// sample with |w - mean| > nsig is flagged out and reported on stderr, the others get w <- log w; maxW = the largest of them
+// (with the reference's unconditional assignment at i == 0), isLog = 1.  The reference compares with nsig itself, not with
+// nsig standard deviations (the scaled deviation is computed and never used): kept.
+void filter_importance_weight_sig(pmc_simu *psim, double nsig, error **err) {
+  if (psim->isLog == 1) {
+    normalize_importance_weight(psim, err);
+    if (isError(*err)) { *err = newError(forwardErr, (char *)__func__, (char *)"", nullptr, *err); return; }
+  }
+  double mean = 0.0, max = 0.0;
+  size_t cnt = 0;
+  for (long i = 0; i < psim->nsamples; ++i)
+    if (psim->flg[i] != 0) { mean += psim->weights[i]; ++cnt; }
+  mean *= 1. / cnt;
+  for (long i = 0; i < psim->nsamples; ++i) {
+    if (psim->flg[i] == 0) continue;
+    const double dev = fabs(psim->weights[i] - mean);
+    if (dev > nsig) {
+      psim->flg[i] = 0;
+      fprintf(stderr, "Flagging %zu %g %g\n ", (size_t)i, dev, nsig);
+      fprintf(stderr, "%1d %10g", 0, psim->weights[i]);  // print_step (tools.c:301-313)
+      for (int a = 0; a < psim->ndim; ++a) fprintf(stderr, " %10g", psim->X[(size_t)i * psim->ndim + a]);
+      fprintf(stderr, "\n");
+      continue;
+    }
+    psim->weights[i] = log(psim->weights[i]);
+    if (i == 0 || psim->weights[i] > max) max = psim->weights[i];
+  }
+  psim->isLog = 1;
+  psim->maxW = max;
+}
+
 // pmc.c:881-1034: permutation that sorts list (order > 0 ascending, else descending).  in_ind == NULL allocates the
 // identity first.  Ties keep their input order (the reference's quick-sort leaves them in an unspecified order).
 size_t *sort_indices(double *list, size_t size, size_t *in_ind, size_t *buf, int order, error **err) {

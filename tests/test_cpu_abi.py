@@ -288,3 +288,23 @@ int main(void) {
         f.write(np.full(K, 1 / K).tobytes()); f.write(np.zeros((K, d)).tobytes()); f.write(np.tile(np.eye(d), (K, 1, 1)).tobytes())
     r = subprocess.run([exe, str(cfg), str(tmp_path / "out.bin"), "3"], capture_output=True, text=True, check=True)
     assert '"is_error": 1' in r.stdout and "-6024" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpmcref.so")), reason="compiled reference not built")
+@pytest.mark.parametrize("N,nsig", [(2000, 0.002), (5000, 1.0), (333, 1e-9)])
+def test_filter_importance_weight_sig_equals_the_compiled_reference(tmp_path, N, nsig):
+    """filter_importance_weight_sig (pmc.c:772-827, a global symbol of libpmc that pmc.h does not declare): the same C program
+    (tests/c/filter_sig_driver.c) linked against libpmcb200.so and against the compiled reference prints byte-identical flags,
+    log-weights, maxW and stderr reports - including the reference's comparison with nsig itself instead of nsig sigma."""
+    src = os.path.join(ROOT, "tests", "c", "filter_sig_driver.c")
+    outs = []
+    for tag, libdir, lib in (("ours", os.path.dirname(LIB_PATH), "pmcb200"), ("ref", os.path.join(ROOT, "oracle", "_ref"), "pmcref")):
+        exe = str(tmp_path / f"fs_{tag}")
+        subprocess.run(["gcc", "-O2", "-std=gnu99", "-I" + os.path.join(ROOT, "include"), src, "-o", exe, "-L" + libdir, "-l" + lib,
+                        "-Wl,-rpath," + libdir, "-lm"], check=True)
+        r = subprocess.run([exe, str(N), repr(nsig)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-500:]
+        outs.append((r.stdout, r.stderr))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] == outs[1][1]
+    assert outs[0][0].startswith("isLog 1 ")
