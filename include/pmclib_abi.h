@@ -14,6 +14,7 @@
 #define PMCLIB_ABI_H
 #include <stddef.h>
 #include <stdio.h>
+#include <time.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -291,6 +292,37 @@ double mean_from_psim(double *X, double *w, short *flg, int nsamples, int ndim, 
 FILE *fopen_err(const char *fname, const char *mode, error **err);  /* io.c:103-109 */
 void *malloc_err(size_t sz, error **err);                          /* io.c:111-120 */
 void *calloc_err(size_t nl, size_t sz1, error **err);              /* io.c:122-131 */
+/* the rest of liberrorio's io.h:34-75 (pmc_hostio.cpp): host-side file and memory helpers of drivers and target likelihoods */
+#define io_base -200
+#define io_file (-2 + io_base)
+unsigned int numberoflines(const char *name, error **err);                                   /* io.c:13-27 */
+unsigned int numberoflines_comments(const char *name, unsigned int *ncomment, error **err);  /* io.c:30-51 */
+int read_double(char **p, double *x);                                                         /* io.c:57-62 */
+int read_int(char **p, int *x);                                                               /* io.c:64-69 */
+double *readASCII(char *filename, int *fnx, int *fny, error **err);                           /* io.c:72-97 */
+void *realloc_err(void *ptr, size_t sz, error **err);                                         /* io.c:136-145 */
+void *resize_err(void *orig, size_t sz_orig, size_t sz_new, int free_orig, error **err);      /* io.c:151-174 */
+size_t read_line(FILE *fp, char *buff, int bmax, error **err);                                /* io.c:176-201 */
+void *read_any_vector(const char *fnm, size_t n, char *prs, size_t sz, error **err);          /* io.c:204-212 */
+void *read_any_list(const char *fnm, size_t *n, char *prs, size_t sz, error **err);           /* io.c:218-227 */
+void *read_any_list_count(const char *fnm, size_t *n, char *prs, size_t sz, size_t *nlines, error **err); /* io.c:236-323 */
+double *read_double_vector(const char *fnm, size_t n, error **err);                           /* io.c:326-387 */
+double *read_double_list(const char *fnm, size_t *n, error **err);
+int *read_int_vector(const char *fnm, size_t n, error **err);
+int *read_int_list(const char *fnm, size_t *n, error **err);
+float *read_float_vector(const char *fnm, size_t n, error **err);
+float *read_float_list(const char *fnm, size_t *n, error **err);
+long *read_long_vector(const char *fnm, size_t n, error **err);
+long *read_long_list(const char *fnm, size_t *n, error **err);
+void write_bin_vector(void *buf, const char *fnm, size_t n, error **err);                     /* io.c:422-436 */
+void *read_bin_vector(const char *fnm, size_t n, error **err);                                /* io.c:389-402 */
+void *read_bin_list(const char *fnm, size_t *n, error **err);                                 /* io.c:404-420 */
+void chomp(char *x);                                                                          /* io.c:438-442 */
+int is_directory(const char *path);                                                           /* io.c:490-502 */
+time_t start_time(FILE *FOUT);                                                                /* io.c:444-488 */
+void end_time(time_t t_start, FILE *FOUT);
+clock_t start_clock(FILE *FOUT);
+void end_clock(clock_t c_start, FILE *FOUT);
 void prepare_update(mix_mvdens *m, size_t *count, pmc_simu *psim, double **pbuf, error **err);                    /* pmc.c:1535-1579 */
 void cleanup_after_update(mix_mvdens *m, size_t *count, double minwgt, pmc_simu *psim, double *buf, error **err); /* pmc.c:1471-1533 */
 int double_cmp(const void *av, const void *bv);                                          /* pmc.c:1122-1131 */

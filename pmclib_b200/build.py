@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libpmcb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-I/usr/include"]
-SOURCES = ["pmc_iter3.cu", "pmc_fused2.cu", "pmc_fused.cu", "pmc_mma.cu", "pmc_generic.cu", "pmc_post.cu", "pmc_api.cu", "pmc_host.cpp", "pmc_dropin.cpp", "pmc_dropin2.cpp", "pmc_dropin_mpi.cpp", "pmc_rc.cpp"]
+SOURCES = ["pmc_iter3.cu", "pmc_fused2.cu", "pmc_fused.cu", "pmc_mma.cu", "pmc_generic.cu", "pmc_post.cu", "pmc_api.cu", "pmc_host.cpp", "pmc_dropin.cpp", "pmc_dropin2.cpp", "pmc_dropin_mpi.cpp", "pmc_rc.cpp", "pmc_hostio.cpp"]
 
 
 def _deps():

@@ -308,3 +308,23 @@ def test_filter_importance_weight_sig_equals_the_compiled_reference(tmp_path, N,
     assert outs[0][0] == outs[1][0]
     assert outs[0][1] == outs[1][1]
     assert outs[0][0].startswith("isLog 1 ")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpmcref.so")), reason="compiled reference not built")
+def test_liberrorio_helpers_equal_the_compiled_reference(tmp_path):
+    """io.h:34-75 (pmc_hostio.cpp): line counting, the text and binary readers, resize_err / realloc_err, chomp, read_double,
+    is_directory, readASCII - tests/c/io_driver.c linked against libpmcb200.so and against the compiled reference prints the
+    same values and the same error codes (err_io -101, err_allocate -102, io_file -202), quirks included."""
+    src = os.path.join(ROOT, "tests", "c", "io_driver.c")
+    outs = []
+    for tag, libdir, lib in (("ours", os.path.dirname(LIB_PATH), "pmcb200"), ("ref", os.path.join(ROOT, "oracle", "_ref"), "pmcref")):
+        exe = str(tmp_path / f"io_{tag}")
+        work = tmp_path / f"work_{tag}"
+        work.mkdir()
+        subprocess.run(["gcc", "-O1", "-std=gnu99", "-w", "-I" + os.path.join(ROOT, "include"), src, "-o", exe, "-L" + libdir, "-l" + lib,
+                        "-Wl,-rpath," + libdir, "-lm"], check=True)
+        r = subprocess.run([exe, "."], capture_output=True, text=True, timeout=120, cwd=str(work))
+        assert r.returncode == 0, r.stderr[-500:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1]
+    assert "read_bin_vector too long -> error -202" in outs[0] and "n 10 lines 4:" in outs[0]
